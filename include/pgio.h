@@ -1,0 +1,78 @@
+/*
+ * pgio.h -- host-side I/O around the hot path (C ABI, no CUDA): PAF reader, GFA/BED writers, option
+ * defaults and the deterministic synthetic-PAF generator used by tests and bench.py.
+ *
+ * These are the SURVEY.md §8(f) "next" rows (callers/data formats either side of the path), written
+ * from scratch; each entry cites the reference interface it stands in for.  The one deliberate
+ * difference from the reference reader: pgio_read_paf() stops after parsing -- the per-genome
+ * preprocessing block that the reference runs at the tail of pg_read_paf() (read.c:243-260) is
+ * hot-path work and is executed by pg_post_process() of libpgx instead (SURVEY.md §3.2 [verified]
+ * output-neutral).
+ */
+#ifndef PGIO_H
+#define PGIO_H
+
+#include "pangene_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+extern int pgio_verbose;
+
+/* option.c:6-26 -- reference defaults */
+void pgio_opt_init(pg_opt_t *opt);
+
+/* read.c:10-32 */
+pg_data_t *pgio_data_init(void);
+void pgio_data_destroy(pg_data_t *d);
+
+/* read.c:107-241 (everything before the postprocessing block). gzip or plain text, "-" = stdin.
+ * Returns 0, or -1 if the file cannot be opened (then no genome is added), like the reference. */
+int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *fn);
+
+/* read.c:305-318: name set for -X/-I/-P from "a,b,c" or "@file" */
+void *pgio_name_set(const char *spec);
+void pgio_name_set_destroy(void *set);
+
+/* format.c:153 + format.c:183 + format.c:113. path "-" = stdout. flags: bit0 = write S/L lines,
+ * bit1 = write W lines.  pgio_write_gfa re-sorts nothing in place (the reference's pg_write_walk
+ * sorts every genome by cm and back; we sort an index instead). */
+int32_t pgio_write_gfa(const pg_graph_t *g, const char *path, int32_t flags);
+int32_t pgio_write_bed(const pg_data_t *d, int32_t is_walk, const char *path);
+
+/* pangene.js:1168-1246 (gfa2matrix, without -d): gene x assembly presence/absence (or counts with
+ * copy_number != 0) computed from a GFA file; written as TSV to out_path. Returns #rows or -1. */
+int32_t pgio_gfa2matrix(const char *gfa_path, const char *out_path, int32_t copy_number);
+
+/* ---- deterministic synthetic input ------------------------------------------- */
+typedef struct {
+	int32_t shape;            /* 0 = eukaryote (configs 2-4), 1 = bacterial (config 5) */
+	int32_t n_genome;         /* genomes to generate in THIS call: global indices [genome_begin, genome_begin+n_genome) */
+	int32_t genome_begin;     /* first global genome index (rank sharding); ids/names are global */
+	int32_t n_genome_total;   /* population size (only used for naming/frequencies) */
+	int32_t n_gene;           /* gene (cluster) count */
+	int32_t iso_per_gene;     /* isoforms per gene: 1 or 4 */
+	int32_t n_ctg;            /* contigs per genome (eukaryote) / max contigs (bacterial) */
+	int32_t hits_per_genome;  /* target hits per genome (approximate) */
+	uint64_t seed;
+	int32_t n_threads;        /* 0 = hardware concurrency */
+} pgio_synth_t;
+
+void pgio_synth_default(pgio_synth_t *p, int32_t config);   /* config = 2,3,5 (BASELINE.json configs) */
+/* Build pg_data_t in memory, exactly what pgio_read_paf() would produce from the PAF text of the same
+ * records (tests/test_io.py checks the round trip). opt supplies the reader-side filters/score coef. */
+pg_data_t *pgio_synth(const pg_opt_t *opt, const pgio_synth_t *p);
+/* Write genome j of a synthetic run as miniprot-dialect PAF text (plain, not gz). */
+int32_t pgio_synth_write_paf(const pg_opt_t *opt, const pgio_synth_t *p, int32_t j_global, const char *path);
+
+/* deep copy (hits, exons, ctg tables share name pointers with the source dictionaries) */
+pg_data_t *pgio_data_clone(const pg_data_t *d);
+void pgio_data_clone_destroy(pg_data_t *d);
+
+int64_t pgio_total_hits(const pg_data_t *d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,591 @@
+// pgio.cpp -- host-side I/O around the hot path: PAF reader, GFA/BED writers, gfa2matrix, option
+// defaults.  Plain C++17 + zlib, exported with a C ABI (include/pgio.h).  No CUDA here.
+//
+// Reference behaviour being matched (cited per function): read.c:107-241 (reader, WITHOUT the
+// postprocessing block at read.c:243-260, which is hot-path work done by libpgx), option.c:6-26,
+// format.c:78-225 (writers), pangene.js:1168-1246 (gfa2matrix).  Written from scratch.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <cassert>
+#include <string>
+#include <string_view>
+#include <vector>
+#include <deque>
+#include <unordered_map>
+#include <algorithm>
+#include <zlib.h>
+#include "pgio.h"
+#include "pgio_priv.hpp"
+
+int pgio_verbose = 3;
+
+// ------------------------------------------------------------------------------------------------
+// options
+// ------------------------------------------------------------------------------------------------
+extern "C" void pgio_opt_init(pg_opt_t *o)   // option.c:6-26
+{
+	memset(o, 0, sizeof(*o));
+	o->gene_delim = ':';
+	o->min_prot_ratio = 0.5;  o->min_prot_iden = 0.5;   o->score_adj_coef = 2.0;
+	o->min_ov_ratio = 0.5;    o->min_vertex_ratio = 0.05;
+	o->branch_diff = 0.02;    o->branch_diff_dist = 0.05; o->branch_diff_cut = 0.5;
+	o->max_avg_occ = 10;      o->max_degree = 15;       o->max_dist_loci = 3;
+	o->n_branch_flt = 15;     o->min_arc_cnt = 1;
+	o->local_dist = 2000000;  o->local_count = 10;
+}
+
+// ------------------------------------------------------------------------------------------------
+// containers
+// ------------------------------------------------------------------------------------------------
+const char *pgio::NameTable::intern(std::string_view s, int32_t *id, bool *absent)
+{
+	auto it = map.find(s);
+	if (it != map.end()) { if (id) *id = it->second; if (absent) *absent = false; return names[it->second]; }
+	char *p = (char*)malloc(s.size() + 1);
+	memcpy(p, s.data(), s.size()); p[s.size()] = 0;
+	int32_t k = (int32_t)names.size();
+	names.push_back(p);
+	map.emplace(std::string_view(p, s.size()), k);
+	if (id) *id = k;
+	if (absent) *absent = true;
+	return p;
+}
+int32_t pgio::NameTable::find(std::string_view s) const
+{
+	auto it = map.find(s);
+	return it == map.end()? -1 : it->second;
+}
+pgio::NameTable::~NameTable() { for (char *p : names) free(p); }
+
+extern "C" pg_data_t *pgio_data_init(void)   // read.c:10-17
+{
+	pg_data_t *d = (pg_data_t*)calloc(1, sizeof(pg_data_t));
+	pgio::DataPriv *pv = new pgio::DataPriv();
+	d->d_ctg = pv;           // all three dictionaries live in one private object
+	d->d_gene = d->d_prot = 0;
+	return d;
+}
+
+extern "C" void pgio_data_destroy(pg_data_t *d)   // read.c:20-32
+{
+	if (d == 0) return;
+	for (int32_t i = 0; i < d->n_genome; ++i) {
+		pg_genome_t *g = &d->genome[i];
+		free(g->ctg); free(g->hit); free(g->exon); free(g->label);
+	}
+	free(d->genome); free(d->gene); free(d->prot);
+	delete (pgio::DataPriv*)d->d_ctg;
+	free(d);
+}
+
+extern "C" int64_t pgio_total_hits(const pg_data_t *d)
+{
+	int64_t n = 0;
+	for (int32_t j = 0; j < d->n_genome; ++j) n += d->genome[j].n_hit;
+	return n;
+}
+
+extern "C" pg_data_t *pgio_data_clone(const pg_data_t *s)
+{
+	pg_data_t *d = (pg_data_t*)calloc(1, sizeof(pg_data_t));
+	*d = *s;
+	d->m_genome = d->n_genome; d->m_gene = d->n_gene; d->m_prot = d->n_prot;
+	d->genome = (pg_genome_t*)malloc(sizeof(pg_genome_t) * (d->n_genome > 0? d->n_genome : 1));
+	d->gene = (pg_gene_t*)malloc(sizeof(pg_gene_t) * (d->n_gene > 0? d->n_gene : 1));
+	d->prot = (pg_prot_t*)malloc(sizeof(pg_prot_t) * (d->n_prot > 0? d->n_prot : 1));
+	memcpy(d->gene, s->gene, sizeof(pg_gene_t) * d->n_gene);
+	memcpy(d->prot, s->prot, sizeof(pg_prot_t) * d->n_prot);
+	for (int32_t j = 0; j < d->n_genome; ++j) {
+		const pg_genome_t *a = &s->genome[j];
+		pg_genome_t *b = &d->genome[j];
+		*b = *a;
+		b->m_ctg = a->n_ctg; b->m_hit = a->n_hit; b->m_exon = a->n_exon;
+		b->ctg = (pg_ctg_t*)malloc(sizeof(pg_ctg_t) * (a->n_ctg > 0? a->n_ctg : 1));
+		b->hit = (pg_hit_t*)malloc(sizeof(pg_hit_t) * (a->n_hit > 0? a->n_hit : 1));
+		b->exon = (pg_exon_t*)malloc(sizeof(pg_exon_t) * (a->n_exon > 0? a->n_exon : 1));
+		memcpy(b->ctg, a->ctg, sizeof(pg_ctg_t) * a->n_ctg);
+		memcpy(b->hit, a->hit, sizeof(pg_hit_t) * a->n_hit);
+		memcpy(b->exon, a->exon, sizeof(pg_exon_t) * a->n_exon);
+		b->label = a->label? strdup(a->label) : 0;
+	}
+	d->d_ctg = d->d_gene = d->d_prot = 0;   // names stay owned by the source
+	return d;
+}
+
+extern "C" void pgio_data_clone_destroy(pg_data_t *d)
+{
+	if (d == 0) return;
+	for (int32_t i = 0; i < d->n_genome; ++i) {
+		pg_genome_t *g = &d->genome[i];
+		free(g->ctg); free(g->hit); free(g->exon); free(g->label);
+	}
+	free(d->genome); free(d->gene); free(d->prot);
+	free(d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// name sets for -X / -I / -P  (read.c:264-318)
+// ------------------------------------------------------------------------------------------------
+static bool read_whole(const char *fn, std::string &out)
+{
+	gzFile fp = (fn && strcmp(fn, "-"))? gzopen(fn, "r") : gzdopen(0, "r");
+	if (fp == 0) return false;
+	char buf[1 << 16];
+	int n;
+	out.clear();
+	while ((n = gzread(fp, buf, sizeof(buf))) > 0) out.append(buf, n);
+	gzclose(fp);
+	return true;
+}
+
+// line iteration with the semantics of the reference's line reader (kseq KS_SEP_LINE): '\n' ends a
+// line, one trailing '\r' is dropped, a last line without '\n' still counts, no phantom empty line.
+template<class F> static void for_each_line(std::string &buf, F f)
+{
+	size_t n = buf.size(), st = 0;
+	while (st < n) {
+		size_t en = st;
+		while (en < n && buf[en] != '\n') ++en;
+		size_t e2 = en;
+		if (e2 > st && buf[e2 - 1] == '\r') --e2;
+		char saved = buf[e2]; // buf has a terminating 0 at buf[n] (std::string guarantee), so e2 <= n is fine
+		buf[e2] = 0;
+		f(&buf[st], e2 - st);
+		if (e2 < n) buf[e2] = saved;
+		st = en + 1;
+	}
+}
+
+extern "C" void *pgio_name_set(const char *o)
+{
+	pgio::NameTable *t = new pgio::NameTable();
+	if (*o != '@') {
+		const char *q = o;
+		for (const char *p = q;; ++p) {
+			if (*p == ',' || *p == ' ' || *p == '\t' || *p == 0) {
+				if (p > q) t->intern(std::string_view(q, p - q), 0, 0);
+				if (*p == 0) break;
+				q = p + 1;
+			}
+		}
+	} else {
+		std::string buf;
+		if (!read_whole(o + 1, buf)) { delete t; return 0; }
+		for_each_line(buf, [&](char *s, size_t) {
+			char *p = s;
+			while (*p && !isspace((unsigned char)*p)) ++p;
+			t->intern(std::string_view(s, p - s), 0, 0);
+		});
+	}
+	return t;
+}
+
+extern "C" void pgio_name_set_destroy(void *s) { delete (pgio::NameTable*)s; }
+
+// ------------------------------------------------------------------------------------------------
+// reader
+// ------------------------------------------------------------------------------------------------
+template<class T> static inline void grow0(T *&p, int64_t i, int32_t &m)   // pgpriv.h:28-36
+{
+	if (i >= m) {
+		int64_t old = m, nm = i + 1;
+		nm += (nm >> 1) + 16;
+		p = (T*)realloc(p, nm * sizeof(T));
+		memset((void*)(p + old), 0, (nm - old) * sizeof(T));
+		m = (int32_t)nm;
+	}
+}
+
+// mid-point of the CDS in contig coordinates (hit.c:14-27)
+int64_t pgio::cds_mid(const pg_hit_t *a, const pg_exon_t *e)
+{
+	int32_t tot = 0;
+	for (int32_t i = 0; i < a->n_exon; ++i) tot += e[i].oe - e[i].os;
+	int32_t half = tot >> 1, acc = 0;
+	for (int32_t i = 0; i < a->n_exon; ++i) {
+		int32_t l = e[i].oe - e[i].os;
+		if (acc <= half && half < acc + l) return a->cs + e[i].os + (half - acc);
+		acc += l;
+	}
+	fprintf(stderr, "[pgio] ERROR: alignment with empty CDS\n");
+	abort();
+}
+
+// CIGAR -> exon list (read.c:47-90). Returns the reference-consumed length x; exons land in `out`
+// in contig orientation; *n_fs = number of F/G operations.
+int64_t pgio::cigar_to_exons(const char *cg, bool rev, std::vector<pg_exon_t> &tmp, std::vector<pg_exon_t> &out, int32_t *n_fs)
+{
+	int64_t x = 0;
+	int32_t fs = 0;
+	tmp.clear();
+	tmp.push_back(pg_exon_t{0, 0});
+	const char *p = cg;
+	while (*p) {
+		char *r;
+		int64_t l = strtol(p, &r, 10);
+		char op = *r;
+		if (op == 'N' || op == 'U' || op == 'V') {
+			int64_t st, en;
+			if (op == 'N') st = x, en = x + l;
+			else if (op == 'U') st = x + 1, en = x + l - 2;
+			else st = x + 2, en = x + l - 1;
+			tmp.back().oe = (int32_t)st;
+			tmp.push_back(pg_exon_t{(int32_t)en, (int32_t)en});
+			x += l;
+		} else if (op == 'M' || op == 'X' || op == '=' || op == 'D') {
+			x += l * 3;
+		} else if (op == 'F' || op == 'G') {
+			x += l, ++fs;
+		}
+		if (op == 0) break;   // malformed tail; the reference would run off the string here
+		p = r + 1;
+	}
+	tmp.back().oe = (int32_t)x;
+	out.clear();
+	if (!rev) out = tmp;
+	else for (int32_t i = (int32_t)tmp.size() - 1; i >= 0; --i)
+		out.push_back(pg_exon_t{(int32_t)(x - tmp[i].oe), (int32_t)(x - tmp[i].os)});
+	*n_fs = fs;
+	return x;
+}
+
+int32_t pgio::adjusted_score(const pg_opt_t *opt, int32_t ms, int32_t mlen, int32_t blen, int32_t qs, int32_t qe, int32_t plen)
+{   // read.c:212-216 -- long-double exp, same expression shape
+	double div = 1.0 - (double)mlen / blen;
+	double uncov = 1.0 - (double)(qe - qs) / plen;
+	return (int32_t)(ms * expl(-opt->score_adj_coef * (div + uncov)) + .499);
+}
+
+static char *label_from_path(const char *fn)   // read.c:92-105
+{
+	int32_t len = (int32_t)strlen(fn), en = len, st;
+	int32_t i;
+	for (i = len - 1; i >= 0 && fn[i] != '/'; --i) {}
+	st = i + 1;
+	if (en >= 3 && strncmp(&fn[en - 3], ".gz", 3) == 0) en -= 3;
+	if (en >= 4 && strncmp(&fn[en - 4], ".paf", 4) == 0) en -= 4;
+	if (st >= en) return 0;
+	char *s = (char*)calloc(en - st + 1, 1);
+	memcpy(s, &fn[st], en - st);
+	return s;
+}
+
+void pgio::push_hit(pg_genome_t *g, pg_hit_t &hit, const std::vector<pg_exon_t> &ex, int32_t cg_fs, int32_t n_fs, int32_t n_stop)
+{
+	grow0(g->exon, (int64_t)g->n_exon + (int64_t)ex.size() - 1, g->m_exon);
+	memcpy(&g->exon[g->n_exon], ex.data(), ex.size() * sizeof(pg_exon_t));
+	hit.n_exon = (int32_t)ex.size();
+	hit.off_exon = g->n_exon;
+	g->n_exon += (int32_t)ex.size();
+	int32_t lof = (n_fs > 0? n_fs : 0) + (n_stop > 0? n_stop : 0);   // read.c:229-230
+	hit.lof = cg_fs > lof? cg_fs : lof;
+	hit.cm = pgio::cds_mid(&hit, &g->exon[hit.off_exon]);
+	grow0(g->hit, g->n_hit, g->m_hit);
+	g->hit[g->n_hit++] = hit;
+}
+
+extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *fn)
+{
+	std::string buf;
+	if (!read_whole(fn, buf)) return -1;                          // read.c:117-118
+	pgio::DataPriv *pv = (pgio::DataPriv*)d->d_ctg;
+	const pgio::NameTable *excl = (const pgio::NameTable*)opt->excl, *incl = (const pgio::NameTable*)opt->incl, *pref = (const pgio::NameTable*)opt->preferred;
+
+	grow0(d->genome, d->n_genome, d->m_genome);
+	pg_genome_t *g = &d->genome[d->n_genome++];
+	memset(g, 0, sizeof(*g));
+	g->label = fn && strcmp(fn, "-")? label_from_path(fn) : label_from_path("-");
+
+	std::unordered_map<std::string_view, int32_t> file_ctg;      // per-file contig ids, first-seen order
+	std::vector<int32_t> seen_cnt;                                // per-protein line count in THIS file (rank, read.c:170)
+	std::vector<pg_exon_t> tmp, ex;
+	std::vector<char*> fld;
+	int64_t n_tot = 0;
+
+	for_each_line(buf, [&](char *s, size_t) {
+		++n_tot;
+		fld.clear();
+		for (char *p = s, *q = s;; ++p)
+			if (*p == '\t' || *p == 0) { int c = *p; *p = 0; fld.push_back(q); q = p + 1; if (c == 0) break; }
+		pg_hit_t hit;
+		memset(&hit, 0, sizeof(hit));
+		hit.pid = hit.pid_dom = hit.cid = hit.off_exon = hit.n_exon = -1;
+		int32_t n_fs = -1, n_stop = -1, cg_fs = 0, pid = -1, gid = -1;
+		bool have_exons = false;
+		const int nf = (int)fld.size();
+		do {
+			// ---- column 0: "gene<delim>protein" (read.c:139-171)
+			char *q = fld[0], *r = q;
+			if (excl && excl->find(q) >= 0) break;
+			while (*r && *r != opt->gene_delim) ++r;
+			bool has_delim = (*r == opt->gene_delim && *r != 0);
+			std::string_view gname(q, r - q);
+			if (excl && excl->find(gname) >= 0) break;
+			int preferred = pref && pref->find(gname) >= 0, included = incl && incl->find(gname) >= 0;
+			bool absent;
+			(void)has_delim;
+			const char *nm = pv->gene.intern(gname, &gid, &absent);
+			if (absent) { d->n_gene++; grow0(d->gene, gid, d->m_gene); }
+			d->gene[gid].name = nm; d->gene[gid].preferred = preferred; d->gene[gid].included = included;
+			nm = pv->prot.intern(q, &pid, &absent);
+			if (absent) { d->n_prot++; grow0(d->prot, pid, d->m_prot); }
+			d->prot[pid].name = nm; d->prot[pid].gid = gid; d->prot[pid].len = 0;
+			hit.pid = pid;
+			if ((size_t)pid >= seen_cnt.size()) seen_cnt.resize(pid + 1 + (pid >> 1), -1);
+			hit.rank = ++seen_cnt[pid];
+			if (nf < 2) break;
+			// ---- columns 1..10 (read.c:172-211)
+			char *e;
+			int32_t len = (int32_t)strtol(fld[1], &e, 10);
+			d->prot[pid].len = len;
+			d->gene[gid].len = (int32_t)d->gene[gid].len > len? d->gene[gid].len : len;
+			if (nf < 3) break;
+			hit.qs = (int32_t)strtol(fld[2], &e, 10);
+			if (nf < 4) break;
+			hit.qe = (int32_t)strtol(fld[3], &e, 10);
+			if (hit.qe - hit.qs < d->prot[pid].len * opt->min_prot_ratio) break;
+			if (nf < 5) break;
+			if (fld[4][0] != '+' && fld[4][0] != '-') break;
+			hit.rev = fld[4][0] == '+'? 0 : 1;
+			if (nf < 6) break;
+			{
+				std::string_view cn(fld[5]);
+				auto it = file_ctg.find(cn);
+				if (it == file_ctg.end()) {
+					const char *gn = pv->ctg.intern(cn, 0, 0);
+					grow0(g->ctg, g->n_ctg, g->m_ctg);
+					g->ctg[g->n_ctg].name = gn;
+					hit.cid = g->n_ctg;
+					file_ctg.emplace(std::string_view(gn, cn.size()), g->n_ctg++);
+				} else hit.cid = it->second;
+			}
+			if (nf < 7) break;
+			g->ctg[hit.cid].len = strtol(fld[6], &e, 10);
+			if (nf < 8) break;
+			hit.cs = strtol(fld[7], &e, 10);
+			if (nf < 9) break;
+			hit.ce = strtol(fld[8], &e, 10);
+			if (nf < 10) break;
+			hit.mlen = (int32_t)strtol(fld[9], &e, 10);
+			if (nf < 11) break;
+			hit.blen = (int32_t)strtol(fld[10], &e, 10);
+			if (hit.mlen < hit.blen * opt->min_prot_iden) break;
+			// ---- tags (read.c:212-224)
+			for (int i = 12; i < nf; ++i) {
+				const char *t = fld[i];
+				if (strncmp(t, "ms:i:", 5) == 0) {
+					hit.score_ori = (int32_t)strtol(t + 5, &e, 10);
+					hit.score_adj = pgio::adjusted_score(opt, hit.score_ori, hit.mlen, hit.blen, hit.qs, hit.qe, d->prot[pid].len);
+				} else if (strncmp(t, "fs:i:", 5) == 0) n_fs = (int32_t)strtol(t + 5, &e, 10);
+				else if (strncmp(t, "st:i:", 5) == 0) n_stop = (int32_t)strtol(t + 5, &e, 10);
+				else if (strncmp(t, "cg:Z:", 5) == 0) {
+					int64_t x = pgio::cigar_to_exons(t + 5, hit.rev, tmp, ex, &cg_fs);
+					if (x != hit.ce - hit.cs) { fprintf(stderr, "[pgio] ERROR: CIGAR length %ld != ce-cs %ld\n", (long)x, (long)(hit.ce - hit.cs)); abort(); } // read.c:75
+					have_exons = true;
+				}
+			}
+		} while (0);
+		if (have_exons) pgio::push_hit(g, hit, ex, cg_fs, n_fs, n_stop);
+	});
+	if (pgio_verbose >= 4)
+		fprintf(stderr, "[M::%s] [%d] %s: %ld lines parsed, %d hits kept\n", __func__, d->n_genome - 1, g->label? g->label : "*", (long)n_tot, g->n_hit);
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// writers
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Out {
+	FILE *fp; bool close_it; std::string s;
+	explicit Out(const char *path) {
+		if (path == 0 || strcmp(path, "-") == 0) fp = stdout, close_it = false;
+		else fp = fopen(path, "w"), close_it = true;
+	}
+	~Out() { flush(); if (fp && close_it) fclose(fp); }
+	void flush() { if (fp && !s.empty()) fwrite(s.data(), 1, s.size(), fp); s.clear(); }
+	void maybe_flush() { if (s.size() > (1u << 20)) flush(); }
+	void num(long v) { char b[24]; int l = 0; bool neg = v < 0; unsigned long x = neg? 0ul - (unsigned long)v : (unsigned long)v;
+		do { b[l++] = '0' + x % 10; x /= 10; } while (x); if (neg) b[l++] = '-'; while (l) s.push_back(b[--l]); }
+	void str(const char *p) { s.append(p); }
+	void ch(char c) { s.push_back(c); }
+};
+}
+
+static void write_seg_lines(const pg_graph_t *g, Out &o)   // format.c:120-135
+{
+	const pg_data_t *d = g->d;
+	for (int32_t i = 0; i < g->n_seg; ++i) {
+		const pg_seg_t *s = &g->seg[i];
+		int32_t pid = d->gene[s->gid].rep_pid;
+		o.str("S\t"); o.str(d->gene[s->gid].name); o.str("\t*\tLN:i:"); o.num(d->prot[pid].len);
+		o.str("\tng:i:"); o.num(s->n_genome); o.str("\tnc:i:"); o.num(s->tot_cnt);
+		o.str("\tc1:i:"); o.num(s->n_dom); o.str("\tc2:i:"); o.num(s->n_sub);
+		o.str("\tpp:Z:"); o.str(d->prot[pid].name); o.ch('\n');
+		o.maybe_flush();
+	}
+}
+
+static void write_arc_lines(const pg_graph_t *g, Out &o)   // format.c:137-151
+{
+	const pg_data_t *d = g->d;
+	for (int32_t i = 0; i < g->n_arc; ++i) {
+		const pg_arc_t *a = &g->arc[i];
+		uint32_t v = (uint32_t)(a->x >> 32), w = (uint32_t)a->x;
+		o.str("L\t"); o.str(d->gene[g->seg[v >> 1].gid].name); o.ch('\t'); o.ch("+-"[v & 1]); o.ch('\t');
+		o.str(d->gene[g->seg[w >> 1].gid].name); o.ch('\t'); o.ch("+-"[w & 1]); o.str("\t0M\tng:i:"); o.num(a->n_genome);
+		o.str("\tnc:i:"); o.num(a->tot_cnt); o.str("\tad:i:"); o.num(a->avg_dist);
+		o.str("\ts1:i:"); o.num(a->s1); o.str("\ts2:i:"); o.num(a->s2); o.ch('\n');
+		o.maybe_flush();
+	}
+}
+
+// "sample#hap#contig" (format.c:159-181): returns hap >= 0 and the sample in `buf`, or -1
+static int32_t parse_sample(std::string &buf, const char *name)
+{
+	const char *h1 = strchr(name, '#');
+	if (h1 == 0) return -1;
+	if (h1 == name) return -1;
+	buf.assign(name, h1 - name);
+	const char *q = h1 + 1, *p = q;
+	while (*p && *p != '#') ++p;
+	char *r;
+	long hap = strtol(q, &r, 10);
+	return (r == p && hap >= 0)? (int32_t)hap : -1;
+}
+
+static void write_walk_lines(const pg_graph_t *q, Out &o)   // format.c:183-225
+{
+	const pg_data_t *d = q->d;
+	std::string sample;
+	std::vector<int32_t> ord;
+	for (int32_t j = 0; j < d->n_genome; ++j) {
+		const pg_genome_t *g = &d->genome[j];
+		// contig-major, then CDS mid-point; ties keep the incoming (cid,cs) order (see DESIGN.md "tie order")
+		ord.resize(g->n_hit);
+		for (int32_t i = 0; i < g->n_hit; ++i) ord[i] = i;
+		std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+			const pg_hit_t &x = g->hit[a], &y = g->hit[b];
+			return x.cid != y.cid? x.cid < y.cid : x.cm < y.cm; });
+		for (int32_t i0 = 0, i = 1; i <= g->n_hit; ++i) {
+			if (i == g->n_hit || g->hit[ord[i]].cid != g->hit[ord[i0]].cid) {
+				int32_t cid = g->hit[ord[i0]].cid, n = 0;
+				for (int32_t k = i0; k < i; ++k) n += !g->hit[ord[k]].flt;
+				if (n > 0) {
+					int32_t hap = parse_sample(sample, g->ctg[cid].name);
+					o.str("W\t");
+					if (hap >= 0) { o.str(sample.c_str()); o.ch('\t'); o.num(hap); }
+					else if (g->label) { o.str(g->label); o.str("\t0"); }
+					else { o.num(j); o.str("\t0"); }
+					o.ch('\t'); o.str(g->ctg[cid].name); o.str("\t*\t*\t");
+					for (int32_t k = i0; k < i; ++k) {
+						const pg_hit_t *a = &g->hit[ord[k]];
+						if (a->flt) continue;
+						o.ch("><"[a->rev]); o.str(d->gene[d->prot[a->pid].gid].name);
+					}
+					o.str("\tlf:B:i");
+					for (int32_t k = i0; k < i; ++k) {
+						const pg_hit_t *a = &g->hit[ord[k]];
+						if (a->flt) continue;
+						o.ch(','); o.num(a->lof);
+					}
+					o.ch('\n');
+					o.maybe_flush();
+				}
+				i0 = i;
+			}
+		}
+	}
+}
+
+extern "C" int32_t pgio_write_gfa(const pg_graph_t *g, const char *path, int32_t flags)
+{
+	Out o(path);
+	if (o.fp == 0) return -1;
+	if (flags & 1) { write_seg_lines(g, o); write_arc_lines(g, o); }
+	if (flags & 2) write_walk_lines(g, o);
+	return 0;
+}
+
+extern "C" int32_t pgio_write_bed(const pg_data_t *d, int32_t is_walk, const char *path)   // format.c:78-118
+{
+	Out o(path);
+	if (o.fp == 0) return -1;
+	for (int32_t j = 0; j < d->n_genome; ++j) {
+		const pg_genome_t *g = &d->genome[j];
+		for (int32_t i = 0; i < g->n_hit; ++i) {
+			const pg_hit_t *a = &g->hit[i];
+			if (is_walk && a->flt) continue;
+			char idbuf[16];
+			// the reference's %ld formatter narrows through int (format.c:43-47); coordinates < 2^31 print identically
+			o.str(g->ctg[a->cid].name); o.ch('\t'); o.num((int)a->cs); o.ch('\t'); o.num((int)a->ce); o.ch('\t');
+			o.str(d->prot[a->pid].name); o.ch('\t'); o.num(a->score_ori); o.ch('\t'); o.ch("+-"[a->rev]); o.ch('\t');
+			o.num((int)a->cs); o.ch('\t'); o.num((int)a->ce); o.str("\t0\t"); o.num(a->n_exon); o.ch('\t');
+			for (int32_t k = 0; k < a->n_exon; ++k) { o.num(g->exon[a->off_exon + k].oe - g->exon[a->off_exon + k].os); o.ch(','); }
+			o.ch('\t');
+			for (int32_t k = 0; k < a->n_exon; ++k) { o.num(g->exon[a->off_exon + k].os); o.ch(','); }
+			snprintf(idbuf, 15, "%.4f", (double)a->mlen / a->blen);
+			o.str("\tft:i:"); o.num(a->flt);
+			o.str("\tpf:Z:"); o.num(a->pseudo); o.num(a->flt_iso_ov); o.num(a->flt_chain); o.num(a->flt_iso_sub_self);
+			o.str("\trk:i:"); o.num(a->rank); o.str("\trp:i:"); o.num(a->rep); o.str("\tsd:i:"); o.num(a->shadow);
+			o.str("\tvt:i:"); o.num(a->vtx); o.str("\tbr:i:"); o.num(a->weak_br); o.str("\tcm:i:"); o.num((int)a->cm);
+			o.str("\tid:f:"); o.str(idbuf); o.str("\tdm:Z:"); o.str(a->pid_dom0 < 0? "*" : d->prot[a->pid_dom0].name); o.ch('\n');
+			o.maybe_flush();
+		}
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gfa2matrix (pangene.js:1168-1246, options -c only; -d/-p CD-HIT merging is not reproduced)
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t pgio_gfa2matrix(const char *gfa_path, const char *out_path, int32_t copy_number)
+{
+	std::string buf;
+	if (!read_whole(gfa_path, buf)) return -1;
+	std::unordered_map<std::string, int32_t> seg_id, asm_id;
+	std::vector<std::string> seg_name, asm_name;
+	struct Walk { int32_t asm_i; std::vector<int32_t> segs; };
+	std::vector<Walk> walks;
+	auto reg_seg = [&](const std::string &n) { auto it = seg_id.find(n); if (it != seg_id.end()) return it->second;
+		int32_t k = (int32_t)seg_name.size(); seg_id.emplace(n, k); seg_name.push_back(n); return k; };
+	for_each_line(buf, [&](char *s, size_t) {
+		std::vector<char*> f;
+		for (char *p = s, *q = s;; ++p) if (*p == '\t' || *p == 0) { int c = *p; *p = 0; f.push_back(q); q = p + 1; if (c == 0) break; }
+		if (f.empty()) return;
+		if (f[0][0] == 'S' && f.size() >= 2) reg_seg(f[1]);
+		else if (f[0][0] == 'L' && f.size() >= 5) { reg_seg(f[1]); reg_seg(f[3]); }
+		else if (f[0][0] == 'W' && f.size() >= 7) {
+			std::string a = std::string(f[1]) + "#" + f[2];
+			auto it = asm_id.find(a);
+			int32_t ai;
+			if (it == asm_id.end()) { ai = (int32_t)asm_name.size(); asm_id.emplace(a, ai); asm_name.push_back(a); } else ai = it->second;
+			Walk w; w.asm_i = ai;
+			for (const char *p = f[6]; *p;) {
+				if (*p == '>' || *p == '<') {
+					const char *q = p + 1;
+					while (*q && *q != '>' && *q != '<' && !isspace((unsigned char)*q)) ++q;
+					auto jt = seg_id.find(std::string(p + 1, q - p - 1));
+					if (jt != seg_id.end()) w.segs.push_back(jt->second);
+					p = q;
+				} else ++p;
+			}
+			walks.push_back(std::move(w));
+		}
+	});
+	std::vector<std::vector<int32_t>> mat(seg_name.size(), std::vector<int32_t>(asm_name.size(), 0));
+	for (const Walk &w : walks) for (int32_t s : w.segs) ++mat[s][w.asm_i];
+	Out o(out_path);
+	if (o.fp == 0) return -1;
+	o.str("Gene");
+	for (auto &a : asm_name) { o.ch('\t'); o.str(a.c_str()); }
+	o.ch('\n');
+	for (size_t i = 0; i < seg_name.size(); ++i) {
+		o.str(seg_name[i].c_str());
+		for (size_t j = 0; j < asm_name.size(); ++j) { o.ch('\t'); o.num(copy_number? mat[i][j] : (mat[i][j] > 1? 1 : mat[i][j])); }
+		o.ch('\n'); o.maybe_flush();
+	}
+	return (int32_t)seg_name.size();
+}

@@ -1,0 +1,33 @@
+// pgio_priv.hpp -- internals shared by pgio.cpp and pgio_synth.cpp (host only)
+#pragma once
+#include <cstdint>
+#include <string_view>
+#include <vector>
+#include <unordered_map>
+#include "pangene_abi.h"
+
+namespace pgio {
+
+// name -> dense id in first-seen order; owns the strings (stands in for the reference's dict.c)
+struct NameTable {
+	std::unordered_map<std::string_view, int32_t> map;
+	std::vector<char*> names;
+	const char *intern(std::string_view s, int32_t *id, bool *absent);
+	int32_t find(std::string_view s) const;
+	NameTable() = default;
+	NameTable(const NameTable&) = delete;
+	~NameTable();
+};
+
+struct DataPriv {           // hangs off pg_data_t::d_ctg
+	NameTable ctg, gene, prot;
+	std::vector<char*> arena;   // bulk name storage of synthetic data
+	~DataPriv() { for (char *p : arena) free(p); }
+};
+
+int64_t cds_mid(const pg_hit_t *a, const pg_exon_t *e);
+int64_t cigar_to_exons(const char *cg, bool rev, std::vector<pg_exon_t> &tmp, std::vector<pg_exon_t> &out, int32_t *n_fs);
+int32_t adjusted_score(const pg_opt_t *opt, int32_t ms, int32_t mlen, int32_t blen, int32_t qs, int32_t qe, int32_t plen);
+void push_hit(pg_genome_t *g, pg_hit_t &hit, const std::vector<pg_exon_t> &ex, int32_t cg_fs, int32_t n_fs, int32_t n_stop);
+
+}
