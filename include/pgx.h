@@ -1,0 +1,89 @@
+/*
+ * pgx.h -- C ABI of libpgx.so, the B200 (sm_100a) implementation of pangene's hot path.
+ *
+ * DROP-IN BOUNDARY.  The four pg_* functions below have exactly the signatures and the post-conditions of
+ * the reference's entry points; a pangene host links libpgx instead of graph.o/vertex.o/branch.o/hit.o/
+ * overlap.o and calls them unchanged (INTEGRATION.md shows the two-line Makefile change and the one-line
+ * reader change).  Everything is plain C: pointers, int32/int64/double, the POD structs of pangene_abi.h.
+ * Results are returned in libc-malloc'd memory that the reference's own destroy functions may free().
+ * CUDA / NCCL failures print to stderr and abort(), matching the reference's fail-fast style.  There is no
+ * CPU fallback: without a usable CUDA device every entry point aborts with a message.
+ */
+#ifndef PGX_H
+#define PGX_H
+
+#include "pangene_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference: `extern int pg_verbose` (pangene.h:126, option.c:4) */
+extern int pg_verbose;
+
+/* reference: pg_post_process(), pangene.h:133 / graph.c:7-32.  ADDITIONALLY runs, first, the per-genome
+ * preprocessing block that the reference executes at the tail of pg_read_paf() (read.c:243-260) -- so `d` must
+ * hold RAW parsed hits (as left by pgio_read_paf(), or by the reference reader with that block removed). On
+ * return every genome's hit[] is a fresh malloc'd array sorted by (cid, cs) with all flags of that stage set
+ * (unless lazy materialisation is on, see pgx_set_lazy). */
+void pg_post_process(const pg_opt_t *opt, pg_data_t *d);
+
+/* reference: pg_graph_init(), pangene.h:135 / graph.c:34-41 */
+pg_graph_t *pg_graph_init(pg_data_t *d);
+
+/* reference: pg_graph_gen(), pangene.h:136 / graph.c:280-322.  Continues on the device-resident state left by
+ * pg_post_process(q->d). Fills q->seg/arc/g2s/idx (malloc'd) and every hit flag the writers print. */
+void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q);
+
+/* reference: pg_graph_destroy(), pangene.h:137 / graph.c:43-47 */
+void pg_graph_destroy(pg_graph_t *g);
+
+/* ---- engine control (no reference counterpart) ------------------------------------------------- */
+
+int  pgx_device_count(void);
+void pgx_set_device(int dev);                 /* default: current CUDA device */
+
+/* 1: pg_post_process() leaves the hits on the device and only updates d->prot/d->gene; pg_graph_gen()
+ * materialises everything once.  0 (default): strict reference post-conditions after each call. */
+void pgx_set_lazy(int lazy);
+
+/* Multi-GPU, one process per GPU.  Genomes are partitioned across ranks (this rank's pg_data_t holds genomes
+ * [genome_begin, genome_begin + d->n_genome) of n_genome_total); gene/protein ids must be global.  The 128-byte
+ * id comes from pgx_comm_unique_id() on rank 0 and is broadcast by the launcher (torch.distributed, MPI, ...).
+ * After pgx_comm_init() the pg_* calls are collective: every rank calls them in the same order. The graph
+ * (seg/arc) comes back replicated on every rank; hits stay with their owner. */
+int  pgx_comm_unique_id(void *out128);
+int  pgx_comm_init(int rank, int nranks, const void *id128, int32_t n_genome_total, int32_t genome_begin);
+void pgx_comm_destroy(void);
+
+/* ---- staged API: the same path with the host<->device boundary made explicit (bench.py, tests) -- */
+typedef struct pgx_session_s pgx_session_t;
+
+pgx_session_t *pgx_upload(const pg_data_t *d);                       /* host AoS -> HBM */
+void pgx_run(pgx_session_t *s, const pg_opt_t *opt, int stage);      /* stage 1: load-time block + pg_post_process; 2: pg_graph_gen; 3: both */
+void pgx_download(pgx_session_t *s, pg_data_t *d, pg_graph_t *q);    /* HBM -> malloc'd host structs; q may be NULL after stage 1 */
+void pgx_session_free(pgx_session_t *s);
+
+typedef struct {
+	uint64_t launches;            /* kernels launched by this library since the last reset */
+	double   sweep_ms;            /* device time of the FIRST (load-time) overlap sweep of the last run, CUDA events */
+	double   sweep_bytes;         /* its algorithmic bytes: sum_unfiltered(52 + 8 n_exon) + 4 n_filtered */
+	double   run_ms[3];           /* device time of stage 1, stage 2, total of the last pgx_run */
+	int64_t  n_hit, n_active;     /* hits uploaded / hits that survived the load-time filters */
+	int64_t  tie[4];              /* tie-order detector, same meaning as oracle pgo_tie_report() */
+	int32_t  n_seg, n_arc;
+	int64_t  h2d_bytes, d2h_bytes;
+} pgx_stats_t;
+void pgx_get_stats(pgx_stats_t *out);
+void pgx_reset_stats(void);
+
+/* test hooks for the device primitives (tests/test_gpu_primitives.py) */
+void pgx_test_radix_sort(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits);
+void pgx_test_exclusive_sum(const uint32_t *in, uint32_t *out, int64_t n);
+void pgx_test_segmented_max(const int32_t *seg, const int32_t *val, int32_t *out, int64_t n);
+void pgx_test_flag_sort_replay(pg128_t *a, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

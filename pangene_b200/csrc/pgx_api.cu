@@ -1,0 +1,201 @@
+// pgx_api.cu -- the C-ABI surface of libpgx.so (include/pgx.h) over the device engine (pgx_engine.cuh).
+// Built for sm_100a only; there is no CPU path behind any of these entry points.
+#include <map>
+#include <mutex>
+#include "pgx_engine.cuh"
+
+namespace pgx {
+LaunchStats g_launch;
+Stats g_stats;
+Comm g_comm;
+static int g_device = -1, g_lazy = 0;
+static std::map<const pg_data_t*, Session*> g_sessions;   // pg_post_process() -> pg_graph_gen() hand-over
+
+static void need_device()
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n < 1) PGX_FATAL("no CUDA device available (%s). libpgx has no CPU fallback.", cudaGetErrorString(e));
+	if (g_device >= 0) PGX_CHECK(cudaSetDevice(g_device));
+	cudaDeviceProp p;
+	int dev = 0;
+	PGX_CHECK(cudaGetDevice(&dev));
+	PGX_CHECK(cudaGetDeviceProperties(&p, dev));
+	if (p.major < 10) PGX_FATAL("device %d (%s, sm_%d%d) is not a Blackwell part; libpgx is built for sm_100a only", dev, p.name, p.major, p.minor);
+}
+
+static void timed_run(Session *s, const pg_opt_t *opt, int stage)
+{
+	cudaEvent_t e0 = s->ev[2], e1 = s->ev[3];
+	float ms;
+	if (stage & 1) {
+		PGX_CHECK(cudaEventRecord(e0, s->st));
+		PGX_CHECK(cudaMemsetAsync(s->counters.p, 0, Session::C_N * 4, s->st));
+		s->stage_load(opt);
+		s->stage_post(opt);
+		PGX_CHECK(cudaEventRecord(e1, s->st));
+		PGX_CHECK(cudaEventSynchronize(e1));
+		PGX_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+		g_stats.run_ms[0] = ms;
+	}
+	if (stage & 2) {
+		PGX_CHECK(cudaEventRecord(e0, s->st));
+		s->stage_graph(opt);
+		PGX_CHECK(cudaEventRecord(e1, s->st));
+		PGX_CHECK(cudaEventSynchronize(e1));
+		PGX_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+		g_stats.run_ms[1] = ms;
+	}
+	g_stats.run_ms[2] = ((stage & 1)? g_stats.run_ms[0] : 0) + ((stage & 2)? g_stats.run_ms[1] : 0);
+	s->collect_stats();
+}
+} // namespace pgx
+
+using namespace pgx;
+
+extern "C" {
+
+int pg_verbose = 3;
+
+void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
+{
+	need_device();
+	if (pg_verbose >= 3) fprintf(stderr, "[M::%s] %d genes and %d proteins\n", __func__, d->n_gene, d->n_prot);
+	auto it = g_sessions.find(d);
+	if (it != g_sessions.end()) { delete it->second; g_sessions.erase(it); }
+	Session *s = new Session();
+	s->upload(d);
+	timed_run(s, opt, 1);
+	if (!g_lazy) s->download(d, nullptr);
+	else {   // the protein/gene tables are cheap and always current
+		for (int32_t i = 0; i < d->n_prot; ++i) { d->prot[i].n = s->rep.prot_n[i]; d->prot[i].avg_score_adj = s->rep.prot_avg[i]; d->prot[i].rep = s->rep.prot_rep[i]; d->prot[i].max_score_ori = s->h_prot_max[i]; }
+		for (int32_t i = 0; i < d->n_gene; ++i) d->gene[i].rep_pid = s->rep.gene_rep_pid[i];
+	}
+	g_sessions[d] = s;
+	int32_t n_pref = 0;
+	for (int32_t i = 0; i < d->n_gene; ++i) n_pref += d->gene[i].preferred;
+	if (pg_verbose >= 3) {
+		fprintf(stderr, "[M::%s] %ld hits in %d genomes; %ld remain after the per-genome filters (device %.2f ms)\n", __func__, (long)s->N, s->G, (long)s->Nw, g_stats.run_ms[0]);
+		fprintf(stderr, "[M::%s] there are %d preferred genes\n", __func__, n_pref);   // graph.c:31
+	}
+}
+
+pg_graph_t *pg_graph_init(pg_data_t *d)   // graph.c:34-41
+{
+	pg_graph_t *g = (pg_graph_t*)calloc(1, sizeof(pg_graph_t));
+	g->d = d;
+	g->seg = (pg_seg_t*)calloc(d->n_gene > 0? d->n_gene : 1, sizeof(pg_seg_t));
+	return g;
+}
+
+void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q)
+{
+	need_device();
+	auto it = g_sessions.find(q->d);
+	if (it == g_sessions.end()) PGX_FATAL("pg_graph_gen(): no device state for this pg_data_t -- call pg_post_process() of libpgx first");
+	Session *s = it->second;
+	timed_run(s, opt, 2);
+	s->download(q->d, q);
+	delete s;
+	g_sessions.erase(it);
+}
+
+void pg_graph_destroy(pg_graph_t *q)   // graph.c:43-47
+{
+	if (q == 0) return;
+	free(q->g2s); free(q->seg); free(q->arc); free(q->idx);
+	free(q);
+}
+
+int pgx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+void pgx_set_device(int dev) { g_device = dev; PGX_CHECK(cudaSetDevice(dev)); }
+void pgx_set_lazy(int lazy) { g_lazy = lazy; }
+
+int pgx_comm_unique_id(void *out128)
+{
+	if (!g_comm.load()) PGX_FATAL("cannot load libnccl.so.2");
+	Comm::UniqueId id;
+	g_comm.check(g_comm.GetUniqueId(&id), "ncclGetUniqueId");
+	memcpy(out128, &id, 128);
+	return 0;
+}
+
+int pgx_comm_init(int rank, int nranks, const void *id128, int32_t n_genome_total, int32_t genome_begin)
+{
+	need_device();
+	g_comm.rank = rank; g_comm.nranks = nranks; g_comm.n_genome_total = n_genome_total; g_comm.genome_begin = genome_begin;
+	if (nranks > 1) {
+		if (!g_comm.load()) PGX_FATAL("cannot load libnccl.so.2");
+		Comm::UniqueId id;
+		memcpy(&id, id128, 128);
+		g_comm.check(g_comm.CommInitRank(&g_comm.comm, nranks, id, rank), "ncclCommInitRank");
+	}
+	return 0;
+}
+
+void pgx_comm_destroy(void)
+{
+	if (g_comm.comm) { g_comm.CommDestroy(g_comm.comm); g_comm.comm = nullptr; }
+	g_comm.rank = 0; g_comm.nranks = 1; g_comm.n_genome_total = -1; g_comm.genome_begin = 0;
+}
+
+struct pgx_session_s { Session s; };
+
+pgx_session_t *pgx_upload(const pg_data_t *d) { need_device(); pgx_session_t *h = new pgx_session_s(); h->s.upload(d); return h; }
+void pgx_run(pgx_session_t *h, const pg_opt_t *opt, int stage) { timed_run(&h->s, opt, stage); }
+void pgx_download(pgx_session_t *h, pg_data_t *d, pg_graph_t *q) { h->s.download(d, q); }
+void pgx_session_free(pgx_session_t *h) { delete h; }
+
+void pgx_get_stats(pgx_stats_t *o)
+{
+	o->launches = g_launch.launches; o->sweep_ms = g_stats.sweep_ms; o->sweep_bytes = g_stats.sweep_bytes;
+	for (int i = 0; i < 3; ++i) o->run_ms[i] = g_stats.run_ms[i];
+	o->n_hit = g_stats.n_hit; o->n_active = g_stats.n_active;
+	for (int i = 0; i < 4; ++i) o->tie[i] = g_stats.tie[i];
+	o->n_seg = g_stats.n_seg; o->n_arc = g_stats.n_arc; o->h2d_bytes = g_stats.h2d; o->d2h_bytes = g_stats.d2h;
+}
+void pgx_reset_stats(void) { g_launch.launches = 0; g_stats = Stats(); }
+
+// ---- test hooks -----------------------------------------------------------------------------------
+void pgx_test_radix_sort(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits)
+{
+	need_device();
+	DBuf<uint64_t> k, ka; DBuf<uint32_t> v, va, hist, agg;
+	k.alloc(n + 1); ka.alloc(n + 1); v.alloc(n + 1); va.alloc(n + 1);
+	size_t he = RadixSortBuffers::hist_elems(n);
+	hist.alloc(he); agg.alloc(scan_scratch_elems((int64_t)he));
+	PGX_CHECK(cudaMemcpy(k.p, keys, n * 8, cudaMemcpyHostToDevice));
+	RadixSortBuffers b; b.keys_alt = ka.p; b.vals_alt = va.p; b.hist = hist.p; b.scan_agg = agg.p;
+	uint64_t *kr; uint32_t *vr;
+	radix_sort_pairs(k.p, v.p, n, n_bits, true, b, &kr, &vr, 0);
+	PGX_CHECK(cudaDeviceSynchronize());
+	PGX_CHECK(cudaMemcpy(keys, kr, n * 8, cudaMemcpyDeviceToHost));
+	PGX_CHECK(cudaMemcpy(vals, vr, n * 4, cudaMemcpyDeviceToHost));
+}
+
+void pgx_test_exclusive_sum(const uint32_t *in, uint32_t *out, int64_t n)
+{
+	need_device();
+	DBuf<uint32_t> a, o, agg;
+	a.alloc(n + 1); o.alloc(n + 2); agg.alloc(scan_scratch_elems(n));
+	PGX_CHECK(cudaMemcpy(a.p, in, n * 4, cudaMemcpyHostToDevice));
+	exclusive_sum_u32(a.p, o.p, n, agg.p, 0);
+	PGX_CHECK(cudaDeviceSynchronize());
+	PGX_CHECK(cudaMemcpy(out, o.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
+}
+
+void pgx_test_segmented_max(const int32_t *seg, const int32_t *val, int32_t *out, int64_t n)
+{
+	need_device();
+	DBuf<int32_t> s, v, o; DBuf<SegVal> agg;
+	s.alloc(n + 1); v.alloc(n + 1); o.alloc(n + 1); agg.alloc((size_t)(n / SCAN_TILE + 2));
+	PGX_CHECK(cudaMemcpy(s.p, seg, n * 4, cudaMemcpyHostToDevice));
+	PGX_CHECK(cudaMemcpy(v.p, val, n * 4, cudaMemcpyHostToDevice));
+	segmented_running_max(s.p, v.p, o.p, n, agg.p, 0);
+	PGX_CHECK(cudaDeviceSynchronize());
+	PGX_CHECK(cudaMemcpy(out, o.p, n * 4, cudaMemcpyDeviceToHost));
+}
+
+void pgx_test_flag_sort_replay(pg128_t *a, int64_t n) { FlagSortReplay::run(a, n); }
+
+} // extern "C"

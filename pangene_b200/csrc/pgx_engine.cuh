@@ -1,0 +1,627 @@
+// pgx_engine.cuh -- host orchestration of the device-resident pipeline (one Session = one pg_data_t on one GPU).
+//
+// Layout in HBM: raw pg_hit_t records as uploaded (kept for the final materialisation), one
+// packed-int32 column per field in (genome, contig, cs) order for ALL hits ("full"), and the same columns for
+// the hits that survive the load-time filters ("active", typically 14-60 % of the input), plus exon lists
+// re-laid contiguously in hit order for both.  Hits are physically sorted ONCE; the (contig, cm) order the
+// reference re-sorts into 33 times is an index permutation of the active set.
+#pragma once
+#include <vector>
+#include <cstring>
+#include <cmath>
+#include "pgx.h"
+#include "pgx_util.cuh"
+#include "pgx_scan.cuh"
+#include "pgx_sort.cuh"
+#include "pgx_kernels.cuh"
+#include "pgx_comm.cuh"
+#include "pgx_host.hpp"
+
+namespace pgx {
+
+struct Stats {
+	double sweep_ms = 0, sweep_bytes = 0, run_ms[3] = {0, 0, 0};
+	int64_t n_hit = 0, n_active = 0, tie[4] = {0, 0, 0, 0}, h2d = 0, d2h = 0;
+	int32_t n_seg = 0, n_arc = 0;
+};
+extern Stats g_stats;
+
+constexpr int TB = 256;   // default block size for the streaming kernels
+
+struct Session {
+	cudaStream_t st = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	// ---- shapes
+	int32_t G = 0, N = 0, n_prot = 0, n_gene = 0, n_ctg = 0, Gtot = 0;
+	int64_t E = 0;
+	std::vector<int32_t> h_hoff, h_coff, h_prot_gid;
+	std::vector<uint32_t> h_eoffg;
+	std::vector<uint8_t> h_gene_pref, h_gene_incl;
+	const pg_gene_t *h_gene_names = nullptr;
+	std::vector<int32_t> rank_G;         // local genome count of every rank (multi-GPU)
+	// ---- host-side results that go back into pg_data_t at download time
+	RepResult rep;
+	std::vector<int32_t> h_prot_max;
+	std::vector<SegHost> h_seg0;
+	bool done_post = false, done_graph = false;
+	// ---- device: constants and raw input
+	DBuf<int32_t> hoff, coff, ctg2g, prot_gid, aos, prot_max, prot_rep, g2s;
+	DBuf<uint32_t> eoffg, src, counters;
+	DBuf<uint8_t> gene_pref;
+	DBuf<int2> ex_raw, ex, wex;
+	DBuf<unsigned long long> z, cs4, idx;
+	// ---- full columns
+	DBuf<int32_t> f_ctg, f_cs, f_ce, f_cm, f_pid, f_gidp, f_sadj, f_rank, f_sori, f_sdom, f_pdom0, f_pdom, f_cds, f_pmax;
+	DBuf<uint32_t> f_bits, f_bits_alt, f_nex, f_eoff, f_esrc;
+	FullCols F;
+	// ---- active columns
+	int32_t Nw = 0;
+	DBuf<int32_t> a_ctg, a_cs, a_ce, a_cm, a_pid, a_gidp, a_sadj, a_rank, a_sori, a_sdom, a_pdom0, a_pdom, a_cds, a_pmax, a_full, goff_act;
+	DBuf<uint32_t> a_bits, a_bits_alt, a_nex, a_eoff, by_cm, sv;
+	ActCols A;
+	int32_t m_sv = 0;
+	// ---- graph
+	int32_t n_seg = 0, n_arc = 0;
+	DBuf<SegDev> seg, seg_alt;
+	DBuf<ArcDev> arc, arc_alt;
+	DBuf<int32_t> seg_ng, seg_tot;
+	Arena scratch;
+	uint32_t *h_pin = nullptr;           // pinned word(s) for small read-backs
+	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_N = 8 };
+
+	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
+	~Session() { if (st) cudaStreamDestroy(st); for (auto &e : ev) if (e) cudaEventDestroy(e); if (h_pin) cudaFreeHost(h_pin); }
+
+	uint32_t read_u32(const uint32_t *dptr)
+	{
+		PGX_CHECK(cudaMemcpyAsync(h_pin, dptr, 4, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		return h_pin[0];
+	}
+	void check_err(const char *where)
+	{
+		uint32_t e = read_u32(counters.p + C_ERR);
+		if (e & 1) PGX_FATAL("%s: a hit coordinate is outside [0, 2^31) or cs > ce -- this build keeps coordinates in int32", where);
+		if (e & 2) PGX_FATAL("%s: contig id out of range", where);
+		if (e & 4) PGX_FATAL("%s: protein id out of range", where);
+		if (e & 8) PGX_FATAL("%s: hit without exons", where);
+		if (e & 16) PGX_FATAL("%s: shadowed hit without a dominating protein (vertex.c:38 assertion)", where);
+		if (e & 32) PGX_FATAL("%s: surviving hit without a segment (graph.c:111 assertion)", where);
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	void upload(const pg_data_t *d)
+	{
+		G = d->n_genome; n_prot = d->n_prot; n_gene = d->n_gene;
+		Gtot = g_comm.active()? g_comm.n_genome_total : G;
+		h_hoff.assign(G + 1, 0); h_coff.assign(G + 1, 0); h_eoffg.assign(G + 1, 0);
+		int64_t nh = 0, nc = 0, ne = 0;
+		for (int32_t j = 0; j < G; ++j) {
+			h_hoff[j] = (int32_t)nh; h_coff[j] = (int32_t)nc; h_eoffg[j] = (uint32_t)ne;
+			nh += d->genome[j].n_hit; nc += d->genome[j].n_ctg; ne += d->genome[j].n_exon;
+		}
+		if (nh >= 0x7fffffffll / AOS_WORDS * 8 || ne >= 0xffffffffll || nc >= 0x7fffffffll) PGX_FATAL("input too large for 32-bit hit/exon indices (%ld hits, %ld exons)", (long)nh, (long)ne);
+		h_hoff[G] = (int32_t)nh; h_coff[G] = (int32_t)nc; h_eoffg[G] = (uint32_t)ne;
+		N = (int32_t)nh; n_ctg = (int32_t)nc; E = ne;
+		h_prot_gid.resize(n_prot); h_gene_pref.resize(n_gene); h_gene_incl.resize(n_gene);
+		for (int32_t i = 0; i < n_prot; ++i) h_prot_gid[i] = d->prot[i].gid;
+		for (int32_t i = 0; i < n_gene; ++i) h_gene_pref[i] = d->gene[i].preferred, h_gene_incl[i] = d->gene[i].included;
+		h_gene_names = d->gene;
+		std::vector<int32_t> h_ctg2g(n_ctg > 0? n_ctg : 1);
+		for (int32_t j = 0; j < G; ++j) for (int32_t c = h_coff[j]; c < h_coff[j + 1]; ++c) h_ctg2g[c] = j;
+
+		hoff.alloc(G + 1); coff.alloc(G + 1); eoffg.alloc(G + 1); ctg2g.alloc(h_ctg2g.size()); prot_gid.alloc(n_prot); gene_pref.alloc(n_gene);
+		PGX_CHECK(cudaMemcpyAsync(hoff.p, h_hoff.data(), (G + 1) * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaMemcpyAsync(coff.p, h_coff.data(), (G + 1) * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaMemcpyAsync(eoffg.p, h_eoffg.data(), (G + 1) * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaMemcpyAsync(ctg2g.p, h_ctg2g.data(), h_ctg2g.size() * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaMemcpyAsync(prot_gid.p, h_prot_gid.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaMemcpyAsync(gene_pref.p, h_gene_pref.data(), (size_t)n_gene, cudaMemcpyHostToDevice, st));
+		aos.alloc((size_t)(N > 0? N : 1) * AOS_WORDS); ex_raw.alloc(E > 0? E : 1);
+		for (int32_t j = 0; j < G; ++j) {
+			const pg_genome_t *g = &d->genome[j];
+			if (g->n_hit) PGX_CHECK(cudaMemcpyAsync(aos.p + (size_t)h_hoff[j] * AOS_WORDS, g->hit, (size_t)g->n_hit * sizeof(pg_hit_t), cudaMemcpyHostToDevice, st));
+			if (g->n_exon) PGX_CHECK(cudaMemcpyAsync(ex_raw.p + h_eoffg[j], g->exon, (size_t)g->n_exon * sizeof(pg_exon_t), cudaMemcpyHostToDevice, st));
+		}
+		g_stats.h2d += (int64_t)N * 88 + E * 8 + (int64_t)n_prot * 4 + n_gene;
+		g_stats.n_hit = N;
+		counters.alloc(C_N); counters.zero(st);
+		size_t tab = (size_t)(G > 0? G : 1);
+		scratch.init((size_t)(N > 0? N : 1) * 96 + tab * n_prot * 16 + tab * n_gene * 48 + ((size_t)256 << 20));
+		// full columns
+		size_t n1 = (size_t)N + 1;
+		f_ctg.alloc(n1); f_cs.alloc(n1); f_ce.alloc(n1); f_cm.alloc(n1); f_pid.alloc(n1); f_gidp.alloc(n1); f_sadj.alloc(n1); f_rank.alloc(n1); f_sori.alloc(n1);
+		f_sdom.alloc(n1); f_pdom0.alloc(n1); f_pdom.alloc(n1); f_cds.alloc(n1); f_pmax.alloc(n1); f_bits.alloc(n1); f_bits_alt.alloc(n1); f_nex.alloc(n1); f_eoff.alloc(n1 + 1); f_esrc.alloc(n1);
+		src.alloc(n1); ex.alloc(E > 0? E : 1);
+		set_full();
+		prot_max.alloc(n_prot); prot_rep.alloc(n_prot); z.alloc(n_prot); cs4.alloc((size_t)n_prot * 4); g2s.alloc(n_gene);
+		prot_rep.zero(st);
+		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
+		if (g_comm.active()) {   // every rank learns every rank's local genome count
+			int32_t *tmp = scratch.get<int32_t>(g_comm.nranks);
+			PGX_CHECK(cudaMemcpyAsync(tmp + g_comm.rank, &G, 4, cudaMemcpyHostToDevice, st));
+			g_comm.allgather(tmp + g_comm.rank, tmp, 4, st);
+			rank_G.resize(g_comm.nranks);
+			PGX_CHECK(cudaMemcpyAsync(rank_G.data(), tmp, 4 * g_comm.nranks, cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaStreamSynchronize(st));
+			scratch.reset(0);
+		} else rank_G.assign(1, G);
+		PGX_CHECK(cudaStreamSynchronize(st));
+		done_post = done_graph = false;
+	}
+	void set_full()
+	{
+		F.ctg = f_ctg.p; F.cs = f_cs.p; F.ce = f_ce.p; F.cm = f_cm.p; F.pid = f_pid.p; F.gidp = f_gidp.p; F.sadj = f_sadj.p; F.rank = f_rank.p; F.sori = f_sori.p;
+		F.sdom = f_sdom.p; F.pdom0 = f_pdom0.p; F.pdom = f_pdom.p; F.cds = f_cds.p; F.pmax = f_pmax.p; F.bits = f_bits.p; F.nex = f_nex.p; F.eoff = f_eoff.p; F.esrc = f_esrc.p;
+	}
+	void set_active()
+	{
+		A.ctg = a_ctg.p; A.cs = a_cs.p; A.ce = a_ce.p; A.cm = a_cm.p; A.pid = a_pid.p; A.gidp = a_gidp.p; A.sadj = a_sadj.p; A.rank = a_rank.p; A.sori = a_sori.p;
+		A.sdom = a_sdom.p; A.pdom0 = a_pdom0.p; A.pdom = a_pdom.p; A.cds = a_cds.p; A.pmax = a_pmax.p; A.full = a_full.p; A.bits = a_bits.p; A.bits_alt = a_bits_alt.p; A.nex = a_nex.p; A.eoff = a_eoff.p;
+	}
+	SweepCols sweep_full() const
+	{
+		SweepCols c; c.n = N; c.ctg = F.ctg; c.cs = F.cs; c.ce = F.ce; c.pid = F.pid; c.gidp = F.gidp; c.sadj = F.sadj; c.rank = F.rank; c.cds = F.cds; c.sori = F.sori; c.pmax = F.pmax;
+		c.bits = F.bits; c.eoff = F.eoff; c.ex = ex.p; return c;
+	}
+	SweepCols sweep_active() const
+	{
+		SweepCols c; c.n = Nw; c.ctg = A.ctg; c.cs = A.cs; c.ce = A.ce; c.pid = A.pid; c.gidp = A.gidp; c.sadj = A.sadj; c.rank = A.rank; c.cds = A.cds; c.sori = A.sori; c.pmax = A.pmax;
+		c.bits = A.bits; c.eoff = A.eoff; c.ex = wex.p; return c;
+	}
+
+	// stable radix sort of n (key, iota) pairs taken from the scratch arena; returns the permutation (device pointer valid until the arena is reset)
+	uint32_t *sort_perm(uint64_t *keys, int64_t n, int n_bits)
+	{
+		RadixSortBuffers b;
+		uint32_t *vals = scratch.get<uint32_t>(n + 1);
+		b.keys_alt = scratch.get<uint64_t>(n + 1); b.vals_alt = scratch.get<uint32_t>(n + 1);
+		size_t he = RadixSortBuffers::hist_elems(n);
+		b.hist = scratch.get<uint32_t>(he); b.scan_agg = scratch.get<uint32_t>(scan_scratch_elems((int64_t)he));
+		uint64_t *kr; uint32_t *vr;
+		radix_sort_pairs(keys, vals, n, n_bits, true, b, &kr, &vr, st);
+		if (kr != keys && n > 0) PGX_CHECK(cudaMemcpyAsync(keys, kr, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));   // callers want sorted keys in place
+		return vr;
+	}
+	// exclusive scan of n flags into pos[n+1]; returns the total
+	uint32_t scan_flags(const uint32_t *flag, uint32_t *pos, int64_t n)
+	{
+		uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(n));
+		exclusive_sum_u32(flag, pos, n, agg, st);
+		return read_u32(pos + n);
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	// stage 1a: the per-genome load-time block (read.c:243-260), all local genomes in single launches
+	// ------------------------------------------------------------------------------------------------
+	void stage_load(const pg_opt_t *opt)
+	{
+		if (N == 0) { Nw = 0; return; }
+		size_t mk = scratch.mark();
+		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
+		// -- raw order: unpack + pseudogene flags (hit.c:66-105)
+		int32_t *r_pid = scratch.get<int32_t>(N), *r_nexon = scratch.get<int32_t>(N), *r_rank = scratch.get<int32_t>(N), *r_gl = scratch.get<int32_t>(N);
+		uint8_t *r_pseudo = scratch.get<uint8_t>(N);
+		uint64_t *key = scratch.get<uint64_t>(N + 1);
+		PGX_LAUNCH(k_unpack, grid_for(N, TB), TB, 0, st, aos.p, N, hoff.p, coff.p, G, r_pid, r_nexon, r_rank, r_gl, key, n_prot, counters.p + C_ERR);
+		{
+			size_t tab = (size_t)G * n_prot, m2 = scratch.mark();
+			int32_t *t_max = scratch.get<int32_t>(tab), *t_min = scratch.get<int32_t>(tab), *t_r1 = scratch.get<int32_t>(tab);
+			PGX_CHECK(cudaMemsetAsync(t_max, 0, tab * 4, st));
+			PGX_CHECK(cudaMemsetAsync(t_min, 0x7f, tab * 4, st));     // 0x7f7f7f7f: larger than any exon count
+			PGX_LAUNCH(k_fill_i32, grid_for((int64_t)tab, TB), TB, 0, st, t_r1, (int64_t)tab, INT32_MAX);
+			PGX_LAUNCH(k_fp_minmax, grid_for(N, TB), TB, 0, st, r_pid, r_nexon, r_gl, N, n_prot, t_max, t_min);
+			PGX_LAUNCH(k_fp_flag, grid_for(N, TB), TB, 0, st, r_pid, r_nexon, r_rank, r_gl, N, n_prot, t_max, t_min, t_r1, r_pseudo);
+			PGX_LAUNCH(k_fp_rank, grid_for(N, TB), TB, 0, st, r_pid, r_gl, N, n_prot, t_max, t_min, t_r1, r_rank);
+			scratch.reset(m2);
+		}
+		check_err("upload");
+		// -- the one physical sort: (genome:contig, cs), stable => ties keep file order
+		{
+			size_t m2 = scratch.mark();
+			uint32_t *perm = sort_perm(key, N, 32 + bits_for((uint64_t)(n_ctg > 0? n_ctg - 1 : 0)));
+			PGX_CHECK(cudaMemcpyAsync(src.p, perm, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
+			scratch.reset(m2);
+		}
+		PGX_LAUNCH(k_gather, grid_for(N, TB), TB, 0, st, aos.p, src.p, N, hoff.p, coff.p, eoffg.p, r_rank, r_pseudo, r_gl, prot_gid.p, gene_pref.p, F);
+		{
+			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(N));
+			exclusive_sum_u32(F.nex, F.eoff, N, agg, st);
+		}
+		PGX_LAUNCH(k_gather_exons, grid_for(N, 128), 128, 0, st, ex_raw.p, F.esrc, F.eoff, N, ex.p, F.cds);
+		{
+			SegVal *agg = scratch.get<SegVal>((size_t)(N / SCAN_TILE + 2));
+			segmented_running_max(F.ctg, F.ce, F.pmax, N, agg, st);
+		}
+		{   // algorithmic bytes of the launch below (stat only, outside the timed window)
+			unsigned long long *tot = scratch.get<unsigned long long>(1);
+			PGX_CHECK(cudaMemsetAsync(tot, 0, 8, st));
+			PGX_LAUNCH(k_sweep_bytes, grid_for(N, TB), TB, 0, st, F.bits, F.eoff, N, tot);
+			unsigned long long h = 0;
+			PGX_CHECK(cudaMemcpyAsync(&h, tot, 8, cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaStreamSynchronize(st));
+			g_stats.sweep_bytes = (double)h;
+		}
+		// -- first sweep: pg_shadow(cal_dom_sc=1) + read.c:249-253; this is the launch the roofline figure is quoted on
+		PGX_CHECK(cudaEventRecord(ev[0], st));
+		PGX_LAUNCH(k_sweep<SW_LOAD>, grid_for(N, 128), 128, 0, st, sweep_full(), so, f_bits_alt.p, F.pdom0, F.sdom, counters.p + C_TIE_DUP);
+		PGX_CHECK(cudaEventRecord(ev[1], st));
+		// (SW_LOAD leaves the flag words unchanged: keep reading F.bits)
+		// -- second sweep: pg_flt_ov_isoform
+		PGX_LAUNCH(k_sweep<SW_ISO>, grid_for(N, 128), 128, 0, st, sweep_full(), so, f_bits_alt.p, (int32_t*)nullptr, (int32_t*)nullptr, counters.p + C_TIE_DUP);
+		f_bits.swap(f_bits_alt); set_full();
+		// -- chain shadow + sub-optimal isoform (hit.c:107-146)
+		{
+			size_t tab = (size_t)G * n_prot, m2 = scratch.mark();
+			uint8_t *t_kept = scratch.get<uint8_t>(tab);
+			PGX_CHECK(cudaMemsetAsync(t_kept, 0, tab, st));
+			PGX_LAUNCH(k_chain_mark, grid_for(N, TB), TB, 0, st, F.ctg, ctg2g.p, F.pid, F.bits, N, n_prot, t_kept);
+			PGX_LAUNCH(k_chain_apply, grid_for(N, TB), TB, 0, st, F.ctg, ctg2g.p, F.pdom0, F.bits, N, n_prot, t_kept);
+			scratch.reset(m2);
+			size_t tg = (size_t)G * n_gene;
+			unsigned long long *t_best = scratch.get<unsigned long long>(tg);
+			PGX_CHECK(cudaMemsetAsync(t_best, 0, tg * 8, st));
+			PGX_LAUNCH(k_subopt_best, grid_for(N, TB), TB, 0, st, F.ctg, ctg2g.p, F.gidp, F.sadj, F.rank, F.bits, N, n_gene, t_best);
+			PGX_LAUNCH(k_subopt_apply, grid_for(N, TB), TB, 0, st, F.ctg, ctg2g.p, F.gidp, F.pid, F.bits, N, n_gene, t_best);
+			scratch.reset(m2);
+		}
+		scratch.reset(mk);
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	// stage 1b: pg_post_process (graph.c:7-32) -- builds the active set on the way
+	// ------------------------------------------------------------------------------------------------
+	void stage_post(const pg_opt_t *opt)
+	{
+		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
+		// pg_cap_score_dom (hit.c:227-247): over ALL hits, filtered ones included
+		prot_max.zero(st);
+		if (N) PGX_LAUNCH(k_cap_max, grid_for(N, TB), TB, 0, st, F.pid, F.sori, N, prot_max.p);
+		g_comm.allreduce(prot_max.p, n_prot, Comm::T_INT32, Comm::OP_MAX, st);
+		if (N) PGX_LAUNCH(k_cap_apply, grid_for(N, TB), TB, 0, st, F.pid, F.sdom, N, prot_max.p);
+		h_prot_max.resize(n_prot);
+		PGX_CHECK(cudaMemcpyAsync(h_prot_max.data(), prot_max.p, (size_t)n_prot * 4, cudaMemcpyDeviceToHost, st));
+		build_active();
+		// per-protein sums (hit.c:196-204, 158-169), one pass, then one reduction across ranks
+		z.zero(st); cs4.zero(st);
+		if (Nw) PGX_LAUNCH(k_prot_stats, grid_for(Nw, TB), TB, 0, st, A.pid, A.sadj, A.sori, A.rank, A.bits, A.eoff, Nw, z.p, cs4.p);
+		g_comm.allreduce(z.p, n_prot, Comm::T_UINT64, Comm::OP_SUM, st);
+		g_comm.allreduce(cs4.p, (size_t)n_prot * 4, Comm::T_UINT64, Comm::OP_SUM, st);
+		std::vector<unsigned long long> hz(n_prot);
+		PGX_CHECK(cudaMemcpyAsync(hz.data(), z.p, (size_t)n_prot * 8, cudaMemcpyDeviceToHost, st));
+		if (!(opt->flag & PG_F_NO_JOINT_PSEUDO) && Nw)
+			PGX_LAUNCH(k_pseudo_joint, grid_for(Nw, TB), TB, 0, st, A.pid, A.bits, A.eoff, Nw, cs4.p, Gtot, opt->min_vertex_ratio, !!(opt->flag & PG_F_DROP_SGL_EXON));
+		if (Nw) {
+			PGX_LAUNCH(k_sweep<SW_SHADOW>, grid_for(Nw, 128), 128, 0, st, sweep_active(), so, A.bits_alt, A.pdom, (int32_t*)nullptr, counters.p + C_TIE_DUP);
+			a_bits.swap(a_bits_alt); set_active();
+		}
+		PGX_CHECK(cudaStreamSynchronize(st));
+		choose_representatives(hz.data(), h_prot_gid.data(), n_prot, n_gene, rep);      // host: exact tie order
+		PGX_CHECK(cudaMemcpyAsync(prot_rep.p, rep.prot_rep.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
+		done_post = true;
+		g_stats.n_active = Nw;
+	}
+
+	void build_active()
+	{
+		size_t mk = scratch.mark();
+		Nw = 0;
+		if (N) {
+			uint32_t *flag = scratch.get<uint32_t>(N + 1), *pos = scratch.get<uint32_t>((size_t)N + 2);
+			PGX_LAUNCH(k_flag_unfiltered, grid_for(N, TB), TB, 0, st, F.bits, N, flag);
+			Nw = (int32_t)scan_flags(flag, pos, N);
+			size_t n1 = (size_t)Nw + 1;
+			a_ctg.alloc(n1); a_cs.alloc(n1); a_ce.alloc(n1); a_cm.alloc(n1); a_pid.alloc(n1); a_gidp.alloc(n1); a_sadj.alloc(n1); a_rank.alloc(n1); a_sori.alloc(n1);
+			a_sdom.alloc(n1); a_pdom0.alloc(n1); a_pdom.alloc(n1); a_cds.alloc(n1); a_pmax.alloc(n1); a_full.alloc(n1); a_bits.alloc(n1); a_bits_alt.alloc(n1); a_nex.alloc(n1); a_eoff.alloc(n1 + 1);
+			by_cm.alloc(n1); sv.alloc(n1);
+			set_active();
+			PGX_LAUNCH(k_build_active, grid_for(N, TB), TB, 0, st, F, pos, N, A);
+			// where each local genome starts inside the active set
+			goff_act.alloc(G + 1);
+			PGX_LAUNCH(k_gather_u32, grid_for(G + 1, TB), TB, 0, st, pos, (const uint32_t*)hoff.p, G + 1, (uint32_t*)goff_act.p);
+		} else { goff_act.alloc(G + 1); goff_act.zero(st); }
+		if (Nw) {
+			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(Nw));
+			exclusive_sum_u32(A.nex, A.eoff, Nw, agg, st);
+			uint32_t ne = read_u32(A.eoff + Nw);
+			wex.alloc(ne > 0? ne : 1);
+			PGX_LAUNCH(k_copy_exons, grid_for(Nw, 128), 128, 0, st, ex.p, F.eoff, A.full, A.eoff, Nw, wex.p);
+			SegVal *sagg = scratch.get<SegVal>((size_t)(Nw / SCAN_TILE + 2));
+			segmented_running_max(A.ctg, A.ce, A.pmax, Nw, sagg, st);
+			// (contig, cm) order as a permutation; ties keep (contig, cs) order
+			uint64_t *key = scratch.get<uint64_t>((size_t)Nw + 1);
+			PGX_LAUNCH(k_make_cm_keys, grid_for(Nw, TB), TB, 0, st, A.ctg, A.cm, Nw, key);
+			uint32_t *perm = sort_perm(key, Nw, 32 + bits_for((uint64_t)(n_ctg > 0? n_ctg - 1 : 0)));
+			PGX_CHECK(cudaMemcpyAsync(by_cm.p, perm, (size_t)Nw * 4, cudaMemcpyDeviceToDevice, st));
+		}
+		scratch.reset(mk);
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	// stage 2: pg_graph_gen (graph.c:280-322)
+	// ------------------------------------------------------------------------------------------------
+	void set_filter(int mode) { if (Nw) PGX_LAUNCH(k_set_filter, grid_for(Nw, TB), TB, 0, st, A.bits, Nw, mode); }
+	void flag_vtx() { if (Nw) PGX_LAUNCH(k_flag_vtx, grid_for(Nw, TB), TB, 0, st, A.gidp, A.bits, Nw, g2s.p, 1); }
+	void regen_g2s()
+	{
+		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
+		if (n_seg) PGX_LAUNCH(k_g2s_fill, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, g2s.p);
+	}
+
+	void gen_vtx(const pg_opt_t *opt)   // vertex.c:6-100
+	{
+		size_t mk = scratch.mark();
+		size_t tab = (size_t)G * n_gene;
+		int Gmax = 0;
+		for (int g : rank_G) Gmax = g > Gmax? g : Gmax;
+		size_t tab_max = (size_t)Gmax * n_gene;
+		uint8_t *t_dom = scratch.get<uint8_t>(tab + 1);
+		int32_t *t_first = scratch.get<int32_t>(tab + 1);
+		int32_t *aux_all = scratch.get<int32_t>(tab_max * g_comm.nranks + 1);
+		int32_t *aux = aux_all + tab_max * g_comm.rank;
+		PGX_CHECK(cudaMemsetAsync(t_dom, 0, tab + 1, st));
+		PGX_LAUNCH(k_fill_i32, grid_for((int64_t)tab + 1, TB), TB, 0, st, t_first, (int64_t)tab + 1, INT32_MAX);
+		if (Nw) PGX_LAUNCH(k_vtx_mark, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, A.rank, A.bits, Nw, n_gene, t_dom, t_first);
+		if (tab) PGX_LAUNCH(k_vtx_resolve, grid_for((int64_t)tab, TB), TB, 0, st, t_dom, t_first, A.pdom, prot_gid.p, tab, aux, counters.p + C_ERR);
+		g_comm.allgather(aux, aux_all, tab_max * 4, st);
+		std::vector<int32_t> h_all(tab_max * g_comm.nranks + 1), h_aux((size_t)Gtot * n_gene + 1);
+		PGX_CHECK(cudaMemcpyAsync(h_all.data(), aux_all, tab_max * g_comm.nranks * 4, cudaMemcpyDeviceToHost, st));
+		check_err("vertex selection");
+		{   // stitch the per-rank blocks into genome order (ranks hold consecutive genome ranges)
+			size_t o = 0;
+			for (int r = 0; r < g_comm.nranks; ++r) { size_t nr = (size_t)rank_G[r] * n_gene; memcpy(h_aux.data() + o, h_all.data() + tab_max * r, nr * 4); o += nr; }
+			if (o != (size_t)Gtot * n_gene) PGX_FATAL("genome partition inconsistent: %zu rows gathered, %d genomes expected", o / (n_gene? n_gene : 1), Gtot);
+		}
+		elect_vertices(h_aux.data(), Gtot, n_gene, rep.gene_rep_pid.data(), rep.prot_avg.data(), h_gene_pref.data(), h_gene_incl.data(), opt->min_vertex_ratio,
+			!!(opt->flag & PG_F_WRITE_VTX_SEL), h_gene_names, h_seg0);
+		n_seg = (int32_t)h_seg0.size();
+		std::vector<SegDev> hs(n_seg > 0? n_seg : 1);
+		for (int32_t i = 0; i < n_seg; ++i) { memset(&hs[i], 0, sizeof(SegDev)); hs[i].gid = h_seg0[i].gid; hs[i].n_dom = h_seg0[i].n_dom; hs[i].n_sub = h_seg0[i].n_sub; }
+		seg.alloc(hs.size()); seg_alt.alloc(hs.size()); seg_ng.alloc(hs.size()); seg_tot.alloc(hs.size()); idx.alloc(hs.size() * 2);
+		PGX_CHECK(cudaMemcpyAsync(seg.p, hs.data(), hs.size() * sizeof(SegDev), cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		regen_g2s();
+		scratch.reset(mk);
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::gen_vtx] selected %d vertices out of %d genes\n", n_seg, n_gene);
+	}
+
+	void gen_arc(const pg_opt_t *opt)   // graph.c:87-177
+	{
+		size_t mk = scratch.mark();
+		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
+		n_arc = 0; m_sv = 0;
+		PGX_CHECK(cudaMemsetAsync(seg_ng.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 4, st));
+		PGX_CHECK(cudaMemsetAsync(seg_tot.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 4, st));
+		ArcPartial *part = nullptr; uint32_t n_part = 0;
+		if (Nw) {
+			PGX_LAUNCH(k_sweep<SW_SHADOW>, grid_for(Nw, 128), 128, 0, st, sweep_active(), so, A.bits_alt, A.pdom, (int32_t*)nullptr, counters.p + C_TIE_DUP);
+			a_bits.swap(a_bits_alt); set_active();
+			uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *pos = scratch.get<uint32_t>((size_t)Nw + 2);
+			PGX_LAUNCH(k_flag_survivor_cm, grid_for(Nw, TB), TB, 0, st, A.bits, by_cm.p, Nw, flag);
+			m_sv = (int32_t)scan_flags(flag, pos, Nw);
+			if (m_sv) PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, Nw, sv.p);
+		}
+		if (m_sv) {
+			size_t nr = 2 * (size_t)m_sv, bm = ((size_t)G * n_seg + 31) / 32 + 1;
+			uint64_t *key = scratch.get<uint64_t>(nr + 1);
+			int32_t *dist = scratch.get<int32_t>(nr), *s1 = scratch.get<int32_t>(nr), *s2 = scratch.get<int32_t>(nr);
+			uint32_t *seen = scratch.get<uint32_t>(bm);
+			PGX_CHECK(cudaMemsetAsync(seen, 0, bm * 4, st));
+			ArcEmit e; e.sv = sv.p; e.m = m_sv; e.ctg = A.ctg; e.cm = A.cm; e.gidp = A.gidp; e.sori = A.sori; e.sdom = A.sdom; e.pdom0 = A.pdom0; e.bits = A.bits;
+			e.g2s = g2s.p; e.prot_gid = prot_gid.p; e.ctg2g = ctg2g.p; e.use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH); e.n_seg = n_seg; e.gbits = bits_for((uint64_t)(G > 1? G - 1 : 1));
+			PGX_LAUNCH(k_arc_emit, grid_for(m_sv, TB), TB, 0, st, e, key, dist, s1, s2, seen, seg_ng.p, seg_tot.p, counters.p + C_TIE_CM, counters.p + C_ERR);
+			uint64_t nv = 2ull * n_seg, maxkey = ((nv * nv - 1) << e.gbits) | ((1ull << e.gbits) - 1);
+			uint32_t *rec = sort_perm(key, (int64_t)nr, bits_for(maxkey) + 1);      // +1: the all-ones "no arc" key sorts strictly last
+			uint32_t *flag = scratch.get<uint32_t>(nr + 1), *pos = scratch.get<uint32_t>(nr + 2);
+			PGX_LAUNCH(k_arc_heads, grid_for((int64_t)nr, TB), TB, 0, st, key, (int32_t)nr, e.gbits, flag);
+			n_part = scan_flags(flag, pos, (int64_t)nr);
+			part = scratch.get<ArcPartial>((size_t)n_part + 1);
+			if (n_part) PGX_LAUNCH(k_arc_reduce, grid_for((int64_t)nr, 128), 128, 0, st, key, rec, dist, s1, s2, (int32_t)nr, e.gbits, n_seg, pos, part);
+		}
+		if (g_comm.active()) merge_partials_across_ranks(part, n_part);
+		else finalize_arcs(part, n_part);
+		g_comm.allreduce(seg_ng.p, n_seg, Comm::T_INT32, Comm::OP_SUM, st);
+		g_comm.allreduce(seg_tot.p, n_seg, Comm::T_INT32, Comm::OP_SUM, st);
+		if (n_seg) PGX_LAUNCH(k_seg_store_occ, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, seg_ng.p, seg_tot.p);
+		scratch.reset(mk);
+	}
+
+	void finalize_arcs(const ArcPartial *part, uint32_t n_part)   // input sorted by x; equal x merged (graph.c:150-175)
+	{
+		n_arc = 0;
+		if (!n_part) return;
+		uint32_t *flag = scratch.get<uint32_t>((size_t)n_part + 1), *pos = scratch.get<uint32_t>((size_t)n_part + 2);
+		PGX_LAUNCH(k_partial_heads, grid_for(n_part, TB), TB, 0, st, part, (int32_t)n_part, flag);
+		n_arc = (int32_t)scan_flags(flag, pos, n_part);
+		arc.ensure((size_t)n_arc + 1); arc_alt.ensure((size_t)n_arc + 1);
+		PGX_LAUNCH(k_arc_finalize, grid_for(n_part, TB), TB, 0, st, part, (int32_t)n_part, pos, arc.p);
+	}
+
+	void merge_partials_across_ranks(const ArcPartial *part, uint32_t n_part)
+	{
+		// every rank contributes its partial table, padded to the largest one; then sort by key and merge equal keys
+		uint32_t *cnt = scratch.get<uint32_t>(g_comm.nranks + 1);
+		PGX_CHECK(cudaMemcpyAsync(cnt + g_comm.rank, &n_part, 4, cudaMemcpyHostToDevice, st));
+		g_comm.allgather(cnt + g_comm.rank, cnt, 4, st);
+		std::vector<uint32_t> hc(g_comm.nranks);
+		PGX_CHECK(cudaMemcpyAsync(hc.data(), cnt, 4 * g_comm.nranks, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		uint32_t mx = 0; uint64_t tot = 0;
+		for (uint32_t c : hc) { mx = c > mx? c : mx; tot += c; }
+		if (tot == 0) { n_arc = 0; return; }
+		ArcPartial *all = scratch.get<ArcPartial>((size_t)mx * g_comm.nranks + 1), *mine = all + (size_t)mx * g_comm.rank;
+		if (n_part) PGX_CHECK(cudaMemcpyAsync(mine, part, (size_t)n_part * sizeof(ArcPartial), cudaMemcpyDeviceToDevice, st));
+		g_comm.allgather(mine, all, (size_t)mx * sizeof(ArcPartial), st);
+		ArcPartial *packed = scratch.get<ArcPartial>(tot + 1), *sorted = scratch.get<ArcPartial>(tot + 1);
+		uint64_t o = 0;
+		for (int r = 0; r < g_comm.nranks; ++r) { if (hc[r]) PGX_CHECK(cudaMemcpyAsync(packed + o, all + (size_t)mx * r, (size_t)hc[r] * sizeof(ArcPartial), cudaMemcpyDeviceToDevice, st)); o += hc[r]; }
+		uint64_t *key = scratch.get<uint64_t>(tot + 1);
+		PGX_LAUNCH(k_partial_keys, grid_for((int64_t)tot, TB), TB, 0, st, packed, (int32_t)tot, n_seg, key);
+		uint64_t nv = 2ull * n_seg;
+		uint32_t *perm = sort_perm(key, (int64_t)tot, bits_for(nv * nv - 1));
+		PGX_LAUNCH(k_partial_gather, grid_for((int64_t)tot, TB), TB, 0, st, packed, perm, (int32_t)tot, sorted);
+		finalize_arcs(sorted, (uint32_t)tot);
+	}
+
+	void arc_index()   // graph.c:202-217
+	{
+		PGX_CHECK(cudaMemsetAsync(idx.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 16, st));
+		if (n_arc) PGX_LAUNCH(k_arc_index, grid_for(n_arc, TB), TB, 0, st, arc.p, n_arc, idx.p);
+	}
+
+	void flt_high_occ(int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)   // graph.c:237-263
+	{
+		if (n_seg) {
+			size_t mk = scratch.mark();
+			uint32_t *keep = scratch.get<uint32_t>((size_t)n_seg + 1), *pos = scratch.get<uint32_t>((size_t)n_seg + 2);
+			PGX_LAUNCH(k_seg_mark_del, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, arc.p, n_arc, max_avg_occ * Gtot, max_degree, max_dist_loci, keep);
+			uint32_t k = scan_flags(keep, pos, n_seg);
+			PGX_LAUNCH(k_seg_compact, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, pos, seg_alt.p);
+			seg.swap(seg_alt);
+			if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::flt_high_occ] removed %d of %d segments\n", n_seg - (int32_t)k, n_seg);
+			n_seg = (int32_t)k;
+			scratch.reset(mk);
+		}
+		regen_g2s();
+		flag_vtx();
+	}
+
+	void branch_round(const pg_opt_t *opt)   // branch.c:48-145 + graph.c:309
+	{
+		size_t mk = scratch.mark();
+		arc_index();
+		if (n_seg) PGX_LAUNCH(k_seg_zero_loci, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg);
+		int32_t n_vtx = 2 * n_seg;
+		if (Nw && n_vtx && n_arc) {
+			// representative position of every gene in every local genome (branch.c:6-29)
+			size_t tab = (size_t)n_gene * G;
+			uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *spos = scratch.get<uint32_t>((size_t)Nw + 2);
+			PGX_LAUNCH(k_flag_survivor_cs, grid_for(Nw, TB), TB, 0, st, A.bits, Nw, flag);
+			uint32_t m_cs = scan_flags(flag, spos, Nw);
+			{   // tie detector: two survivors with one (contig, cs)
+				size_t m2 = scratch.mark();
+				uint32_t *svcs = scratch.get<uint32_t>((size_t)m_cs + 1);
+				if (m_cs > 1) {
+					PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, spos, (const uint32_t*)nullptr, Nw, svcs);
+					PGX_LAUNCH(k_cs_tie_count, grid_for(m_cs, TB), TB, 0, st, A.ctg, A.cs, svcs, (int32_t)m_cs, counters.p + C_TIE_CS);
+				}
+				scratch.reset(m2);
+			}
+			int32_t *t_last = scratch.get<int32_t>(tab + 1);
+			GenePos *gpos = scratch.get<GenePos>(tab + 1);
+			PGX_CHECK(cudaMemsetAsync(t_last, 0xff, (tab + 1) * 4, st));
+			PGX_LAUNCH(k_pos_last, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, spos, Nw, G, t_last);
+			PGX_LAUNCH(k_pos_fill, grid_for((int64_t)tab, TB), TB, 0, st, t_last, tab, G, A.ctg, A.cm, spos, goff_act.p, gpos);
+			// n_local for every pair of out-arcs of every oriented vertex: local partial sums, one reduction, then the decisions
+			uint32_t *cnt = scratch.get<uint32_t>((size_t)n_vtx + 1), *off = scratch.get<uint32_t>((size_t)n_vtx + 2);
+			PGX_LAUNCH(k_branch_count, grid_for(n_vtx, TB), TB, 0, st, idx.p, n_vtx, cnt);
+			uint32_t n_nl = scan_flags(cnt, off, n_vtx);
+			int32_t *nl = scratch.get<int32_t>((size_t)n_nl + 1), *grp = scratch.get<int32_t>((size_t)n_arc + 1);
+			BranchOpt bo; bo.local_dist = opt->local_dist; bo.local_count = opt->local_count; bo.frag_mode = !!(opt->flag & PG_F_FRAG_MODE);
+			bo.branch_diff = opt->branch_diff; bo.branch_diff_dist = opt->branch_diff_dist; bo.branch_diff_cut = opt->branch_diff_cut;
+			if (n_nl) {
+				PGX_LAUNCH(k_branch_nlocal, grid_for((int64_t)n_vtx * 32, TB), TB, 0, st, idx.p, n_vtx, arc.p, seg.p, gpos, G, off, bo, nl);
+				g_comm.allreduce(nl, n_nl, Comm::T_INT32, Comm::OP_SUM, st);
+			}
+			PGX_LAUNCH(k_branch_decide, grid_for(n_vtx, 128), 128, 0, st, idx.p, n_vtx, arc.p, seg.p, off, nl, bo, grp);
+			// hits inherit the weakness of the arcs they sit on; weak_br == 2 filters (branch.c:108-145, graph.c:309)
+			if (m_sv) PGX_LAUNCH(k_branch_hits, grid_for(m_sv, TB), TB, 0, st, sv.p, m_sv, A.ctg, A.gidp, A.bits, g2s.p, arc.p, n_arc);
+		}
+		scratch.reset(mk);
+	}
+
+	void stage_graph(const pg_opt_t *opt)
+	{
+		if (!done_post) PGX_FATAL("pg_graph_gen() called before pg_post_process()");
+		set_filter(SF_PSEUDO);                                                           // graph.c:285
+		gen_vtx(opt);                                                                    // graph.c:286
+		flag_vtx();                                                                      // graph.c:287-288
+		gen_arc(opt);                                                                    // graph.c:289
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] round-1 graph: %d genes and %d arcs\n", n_seg, n_arc);
+		flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);     // graph.c:294-295
+		gen_arc(opt);                                                                    // graph.c:296
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] round-2 graph: %d genes and %d arcs\n", n_seg, n_arc);
+		for (int32_t i = 0; i < opt->n_branch_flt; ++i) {                                // graph.c:301-315
+			double r = 1.0 + (double)(opt->n_branch_flt - 1 - i) / opt->n_branch_flt;
+			int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
+			int32_t max_degree = (int32_t)(opt->max_degree * r + .499);
+			int32_t max_dist_loci = (int32_t)(opt->max_dist_loci * r + .499);
+			branch_round(opt);
+			if (i > 0) flt_high_occ(max_avg_occ, max_degree, max_dist_loci);
+			gen_arc(opt);
+		}
+		set_filter(SF_SHADOW);                                                           // graph.c:316
+		if (opt->min_arc_cnt > 1 && n_arc) {                                             // graph.c:317-318
+			size_t mk = scratch.mark();
+			uint32_t *keep = scratch.get<uint32_t>((size_t)n_arc + 1), *pos = scratch.get<uint32_t>((size_t)n_arc + 2);
+			PGX_LAUNCH(k_arc_keep_min_cnt, grid_for(n_arc, TB), TB, 0, st, arc.p, n_arc, opt->min_arc_cnt, keep);
+			uint32_t k = scan_flags(keep, pos, n_arc);
+			PGX_LAUNCH(k_arc_compact, grid_for(n_arc, TB), TB, 0, st, arc.p, n_arc, pos, arc_alt.p);
+			arc.swap(arc_alt);
+			n_arc = (int32_t)k;
+			scratch.reset(mk);
+		}
+		arc_index();                                                                     // graph.c:319
+		check_err("graph generation");
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] round-3 graph: %d genes and %d arcs\n", n_seg, n_arc);
+		done_graph = true;
+		g_stats.n_seg = n_seg; g_stats.n_arc = n_arc;
+	}
+
+	void collect_stats()
+	{
+		uint32_t h[C_N];
+		PGX_CHECK(cudaMemcpyAsync(h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		g_stats.tie[0] = h[C_TIE_CM]; g_stats.tie[1] = h[C_TIE_CS]; g_stats.tie[2] = h[C_TIE_DUP]; g_stats.tie[3] = h[C_TIE_SUB];
+		float ms = 0;
+		if (N) { PGX_CHECK(cudaEventElapsedTime(&ms, ev[0], ev[1])); }
+		g_stats.sweep_ms = ms;
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	// results back into the caller's structs (malloc'd, as the reference's destroy functions expect)
+	// ------------------------------------------------------------------------------------------------
+	void download(pg_data_t *d, pg_graph_t *q)
+	{
+		if (d->n_genome != G) PGX_FATAL("download: pg_data_t does not match the uploaded one");
+		if (Nw) PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
+		if (N) {
+			DBuf<int32_t> out;
+			out.alloc((size_t)N * AOS_WORDS);
+			PGX_LAUNCH(k_materialize, grid_for((int64_t)N * AOS_WORDS, TB), TB, 0, st, aos.p, src.p, N, F, g2s.p, prot_rep.p, done_graph? 1 : 0, out.p);
+			std::vector<pg_hit_t*> fresh(G, nullptr);
+			for (int32_t j = 0; j < G; ++j) {
+				pg_genome_t *g = &d->genome[j];
+				int32_t n = h_hoff[j + 1] - h_hoff[j];
+				if (n != g->n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
+				fresh[j] = (pg_hit_t*)malloc(sizeof(pg_hit_t) * (n > 0? n : 1));
+				if (n) PGX_CHECK(cudaMemcpyAsync(fresh[j], out.p + (size_t)h_hoff[j] * AOS_WORDS, (size_t)n * sizeof(pg_hit_t), cudaMemcpyDeviceToHost, st));
+			}
+			PGX_CHECK(cudaStreamSynchronize(st));
+			for (int32_t j = 0; j < G; ++j) { free(d->genome[j].hit); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = d->genome[j].n_hit; }   // hit.c:62-63
+			g_stats.d2h += (int64_t)N * 88;
+		}
+		for (int32_t i = 0; i < n_prot; ++i) {   // hit.c:206-207,215,230-237
+			d->prot[i].n = rep.prot_n[i]; d->prot[i].avg_score_adj = rep.prot_avg[i]; d->prot[i].rep = rep.prot_rep[i]; d->prot[i].max_score_ori = h_prot_max[i];
+		}
+		for (int32_t i = 0; i < n_gene; ++i) d->gene[i].rep_pid = rep.gene_rep_pid[i];
+		if (q && done_graph) {
+			free(q->seg); free(q->arc); free(q->g2s); free(q->idx);
+			q->n_seg = q->m_seg = n_seg; q->n_arc = q->m_arc = n_arc;
+			q->seg = (pg_seg_t*)calloc(n_seg > 0? n_seg : 1, sizeof(pg_seg_t));
+			q->arc = (pg_arc_t*)calloc(n_arc > 0? n_arc : 1, sizeof(pg_arc_t));
+			q->g2s = (int32_t*)malloc(sizeof(int32_t) * (n_gene > 0? n_gene : 1));
+			q->idx = (uint64_t*)calloc((size_t)(n_seg > 0? n_seg : 1) * 2, sizeof(uint64_t));
+			static_assert(sizeof(SegDev) == sizeof(pg_seg_t) && sizeof(ArcDev) == sizeof(pg_arc_t), "device mirrors of the graph records");
+			if (n_seg) PGX_CHECK(cudaMemcpyAsync(q->seg, seg.p, (size_t)n_seg * sizeof(pg_seg_t), cudaMemcpyDeviceToHost, st));
+			if (n_arc) PGX_CHECK(cudaMemcpyAsync(q->arc, arc.p, (size_t)n_arc * sizeof(pg_arc_t), cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaMemcpyAsync(q->g2s, g2s.p, (size_t)n_gene * 4, cudaMemcpyDeviceToHost, st));
+			if (n_seg) PGX_CHECK(cudaMemcpyAsync(q->idx, idx.p, (size_t)n_seg * 16, cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaStreamSynchronize(st));
+			g_stats.d2h += (int64_t)n_seg * 48 + (int64_t)n_arc * 32 + (int64_t)n_gene * 4;
+		}
+	}
+};
+
+} // namespace pgx

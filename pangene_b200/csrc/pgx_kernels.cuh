@@ -1,0 +1,855 @@
+// pgx_kernels.cuh -- the hot-path kernels (sm_100a).  Integer / indexing work: no tensor cores.
+// Each kernel cites the reference lines whose result it must reproduce bit for bit; the order-free
+// formulation they implement is spelled out (and pinned against the compiled reference) in oracle/pg_oracle.c.
+#pragma once
+#include "pgx_util.cuh"
+#include "pangene_abi.h"
+
+namespace pgx {
+
+// internal marker kept in the unused high bits of the pg_hit_t bit-field word; stripped on materialisation
+constexpr uint32_t HB_FIRST = 0x80000000u;       // first hit of its genome in (contig, cs) order (overlap.c:108 quirk)
+constexpr uint32_t HB_ABI_MASK = 0x7ffu;
+
+constexpr int AOS_WORDS = 22;                    // sizeof(pg_hit_t) / 4
+// word offsets inside pg_hit_t (include/pangene_abi.h)
+constexpr int W_PID = 0, W_CID = 3, W_RANK = 7, W_SORI = 8, W_SADJ = 9, W_SDOM = 10, W_NEXON = 11, W_OFFEXON = 12, W_PDOM = 13, W_PDOM0 = 14, W_BITS = 15, W_CS = 16, W_CM = 18, W_CE = 20;
+
+__device__ __forceinline__ uint32_t mix32(uint32_t k)   // pgpriv.h:88-97
+{
+	k += ~(k << 15); k ^= k >> 10; k += k << 3; k ^= k >> 6; k += ~(k << 11); k ^= k >> 16;
+	return k;
+}
+// overlap.c:82,137: score_adj<<33 | preferred<<32 | hash(pid)
+__device__ __forceinline__ uint64_t score_key(int32_t sadj, int32_t gidp, int32_t pid)
+{
+	return (uint64_t)(int64_t)sadj << 33 | (uint64_t)(gidp & 1) << 32 | mix32((uint32_t)pid);
+}
+
+__device__ __forceinline__ int upper_bound_i32(const int32_t *a, int n, int32_t x)   // first k with a[k] > x
+{
+	int lo = 0, hi = n;
+	while (lo < hi) { int m = (lo + hi) >> 1; if (a[m] <= x) lo = m + 1; else hi = m; }
+	return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage A: raw (file) order -- unpack, per-(genome,protein) pseudogene flags (hit.c:66-105)
+// ------------------------------------------------------------------------------------------------
+// hoff[G+1]: hit offsets of the local genomes; coff[G+1]: contig-key offsets; one thread per raw hit.
+__global__ void k_unpack(const int32_t *__restrict__ aos, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff, int G,
+	int32_t *r_pid, int32_t *r_nexon, int32_t *r_rank, int32_t *r_gl, uint64_t *key, int32_t n_prot, uint32_t *err)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	const int32_t *w = aos + (size_t)t * AOS_WORDS;
+	int gl = upper_bound_i32(hoff, G + 1, t) - 1;
+	int32_t pid = w[W_PID], cid = w[W_CID];
+	int64_t cs = *(const int64_t*)(w + W_CS), cm = *(const int64_t*)(w + W_CM), ce = *(const int64_t*)(w + W_CE);
+	uint32_t bad = 0;
+	if (cs < 0 || ce > 0x7fffffffll || cm < 0 || cm > 0x7fffffffll || cs > ce) bad |= 1;   // this build keeps coordinates in int32
+	if (cid < 0 || cid >= coff[gl + 1] - coff[gl]) bad |= 2;
+	if (pid < 0 || pid >= n_prot) bad |= 4;
+	if (w[W_NEXON] < 1) bad |= 8;
+	if (bad) { atomicOr(err, bad); cid = 0; cs = 0; pid = 0; }
+	r_pid[t] = pid; r_nexon[t] = w[W_NEXON]; r_rank[t] = w[W_RANK]; r_gl[t] = gl;
+	key[t] = (uint64_t)(uint32_t)(coff[gl] + cid) << 32 | (uint32_t)cs;
+}
+
+__global__ void k_fp_minmax(const int32_t *__restrict__ r_pid, const int32_t *__restrict__ r_nexon, const int32_t *__restrict__ r_gl, int32_t n, int32_t n_prot,
+	int32_t *t_max, int32_t *t_min)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	size_t k = (size_t)r_gl[t] * n_prot + r_pid[t];
+	atomicMax(&t_max[k], r_nexon[t]);
+	atomicMin(&t_min[k], r_nexon[t]);
+}
+
+__device__ __forceinline__ bool fp_group_flagged(int32_t M, int32_t m) { return M > 1 && (m == 1 || m * 2 <= M); }   // hit.c:84
+
+__global__ void k_fp_flag(const int32_t *__restrict__ r_pid, const int32_t *__restrict__ r_nexon, const int32_t *__restrict__ r_rank, const int32_t *__restrict__ r_gl,
+	int32_t n, int32_t n_prot, const int32_t *__restrict__ t_max, const int32_t *__restrict__ t_min, int32_t *t_r1, uint8_t *r_pseudo)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	size_t k = (size_t)r_gl[t] * n_prot + r_pid[t];
+	int32_t M = t_max[k], m = t_min[k], ne = r_nexon[t];
+	uint8_t ps = 0;
+	if (fp_group_flagged(M, m)) {
+		if (ne == 1 || ne * 2 <= M) ps = 1;                 // hit.c:88-89
+		else atomicMin(&t_r1[k], r_rank[t]);                // lowest-rank survivor = "j1" of hit.c:90-91
+	}
+	r_pseudo[t] = ps;
+}
+
+__global__ void k_fp_rank(const int32_t *__restrict__ r_pid, const int32_t *__restrict__ r_gl, int32_t n, int32_t n_prot,
+	const int32_t *__restrict__ t_max, const int32_t *__restrict__ t_min, const int32_t *__restrict__ t_r1, int32_t *r_rank)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n) return;
+	size_t k = (size_t)r_gl[t] * n_prot + r_pid[t];
+	if (!fp_group_flagged(t_max[k], t_min[k])) return;
+	int32_t r1 = t_r1[k], r = r_rank[t];
+	if (r1 <= 0 || r1 == INT32_MAX) return;                 // hit.c:94
+	if (r < r1) r_rank[t] = r + 1; else if (r == r1) r_rank[t] = 0;   // hit.c:95-97
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage B: gather into (contig, cs) order -- the one and only physical reordering of hits
+// ------------------------------------------------------------------------------------------------
+struct FullCols {            // all hits, (genome, contig, cs) order, packed int32 columns
+	int32_t *ctg, *cs, *ce, *cm, *pid, *gidp, *sadj, *rank, *sori, *sdom, *pdom0, *pdom, *cds, *pmax;
+	uint32_t *bits, *nex, *eoff, *esrc;
+};
+
+__global__ void k_gather(const int32_t *__restrict__ aos, const uint32_t *__restrict__ src, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff,
+	const uint32_t *__restrict__ eoff_g, const int32_t *__restrict__ r_rank, const uint8_t *__restrict__ r_pseudo, const int32_t *__restrict__ r_gl,
+	const int32_t *__restrict__ prot_gid, const uint8_t *__restrict__ gene_pref, FullCols c)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t s = src[i];
+	const int32_t *w = aos + (size_t)s * AOS_WORDS;
+	int gl = r_gl[s];
+	int32_t pid = w[W_PID], gid = prot_gid[pid];
+	uint32_t b = (uint32_t)w[W_BITS] & PG_HB_REV;
+	if (r_pseudo[s]) b |= PG_HB_PSEUDO | PG_HB_FLT;          // read.c:246
+	if (i == hoff[gl]) b |= HB_FIRST;
+	c.ctg[i] = coff[gl] + w[W_CID];
+	c.cs[i] = (int32_t)*(const int64_t*)(w + W_CS); c.cm[i] = (int32_t)*(const int64_t*)(w + W_CM); c.ce[i] = (int32_t)*(const int64_t*)(w + W_CE);
+	c.pid[i] = pid; c.gidp[i] = gid << 1 | gene_pref[gid];
+	c.sadj[i] = w[W_SADJ]; c.sori[i] = w[W_SORI]; c.rank[i] = r_rank[s];
+	c.sdom[i] = 0; c.pdom0[i] = -1; c.pdom[i] = -1;          // parser state: read.c:133-134
+	c.bits[i] = b;
+	c.nex[i] = (uint32_t)w[W_NEXON];
+	c.esrc[i] = eoff_g[gl] + (uint32_t)w[W_OFFEXON];
+}
+
+// copy each hit's exon list to its new home (contiguous in hit order) and sum the CDS length (overlap.c:45-51)
+__global__ void k_gather_exons(const int2 *__restrict__ ex_raw, const uint32_t *__restrict__ esrc, const uint32_t *__restrict__ eoff, int32_t n, int2 *ex, int32_t *cds)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t b = eoff[i], e = eoff[i + 1], s = esrc[i];
+	int32_t len = 0;
+	for (uint32_t k = 0; k < e - b; ++k) { int2 x = ex_raw[s + k]; ex[b + k] = x; len += x.y - x.x; }
+	cds[i] = len;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the interval sweep (overlap.c:58-178) as a set of pairs, evaluated from both members of every pair
+// ------------------------------------------------------------------------------------------------
+struct SweepCols {
+	int32_t n;
+	const int32_t *ctg, *cs, *ce, *pid, *gidp, *sadj, *rank, *cds, *sori, *pmax;
+	const uint32_t *bits, *eoff;
+	const int2 *ex;
+};
+struct SweepOpt { double min_ov_ratio; int32_t check_strand; };
+
+enum { SW_LOAD = 0, SW_SHADOW = 1, SW_ISO = 2 };
+
+// |CDS(lo) & CDS(hi)| (overlap.c:6-42); lo precedes hi in (contig, cs) order
+__device__ __forceinline__ int32_t cds_overlap(const int2 *__restrict__ ex, uint32_t b0, uint32_t e0, int32_t cs0, int32_t ce0, uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1)
+{
+	if (!(cs0 < ce1 && ce0 > cs1)) return 0;
+	int32_t inter = 0;
+	int2 x0 = ex[b0], x1 = ex[b1];
+	while (true) {
+		int32_t s0 = cs0 + x0.x, t0 = cs0 + x0.y, s1 = cs1 + x1.x, t1 = cs1 + x1.y;
+		if (s0 < s1) {
+			if (t0 < t1) { int32_t o = t0 - s1; inter += o > 0? o : 0; if (++b0 == e0) break; x0 = ex[b0]; }
+			else { inter += x1.y - x1.x; if (++b1 == e1) break; x1 = ex[b1]; }
+		} else {
+			if (t1 < t0) { int32_t o = t1 - s0; inter += o > 0? o : 0; if (++b1 == e1) break; x1 = ex[b1]; }
+			else { inter += x0.y - x0.x; if (++b0 == e0) break; x0 = ex[b0]; }
+		}
+	}
+	return inter;
+}
+
+struct Mine {            // the hit a thread owns
+	int32_t i, ctg, cs, ce, pid, gidp, rank, cds; uint32_t bits, eb, ee; uint64_t key;
+};
+
+// Decide the pair (me, p). Returns true when `me` LOSES to p; *ov = CDS overlap. me_is_hi: me is the later hit.
+template<int MODE> __device__ __forceinline__ bool pair_me_loses(const SweepCols &c, const SweepOpt &o, const Mine &m, int32_t p, uint32_t pbits, int32_t pcs, int32_t pce, bool me_is_hi, int32_t *ov_, uint64_t *pkey_)
+{
+	int32_t pgidp = c.gidp[p];
+	bool same_gene = (pgidp >> 1) == (m.gidp >> 1);
+	if (MODE == SW_ISO && !same_gene) return false;                                  // overlap.c:77
+	if (o.check_strand && ((pbits ^ m.bits) & PG_HB_REV)) return false;               // overlap.c:78,128
+	uint32_t pb = c.eoff[p], pe = c.eoff[p + 1];
+	int32_t ov = me_is_hi? cds_overlap(c.ex, pb, pe, pcs, pce, m.eb, m.ee, m.cs, m.ce)
+	                     : cds_overlap(c.ex, m.eb, m.ee, m.cs, m.ce, pb, pe, pcs, pce);
+	if (ov == 0) return false;                                                        // overlap.c:81,132
+	if (MODE != SW_ISO && !same_gene) {
+		int32_t pcds = c.cds[p], shorter = m.cds < pcds? m.cds : pcds;
+		double cov_short = (double)(uint64_t)ov / shorter;                            // overlap.c:134
+		if (cov_short < o.min_ov_ratio) return false;                                 // overlap.c:136
+	}
+	int32_t ppid = c.pid[p];
+	uint64_t pkey = score_key(c.sadj[p], pgidp, ppid);
+	int32_t prank = c.rank[p];
+	// the reference names the later hit "i" and the earlier one "j" (overlap.c:139-147)
+	uint64_t si = me_is_hi? m.key : pkey, sj = me_is_hi? pkey : m.key;
+	int32_t ri = me_is_hi? m.rank : prank, rj = me_is_hi? prank : m.rank;
+	uint32_t wi = ((me_is_hi? m.bits : pbits) & PG_HB_WBR_MASK), wj = ((me_is_hi? pbits : m.bits) & PG_HB_WBR_MASK);
+	bool hi_loses;
+	if (MODE == SW_ISO || same_gene || wi == wj) hi_loses = si < sj || (si == sj && ri > rj);
+	else hi_loses = wi > wj;
+	*ov_ = ov; *pkey_ = pkey;
+	return hi_loses == me_is_hi;
+}
+
+// One thread per hit. bits_out may not alias c.bits (the pass reads every neighbour's pre-pass flags).
+//   SW_LOAD   = pg_shadow(cal_dom_sc=1) followed by read.c:249-253: writes pid_dom0, score_dom; shadow/pid_dom stay reset
+//   SW_SHADOW = pg_shadow(cal_dom_sc=0): writes the shadow bit and pid_dom
+//   SW_ISO    = pg_flt_ov_isoform: writes flt_iso_ov|flt
+template<int MODE> __global__ void __launch_bounds__(128) k_sweep(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= c.n) return;
+	Mine m;
+	m.bits = c.bits[i];
+	if (m.bits & PG_HB_FLT) { bits_out[i] = m.bits; return; }                        // overlap.c:63,112
+	m.i = i; m.ctg = c.ctg[i]; m.cs = c.cs[i]; m.ce = c.ce[i]; m.pid = c.pid[i]; m.gidp = c.gidp[i]; m.rank = c.rank[i]; m.cds = c.cds[i];
+	m.eb = c.eoff[i]; m.ee = c.eoff[i + 1];
+	m.key = score_key(c.sadj[i], m.gidp, m.pid);
+	bool lose = false;
+	uint64_t best_key = 0; int32_t best_p = INT32_MAX, best_ov = 0;
+	// earlier hits still open at my start (overlap.c:67-71,114-120); pmax = running max of ce inside the contig
+	for (int32_t p = i - 1; p >= 0; --p) {
+		if (c.ctg[p] != m.ctg || c.pmax[p] <= m.cs) break;
+		int32_t pce = c.ce[p];
+		if (pce <= m.cs) continue;
+		uint32_t pbits = c.bits[p];
+		if (pbits & PG_HB_FLT) continue;
+		int32_t ov; uint64_t pkey;
+		if (pair_me_loses<MODE>(c, o, m, p, pbits, c.cs[p], pce, true, &ov, &pkey)) {
+			lose = true;
+			if (pkey > best_key || (pkey == best_key && pkey > 0 && p < best_p)) {
+				if (MODE == SW_LOAD && pkey == best_key && c.cs[p] == c.cs[best_p]) atomicAdd(tie_cnt, 1u);
+				best_key = pkey, best_p = p, best_ov = ov;
+			}
+		}
+	}
+	// later hits that start before my end
+	for (int32_t p = i + 1; p < c.n; ++p) {
+		if (c.ctg[p] != m.ctg) break;
+		int32_t pcs = c.cs[p];
+		if (pcs >= m.ce) break;
+		uint32_t pbits = c.bits[p];
+		if (pbits & PG_HB_FLT) continue;
+		int32_t ov; uint64_t pkey;
+		if (pair_me_loses<MODE>(c, o, m, p, pbits, pcs, c.ce[p], false, &ov, &pkey)) {
+			lose = true;
+			if (pkey > best_key) best_key = pkey, best_p = p, best_ov = ov;           // ascending p: strict > keeps the first (overlap.c:150,153)
+			else if (MODE == SW_LOAD && pkey == best_key && pkey > 0 && c.cs[p] == c.cs[best_p]) atomicAdd(tie_cnt, 1u);
+		}
+	}
+	if (MODE == SW_ISO) {
+		bits_out[i] = lose? (m.bits | PG_HB_FLT_OV | PG_HB_FLT) : m.bits;             // overlap.c:85-91
+	} else if (MODE == SW_SHADOW) {
+		uint32_t b = m.bits;
+		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;                                       // overlap.c:108,113: hit 0 is never reset
+		if (lose) b |= PG_HB_SHADOW;
+		bits_out[i] = b;
+		pdom_out[i] = best_key > 0? c.pid[best_p] : -1;                               // overlap.c:160-165
+	} else {
+		bits_out[i] = m.bits;
+		int32_t pd = -1, sd = -1;
+		if (best_key > 0) {
+			pd = c.pid[best_p];
+			// overlap.c:170, IEEE double, left to right; -fmad=false keeps the products and sums un-contracted
+			sd = (int32_t)(c.sori[i] * (1.0 - (double)best_ov / m.cds) + c.sori[best_p] * ((double)best_ov / c.cds[best_p]) + .499);
+		}
+		pdom_out[i] = pd; sdom_out[i] = sd;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// rest of the load-time block (hit.c:107-146)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_chain_mark(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ pid, const uint32_t *__restrict__ bits, int32_t n, int32_t n_prot, uint8_t *t_kept)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (!(bits[i] & PG_HB_FLT_OV)) t_kept[(size_t)ctg2g[ctg[i]] * n_prot + pid[i]] = 1;   // hit.c:136-138
+}
+
+__global__ void k_chain_apply(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ pdom0, uint32_t *bits, int32_t n, int32_t n_prot, const uint8_t *__restrict__ t_kept)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int32_t p0 = pdom0[i];
+	if (p0 >= 0 && !t_kept[(size_t)ctg2g[ctg[i]] * n_prot + p0]) bits[i] |= PG_HB_FLT | PG_HB_FLT_CHAIN;   // hit.c:141-142
+}
+
+// hit.c:112-118 as one atomicMax: a positive score wins by value, first in order on ties; any negative score always
+// replaces the incumbent in the reference's signed-vs-unsigned compare, so the LAST negative in order wins outright.
+__global__ void k_subopt_best(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ gidp, const int32_t *__restrict__ sadj,
+	const int32_t *__restrict__ rank, const uint32_t *__restrict__ bits, int32_t n, int32_t n_gene, unsigned long long *t_best)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if ((bits[i] & PG_HB_FLT) || rank[i] > 0) return;
+	int32_t s = sadj[i];
+	if (s == 0) return;
+	unsigned long long enc = s > 0? ((unsigned long long)(uint32_t)s << 32 | (0xffffffffu - (uint32_t)i)) : (1ull << 63 | (uint32_t)i);
+	atomicMax(&t_best[(size_t)ctg2g[ctg[i]] * n_gene + (gidp[i] >> 1)], enc);
+}
+
+__global__ void k_subopt_apply(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ gidp, const int32_t *__restrict__ pid,
+	uint32_t *bits, int32_t n, int32_t n_gene, const unsigned long long *__restrict__ t_best)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t b = bits[i];
+	if (b & PG_HB_FLT) return;
+	unsigned long long e = t_best[(size_t)ctg2g[ctg[i]] * n_gene + (gidp[i] >> 1)];
+	int32_t keep = 0;                                                                  // hit.c:111,123: no winner -> protein 0
+	if (e) { uint32_t w = (e >> 63)? (uint32_t)e : 0xffffffffu - (uint32_t)e; keep = pid[w]; }
+	if (pid[i] != keep) bits[i] = b | PG_HB_FLT | PG_HB_FLT_SUB;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pg_post_process pieces (hit.c:153-247)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cap_max(const int32_t *__restrict__ pid, const int32_t *__restrict__ sori, int32_t n, int32_t *prot_max)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) atomicMax(&prot_max[pid[i]], sori[i]);                                  // hit.c:231-238 (floor 0 = initial value)
+}
+__global__ void k_cap_apply(const int32_t *__restrict__ pid, int32_t *sdom, int32_t n, const int32_t *__restrict__ prot_max)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { int32_t m = prot_max[pid[i]]; if (sdom[i] > m) sdom[i] = m; }         // hit.c:243-244
+}
+
+// per-protein sums over rank-0 unfiltered hits: z = sum(score_adj<<32|1) (hit.c:201), c[w]/s[w] (hit.c:163-167)
+__global__ void k_prot_stats(const int32_t *__restrict__ pid, const int32_t *__restrict__ sadj, const int32_t *__restrict__ sori, const int32_t *__restrict__ rank,
+	const uint32_t *__restrict__ bits, const uint32_t *__restrict__ eoff, int32_t n, unsigned long long *z, unsigned long long *cs4)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if ((bits[i] & PG_HB_FLT) || rank[i] != 0) return;
+	int32_t p = pid[i];
+	atomicAdd(&z[p], (unsigned long long)(long long)sadj[i] << 32 | 1ull);
+	int w = (eoff[i + 1] - eoff[i]) != 1;
+	atomicAdd(&cs4[(size_t)p * 4 + w], 1ull);                                          // c[w]
+	atomicAdd(&cs4[(size_t)p * 4 + 2 + w], (unsigned long long)(long long)sori[i]);    // s[w]
+}
+
+__global__ void k_pseudo_joint(const int32_t *__restrict__ pid, uint32_t *bits, const uint32_t *__restrict__ eoff, int32_t n, const unsigned long long *__restrict__ cs4,
+	int32_t n_genome_total, double min_vertex_ratio, int32_t drop_sgl)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t b = bits[i];
+	if ((b & (PG_HB_FLT | PG_HB_PSEUDO)) || eoff[i + 1] - eoff[i] != 1) return;         // hit.c:175-176
+	const unsigned long long *q = &cs4[(size_t)pid[i] * 4];
+	int32_t c0 = (int32_t)q[0], c1 = (int32_t)q[1];
+	long long s0 = (long long)q[2], s1 = (long long)q[3];
+	double thr = n_genome_total * min_vertex_ratio;
+	bool ps = false;
+	if (c1 > 0 && c1 >= thr && ((double)s1 / c1) / ((double)s0 / c0) >= 0.99) ps = true;   // hit.c:176-179
+	else if ((c1 == 0 || c1 <= thr) && drop_sgl) ps = true;                           // hit.c:180-181
+	if (ps) bits[i] = b | PG_HB_PSEUDO;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic flag passes (pgpriv.h:109-116 and friends)
+// ------------------------------------------------------------------------------------------------
+enum { SF_PSEUDO = 0, SF_SHADOW = 1, SF_WBR2 = 2 };
+__global__ void k_set_filter(uint32_t *bits, int32_t n, int mode)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t b = bits[i];
+	bool hit = mode == SF_PSEUDO? (b & PG_HB_PSEUDO) != 0 : mode == SF_SHADOW? (b & PG_HB_SHADOW) != 0 : ((b & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT) == 2;
+	if (hit && !(b & PG_HB_FLT)) bits[i] = b | PG_HB_FLT;
+}
+
+// graph.c:61-69 + PG_SET_FILTER(vtx == 0)
+__global__ void k_flag_vtx(const int32_t *__restrict__ gidp, uint32_t *bits, int32_t n, const int32_t *__restrict__ g2s, int set_filter)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t b = bits[i];
+	if (g2s[gidp[i] >> 1] >= 0) b |= PG_HB_VTX; else { b &= ~PG_HB_VTX; if (set_filter) b |= PG_HB_FLT; }
+	bits[i] = b;
+}
+
+__global__ void k_flag_unfiltered(const uint32_t *__restrict__ bits, int32_t n, uint32_t *flag)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) flag[i] = (bits[i] & PG_HB_FLT)? 0u : 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// active set W: the hits that survived the load-time block, same order, compact columns
+// ------------------------------------------------------------------------------------------------
+struct ActCols {
+	int32_t *ctg, *cs, *ce, *cm, *pid, *gidp, *sadj, *rank, *sori, *sdom, *pdom0, *pdom, *cds, *pmax, *full;
+	uint32_t *bits, *bits_alt, *nex, *eoff;
+};
+
+__global__ void k_build_active(FullCols f, const uint32_t *__restrict__ pos, int32_t n, ActCols a)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t p = pos[i];
+	if (pos[i + 1] == p) return;                            // filtered
+	a.ctg[p] = f.ctg[i]; a.cs[p] = f.cs[i]; a.ce[p] = f.ce[i]; a.cm[p] = f.cm[i]; a.pid[p] = f.pid[i]; a.gidp[p] = f.gidp[i];
+	a.sadj[p] = f.sadj[i]; a.rank[p] = f.rank[i]; a.sori[p] = f.sori[i]; a.sdom[p] = f.sdom[i]; a.pdom0[p] = f.pdom0[i]; a.pdom[p] = -1;
+	a.cds[p] = f.cds[i]; a.full[p] = i; a.bits[p] = f.bits[i]; a.nex[p] = f.nex[i];
+}
+
+__global__ void k_copy_exons(const int2 *__restrict__ ex_src, const uint32_t *__restrict__ eoff_src, const int32_t *__restrict__ full, const uint32_t *__restrict__ eoff_dst, int32_t n, int2 *ex_dst)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	uint32_t s = eoff_src[full[p]], b = eoff_dst[p], e = eoff_dst[p + 1];
+	for (uint32_t k = 0; k < e - b; ++k) ex_dst[b + k] = ex_src[s + k];
+}
+
+__global__ void k_make_cm_keys(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cm, int32_t n, uint64_t *key)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) key[i] = (uint64_t)(uint32_t)ctg[i] << 32 | (uint32_t)cm[i];
+}
+
+// write the active set's state back into the full columns
+__global__ void k_scatter_back(ActCols a, int32_t n, FullCols f)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	int32_t i = a.full[p];
+	f.bits[i] = a.bits[p]; f.pdom[i] = a.pdom[p]; f.sdom[i] = a.sdom[p];
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertex selection inputs (vertex.c:28-51)
+// ------------------------------------------------------------------------------------------------
+// t_dom[g*n_gene+gene] = 1 if an unshadowed rank-0 unfiltered hit exists; t_first = smallest index of a shadowed one
+__global__ void k_vtx_mark(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ gidp, const int32_t *__restrict__ rank,
+	const uint32_t *__restrict__ bits, int32_t n, int32_t n_gene, uint8_t *t_dom, int32_t *t_first)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t b = bits[i];
+	if ((b & PG_HB_FLT) || rank[i] != 0) return;
+	size_t k = (size_t)ctg2g[ctg[i]] * n_gene + (gidp[i] >> 1);
+	if (b & PG_HB_SHADOW) atomicMin(&t_first[k], i); else t_dom[k] = 1;
+}
+// aux[k] = -2 (dominant) | gene that shadows it | -1 (absent)
+__global__ void k_vtx_resolve(const uint8_t *__restrict__ t_dom, const int32_t *__restrict__ t_first, const int32_t *__restrict__ pdom, const int32_t *__restrict__ prot_gid, size_t n_tab, int32_t *aux, uint32_t *err)
+{
+	size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_tab) return;
+	int32_t v = -1;
+	if (t_dom[k]) v = -2;
+	else if (t_first[k] != INT32_MAX) { int32_t pd = pdom[t_first[k]]; if (pd < 0) { atomicOr(err, 16u); pd = 0; } v = prot_gid[pd]; }   // vertex.c:38 assert
+	aux[k] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// arc generation (graph.c:87-177)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_flag_survivor_cm(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ by_cm, int32_t n, uint32_t *flag)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) flag[k] = (bits[by_cm[k]] & (PG_HB_FLT | PG_HB_SHADOW))? 0u : 1u;       // graph.c:109
+}
+__global__ void k_flag_survivor_cs(const uint32_t *__restrict__ bits, int32_t n, uint32_t *flag)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) flag[k] = (bits[k] & (PG_HB_FLT | PG_HB_SHADOW))? 0u : 1u;              // branch.c:20
+}
+__global__ void k_compact_idx(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ src, int32_t n, uint32_t *out)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n && pos[k + 1] != pos[k]) out[pos[k]] = src? src[k] : (uint32_t)k;
+}
+
+struct ArcEmit {
+	const uint32_t *sv; int32_t m;            // survivors in (contig, cm) order (indices into the active set)
+	const int32_t *ctg, *cm, *gidp, *sori, *sdom, *pdom0; const uint32_t *bits;
+	const int32_t *g2s, *prot_gid, *ctg2g;
+	int32_t use_ori, n_seg, gbits;
+};
+__device__ __forceinline__ int32_t arc_score(const ArcEmit &e, uint32_t h)   // graph.c:82-85
+{
+	int32_t so = e.sori[h], sd = e.sdom[h], p0 = e.pdom0[h];
+	return (e.use_ori || so > sd || p0 < 0 || e.g2s[e.prot_gid[p0]] >= 0)? so : sd;
+}
+// record t>0 with a predecessor on the same contig yields two keyed records (graph.c:115-120); others get the all-ones key
+// key = ((v * 2n_seg + w) << gbits) | local genome;  payload = (dist, s1, s2)
+__global__ void k_arc_emit(ArcEmit e, uint64_t *key, int32_t *dist, int32_t *s1, int32_t *s2, uint32_t *seg_seen, int32_t *seg_ng, int32_t *seg_tot, uint32_t *tie_cnt, uint32_t *err)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= e.m) return;
+	uint32_t h = e.sv[t];
+	int32_t sid = e.g2s[e.gidp[h] >> 1];
+	if (sid < 0) { atomicOr(err, 32u); sid = 0; }                                       // graph.c:111 assert
+	int32_t c = e.ctg[h], gl = e.ctg2g[c];
+	// seg occupancy (graph.c:113,125-126): first sighting of (genome, segment) bumps n_genome
+	{
+		size_t bit = (size_t)gl * e.n_seg + sid;
+		uint32_t old = atomicOr(&seg_seen[bit >> 5], 1u << (bit & 31));
+		if (!(old >> (bit & 31) & 1u)) atomicAdd(&seg_ng[sid], 1);
+		atomicAdd(&seg_tot[sid], 1);
+	}
+	uint64_t k0 = ~0ull, k1 = ~0ull;
+	int32_t d = 0, sa = 0, sp = 0;
+	if (t > 0) {
+		uint32_t hp = e.sv[t - 1];
+		if (e.ctg[hp] == c) {
+			uint32_t w = (uint32_t)sid << 1 | (e.bits[h] & PG_HB_REV);
+			uint32_t v = (uint32_t)e.g2s[e.gidp[hp] >> 1] << 1 | (e.bits[hp] & PG_HB_REV);
+			uint64_t nv = 2ull * e.n_seg;
+			d = e.cm[h] - e.cm[hp];
+			if (d == 0) atomicAdd(tie_cnt, 1u);
+			sp = arc_score(e, hp); sa = arc_score(e, h);
+			k0 = ((uint64_t)v * nv + w) << e.gbits | (uint32_t)gl;
+			k1 = ((uint64_t)(w ^ 1) * nv + (v ^ 1)) << e.gbits | (uint32_t)gl;
+		}
+	}
+	key[2 * (size_t)t] = k0; dist[2 * (size_t)t] = d; s1[2 * (size_t)t] = sp; s2[2 * (size_t)t] = sa;
+	key[2 * (size_t)t + 1] = k1; dist[2 * (size_t)t + 1] = d; s1[2 * (size_t)t + 1] = sa; s2[2 * (size_t)t + 1] = sp;
+}
+
+// partial arc = sums over the LOCAL genomes of one key (graph.c:128-145 per genome, then the additive part of 153-163)
+struct ArcPartial { uint64_t x; int64_t sum_dist, sum_s1, sum_s2; int32_t n_genome, tot_cnt; };
+
+__global__ void k_arc_heads(const uint64_t *__restrict__ key, int32_t n, int gbits, uint32_t *flag)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	uint64_t k = key[p];
+	flag[p] = (k != ~0ull && (p == 0 || (key[p - 1] >> gbits) != (k >> gbits)))? 1u : 0u;
+}
+
+__global__ void k_arc_reduce(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rec, const int32_t *__restrict__ dist, const int32_t *__restrict__ s1, const int32_t *__restrict__ s2,
+	int32_t n, int gbits, int32_t n_seg, const uint32_t *__restrict__ pos, ArcPartial *out)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n || pos[p + 1] == pos[p]) return;
+	uint64_t xk = key[p] >> gbits;
+	ArcPartial a; a.sum_dist = a.sum_s1 = a.sum_s2 = 0; a.n_genome = a.tot_cnt = 0;
+	int32_t q = p;
+	while (q < n && (key[q] >> gbits) == xk) {                 // one (key, genome) group per outer iteration
+		uint64_t kg = key[q];
+		unsigned long long dsum = 0; int32_t m1 = 0, m2 = 0, cnt = 0;
+		while (q < n && key[q] == kg) {
+			uint32_t r = rec[q];
+			dsum += (unsigned long long)(long long)dist[r];
+			int32_t a1 = s1[r], a2 = s2[r];
+			m1 = m1 > a1? m1 : a1; m2 = m2 > a2? m2 : a2;
+			++cnt; ++q;
+		}
+		int32_t dg = (int32_t)((double)dsum / cnt + .499);                               // graph.c:141
+		a.n_genome += 1; a.tot_cnt += cnt;
+		a.sum_dist += (long long)((unsigned long long)(long long)dg * (unsigned long long)(long long)cnt);   // graph.c:160
+		a.sum_s1 += m1; a.sum_s2 += m2;
+	}
+	uint64_t nv = 2ull * n_seg, v = xk / nv, w = xk % nv;
+	a.x = v << 32 | w;
+	out[pos[p]] = a;
+}
+
+// merge partials that share a key (multi-GPU: the same arc seen by several ranks), input sorted by x
+__global__ void k_partial_heads(const ArcPartial *__restrict__ in, int32_t n, uint32_t *flag)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n) flag[p] = (p == 0 || in[p - 1].x != in[p].x)? 1u : 0u;
+}
+struct ArcDev { uint64_t x; int32_t n_genome, tot_cnt, avg_dist, s1, s2; uint32_t bits; };   // == pg_arc_t
+__global__ void k_arc_finalize(const ArcPartial *__restrict__ in, int32_t n, const uint32_t *__restrict__ pos, ArcDev *arc)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n || pos[p + 1] == pos[p]) return;
+	ArcPartial a = in[p];
+	for (int32_t q = p + 1; q < n && in[q].x == a.x; ++q) {
+		a.sum_dist += in[q].sum_dist; a.sum_s1 += in[q].sum_s1; a.sum_s2 += in[q].sum_s2; a.n_genome += in[q].n_genome; a.tot_cnt += in[q].tot_cnt;
+	}
+	ArcDev o;
+	o.x = a.x; o.n_genome = a.n_genome; o.tot_cnt = a.tot_cnt; o.bits = 0;
+	o.avg_dist = (int32_t)(long long)((double)a.sum_dist / a.tot_cnt + .499);           // graph.c:170
+	o.s1 = (int32_t)((double)a.sum_s1 / a.n_genome + .499);                             // graph.c:171
+	o.s2 = (int32_t)((double)a.sum_s2 / a.n_genome + .499);                             // graph.c:172
+	arc[pos[p]] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small graph edits (graph.c:179-263)
+// ------------------------------------------------------------------------------------------------
+struct SegDev { int32_t gid, n_dom, n_sub, n_genome, tot_cnt; uint32_t del; int32_t n_dist_loci[2]; };   // == pg_seg_t
+
+__global__ void k_arc_index(const ArcDev *__restrict__ arc, int32_t n_arc, unsigned long long *idx)   // graph.c:202-211
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_arc) return;
+	uint32_t v = (uint32_t)(arc[p].x >> 32);
+	if (p > 0 && (uint32_t)(arc[p - 1].x >> 32) == v) return;
+	int32_t q = p + 1;
+	while (q < n_arc && (uint32_t)(arc[q].x >> 32) == v) ++q;
+	idx[v] = (unsigned long long)p << 32 | (uint32_t)(q - p);
+}
+
+__global__ void k_seg_store_occ(SegDev *seg, int32_t n_seg, const int32_t *__restrict__ ng, const int32_t *__restrict__ tot)
+{
+	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < n_seg) { seg[s].n_genome = ng[s]; seg[s].tot_cnt = tot[s]; }
+}
+
+// graph.c:237-256; degrees are taken from the arc list itself (idx may be stale or absent, as in the reference)
+__global__ void k_seg_mark_del(SegDev *seg, int32_t n_seg, const ArcDev *__restrict__ arc, int32_t n_arc, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, uint32_t *keep)
+{
+	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n_seg) return;
+	bool del = seg[s].tot_cnt > max_occ_total;
+	for (int o = 0; o < 2 && !del; ++o) {
+		uint64_t v = (uint64_t)(2 * s + o) << 32;
+		int32_t lo = 0, hi = n_arc;                             // first arc with x >= v<<32
+		while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < v) lo = m + 1; else hi = m; }
+		int32_t a = lo; hi = n_arc;
+		uint64_t v1 = (uint64_t)(2 * s + o + 1) << 32;
+		while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < v1) lo = m + 1; else hi = m; }
+		if (lo - a > max_degree) del = true;
+	}
+	int32_t m = seg[s].n_dist_loci[0] > seg[s].n_dist_loci[1]? seg[s].n_dist_loci[0] : seg[s].n_dist_loci[1];
+	if (m > max_dist_loci) del = true;
+	keep[s] = del? 0u : 1u;
+}
+__global__ void k_seg_compact(const SegDev *__restrict__ in, int32_t n_seg, const uint32_t *__restrict__ pos, SegDev *out)
+{
+	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < n_seg && pos[s + 1] != pos[s]) out[pos[s]] = in[s];
+}
+__global__ void k_g2s_fill(const SegDev *__restrict__ seg, int32_t n_seg, int32_t *g2s)
+{
+	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < n_seg) g2s[seg[s].gid] = s;
+}
+__global__ void k_arc_keep_min_cnt(const ArcDev *__restrict__ arc, int32_t n_arc, int32_t min_cnt, uint32_t *keep)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n_arc) keep[p] = arc[p].n_genome >= min_cnt? 1u : 0u;                       // graph.c:195
+}
+__global__ void k_arc_compact(const ArcDev *__restrict__ in, int32_t n_arc, const uint32_t *__restrict__ pos, ArcDev *out)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n_arc && pos[p + 1] != pos[p]) out[pos[p]] = in[p];
+}
+
+// ------------------------------------------------------------------------------------------------
+// branch filtering (branch.c)
+// ------------------------------------------------------------------------------------------------
+// last survivor of each gene per genome in (contig, cs) order (branch.c:6-29): atomicMax over the active index
+__global__ void k_pos_last(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ gidp, const uint32_t *__restrict__ surv_pos, int32_t n, int32_t G, int32_t *t_last)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || surv_pos[i + 1] == surv_pos[i]) return;
+	atomicMax(&t_last[(size_t)(gidp[i] >> 1) * G + ctg2g[ctg[i]]], i);                 // layout [gene][genome]: n_local reads are contiguous
+}
+struct GenePos { int32_t cid, ord, cm, pad; };                  // cid < 0: absent
+__global__ void k_pos_fill(const int32_t *__restrict__ t_last, size_t n_tab, int32_t G, const int32_t *__restrict__ ctg, const int32_t *__restrict__ cm, const uint32_t *__restrict__ surv_pos,
+	const int32_t *__restrict__ goff_act, GenePos *pos)
+{
+	size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_tab) return;
+	int32_t i = t_last[k];
+	GenePos g; g.cid = -1; g.ord = 0; g.cm = 0; g.pad = 0;
+	if (i >= 0) { int32_t gl = (int32_t)(k % G); g.cid = ctg[i]; g.cm = cm[i]; g.ord = (int32_t)(surv_pos[i] - surv_pos[goff_act[gl]]); }
+	pos[k] = g;
+}
+
+__global__ void k_cs_tie_count(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, const uint32_t *__restrict__ sv_cs, int32_t m, uint32_t *tie_cnt)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < 1 || t >= m) return;
+	uint32_t a = sv_cs[t - 1], b = sv_cs[t];
+	if (ctg[a] == ctg[b] && cs[a] == cs[b]) atomicAdd(tie_cnt, 1u);
+}
+
+// number of n_local values a vertex needs: all arc pairs (i <= k) of its out-list
+__global__ void k_branch_count(const unsigned long long *__restrict__ idx, int32_t n_vtx, uint32_t *cnt)
+{
+	int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n_vtx) return;
+	uint32_t n = (uint32_t)idx[v];
+	cnt[v] = n >= 2? n * (n + 1) / 2 : 0u;
+}
+
+struct BranchOpt { int32_t local_dist, local_count, frag_mode; double branch_diff, branch_diff_dist, branch_diff_cut; };
+
+__device__ __forceinline__ uint32_t tri_index(uint32_t i, uint32_t k, uint32_t n) { return i * n - i * (i - 1) / 2 + (k - i); }   // i <= k
+
+// one warp per oriented vertex: partial n_local (branch.c:31-46) over the LOCAL genomes for every arc pair
+__global__ void k_branch_nlocal(const unsigned long long *__restrict__ idx, int32_t n_vtx, const ArcDev *__restrict__ arc, const SegDev *__restrict__ seg, const GenePos *__restrict__ pos, int32_t G,
+	const uint32_t *__restrict__ off, BranchOpt o, int32_t *nl)
+{
+	int32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (v >= n_vtx) return;
+	unsigned long long e = idx[v];
+	uint32_t n = (uint32_t)e;
+	if (n < 2) return;
+	const ArcDev *a = arc + (e >> 32);
+	int32_t *out = nl + off[v];
+	for (uint32_t i = 0; i < n; ++i) {
+		const GenePos *p1 = pos + (size_t)seg[(uint32_t)a[i].x >> 1].gid * G;
+		for (uint32_t k = i; k < n; ++k) {
+			const GenePos *p2 = pos + (size_t)seg[(uint32_t)a[k].x >> 1].gid * G;
+			int32_t c = 0;
+			for (int32_t j = lane; j < G; j += 32) {
+				GenePos x = p1[j], y = p2[j];
+				if (x.cid < 0 || y.cid < 0) continue;
+				if (!o.frag_mode && x.cid != y.cid) continue;
+				long long dd = (long long)x.cm - y.cm; int32_t dc = x.ord - y.ord;
+				if ((dd >= -o.local_dist && dd <= o.local_dist) || (dc >= -o.local_count && dc <= o.local_count)) ++c;
+			}
+			for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+			if (lane == 0) out[tri_index(i, k, n)] = c;
+		}
+	}
+}
+
+// one thread per oriented vertex: branch.c:60-98 with the (summed) n_local table
+__global__ void k_branch_decide(const unsigned long long *__restrict__ idx, int32_t n_vtx, ArcDev *arc, SegDev *seg, const uint32_t *__restrict__ off, const int32_t *__restrict__ nl, BranchOpt o, int32_t *grp_scratch)
+{
+	int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+	if (v >= n_vtx) return;
+	unsigned long long e = idx[v];
+	int32_t n = (int32_t)(uint32_t)e;
+	if (n < 2) return;
+	ArcDev *a = arc + (e >> 32);
+	const int32_t *t = nl + off[v];
+	int32_t best = 0;
+	for (int32_t i = 0; i < n; ++i) best = best > a[i].s1? best : a[i].s1;
+	for (int32_t i = 0; i < n; ++i) {
+		double r = 1.0 - (double)a[i].s1 / best;
+		if (r > o.branch_diff) {
+			int32_t sum = 0;
+			for (int32_t k = 0; k < n; ++k)
+				if (a[k].s1 == best) sum += t[k < i? tri_index(k, i, n) : tri_index(i, k, n)];
+			uint32_t wb = ((sum == 0 && r > o.branch_diff_dist) || r > o.branch_diff_cut)? 2u : 1u;   // branch.c:76-77
+			a[i].bits = (a[i].bits & ~6u) | wb << 1;            // pg_arc_t: del:1, weak_br:2
+		}
+	}
+	// branch.c:82-90: greedy grouping of the out-neighbours by locality; labels live in a scratch slice parallel to the arc list
+	int32_t n_grp = 0;
+	int32_t *grp = grp_scratch + (e >> 32);
+	for (int32_t i = 0; i < n; ++i) grp[i] = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		if (grp[i] == 0) grp[i] = ++n_grp;
+		for (int32_t k = i + 1; k < n; ++k)
+			if (grp[k] == 0 && t[tri_index(i, k, n)] > 0) grp[k] = grp[i];
+	}
+	seg[v >> 1].n_dist_loci[v & 1] = n_grp;
+}
+
+// branch.c:108-145 + PG_SET_FILTER(weak_br == 2): survivors in (contig, cm) order look up the two arcs they sit on
+__device__ __forceinline__ uint32_t arc_weak(const ArcDev *__restrict__ arc, int32_t n_arc, uint64_t x)
+{
+	int32_t lo = 0, hi = n_arc;
+	while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < x) lo = m + 1; else hi = m; }
+	return (lo < n_arc && arc[lo].x == x)? (arc[lo].bits >> 1 & 3u) : 0u;
+}
+__global__ void k_branch_hits(const uint32_t *__restrict__ sv, int32_t m, const int32_t *__restrict__ ctg, const int32_t *__restrict__ gidp, uint32_t *bits, const int32_t *__restrict__ g2s,
+	const ArcDev *__restrict__ arc, int32_t n_arc)
+{
+	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= m) return;
+	uint32_t h = sv[t], b = bits[h];
+	int32_t c = ctg[h];
+	uint32_t w = (uint32_t)g2s[gidp[h] >> 1] << 1 | (b & PG_HB_REV);
+	uint32_t wb = (b & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT;
+	if (t > 0) {                                            // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
+		uint32_t hp = sv[t - 1];
+		if (ctg[hp] == c) {
+			uint32_t v = (uint32_t)g2s[gidp[hp] >> 1] << 1 | (bits[hp] & PG_HB_REV);
+			uint32_t x = arc_weak(arc, n_arc, (uint64_t)(w ^ 1) << 32 | (v ^ 1));
+			wb = wb > x? wb : x;
+		}
+	}
+	if (t + 1 < m) {                                        // I am the earlier hit of (me, next): arc (v -> w), branch.c:127-129
+		uint32_t hn = sv[t + 1];
+		if (ctg[hn] == c) {
+			uint32_t wn = (uint32_t)g2s[gidp[hn] >> 1] << 1 | (bits[hn] & PG_HB_REV);
+			uint32_t x = arc_weak(arc, n_arc, (uint64_t)w << 32 | wn);
+			wb = wb > x? wb : x;
+		}
+	}
+	// only the weak_br bits (and flt) of my own word change; neighbours read rev only, which never changes
+	b = (b & ~PG_HB_WBR_MASK) | wb << PG_HB_WBR_SHIFT;
+	if (wb == 2) b |= PG_HB_FLT;                             // graph.c:309
+	bits[h] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// materialisation: pg_hit_t records in (contig, cs) order with every field final
+// ------------------------------------------------------------------------------------------------
+__global__ void k_materialize(const int32_t *__restrict__ aos, const uint32_t *__restrict__ src, int32_t n, FullCols c, const int32_t *__restrict__ g2s, const int32_t *__restrict__ prot_rep,
+	int32_t have_graph, int32_t *out)
+{
+	// 22 consecutive threads cooperate on one record so that both the gather and the store are word-coalesced
+	int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t i = gt / AOS_WORDS; int w = (int)(gt % AOS_WORDS);
+	if (i >= n) return;
+	int32_t x = aos[(size_t)src[i] * AOS_WORDS + w];
+	if (w == W_RANK) x = c.rank[i];
+	else if (w == W_SDOM) x = c.sdom[i];
+	else if (w == W_PDOM) x = c.pdom[i];
+	else if (w == W_PDOM0) x = c.pdom0[i];
+	else if (w == W_BITS) {
+		uint32_t b = c.bits[i] & HB_ABI_MASK & ~(PG_HB_VTX | PG_HB_REP);
+		int32_t pid = c.pid[i];
+		if (prot_rep[pid]) b |= PG_HB_REP;                                              // hit.c:219-224
+		if (have_graph && g2s[c.gidp[i] >> 1] >= 0) b |= PG_HB_VTX;                     // graph.c:61-69 (last call)
+		x = (int32_t)b;
+	}
+	out[(size_t)i * AOS_WORDS + w] = x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// odds and ends
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_i32(int32_t *a, int64_t n, int32_t v)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) a[i] = v;
+}
+__global__ void k_gather_u32(const uint32_t *__restrict__ table, const uint32_t *__restrict__ index, int32_t n, uint32_t *out)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = table[index[i]];
+}
+__global__ void k_seg_zero_loci(SegDev *seg, int32_t n_seg)   // branch.c:56-57
+{
+	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < n_seg) seg[s].n_dist_loci[0] = seg[s].n_dist_loci[1] = 0;
+}
+__global__ void k_partial_keys(const ArcPartial *__restrict__ in, int32_t n, int32_t n_seg, uint64_t *key)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n) key[p] = (in[p].x >> 32) * (2ull * n_seg) + (uint32_t)in[p].x;
+}
+__global__ void k_partial_gather(const ArcPartial *__restrict__ in, const uint32_t *__restrict__ perm, int32_t n, ArcPartial *out)
+{
+	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p < n) out[p] = in[perm[p]];
+}
+// algorithmic bytes of one sweep launch: 52 + 8 n_exon per unfiltered hit, 4 per filtered hit
+__global__ void k_sweep_bytes(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ eoff, int32_t n, unsigned long long *total)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned long long b = 0;
+	if (i < n) b = (bits[i] & PG_HB_FLT)? 4ull : 52ull + 8ull * (eoff[i + 1] - eoff[i]);
+	for (int s = 16; s > 0; s >>= 1) b += __shfl_xor_sync(0xffffffffu, b, s);
+	if ((threadIdx.x & 31) == 0 && b) atomicAdd(total, b);
+}
+
+} // namespace pgx

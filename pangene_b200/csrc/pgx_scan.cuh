@@ -1,0 +1,171 @@
+// pgx_scan.cuh -- device-wide prefix sums and the segmented running maximum (hand-written, no CUB).
+//
+// Three launches per scan: (1) every 2048-element tile is scanned on its own and leaves one aggregate,
+// (2) ONE block walks the aggregates (<= a few thousand) and turns them into tile prefixes, (3) tiles add
+// their prefix.  Bandwidth: reads n, writes n, reads+writes n again (phase 3) -- these scans feed stream
+// compactions that are a small part of a round, see DESIGN.md.
+#pragma once
+#include "pgx_util.cuh"
+
+namespace pgx {
+
+constexpr int SCAN_B = 256, SCAN_I = 8, SCAN_TILE = SCAN_B * SCAN_I;
+
+// ---- exclusive sum of uint32 -------------------------------------------------------------------
+// out has n_in+1 entries: out[i] = sum(in[0..i)), out[n_in] = grand total. in may alias out.
+__global__ void k_scan_sum_tiles(const uint32_t *__restrict__ in, uint32_t *out, uint32_t *agg, int64_t n_in)
+{
+	__shared__ uint32_t sh[SCAN_B];
+	const int tid = threadIdx.x;
+	const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * SCAN_I;
+	uint32_t v[SCAN_I], sum = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) { int64_t i = base + k; v[k] = i < n_in? in[i] : 0u; sum += v[k]; }
+	sh[tid] = sum;
+	__syncthreads();
+	for (int d = 1; d < SCAN_B; d <<= 1) {
+		uint32_t t = tid >= d? sh[tid - d] : 0u;
+		__syncthreads();
+		sh[tid] += t;
+		__syncthreads();
+	}
+	uint32_t run = sh[tid] - sum;
+	if (tid == SCAN_B - 1) agg[blockIdx.x] = sh[tid];
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) { int64_t i = base + k; if (i <= n_in) out[i] = run; run += v[k]; }
+}
+
+// one block: agg[i] <- exclusive prefix of agg (in place)
+__global__ void k_scan_sum_agg(uint32_t *agg, int n)
+{
+	__shared__ uint32_t sh[SCAN_B];
+	__shared__ uint32_t carry;
+	const int tid = threadIdx.x;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (int c0 = 0; c0 < n; c0 += SCAN_B) {
+		int i = c0 + tid;
+		uint32_t x = i < n? agg[i] : 0u;
+		sh[tid] = x;
+		__syncthreads();
+		for (int d = 1; d < SCAN_B; d <<= 1) {
+			uint32_t t = tid >= d? sh[tid - d] : 0u;
+			__syncthreads();
+			sh[tid] += t;
+			__syncthreads();
+		}
+		uint32_t c = carry;
+		if (i < n) agg[i] = c + sh[tid] - x;
+		__syncthreads();
+		if (tid == SCAN_B - 1) carry = c + sh[tid];
+		__syncthreads();
+	}
+}
+
+__global__ void k_scan_sum_add(uint32_t *out, const uint32_t *__restrict__ agg, int64_t n_out)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_out) out[i] += agg[i / SCAN_TILE];
+}
+
+// scratch must hold ceil((n_in+1)/SCAN_TILE) uint32
+static inline size_t scan_scratch_elems(int64_t n_in) { return (size_t)((n_in + 1 + SCAN_TILE - 1) / SCAN_TILE); }
+
+static void exclusive_sum_u32(const uint32_t *in, uint32_t *out, int64_t n_in, uint32_t *agg_scratch, cudaStream_t s)
+{
+	int64_t n_out = n_in + 1;
+	int tiles = (int)((n_out + SCAN_TILE - 1) / SCAN_TILE);
+	PGX_LAUNCH(k_scan_sum_tiles, tiles, SCAN_B, 0, s, in, out, agg_scratch, n_in);
+	if (tiles > 1) {
+		PGX_LAUNCH(k_scan_sum_agg, 1, SCAN_B, 0, s, agg_scratch, tiles);
+		PGX_LAUNCH(k_scan_sum_add, grid_for(n_out, 256), 256, 0, s, out, agg_scratch, n_out);
+	}
+}
+
+// ---- segmented inclusive running max -----------------------------------------------------------
+// out[i] = max(val[k] : k <= i, seg[k] == seg[i]);  seg must be non-decreasing (sorted contig keys)
+struct SegVal { int32_t seg, val; };
+__device__ __forceinline__ SegVal seg_op(SegVal a, SegVal b) { SegVal r; r.seg = b.seg; r.val = (a.seg == b.seg && a.val > b.val)? a.val : b.val; return r; }
+
+__global__ void k_segmax_tiles(const int32_t *__restrict__ seg, const int32_t *__restrict__ val, int32_t *out, SegVal *agg, int64_t n)
+{
+	__shared__ SegVal sh[SCAN_B];
+	const int tid = threadIdx.x;
+	const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * SCAN_I;
+	SegVal it[SCAN_I], tot;
+	tot.seg = -1; tot.val = INT32_MIN;
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) {
+		int64_t i = base + k;
+		if (i < n) { it[k].seg = seg[i]; it[k].val = val[i]; } else { it[k].seg = -1; it[k].val = INT32_MIN; }
+		tot = seg_op(tot, it[k]);
+	}
+	sh[tid] = tot;
+	__syncthreads();
+	for (int d = 1; d < SCAN_B; d <<= 1) {
+		SegVal t, me = sh[tid];
+		if (tid >= d) t = sh[tid - d];
+		__syncthreads();
+		if (tid >= d) sh[tid] = seg_op(t, me);
+		__syncthreads();
+	}
+	SegVal run;
+	if (tid > 0) run = sh[tid - 1]; else { run.seg = -1; run.val = INT32_MIN; }
+	if (tid == SCAN_B - 1) agg[blockIdx.x] = sh[tid];
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) { int64_t i = base + k; run = seg_op(run, it[k]); if (i < n) out[i] = run.val; }
+}
+
+// one block: agg[i] <- INCLUSIVE scan of agg under seg_op (in place)
+__global__ void k_segmax_agg(SegVal *agg, int n)
+{
+	__shared__ SegVal sh[SCAN_B];
+	__shared__ SegVal carry;
+	const int tid = threadIdx.x;
+	if (tid == 0) { carry.seg = -1; carry.val = INT32_MIN; }
+	__syncthreads();
+	for (int c0 = 0; c0 < n; c0 += SCAN_B) {
+		int i = c0 + tid;
+		SegVal x; x.seg = -1; x.val = INT32_MIN;
+		if (i < n) x = agg[i];
+		// out-of-range lanes sit to the right of every valid one, so their garbage never flows into a valid result
+		sh[tid] = x;
+		__syncthreads();
+		for (int d = 1; d < SCAN_B; d <<= 1) {
+			SegVal t, me = sh[tid];
+			if (tid >= d) t = sh[tid - d];
+			__syncthreads();
+			if (tid >= d) sh[tid] = seg_op(t, me);
+			__syncthreads();
+		}
+		SegVal c = carry, r = seg_op(c, sh[tid]);
+		if (i < n) agg[i] = r;
+		__syncthreads();
+		int last = (n - c0 < SCAN_B? n - c0 : SCAN_B) - 1;
+		if (tid == last) carry = r;
+		__syncthreads();
+	}
+}
+
+__global__ void k_segmax_apply(const int32_t *__restrict__ seg, int32_t *out, const SegVal *__restrict__ agg, int64_t n)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int64_t t = i / SCAN_TILE;
+	if (t == 0) return;
+	SegVal p = agg[t - 1];
+	if (p.seg == seg[i] && p.val > out[i]) out[i] = p.val;
+}
+
+static void segmented_running_max(const int32_t *seg, const int32_t *val, int32_t *out, int64_t n, SegVal *agg_scratch, cudaStream_t s)
+{
+	if (n <= 0) return;
+	int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+	PGX_LAUNCH(k_segmax_tiles, tiles, SCAN_B, 0, s, seg, val, out, agg_scratch, n);
+	if (tiles > 1) {
+		PGX_LAUNCH(k_segmax_agg, 1, SCAN_B, 0, s, agg_scratch, tiles);
+		PGX_LAUNCH(k_segmax_apply, grid_for(n, 256), 256, 0, s, seg, out, agg_scratch, n);
+	}
+}
+
+} // namespace pgx

@@ -1,0 +1,149 @@
+"""GPU suite, part 2: the CUDA hot path, called through the C ABI (libpgx.so), against
+   (a) the committed goldens printed by the unmodified reference binary,
+   (b) the oracle restatement (libpgoracle.so) on the same inputs,
+   (c) the compiled reference itself in-process (oracle/_ref/libpgref.so), which travels with the snapshot.
+Bit-exact: GFA lines as sorted sets (S/L/W "modulo record order"), BED lines as sorted sets (every per-hit flag),
+and the seg/arc structs element by element."""
+import os
+import random
+
+import pytest
+
+import common
+import refharness
+from oracle import pgoracle
+from pangene_b200 import abi, engine, hostio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    engine.set_verbose(1)
+
+
+def check_against(opt, make, ref_kind="oracle", lazy=False):
+    d_ref, d_gpu = make(), make()
+    if ref_kind == "reference":
+        rh = refharness.RefHot()
+        g_ref, _ = rh.hot_path(opt, d_ref)
+    else:
+        g_ref = pgoracle.hot_path(opt, d_ref)
+    g_gpu = engine.hot_path(opt, d_gpu, lazy=lazy)
+    a, b = common.gfa_bytes(g_ref), common.gfa_bytes(g_gpu)
+    assert sorted(a.splitlines()) == sorted(b.splitlines()), common.first_diff(a, b)
+    ba, bb = common.bed_bytes(d_ref), common.bed_bytes(d_gpu)
+    assert sorted(ba.splitlines()) == sorted(bb.splitlines()), common.first_diff(ba, bb)
+    assert common.graph_tuple(g_ref) == common.graph_tuple(g_gpu)
+    q1, q2 = g_ref.contents, g_gpu.contents
+    assert [q1.g2s[i] for i in range(d_ref.contents.n_gene)] == [q2.g2s[i] for i in range(d_gpu.contents.n_gene)]
+    assert [q1.idx[i] for i in range(2 * q1.n_seg)] == [q2.idx[i] for i in range(2 * q2.n_seg)]
+    for i in range(d_ref.contents.n_prot):
+        p1, p2 = d_ref.contents.prot[i], d_gpu.contents.prot[i]
+        assert (p1.n, p1.avg_score_adj, p1.max_score_ori, p1.rep) == (p2.n, p2.avg_score_adj, p2.max_score_ori, p2.rep)
+    st = engine.stats()
+    engine.destroy(g_gpu)
+    (refharness.RefHot().destroy if ref_kind == "reference" else pgoracle.destroy)(g_ref)
+    hostio.destroy(d_ref); hostio.destroy(d_gpu)
+    return st, a
+
+
+def test_c4_golden(tmp_path):
+    files = common.c4_files(tmp_path)
+    opt = hostio.default_opt()
+    d = hostio.read_pafs(opt, files)
+    g = engine.hot_path(opt, d)
+    assert common.gfa_bytes(g) == open(os.path.join(common.GOLDEN, "C4.gfa"), "rb").read()
+    assert common.bed_bytes(d) == open(os.path.join(common.GOLDEN, "C4.bed_flag"), "rb").read()
+    assert common.bed_bytes(d, True) == open(os.path.join(common.GOLDEN, "C4.bed_walk"), "rb").read()
+    engine.destroy(g); hostio.destroy(d)
+
+
+def test_c4_bed_raw_after_post_process(tmp_path):
+    opt = hostio.default_opt()
+    d = hostio.read_pafs(opt, common.c4_files(tmp_path))
+    engine.hot_path(opt, d, stop_after_post=True)
+    assert common.bed_bytes(d) == open(os.path.join(common.GOLDEN, "C4.bed_raw"), "rb").read()
+    hostio.destroy(d)
+
+
+@pytest.mark.parametrize("name", sorted(common.synth_golden().keys()))
+def test_synthetic_goldens(name):
+    case = common.synth_golden()[name]
+    opt, d = common.synth_case_data(case)
+    g = engine.hot_path(opt, d, lazy=True)
+    assert common.sorted_md5(common.gfa_bytes(g)) == case["gfa_sorted_md5"]
+    assert common.sorted_md5(common.bed_bytes(d)) == case["bed_flag_sorted_md5"]
+    engine.destroy(g); hostio.destroy(d)
+
+
+OPTION_SETS = [[], ["-S"], ["-J"], ["-E"], ["-F", "-T2"], ["-T0"], ["--ori-sc"], ["-p0", "-a2"], ["-f0.2", "-c4", "-g6"], ["-b0.1", "-y0.3", "-B0.9", "-r1"]]
+
+
+@pytest.mark.parametrize("k", range(len(OPTION_SETS)))
+def test_randomized_vs_oracle(k):
+    rnd = random.Random(5000 + k)
+    case = dict(config=2, n_genome=rnd.randint(2, 9), n_gene=rnd.randint(300, 2500), iso_per_gene=rnd.choice([1, 4]), hits_per_genome=0, args=OPTION_SETS[k])
+    case["hits_per_genome"] = int(case["n_gene"] * case["iso_per_gene"] * rnd.uniform(1.5, 3.0))
+    opt = common.opt_from_args(case["args"])
+    check_against(opt, lambda: common.synth_case_data(case)[1], "oracle", lazy=bool(k & 1))
+
+
+@pytest.mark.skipif(not refharness.available(), reason="oracle/_ref did not travel")
+@pytest.mark.parametrize("cfg", ["euk", "bact"])
+def test_vs_compiled_reference(cfg):
+    if cfg == "euk":
+        case = dict(config=2, n_genome=6, n_gene=4000, iso_per_gene=4, hits_per_genome=40000, args=[])
+    else:
+        case = dict(config=5, n_genome=150, n_gene=2000, iso_per_gene=1, hits_per_genome=1700, args=["-p0", "-a2"])
+    opt = common.opt_from_args(case["args"])
+    check_against(opt, lambda: common.synth_case_data(case)[1], "reference")
+
+
+def test_config2_bit_exact_and_matrix(tmp_path):
+    """BASELINE.json configs[1]: 10 genomes x 50k hits, 20k proteins, 1 GPU, bit-exact GFA (vs the oracle)"""
+    case = dict(config=2, n_genome=10, n_gene=20000, iso_per_gene=1, hits_per_genome=50000, args=[])
+    opt = common.opt_from_args([])
+    st, gfa = check_against(opt, lambda: common.synth_case_data(case)[1], "oracle", lazy=True)
+    assert st.n_hit > 450000 and st.n_seg > 16000
+    assert gfa.count(b"\nS\t") + gfa.startswith(b"S\t") >= 0.8 * 20000   # generator non-degeneracy
+
+
+def test_full_size_properties():
+    """configs[2] shape at reduced genome count (the oracle needs minutes at 100 genomes): size-independent properties
+    of the GFA: arc mirror symmetry, ng <= nc, sortedness, walks consistent with segments."""
+    opt = hostio.default_opt()
+    p = hostio.synth_params(3, n_genome=12, n_genome_total=12)
+    d = hostio.synth(opt, p)
+    g = engine.hot_path(opt, d, lazy=True)
+    segs, arcs = common.graph_tuple(g)
+    amap = {a[0]: a for a in arcs}
+    assert [a[0] for a in arcs] == sorted(amap)                      # sorted, unique keys
+    for x, ng, nc, ad, s1, s2 in arcs:
+        v, w = x >> 32, x & 0xffffffff
+        m = amap[((w ^ 1) << 32) | (v ^ 1)]                          # graph.c:117-119: every arc has its mirror
+        assert (m[1], m[2], m[3], m[4], m[5]) == (ng, nc, ad, s2, s1)
+        assert 1 <= ng <= nc and ng <= 12
+    assert [s[0] for s in segs] == sorted(s[0] for s in segs)
+    assert all(s[3] <= s[4] for s in segs)
+    # S-line nc == number of unfiltered hits of that gene over all genomes (graph.c:125-126 after the last round)
+    cnt = {}
+    dd = d.contents
+    for j in range(dd.n_genome):
+        gg = dd.genome[j]
+        for i in range(gg.n_hit):
+            h = gg.hit[i]
+            if not (h.bits & 2):
+                gid = dd.prot[h.pid].gid
+                cnt[gid] = cnt.get(gid, 0) + 1
+    assert {s[0]: s[4] for s in segs if s[4]} == cnt
+    engine.destroy(g); hostio.destroy(d)
+
+
+def test_tie_detector_reports_zero_on_goldens():
+    case = common.synth_golden()["euk_iso4"]
+    opt, d = common.synth_case_data(case)
+    g = engine.hot_path(opt, d, lazy=True)
+    st = engine.stats()
+    assert st.tie[0] == 0 and st.tie[2] == 0
+    engine.destroy(g); hostio.destroy(d)

@@ -1,0 +1,110 @@
+"""CPU suite, part 2: host I/O (reader, generator, writers, gfa2matrix) and the C-ABI surface of libpgx."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import common
+import refharness
+from pangene_b200 import abi, hostio
+
+ROOT = common.ROOT
+
+
+def test_reader_plus_generator_round_trip(tmp_path):
+    """PAF text of the synthetic records parses back to exactly the in-memory pg_data_t (every byte of every hit)"""
+    opt = hostio.default_opt()
+    for cfg, kw in [(2, dict(n_genome=3, n_gene=800, iso_per_gene=4, hits_per_genome=8000)), (5, dict(n_genome=12, n_gene=500, iso_per_gene=1, hits_per_genome=400))]:
+        p = hostio.synth_params(cfg, **kw)
+        d = hostio.synth(opt, p)
+        files = hostio.synth_write_pafs(opt, p, str(tmp_path / ("c%d" % cfg)))
+        d2 = hostio.read_pafs(opt, files)
+        assert (d.contents.n_genome, d.contents.n_gene, d.contents.n_prot) == (d2.contents.n_genome, d2.contents.n_gene, d2.contents.n_prot)
+        for j in range(d.contents.n_genome):
+            a, b = d.contents.genome[j], d2.contents.genome[j]
+            assert (a.n_hit, a.n_exon, a.n_ctg) == (b.n_hit, b.n_exon, b.n_ctg)
+            assert C.string_at(a.hit, a.n_hit * 88) == C.string_at(b.hit, b.n_hit * 88)
+            assert C.string_at(a.exon, a.n_exon * 8) == C.string_at(b.exon, b.n_exon * 8)
+            assert [a.ctg[c].name for c in range(a.n_ctg)] == [b.ctg[c].name for c in range(b.n_ctg)]
+            assert a.label == b.label
+        for i in range(d.contents.n_prot):
+            assert (d.contents.prot[i].name, d.contents.prot[i].len, d.contents.prot[i].gid) == (d2.contents.prot[i].name, d2.contents.prot[i].len, d2.contents.prot[i].gid)
+        hostio.destroy(d); hostio.destroy(d2)
+
+
+def test_generator_is_deterministic_and_shardable():
+    opt = hostio.default_opt()
+    whole = hostio.synth(opt, hostio.synth_params(2, n_genome=4, n_gene=500, iso_per_gene=1, hits_per_genome=1200, n_genome_total=4))
+    part = hostio.synth(opt, hostio.synth_params(2, n_genome=2, genome_begin=2, n_gene=500, iso_per_gene=1, hits_per_genome=1200, n_genome_total=4))
+    for j in range(2):
+        a, b = whole.contents.genome[2 + j], part.contents.genome[j]
+        assert a.n_hit == b.n_hit and C.string_at(a.hit, a.n_hit * 88) == C.string_at(b.hit, b.n_hit * 88)
+    hostio.destroy(whole); hostio.destroy(part)
+
+
+@pytest.mark.skipif(not refharness.available(), reason="oracle/_ref not built")
+def test_reader_and_writers_against_reference_cli(tmp_path):
+    """our reader + the reference's own hot path + our writers == the stock CLI, byte for byte"""
+    files = common.c4_files(tmp_path)
+    opt = hostio.default_opt()
+    d = hostio.read_pafs(opt, files)
+    rh = refharness.RefHot()
+    g, _ = rh.hot_path(opt, d)
+    assert common.gfa_bytes(g) == refharness.ref_cli(files)
+    assert common.bed_bytes(d) == refharness.ref_cli(files, ["--bed=flag"])
+    assert common.bed_bytes(d, True) == refharness.ref_cli(files, ["--bed"])
+    rh.destroy(g); hostio.destroy(d)
+
+
+def test_gfa2matrix(tmp_path):
+    gfa = os.path.join(common.GOLDEN, "C4.gfa")
+    out = str(tmp_path / "m.tsv")
+    n = hostio.lib().pgio_gfa2matrix(os.fsencode(gfa), os.fsencode(out), 0)
+    rows = [l.rstrip("\n").split("\t") for l in open(out)]
+    assert n == 7 and rows[0][0] == "Gene" and len(rows) == 8
+    n_asm = len(rows[0]) - 1
+    assert all(len(r) == n_asm + 1 and set(r[1:]) <= {"0", "1"} for r in rows[1:])
+    # presence must agree with a direct count of the W lines
+    walks = [l.split("\t") for l in open(gfa) if l.startswith("W")]
+    asm = []
+    for w in walks:
+        a = w[1] + "#" + w[2]
+        if a not in asm: asm.append(a)
+    assert rows[0][1:] == asm
+    for r in rows[1:]:
+        for k, a in enumerate(asm):
+            present = any((w[1] + "#" + w[2]) == a and re.search(r"[><]%s(?=[><\s]|$)" % re.escape(r[0]), w[6]) for w in walks)
+            assert (r[1 + k] == "1") == bool(present)
+
+
+def test_libpgx_exports_every_declared_symbol():
+    """the C-ABI library loads without a GPU and exports every function include/pgx.h declares (no compute call)"""
+    hdr = open(os.path.join(ROOT, "include", "pgx.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(pgx?_[a-z0-9_]+)\s*\(", hdr))
+    assert {"pg_post_process", "pg_graph_init", "pg_graph_gen", "pg_graph_destroy", "pgx_upload", "pgx_run", "pgx_download", "pgx_comm_init"} <= names
+    L = C.CDLL(os.path.join(ROOT, "pangene_b200", "csrc", "libpgx.so"))
+    for n in sorted(names):
+        assert hasattr(L, n), n
+    assert C.c_int.in_dll(L, "pg_verbose").value == 3
+    # built for sm_100a and nothing else
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "pangene_b200", "csrc", "libpgx.so")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT).stdout.decode()
+    if "sm_" in out:
+        assert set(re.findall(r"sm_\d+a?", out)) == {"sm_100a"}, out
+
+
+def test_host_side_radix_replay_of_libpgx_matches_oracle():
+    import random
+    from oracle import pgoracle
+    from pangene_b200 import engine
+    rnd = random.Random(7)
+    for n, bits in [(50, 4), (3000, 5), (3000, 64), (70000, 17)]:
+        A = (C.c_uint64 * (2 * n))()
+        for i in range(n):
+            A[2 * i] = rnd.getrandbits(bits) << rnd.choice([0, 8, 31]) & (2 ** 64 - 1); A[2 * i + 1] = i
+        B = (C.c_uint64 * (2 * n))(*A)
+        engine.lib().pgx_test_flag_sort_replay(C.byref(A), n)
+        pgoracle.lib().pgo_radix_replay128(C.byref(B), n)
+        assert list(A) == list(B)
