@@ -1,6 +1,7 @@
 // pgx_api.cu -- the C-ABI surface of libpgx.so (include/pgx.h) over the device engine (pgx_engine.cuh).
 // Built for sm_100a only; there is no CPU path behind any of these entry points.
 #include <map>
+#include <time.h>
 #include <mutex>
 #include "pgx_engine.cuh"
 
@@ -10,6 +11,9 @@ Stats g_stats;
 Comm g_comm;
 static int g_device = -1, g_lazy = 0;
 static std::map<const pg_data_t*, Session*> g_sessions;   // pg_post_process() -> pg_graph_gen() hand-over
+
+static double wall() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
+static bool timing_on() { static const bool on = getenv("PGX_TIMING") != nullptr; return on; }
 
 static void need_device()
 {
@@ -63,9 +67,13 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	if (pg_verbose >= 3) fprintf(stderr, "[M::%s] %d genes and %d proteins\n", __func__, d->n_gene, d->n_prot);
 	auto it = g_sessions.find(d);
 	if (it != g_sessions.end()) { delete it->second; g_sessions.erase(it); }
+	double t0 = wall();
 	Session *s = new Session();
 	s->upload(d);
+	double t1 = wall();
 	timed_run(s, opt, 1);
+	double t2 = wall();
+	if (timing_on()) fprintf(stderr, "[pgx timing] session+upload %.1f ms, stage 1 %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3);
 	if (!g_lazy) s->download(d, nullptr);
 	else {   // the protein/gene tables are cheap and always current
 		for (int32_t i = 0; i < d->n_prot; ++i) { d->prot[i].n = s->rep.prot_n[i]; d->prot[i].avg_score_adj = s->rep.prot_avg[i]; d->prot[i].rep = s->rep.prot_rep[i]; d->prot[i].max_score_ori = s->h_prot_max[i]; }
@@ -94,10 +102,14 @@ void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q)
 	auto it = g_sessions.find(q->d);
 	if (it == g_sessions.end()) PGX_FATAL("pg_graph_gen(): no device state for this pg_data_t -- call pg_post_process() of libpgx first");
 	Session *s = it->second;
+	double t0 = wall();
 	timed_run(s, opt, 2);
+	double t1 = wall();
 	s->download(q->d, q);
+	double t2 = wall();
 	delete s;
 	g_sessions.erase(it);
+	if (timing_on()) fprintf(stderr, "[pgx timing] stage 2 %.1f ms, download %.1f ms, free %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (wall() - t2) * 1e3);
 }
 
 void pg_graph_destroy(pg_graph_t *q)   // graph.c:43-47

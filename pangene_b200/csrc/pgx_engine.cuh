@@ -53,6 +53,7 @@ struct Session {
 	// ---- full columns
 	DBuf<int32_t> f_ctg, f_cs, f_ce, f_cm, f_pid, f_gidp, f_sadj, f_rank, f_sori, f_sdom, f_pdom0, f_pdom, f_cds, f_pmax;
 	DBuf<uint32_t> f_bits, f_bits_alt, f_nex, f_eoff, f_esrc;
+	DBuf<uint64_t> f_key, a_key;
 	FullCols F;
 	// ---- active columns
 	int32_t Nw = 0;
@@ -129,10 +130,10 @@ struct Session {
 		size_t tab = (size_t)(G > 0? G : 1);
 		scratch.init((size_t)(N > 0? N : 1) * 96 + tab * n_prot * 16 + tab * n_gene * 48 + ((size_t)256 << 20));
 		// full columns
-		size_t n1 = (size_t)N + 1;
-		f_ctg.alloc(n1); f_cs.alloc(n1); f_ce.alloc(n1); f_cm.alloc(n1); f_pid.alloc(n1); f_gidp.alloc(n1); f_sadj.alloc(n1); f_rank.alloc(n1); f_sori.alloc(n1);
-		f_sdom.alloc(n1); f_pdom0.alloc(n1); f_pdom.alloc(n1); f_cds.alloc(n1); f_pmax.alloc(n1); f_bits.alloc(n1); f_bits_alt.alloc(n1); f_nex.alloc(n1); f_eoff.alloc(n1 + 1); f_esrc.alloc(n1);
-		src.alloc(n1); ex.alloc(E > 0? E : 1);
+		size_t n1 = (size_t)N + 16;   // slack: the tiled sweep stages 16-byte-granular column windows
+		f_key.alloc(n1); f_ctg.alloc(n1); f_cs.alloc(n1); f_ce.alloc(n1); f_cm.alloc(n1); f_pid.alloc(n1); f_gidp.alloc(n1); f_sadj.alloc(n1); f_rank.alloc(n1); f_sori.alloc(n1);
+		f_sdom.alloc(n1); f_pdom0.alloc(n1); f_pdom.alloc(n1); f_cds.alloc(n1); f_pmax.alloc(n1); f_bits.alloc(n1); f_bits_alt.alloc(n1); f_nex.alloc(n1); f_eoff.alloc(n1 + 16); f_esrc.alloc(n1);
+		src.alloc(n1); ex.alloc((size_t)E + 16);
 		set_full();
 		prot_max.alloc(n_prot); prot_rep.alloc(n_prot); z.alloc(n_prot); cs4.alloc((size_t)n_prot * 4); g2s.alloc(n_gene);
 		prot_rep.zero(st);
@@ -152,22 +153,31 @@ struct Session {
 	void set_full()
 	{
 		F.ctg = f_ctg.p; F.cs = f_cs.p; F.ce = f_ce.p; F.cm = f_cm.p; F.pid = f_pid.p; F.gidp = f_gidp.p; F.sadj = f_sadj.p; F.rank = f_rank.p; F.sori = f_sori.p;
-		F.sdom = f_sdom.p; F.pdom0 = f_pdom0.p; F.pdom = f_pdom.p; F.cds = f_cds.p; F.pmax = f_pmax.p; F.bits = f_bits.p; F.nex = f_nex.p; F.eoff = f_eoff.p; F.esrc = f_esrc.p;
+		F.sdom = f_sdom.p; F.pdom0 = f_pdom0.p; F.pdom = f_pdom.p; F.cds = f_cds.p; F.pmax = f_pmax.p; F.bits = f_bits.p; F.nex = f_nex.p; F.eoff = f_eoff.p; F.esrc = f_esrc.p; F.key = f_key.p;
 	}
 	void set_active()
 	{
 		A.ctg = a_ctg.p; A.cs = a_cs.p; A.ce = a_ce.p; A.cm = a_cm.p; A.pid = a_pid.p; A.gidp = a_gidp.p; A.sadj = a_sadj.p; A.rank = a_rank.p; A.sori = a_sori.p;
-		A.sdom = a_sdom.p; A.pdom0 = a_pdom0.p; A.pdom = a_pdom.p; A.cds = a_cds.p; A.pmax = a_pmax.p; A.full = a_full.p; A.bits = a_bits.p; A.bits_alt = a_bits_alt.p; A.nex = a_nex.p; A.eoff = a_eoff.p;
+		A.sdom = a_sdom.p; A.pdom0 = a_pdom0.p; A.pdom = a_pdom.p; A.cds = a_cds.p; A.pmax = a_pmax.p; A.full = a_full.p; A.bits = a_bits.p; A.bits_alt = a_bits_alt.p; A.nex = a_nex.p; A.eoff = a_eoff.p; A.key = a_key.p;
 	}
 	SweepCols sweep_full() const
 	{
-		SweepCols c; c.n = N; c.ctg = F.ctg; c.cs = F.cs; c.ce = F.ce; c.pid = F.pid; c.gidp = F.gidp; c.sadj = F.sadj; c.rank = F.rank; c.cds = F.cds; c.sori = F.sori; c.pmax = F.pmax;
+		SweepCols c; c.n = N; c.ctg = F.ctg; c.cs = F.cs; c.ce = F.ce; c.pid = F.pid; c.gidp = F.gidp; c.key = F.key; c.rank = F.rank; c.cds = F.cds; c.sori = F.sori; c.pmax = F.pmax;
 		c.bits = F.bits; c.eoff = F.eoff; c.ex = ex.p; return c;
 	}
 	SweepCols sweep_active() const
 	{
-		SweepCols c; c.n = Nw; c.ctg = A.ctg; c.cs = A.cs; c.ce = A.ce; c.pid = A.pid; c.gidp = A.gidp; c.sadj = A.sadj; c.rank = A.rank; c.cds = A.cds; c.sori = A.sori; c.pmax = A.pmax;
+		SweepCols c; c.n = Nw; c.ctg = A.ctg; c.cs = A.cs; c.ce = A.ce; c.pid = A.pid; c.gidp = A.gidp; c.key = A.key; c.rank = A.rank; c.cds = A.cds; c.sori = A.sori; c.pmax = A.pmax;
 		c.bits = A.bits; c.eoff = A.eoff; c.ex = wex.p; return c;
+	}
+
+	// one sweep launch; PGX_SWEEP=global selects the plain variant (debug / A-B timing), default is the TMA-tiled one
+	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out)
+	{
+		static const int use_tile = []() { const char *e = getenv("PGX_SWEEP"); return !(e && strcmp(e, "global") == 0); }();
+		if (c.n <= 0) return;
+		if (use_tile) PGX_LAUNCH(k_sweep_tile<MODE>, grid_for(c.n, SWT_TILE), SWT_TILE, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
+		else PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 	}
 
 	// stable radix sort of n (key, iota) pairs taken from the scratch arena; returns the permutation (device pointer valid until the arena is reset)
@@ -244,11 +254,11 @@ struct Session {
 		}
 		// -- first sweep: pg_shadow(cal_dom_sc=1) + read.c:249-253; this is the launch the roofline figure is quoted on
 		PGX_CHECK(cudaEventRecord(ev[0], st));
-		PGX_LAUNCH(k_sweep<SW_LOAD>, grid_for(N, 128), 128, 0, st, sweep_full(), so, f_bits_alt.p, F.pdom0, F.sdom, counters.p + C_TIE_DUP);
+		launch_sweep<SW_LOAD>(sweep_full(), so, f_bits_alt.p, F.pdom0, F.sdom);
 		PGX_CHECK(cudaEventRecord(ev[1], st));
 		// (SW_LOAD leaves the flag words unchanged: keep reading F.bits)
 		// -- second sweep: pg_flt_ov_isoform
-		PGX_LAUNCH(k_sweep<SW_ISO>, grid_for(N, 128), 128, 0, st, sweep_full(), so, f_bits_alt.p, (int32_t*)nullptr, (int32_t*)nullptr, counters.p + C_TIE_DUP);
+		launch_sweep<SW_ISO>(sweep_full(), so, f_bits_alt.p, nullptr, nullptr);
 		f_bits.swap(f_bits_alt); set_full();
 		// -- chain shadow + sub-optimal isoform (hit.c:107-146)
 		{
@@ -292,7 +302,7 @@ struct Session {
 		if (!(opt->flag & PG_F_NO_JOINT_PSEUDO) && Nw)
 			PGX_LAUNCH(k_pseudo_joint, grid_for(Nw, TB), TB, 0, st, A.pid, A.bits, A.eoff, Nw, cs4.p, Gtot, opt->min_vertex_ratio, !!(opt->flag & PG_F_DROP_SGL_EXON));
 		if (Nw) {
-			PGX_LAUNCH(k_sweep<SW_SHADOW>, grid_for(Nw, 128), 128, 0, st, sweep_active(), so, A.bits_alt, A.pdom, (int32_t*)nullptr, counters.p + C_TIE_DUP);
+			launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits_alt, A.pdom, nullptr);
 			a_bits.swap(a_bits_alt); set_active();
 		}
 		PGX_CHECK(cudaStreamSynchronize(st));
@@ -310,9 +320,9 @@ struct Session {
 			uint32_t *flag = scratch.get<uint32_t>(N + 1), *pos = scratch.get<uint32_t>((size_t)N + 2);
 			PGX_LAUNCH(k_flag_unfiltered, grid_for(N, TB), TB, 0, st, F.bits, N, flag);
 			Nw = (int32_t)scan_flags(flag, pos, N);
-			size_t n1 = (size_t)Nw + 1;
-			a_ctg.alloc(n1); a_cs.alloc(n1); a_ce.alloc(n1); a_cm.alloc(n1); a_pid.alloc(n1); a_gidp.alloc(n1); a_sadj.alloc(n1); a_rank.alloc(n1); a_sori.alloc(n1);
-			a_sdom.alloc(n1); a_pdom0.alloc(n1); a_pdom.alloc(n1); a_cds.alloc(n1); a_pmax.alloc(n1); a_full.alloc(n1); a_bits.alloc(n1); a_bits_alt.alloc(n1); a_nex.alloc(n1); a_eoff.alloc(n1 + 1);
+			size_t n1 = (size_t)Nw + 16;
+			a_key.alloc(n1); a_ctg.alloc(n1); a_cs.alloc(n1); a_ce.alloc(n1); a_cm.alloc(n1); a_pid.alloc(n1); a_gidp.alloc(n1); a_sadj.alloc(n1); a_rank.alloc(n1); a_sori.alloc(n1);
+			a_sdom.alloc(n1); a_pdom0.alloc(n1); a_pdom.alloc(n1); a_cds.alloc(n1); a_pmax.alloc(n1); a_full.alloc(n1); a_bits.alloc(n1); a_bits_alt.alloc(n1); a_nex.alloc(n1); a_eoff.alloc(n1 + 16);
 			by_cm.alloc(n1); sv.alloc(n1);
 			set_active();
 			PGX_LAUNCH(k_build_active, grid_for(N, TB), TB, 0, st, F, pos, N, A);
@@ -324,7 +334,7 @@ struct Session {
 			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(Nw));
 			exclusive_sum_u32(A.nex, A.eoff, Nw, agg, st);
 			uint32_t ne = read_u32(A.eoff + Nw);
-			wex.alloc(ne > 0? ne : 1);
+			wex.alloc((size_t)ne + 16);
 			PGX_LAUNCH(k_copy_exons, grid_for(Nw, 128), 128, 0, st, ex.p, F.eoff, A.full, A.eoff, Nw, wex.p);
 			SegVal *sagg = scratch.get<SegVal>((size_t)(Nw / SCAN_TILE + 2));
 			segmented_running_max(A.ctg, A.ce, A.pmax, Nw, sagg, st);
@@ -394,7 +404,7 @@ struct Session {
 		PGX_CHECK(cudaMemsetAsync(seg_tot.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 4, st));
 		ArcPartial *part = nullptr; uint32_t n_part = 0;
 		if (Nw) {
-			PGX_LAUNCH(k_sweep<SW_SHADOW>, grid_for(Nw, 128), 128, 0, st, sweep_active(), so, A.bits_alt, A.pdom, (int32_t*)nullptr, counters.p + C_TIE_DUP);
+			launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits_alt, A.pdom, nullptr);
 			a_bits.swap(a_bits_alt); set_active();
 			uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *pos = scratch.get<uint32_t>((size_t)Nw + 2);
 			PGX_LAUNCH(k_flag_survivor_cm, grid_for(Nw, TB), TB, 0, st, A.bits, by_cm.p, Nw, flag);
@@ -416,7 +426,11 @@ struct Session {
 			PGX_LAUNCH(k_arc_heads, grid_for((int64_t)nr, TB), TB, 0, st, key, (int32_t)nr, e.gbits, flag);
 			n_part = scan_flags(flag, pos, (int64_t)nr);
 			part = scratch.get<ArcPartial>((size_t)n_part + 1);
-			if (n_part) PGX_LAUNCH(k_arc_reduce, grid_for((int64_t)nr, 128), 128, 0, st, key, rec, dist, s1, s2, (int32_t)nr, e.gbits, n_seg, pos, part);
+			if (n_part) {
+				uint32_t *start = scratch.get<uint32_t>((size_t)n_part + 1);
+				PGX_LAUNCH(k_compact_idx, grid_for((int64_t)nr, TB), TB, 0, st, pos, (const uint32_t*)nullptr, (int32_t)nr, start);
+				PGX_LAUNCH(k_arc_reduce, grid_for((int64_t)n_part * 32, TB), TB, 0, st, key, rec, dist, s1, s2, (int32_t)nr, e.gbits, n_seg, start, (int32_t)n_part, part);
+			}
 		}
 		if (g_comm.active()) merge_partials_across_ranks(part, n_part);
 		else finalize_arcs(part, n_part);

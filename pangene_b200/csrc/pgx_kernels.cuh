@@ -101,6 +101,7 @@ __global__ void k_fp_rank(const int32_t *__restrict__ r_pid, const int32_t *__re
 struct FullCols {            // all hits, (genome, contig, cs) order, packed int32 columns
 	int32_t *ctg, *cs, *ce, *cm, *pid, *gidp, *sadj, *rank, *sori, *sdom, *pdom0, *pdom, *cds, *pmax;
 	uint32_t *bits, *nex, *eoff, *esrc;
+	uint64_t *key;
 };
 
 __global__ void k_gather(const int32_t *__restrict__ aos, const uint32_t *__restrict__ src, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff,
@@ -120,6 +121,7 @@ __global__ void k_gather(const int32_t *__restrict__ aos, const uint32_t *__rest
 	c.cs[i] = (int32_t)*(const int64_t*)(w + W_CS); c.cm[i] = (int32_t)*(const int64_t*)(w + W_CM); c.ce[i] = (int32_t)*(const int64_t*)(w + W_CE);
 	c.pid[i] = pid; c.gidp[i] = gid << 1 | gene_pref[gid];
 	c.sadj[i] = w[W_SADJ]; c.sori[i] = w[W_SORI]; c.rank[i] = r_rank[s];
+	c.key[i] = score_key(w[W_SADJ], gid << 1 | gene_pref[gid], pid);
 	c.sdom[i] = 0; c.pdom0[i] = -1; c.pdom[i] = -1;          // parser state: read.c:133-134
 	c.bits[i] = b;
 	c.nex[i] = (uint32_t)w[W_NEXON];
@@ -142,7 +144,8 @@ __global__ void k_gather_exons(const int2 *__restrict__ ex_raw, const uint32_t *
 // ------------------------------------------------------------------------------------------------
 struct SweepCols {
 	int32_t n;
-	const int32_t *ctg, *cs, *ce, *pid, *gidp, *sadj, *rank, *cds, *sori, *pmax;
+	const int32_t *ctg, *cs, *ce, *pid, *gidp, *rank, *cds, *sori, *pmax;
+	const uint64_t *key;         // score_key() of every hit, immutable
 	const uint32_t *bits, *eoff;
 	const int2 *ex;
 };
@@ -150,123 +153,251 @@ struct SweepOpt { double min_ov_ratio; int32_t check_strand; };
 
 enum { SW_LOAD = 0, SW_SHADOW = 1, SW_ISO = 2 };
 
+// ---- accessors: the pair logic below is written once and instantiated over "columns in global memory" and
+// ---- "columns staged in shared memory by TMA bulk copies, global memory outside the staged window"
+struct AccGlobal {
+	SweepCols c;
+	__device__ __forceinline__ int32_t ctg(int32_t p) const { return c.ctg[p]; }
+	__device__ __forceinline__ int32_t cs(int32_t p) const { return c.cs[p]; }
+	__device__ __forceinline__ int32_t ce(int32_t p) const { return c.ce[p]; }
+	__device__ __forceinline__ int32_t pmax(int32_t p) const { return c.pmax[p]; }
+	__device__ __forceinline__ uint32_t bits(int32_t p) const { return c.bits[p]; }
+	__device__ __forceinline__ int32_t gidp(int32_t p) const { return c.gidp[p]; }
+	__device__ __forceinline__ int32_t rank(int32_t p) const { return c.rank[p]; }
+	__device__ __forceinline__ int32_t cds(int32_t p) const { return c.cds[p]; }
+	__device__ __forceinline__ uint64_t key(int32_t p) const { return c.key[p]; }
+	__device__ __forceinline__ uint32_t eoff(int32_t p) const { return c.eoff[p]; }
+	__device__ __forceinline__ int2 exon(uint32_t k) const { return c.ex[k]; }
+};
+
+constexpr int SWT_TILE = 256, SWT_HALO = 64, SWT_STG = SWT_TILE + 2 * SWT_HALO + 8, SWT_EXCAP = 3072;
+
+struct AccTile {
+	SweepCols c;
+	int32_t lo, hi;              // staged hits [lo, hi)
+	uint32_t elo, ehi;           // staged exons [elo, ehi)
+	const int32_t *s_ctg, *s_cs, *s_ce, *s_pmax, *s_gidp, *s_rank, *s_cds;
+	const uint32_t *s_bits, *s_eoff;
+	const uint64_t *s_key;
+	const int2 *s_ex;
+	__device__ __forceinline__ bool in(int32_t p) const { return p >= lo && p < hi; }
+	__device__ __forceinline__ int32_t ctg(int32_t p) const { return in(p)? s_ctg[p - lo] : c.ctg[p]; }
+	__device__ __forceinline__ int32_t cs(int32_t p) const { return in(p)? s_cs[p - lo] : c.cs[p]; }
+	__device__ __forceinline__ int32_t ce(int32_t p) const { return in(p)? s_ce[p - lo] : c.ce[p]; }
+	__device__ __forceinline__ int32_t pmax(int32_t p) const { return in(p)? s_pmax[p - lo] : c.pmax[p]; }
+	__device__ __forceinline__ uint32_t bits(int32_t p) const { return in(p)? s_bits[p - lo] : c.bits[p]; }
+	__device__ __forceinline__ int32_t gidp(int32_t p) const { return in(p)? s_gidp[p - lo] : c.gidp[p]; }
+	__device__ __forceinline__ int32_t rank(int32_t p) const { return in(p)? s_rank[p - lo] : c.rank[p]; }
+	__device__ __forceinline__ int32_t cds(int32_t p) const { return in(p)? s_cds[p - lo] : c.cds[p]; }
+	__device__ __forceinline__ uint64_t key(int32_t p) const { return in(p)? s_key[p - lo] : c.key[p]; }
+	__device__ __forceinline__ uint32_t eoff(int32_t p) const { return (p >= lo && p <= hi)? s_eoff[p - lo] : c.eoff[p]; }
+	__device__ __forceinline__ int2 exon(uint32_t k) const { return (k >= elo && k < ehi)? s_ex[k - elo] : c.ex[k]; }
+};
+
 // |CDS(lo) & CDS(hi)| (overlap.c:6-42); lo precedes hi in (contig, cs) order
-__device__ __forceinline__ int32_t cds_overlap(const int2 *__restrict__ ex, uint32_t b0, uint32_t e0, int32_t cs0, int32_t ce0, uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1)
+template<class Acc> __device__ __forceinline__ int32_t cds_overlap(const Acc &A, uint32_t b0, uint32_t e0, int32_t cs0, int32_t ce0, uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1)
 {
 	if (!(cs0 < ce1 && ce0 > cs1)) return 0;
 	int32_t inter = 0;
-	int2 x0 = ex[b0], x1 = ex[b1];
+	int2 x0 = A.exon(b0), x1 = A.exon(b1);
 	while (true) {
 		int32_t s0 = cs0 + x0.x, t0 = cs0 + x0.y, s1 = cs1 + x1.x, t1 = cs1 + x1.y;
 		if (s0 < s1) {
-			if (t0 < t1) { int32_t o = t0 - s1; inter += o > 0? o : 0; if (++b0 == e0) break; x0 = ex[b0]; }
-			else { inter += x1.y - x1.x; if (++b1 == e1) break; x1 = ex[b1]; }
+			if (t0 < t1) { int32_t o = t0 - s1; inter += o > 0? o : 0; if (++b0 == e0) break; x0 = A.exon(b0); }
+			else { inter += x1.y - x1.x; if (++b1 == e1) break; x1 = A.exon(b1); }
 		} else {
-			if (t1 < t0) { int32_t o = t1 - s0; inter += o > 0? o : 0; if (++b1 == e1) break; x1 = ex[b1]; }
-			else { inter += x0.y - x0.x; if (++b0 == e0) break; x0 = ex[b0]; }
+			if (t1 < t0) { int32_t o = t1 - s0; inter += o > 0? o : 0; if (++b1 == e1) break; x1 = A.exon(b1); }
+			else { inter += x0.y - x0.x; if (++b0 == e0) break; x0 = A.exon(b0); }
 		}
 	}
 	return inter;
 }
 
-struct Mine {            // the hit a thread owns
-	int32_t i, ctg, cs, ce, pid, gidp, rank, cds; uint32_t bits, eb, ee; uint64_t key;
-};
-
-// Decide the pair (me, p). Returns true when `me` LOSES to p; *ov = CDS overlap. me_is_hi: me is the later hit.
-template<int MODE> __device__ __forceinline__ bool pair_me_loses(const SweepCols &c, const SweepOpt &o, const Mine &m, int32_t p, uint32_t pbits, int32_t pcs, int32_t pce, bool me_is_hi, int32_t *ov_, uint64_t *pkey_)
+// Same walk, but only answers "are the two hits in relation?": overlap > 0 and, when `shorter` > 0 (different genes,
+// overlap.c:134-136), (double)overlap/shorter >= ratio.  The running overlap only grows, and x -> (double)x/shorter is
+// monotone, so the walk stops as soon as the answer is yes.
+template<class Acc> __device__ __forceinline__ bool cds_related(const Acc &A, uint32_t b0, uint32_t e0, int32_t cs0, int32_t ce0, uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1, int32_t shorter, double ratio)
 {
-	int32_t pgidp = c.gidp[p];
-	bool same_gene = (pgidp >> 1) == (m.gidp >> 1);
-	if (MODE == SW_ISO && !same_gene) return false;                                  // overlap.c:77
-	if (o.check_strand && ((pbits ^ m.bits) & PG_HB_REV)) return false;               // overlap.c:78,128
-	uint32_t pb = c.eoff[p], pe = c.eoff[p + 1];
-	int32_t ov = me_is_hi? cds_overlap(c.ex, pb, pe, pcs, pce, m.eb, m.ee, m.cs, m.ce)
-	                     : cds_overlap(c.ex, m.eb, m.ee, m.cs, m.ce, pb, pe, pcs, pce);
-	if (ov == 0) return false;                                                        // overlap.c:81,132
-	if (MODE != SW_ISO && !same_gene) {
-		int32_t pcds = c.cds[p], shorter = m.cds < pcds? m.cds : pcds;
-		double cov_short = (double)(uint64_t)ov / shorter;                            // overlap.c:134
-		if (cov_short < o.min_ov_ratio) return false;                                 // overlap.c:136
+	if (!(cs0 < ce1 && ce0 > cs1)) return false;
+	int32_t inter = 0;
+	int2 x0 = A.exon(b0), x1 = A.exon(b1);
+	while (true) {
+		int32_t s0 = cs0 + x0.x, t0 = cs0 + x0.y, s1 = cs1 + x1.x, t1 = cs1 + x1.y;
+		bool adv0;
+		if (s0 < s1) {
+			if (t0 < t1) { int32_t o = t0 - s1; inter += o > 0? o : 0; adv0 = true; }
+			else { inter += x1.y - x1.x; adv0 = false; }
+		} else {
+			if (t1 < t0) { int32_t o = t1 - s0; inter += o > 0? o : 0; adv0 = false; }
+			else { inter += x0.y - x0.x; adv0 = true; }
+		}
+		if (inter > 0 && (shorter <= 0 || !((double)(uint64_t)inter / shorter < ratio))) return true;
+		if (adv0) { if (++b0 == e0) break; x0 = A.exon(b0); } else { if (++b1 == e1) break; x1 = A.exon(b1); }
 	}
-	int32_t ppid = c.pid[p];
-	uint64_t pkey = score_key(c.sadj[p], pgidp, ppid);
-	int32_t prank = c.rank[p];
-	// the reference names the later hit "i" and the earlier one "j" (overlap.c:139-147)
-	uint64_t si = me_is_hi? m.key : pkey, sj = me_is_hi? pkey : m.key;
-	int32_t ri = me_is_hi? m.rank : prank, rj = me_is_hi? prank : m.rank;
-	uint32_t wi = ((me_is_hi? m.bits : pbits) & PG_HB_WBR_MASK), wj = ((me_is_hi? pbits : m.bits) & PG_HB_WBR_MASK);
-	bool hi_loses;
-	if (MODE == SW_ISO || same_gene || wi == wj) hi_loses = si < sj || (si == sj && ri > rj);
-	else hi_loses = wi > wj;
-	*ov_ = ov; *pkey_ = pkey;
-	return hi_loses == me_is_hi;
+	return false;
 }
 
-// One thread per hit. bits_out may not alias c.bits (the pass reads every neighbour's pre-pass flags).
+// One hit against its window.  Every pair is visited from both members, but only the member that WOULD LOSE if the pair
+// is in relation ever walks the exon lists, and it skips the walk when the outcome cannot change its result any more
+// (already shadowed and the partner's key cannot beat the current dominator).  Exactness: shadow = OR over losing related
+// pairs; dominator = max key over them, ties to the smallest partner index (overlap.c:150,153 strict '<' in ascending
+// partner order) -- a skipped pair can alter neither.
 //   SW_LOAD   = pg_shadow(cal_dom_sc=1) followed by read.c:249-253: writes pid_dom0, score_dom; shadow/pid_dom stay reset
 //   SW_SHADOW = pg_shadow(cal_dom_sc=0): writes the shadow bit and pid_dom
 //   SW_ISO    = pg_flt_ov_isoform: writes flt_iso_ov|flt
+template<int MODE, class Acc> __device__ __forceinline__ void sweep_hit(const Acc &A, const SweepOpt &o, int32_t i, int32_t n, uint32_t mbits, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+{
+	const int32_t mctg = A.ctg(i), mcs = A.cs(i), mce = A.ce(i), mgidp = A.gidp(i), mcds = A.cds(i);
+	const uint32_t meb = A.eoff(i), mee = A.eoff(i + 1);
+	const uint64_t mkey = A.key(i);
+	int32_t mrank = INT32_MIN;           // loaded on the first key tie only
+	bool lose = false;
+	uint64_t best_key = 0; int32_t best_p = INT32_MAX;
+#pragma unroll 1
+	for (int side = 0; side < 2; ++side) {
+		// side 0: earlier hits still open at my start (overlap.c:67-71,114-120), walking back; side 1: later hits that start before my end
+#pragma unroll 1
+		for (int32_t p = side == 0? i - 1 : i + 1; p >= 0 && p < n; p += side == 0? -1 : 1) {
+			if (A.ctg(p) != mctg) break;
+			int32_t pcs, pce;
+			if (side == 0) {
+				if (A.pmax(p) <= mcs) break;               // nothing further back reaches my start
+				pce = A.ce(p);
+				if (pce <= mcs) continue;
+				pcs = A.cs(p);
+			} else {
+				pcs = A.cs(p);
+				if (pcs >= mce) break;
+				pce = A.ce(p);
+			}
+			const uint32_t pbits = A.bits(p);
+			if (pbits & PG_HB_FLT) continue;                                              // overlap.c:70,122
+			const int32_t pgidp = A.gidp(p);
+			const bool same_gene = (pgidp >> 1) == (mgidp >> 1);
+			if (MODE == SW_ISO && !same_gene) continue;                                   // overlap.c:77
+			if (o.check_strand && ((pbits ^ mbits) & PG_HB_REV)) continue;                // overlap.c:78,128
+			const uint64_t pkey = A.key(p);
+			// would I be the loser?  the reference calls the later hit "i", the earlier "j" (overlap.c:139-147)
+			bool me_loses;
+			const uint32_t mw = mbits & PG_HB_WBR_MASK, pw = pbits & PG_HB_WBR_MASK;
+			if (MODE == SW_ISO || same_gene || mw == pw) {
+				if (mkey != pkey) me_loses = mkey < pkey;
+				else {
+					if (mrank == INT32_MIN) mrank = A.rank(i);
+					int32_t prank = A.rank(p);
+					// hi loses iff rank_hi > rank_lo; otherwise lo loses
+					me_loses = side == 0? (mrank > prank) : !(prank > mrank);
+				}
+			} else me_loses = mw > pw;
+			if (!me_loses) continue;
+			const bool improves = pkey > best_key || (pkey == best_key && pkey > 0 && p < best_p);
+			if (MODE == SW_LOAD && pkey == best_key && pkey > 0 && A.cs(p) == A.cs(best_p)) atomicAdd(tie_cnt, 1u);
+			if (MODE != SW_ISO && lose && !improves) continue;
+			int32_t shorter = 0;
+			if (MODE != SW_ISO && !same_gene) { int32_t pcds = A.cds(p); shorter = mcds < pcds? mcds : pcds; }
+			const uint32_t pb = A.eoff(p), pe = A.eoff(p + 1);
+			const bool rel = side == 0? cds_related(A, pb, pe, pcs, pce, meb, mee, mcs, mce, shorter, o.min_ov_ratio)
+			                          : cds_related(A, meb, mee, mcs, mce, pb, pe, pcs, pce, shorter, o.min_ov_ratio);
+			if (!rel) continue;
+			lose = true;
+			if (MODE == SW_ISO) { side = 2; break; }                                      // one loss is all there is to know
+			if (improves) best_key = pkey, best_p = p;
+		}
+	}
+	if (MODE == SW_ISO) {
+		bits_out[i] = lose? (mbits | PG_HB_FLT_OV | PG_HB_FLT) : mbits;                  // overlap.c:85-91
+	} else if (MODE == SW_SHADOW) {
+		uint32_t b = mbits;
+		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;                                          // overlap.c:108,113: hit 0 is never reset
+		if (lose) b |= PG_HB_SHADOW;
+		bits_out[i] = b;
+		pdom_out[i] = best_key > 0? A.c.pid[best_p] : -1;                                 // overlap.c:160-165
+	} else {
+		bits_out[i] = mbits;
+		int32_t pd = -1, sd = -1;
+		if (best_key > 0) {
+			pd = A.c.pid[best_p];
+			const int32_t pcs = A.cs(best_p), pce = A.ce(best_p);
+			const uint32_t pb = A.eoff(best_p), pe = A.eoff(best_p + 1);
+			const int32_t ov = best_p < i? cds_overlap(A, pb, pe, pcs, pce, meb, mee, mcs, mce) : cds_overlap(A, meb, mee, mcs, mce, pb, pe, pcs, pce);
+			// overlap.c:170, IEEE double, left to right; -fmad=false keeps the products and sums un-contracted
+			sd = (int32_t)(A.c.sori[i] * (1.0 - (double)ov / mcds) + A.c.sori[best_p] * ((double)ov / A.cds(best_p)) + .499);
+		}
+		pdom_out[i] = pd; sdom_out[i] = sd;
+	}
+}
+
+// plain variant: one thread per hit, everything through L1/L2.  bits_out may not alias c.bits.
 template<int MODE> __global__ void __launch_bounds__(128) k_sweep(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
 {
 	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= c.n) return;
-	Mine m;
-	m.bits = c.bits[i];
-	if (m.bits & PG_HB_FLT) { bits_out[i] = m.bits; return; }                        // overlap.c:63,112
-	m.i = i; m.ctg = c.ctg[i]; m.cs = c.cs[i]; m.ce = c.ce[i]; m.pid = c.pid[i]; m.gidp = c.gidp[i]; m.rank = c.rank[i]; m.cds = c.cds[i];
-	m.eb = c.eoff[i]; m.ee = c.eoff[i + 1];
-	m.key = score_key(c.sadj[i], m.gidp, m.pid);
-	bool lose = false;
-	uint64_t best_key = 0; int32_t best_p = INT32_MAX, best_ov = 0;
-	// earlier hits still open at my start (overlap.c:67-71,114-120); pmax = running max of ce inside the contig
-	for (int32_t p = i - 1; p >= 0; --p) {
-		if (c.ctg[p] != m.ctg || c.pmax[p] <= m.cs) break;
-		int32_t pce = c.ce[p];
-		if (pce <= m.cs) continue;
-		uint32_t pbits = c.bits[p];
-		if (pbits & PG_HB_FLT) continue;
-		int32_t ov; uint64_t pkey;
-		if (pair_me_loses<MODE>(c, o, m, p, pbits, c.cs[p], pce, true, &ov, &pkey)) {
-			lose = true;
-			if (pkey > best_key || (pkey == best_key && pkey > 0 && p < best_p)) {
-				if (MODE == SW_LOAD && pkey == best_key && c.cs[p] == c.cs[best_p]) atomicAdd(tie_cnt, 1u);
-				best_key = pkey, best_p = p, best_ov = ov;
-			}
-		}
+	uint32_t mbits = c.bits[i];
+	if (mbits & PG_HB_FLT) { bits_out[i] = mbits; return; }                              // overlap.c:63,112
+	AccGlobal A; A.c = c;
+	sweep_hit<MODE>(A, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
+}
+
+// ---- TMA plumbing (1-D bulk copies global -> shared, completion on an mbarrier) ------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+
+// tiled variant: a CTA owns SWT_TILE consecutive hits; the ten packed columns of [tile - halo, tile + halo) and the exon
+// lists of those hits are pulled into shared memory by one thread issuing eleven cp.async.bulk copies (TMA, UBLKCP in SASS)
+// that complete on one mbarrier; several CTAs per SM overlap each other's copy and compute phases.  Windows that reach
+// past the halo (a hit with a megabase intron) fall through to global memory inside the accessor -- same results.
+template<int MODE> __global__ void __launch_bounds__(SWT_TILE) k_sweep_tile(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+{
+	__shared__ __align__(16) uint64_t s_key[SWT_STG];
+	__shared__ __align__(16) int32_t s_ctg[SWT_STG], s_cs[SWT_STG], s_ce[SWT_STG], s_pmax[SWT_STG], s_gidp[SWT_STG], s_rank[SWT_STG], s_cds[SWT_STG];
+	__shared__ __align__(16) uint32_t s_bits[SWT_STG], s_eoff[SWT_STG + 4];
+	__shared__ __align__(16) int2 s_ex[SWT_EXCAP];
+	__shared__ __align__(8) uint64_t bar;
+	__shared__ uint32_t s_e[2];
+	const int32_t t0 = blockIdx.x * SWT_TILE;
+	int32_t lo = t0 - SWT_HALO; if (lo < 0) lo = 0;
+	lo &= ~3;                                                      // 16-byte aligned column offsets
+	int32_t hi = t0 + SWT_TILE + SWT_HALO; if (hi > c.n) hi = c.n;
+	const int32_t cnt4 = (hi - lo + 3) & ~3, cnte = (hi - lo + 1 + 3) & ~3;   // columns are allocated with slack past n
+	if (threadIdx.x == 0) {
+		mbar_init(&bar, 1);
+		fence_mbar_init();
+		uint32_t e0 = c.eoff[lo] & ~1u, e1 = c.eoff[hi];
+		uint32_t ne = (e1 - e0 + 1) & ~1u;
+		if (ne > SWT_EXCAP) ne = SWT_EXCAP;
+		s_e[0] = e0; s_e[1] = e0 + ne;
+		fence_proxy_async();
+		mbar_expect_tx(&bar, (uint32_t)cnt4 * 4u * 8u + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
+		bulk_g2s(s_ctg, c.ctg + lo, cnt4 * 4, &bar); bulk_g2s(s_cs, c.cs + lo, cnt4 * 4, &bar); bulk_g2s(s_ce, c.ce + lo, cnt4 * 4, &bar);
+		bulk_g2s(s_pmax, c.pmax + lo, cnt4 * 4, &bar); bulk_g2s(s_gidp, c.gidp + lo, cnt4 * 4, &bar); bulk_g2s(s_rank, c.rank + lo, cnt4 * 4, &bar);
+		bulk_g2s(s_cds, c.cds + lo, cnt4 * 4, &bar); bulk_g2s(s_bits, c.bits + lo, cnt4 * 4, &bar);
+		bulk_g2s(s_key, c.key + lo, cnt4 * 8, &bar);
+		bulk_g2s(s_eoff, c.eoff + lo, cnte * 4, &bar);
+		bulk_g2s(s_ex, c.ex + e0, ne * 8, &bar);
 	}
-	// later hits that start before my end
-	for (int32_t p = i + 1; p < c.n; ++p) {
-		if (c.ctg[p] != m.ctg) break;
-		int32_t pcs = c.cs[p];
-		if (pcs >= m.ce) break;
-		uint32_t pbits = c.bits[p];
-		if (pbits & PG_HB_FLT) continue;
-		int32_t ov; uint64_t pkey;
-		if (pair_me_loses<MODE>(c, o, m, p, pbits, pcs, c.ce[p], false, &ov, &pkey)) {
-			lose = true;
-			if (pkey > best_key) best_key = pkey, best_p = p, best_ov = ov;           // ascending p: strict > keeps the first (overlap.c:150,153)
-			else if (MODE == SW_LOAD && pkey == best_key && pkey > 0 && c.cs[p] == c.cs[best_p]) atomicAdd(tie_cnt, 1u);
-		}
-	}
-	if (MODE == SW_ISO) {
-		bits_out[i] = lose? (m.bits | PG_HB_FLT_OV | PG_HB_FLT) : m.bits;             // overlap.c:85-91
-	} else if (MODE == SW_SHADOW) {
-		uint32_t b = m.bits;
-		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;                                       // overlap.c:108,113: hit 0 is never reset
-		if (lose) b |= PG_HB_SHADOW;
-		bits_out[i] = b;
-		pdom_out[i] = best_key > 0? c.pid[best_p] : -1;                               // overlap.c:160-165
-	} else {
-		bits_out[i] = m.bits;
-		int32_t pd = -1, sd = -1;
-		if (best_key > 0) {
-			pd = c.pid[best_p];
-			// overlap.c:170, IEEE double, left to right; -fmad=false keeps the products and sums un-contracted
-			sd = (int32_t)(c.sori[i] * (1.0 - (double)best_ov / m.cds) + c.sori[best_p] * ((double)best_ov / c.cds[best_p]) + .499);
-		}
-		pdom_out[i] = pd; sdom_out[i] = sd;
-	}
+	__syncthreads();
+	while (!mbar_try_wait(&bar, 0)) { }
+	const int32_t i = t0 + threadIdx.x;
+	if (i >= c.n) return;
+	const uint32_t mbits = s_bits[i - lo];
+	if (mbits & PG_HB_FLT) { bits_out[i] = mbits; return; }
+	AccTile A;
+	A.c = c; A.lo = lo; A.hi = hi; A.elo = s_e[0]; A.ehi = s_e[1];
+	A.s_ctg = s_ctg; A.s_cs = s_cs; A.s_ce = s_ce; A.s_pmax = s_pmax; A.s_gidp = s_gidp; A.s_rank = s_rank; A.s_cds = s_cds; A.s_bits = s_bits; A.s_eoff = s_eoff; A.s_key = s_key; A.s_ex = s_ex;
+	sweep_hit<MODE>(A, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,6 +525,7 @@ __global__ void k_flag_unfiltered(const uint32_t *__restrict__ bits, int32_t n, 
 struct ActCols {
 	int32_t *ctg, *cs, *ce, *cm, *pid, *gidp, *sadj, *rank, *sori, *sdom, *pdom0, *pdom, *cds, *pmax, *full;
 	uint32_t *bits, *bits_alt, *nex, *eoff;
+	uint64_t *key;
 };
 
 __global__ void k_build_active(FullCols f, const uint32_t *__restrict__ pos, int32_t n, ActCols a)
@@ -404,7 +536,7 @@ __global__ void k_build_active(FullCols f, const uint32_t *__restrict__ pos, int
 	if (pos[i + 1] == p) return;                            // filtered
 	a.ctg[p] = f.ctg[i]; a.cs[p] = f.cs[i]; a.ce[p] = f.ce[i]; a.cm[p] = f.cm[i]; a.pid[p] = f.pid[i]; a.gidp[p] = f.gidp[i];
 	a.sadj[p] = f.sadj[i]; a.rank[p] = f.rank[i]; a.sori[p] = f.sori[i]; a.sdom[p] = f.sdom[i]; a.pdom0[p] = f.pdom0[i]; a.pdom[p] = -1;
-	a.cds[p] = f.cds[i]; a.full[p] = i; a.bits[p] = f.bits[i]; a.nex[p] = f.nex[i];
+	a.cds[p] = f.cds[i]; a.full[p] = i; a.bits[p] = f.bits[i]; a.nex[p] = f.nex[i]; a.key[p] = f.key[i];
 }
 
 __global__ void k_copy_exons(const int2 *__restrict__ ex_src, const uint32_t *__restrict__ eoff_src, const int32_t *__restrict__ full, const uint32_t *__restrict__ eoff_dst, int32_t n, int2 *ex_dst)
@@ -532,32 +664,45 @@ __global__ void k_arc_heads(const uint64_t *__restrict__ key, int32_t n, int gbi
 	flag[p] = (k != ~0ull && (p == 0 || (key[p - 1] >> gbits) != (k >> gbits)))? 1u : 0u;
 }
 
+// one WARP per arc key: lanes stride over the key's records (sorted by key, then genome); a lane that sits on the first
+// record of a (key, genome) run folds that run (graph.c:128-145: count, mean distance, max scores) and adds it to its
+// private sums; a shuffle reduction finishes the key (the additive part of graph.c:153-163).
 __global__ void k_arc_reduce(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rec, const int32_t *__restrict__ dist, const int32_t *__restrict__ s1, const int32_t *__restrict__ s2,
-	int32_t n, int gbits, int32_t n_seg, const uint32_t *__restrict__ pos, ArcPartial *out)
+	int32_t n, int gbits, int32_t n_seg, const uint32_t *__restrict__ start, int32_t n_part, ArcPartial *out)
 {
-	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= n || pos[p + 1] == pos[p]) return;
-	uint64_t xk = key[p] >> gbits;
-	ArcPartial a; a.sum_dist = a.sum_s1 = a.sum_s2 = 0; a.n_genome = a.tot_cnt = 0;
-	int32_t q = p;
-	while (q < n && (key[q] >> gbits) == xk) {                 // one (key, genome) group per outer iteration
+	int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (g >= n_part) return;
+	const int32_t b = start[g], e = g + 1 < n_part? (int32_t)start[g + 1] : n;
+	const uint64_t xk = key[b] >> gbits;
+	long long sum_dist = 0, sum_s1 = 0, sum_s2 = 0;
+	int32_t n_genome = 0, tot = 0;
+	for (int32_t q = b + lane; q < e; q += 32) {
 		uint64_t kg = key[q];
+		if (kg == ~0ull) break;
+		if (q > b && key[q - 1] == kg) continue;            // not the first record of its (key, genome) run
 		unsigned long long dsum = 0; int32_t m1 = 0, m2 = 0, cnt = 0;
-		while (q < n && key[q] == kg) {
-			uint32_t r = rec[q];
-			dsum += (unsigned long long)(long long)dist[r];
-			int32_t a1 = s1[r], a2 = s2[r];
+		for (int32_t r = q; r < e && key[r] == kg; ++r) {
+			uint32_t o = rec[r];
+			dsum += (unsigned long long)(long long)dist[o];
+			int32_t a1 = s1[o], a2 = s2[o];
 			m1 = m1 > a1? m1 : a1; m2 = m2 > a2? m2 : a2;
-			++cnt; ++q;
+			++cnt;
 		}
 		int32_t dg = (int32_t)((double)dsum / cnt + .499);                               // graph.c:141
-		a.n_genome += 1; a.tot_cnt += cnt;
-		a.sum_dist += (long long)((unsigned long long)(long long)dg * (unsigned long long)(long long)cnt);   // graph.c:160
-		a.sum_s1 += m1; a.sum_s2 += m2;
+		n_genome += 1; tot += cnt;
+		sum_dist += (long long)((unsigned long long)(long long)dg * (unsigned long long)(long long)cnt);   // graph.c:160
+		sum_s1 += m1; sum_s2 += m2;
 	}
-	uint64_t nv = 2ull * n_seg, v = xk / nv, w = xk % nv;
-	a.x = v << 32 | w;
-	out[pos[p]] = a;
+	for (int s = 16; s > 0; s >>= 1) {
+		sum_dist += __shfl_xor_sync(0xffffffffu, sum_dist, s); sum_s1 += __shfl_xor_sync(0xffffffffu, sum_s1, s); sum_s2 += __shfl_xor_sync(0xffffffffu, sum_s2, s);
+		n_genome += __shfl_xor_sync(0xffffffffu, n_genome, s); tot += __shfl_xor_sync(0xffffffffu, tot, s);
+	}
+	if (lane == 0) {
+		ArcPartial a;
+		uint64_t nv = 2ull * n_seg, v = xk / nv, w = xk % nv;
+		a.x = v << 32 | w; a.sum_dist = sum_dist; a.sum_s1 = sum_s1; a.sum_s2 = sum_s2; a.n_genome = n_genome; a.tot_cnt = tot;
+		out[g] = a;
+	}
 }
 
 // merge partials that share a key (multi-GPU: the same arc seen by several ranks), input sorted by x
