@@ -76,6 +76,7 @@ typedef struct {
 } pgx_stats_t;
 void pgx_get_stats(pgx_stats_t *out);
 void pgx_reset_stats(void);
+void pgx_trim(void);                          /* give cached device memory back to the driver */
 
 /* test hooks for the device primitives (tests/test_gpu_primitives.py) */
 void pgx_test_radix_sort(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits);

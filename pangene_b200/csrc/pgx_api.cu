@@ -167,6 +167,7 @@ void pgx_get_stats(pgx_stats_t *o)
 	o->n_seg = g_stats.n_seg; o->n_arc = g_stats.n_arc; o->h2d_bytes = g_stats.h2d; o->d2h_bytes = g_stats.d2h;
 }
 void pgx_reset_stats(void) { g_launch.launches = 0; g_stats = Stats(); }
+void pgx_trim(void) { DevCache::get_cache().trim(); }
 
 // ---- test hooks -----------------------------------------------------------------------------------
 void pgx_test_radix_sort(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits)

@@ -16,6 +16,9 @@
 #include "pgx_kernels.cuh"
 #include "pgx_comm.cuh"
 #include "pgx_host.hpp"
+#include "pgx_hostpipe.hpp"
+#include <atomic>
+#include <algorithm>
 
 namespace pgx {
 
@@ -45,7 +48,9 @@ struct Session {
 	std::vector<SegHost> h_seg0;
 	bool done_post = false, done_graph = false;
 	// ---- device: constants and raw input
-	DBuf<int32_t> hoff, coff, ctg2g, prot_gid, aos, prot_max, prot_rep, g2s;
+	DBuf<int32_t> hoff, coff, ctg2g, prot_gid, prot_max, prot_rep, g2s;
+	DBuf<RawHit> raw;
+	bool host_sorted = false;            // the caller's hit arrays are already in (contig, cs) order (after a first download)
 	DBuf<uint32_t> eoffg, src, counters;
 	DBuf<uint8_t> gene_pref;
 	DBuf<int2> ex_raw, ex, wex;
@@ -118,13 +123,9 @@ struct Session {
 		PGX_CHECK(cudaMemcpyAsync(ctg2g.p, h_ctg2g.data(), h_ctg2g.size() * 4, cudaMemcpyHostToDevice, st));
 		PGX_CHECK(cudaMemcpyAsync(prot_gid.p, h_prot_gid.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
 		PGX_CHECK(cudaMemcpyAsync(gene_pref.p, h_gene_pref.data(), (size_t)n_gene, cudaMemcpyHostToDevice, st));
-		aos.alloc((size_t)(N > 0? N : 1) * AOS_WORDS); ex_raw.alloc(E > 0? E : 1);
-		for (int32_t j = 0; j < G; ++j) {
-			const pg_genome_t *g = &d->genome[j];
-			if (g->n_hit) PGX_CHECK(cudaMemcpyAsync(aos.p + (size_t)h_hoff[j] * AOS_WORDS, g->hit, (size_t)g->n_hit * sizeof(pg_hit_t), cudaMemcpyHostToDevice, st));
-			if (g->n_exon) PGX_CHECK(cudaMemcpyAsync(ex_raw.p + h_eoffg[j], g->exon, (size_t)g->n_exon * sizeof(pg_exon_t), cudaMemcpyHostToDevice, st));
-		}
-		g_stats.h2d += (int64_t)N * 88 + E * 8 + (int64_t)n_prot * 4 + n_gene;
+		raw.alloc((size_t)N + 1); ex_raw.alloc((size_t)E + 16);
+		upload_hits(d);
+		g_stats.h2d += (int64_t)N * (int64_t)sizeof(RawHit) + E * 8 + (int64_t)n_prot * 4 + n_gene;
 		g_stats.n_hit = N;
 		counters.alloc(C_N); counters.zero(st);
 		size_t tab = (size_t)(G > 0? G : 1);
@@ -148,7 +149,47 @@ struct Session {
 			scratch.reset(0);
 		} else rank_G.assign(1, G);
 		PGX_CHECK(cudaStreamSynchronize(st));
-		done_post = done_graph = false;
+		done_post = done_graph = false; host_sorted = false;
+	}
+
+	// host threads pack 48-byte RawHit records from the caller's pg_hit_t arrays into pinned chunks while the copy engine
+	// drains the previous chunk; exon lists follow through the same ring
+	void upload_hits(const pg_data_t *d)
+	{
+		ThreadPool &pool = ThreadPool::get();
+		std::atomic<uint32_t> bad{0};
+		const int64_t BLK = 1 << 14;
+		if (N) staged_h2d(raw.p, (size_t)N * sizeof(RawHit), sizeof(RawHit), [&](size_t off, size_t len, char *dst) {
+			const int64_t h0 = (int64_t)(off / sizeof(RawHit)), h1 = h0 + (int64_t)(len / sizeof(RawHit));
+			pool.parallel_for((h1 - h0 + BLK - 1) / BLK, [&](int64_t b) {
+				const int64_t a = h0 + b * BLK, e = std::min(h1, a + BLK);
+				int g = (int)(std::upper_bound(h_hoff.begin(), h_hoff.end(), (int32_t)a) - h_hoff.begin()) - 1;
+				RawHit *o = (RawHit*)dst + (a - h0);
+				uint32_t err = 0;
+				for (int64_t t = a; t < e; ++t, ++o) {
+					while (t >= h_hoff[g + 1]) ++g;
+					const pg_hit_t &h = d->genome[g].hit[t - h_hoff[g]];
+					if (h.cs < 0 || h.ce > 0x7fffffffll || h.cm < 0 || h.cm > 0x7fffffffll || h.cs > h.ce) err = 1;
+					o->pid = h.pid; o->cid = h.cid; o->rank = h.rank; o->sori = h.score_ori; o->sadj = h.score_adj; o->nexon = h.n_exon; o->offexon = h.off_exon;
+					o->rev = h.rev; o->cs = (int32_t)h.cs; o->cm = (int32_t)h.cm; o->ce = (int32_t)h.ce; o->pad = 0;
+				}
+				if (err) bad.store(1);
+			});
+		}, st);
+		if (bad.load()) PGX_FATAL("upload: a hit coordinate is outside [0, 2^31) or cs > ce -- this build keeps coordinates in int32");
+		if (E) staged_h2d(ex_raw.p, (size_t)E * 8, 8, [&](size_t off, size_t len, char *dst) {
+			const int64_t e0 = (int64_t)(off / 8), e1 = e0 + (int64_t)(len / 8), EB = 1 << 17;
+			pool.parallel_for((e1 - e0 + EB - 1) / EB, [&](int64_t b) {
+				int64_t a = e0 + b * EB, e = std::min(e1, a + EB);
+				int g = (int)(std::upper_bound(h_eoffg.begin(), h_eoffg.end(), (uint32_t)a) - h_eoffg.begin()) - 1;
+				while (a < e) {
+					while (a >= (int64_t)h_eoffg[g + 1]) ++g;
+					int64_t m = std::min<int64_t>(e, h_eoffg[g + 1]) - a;
+					memcpy(dst + (a - e0) * 8, d->genome[g].exon + (a - h_eoffg[g]), (size_t)m * 8);
+					a += m;
+				}
+			});
+		}, st);
 	}
 	void set_full()
 	{
@@ -174,9 +215,19 @@ struct Session {
 	// one sweep launch; PGX_SWEEP=global selects the plain variant (debug / A-B timing), default is the TMA-tiled one
 	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out)
 	{
-		static const int use_tile = []() { const char *e = getenv("PGX_SWEEP"); return !(e && strcmp(e, "global") == 0); }();
+		// PGX_SWEEP=global | tile | pairs (default): plain, TMA-staged thread-per-hit, TMA-staged pair-parallel
+		static const int variant = []() { const char *e = getenv("PGX_SWEEP"); return (e && strcmp(e, "global") == 0)? 0 : (e && strcmp(e, "tile") == 0)? 1 : 2; }();
 		if (c.n <= 0) return;
-		if (use_tile) PGX_LAUNCH(k_sweep_tile<MODE>, grid_for(c.n, SWT_TILE), SWT_TILE, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
+		if (variant == 2) {
+			static bool attr_set = false;
+			if (!attr_set) {
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_pairs<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_pairs<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_pairs<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				attr_set = true;
+			}
+			PGX_LAUNCH(k_sweep_pairs<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
+		} else if (variant == 1) PGX_LAUNCH(k_sweep_tile<MODE>, grid_for(c.n, SWT_TILE), SWT_TILE, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 		else PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 	}
 
@@ -210,19 +261,19 @@ struct Session {
 		size_t mk = scratch.mark();
 		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
 		// -- raw order: unpack + pseudogene flags (hit.c:66-105)
-		int32_t *r_pid = scratch.get<int32_t>(N), *r_nexon = scratch.get<int32_t>(N), *r_rank = scratch.get<int32_t>(N), *r_gl = scratch.get<int32_t>(N);
+		int32_t *r_rank = scratch.get<int32_t>(N), *r_gl = scratch.get<int32_t>(N);
 		uint8_t *r_pseudo = scratch.get<uint8_t>(N);
 		uint64_t *key = scratch.get<uint64_t>(N + 1);
-		PGX_LAUNCH(k_unpack, grid_for(N, TB), TB, 0, st, aos.p, N, hoff.p, coff.p, G, r_pid, r_nexon, r_rank, r_gl, key, n_prot, counters.p + C_ERR);
+		PGX_LAUNCH(k_unpack, grid_for(N, TB), TB, 0, st, raw.p, N, hoff.p, coff.p, G, r_rank, r_gl, key, n_prot, counters.p + C_ERR);
 		{
 			size_t tab = (size_t)G * n_prot, m2 = scratch.mark();
 			int32_t *t_max = scratch.get<int32_t>(tab), *t_min = scratch.get<int32_t>(tab), *t_r1 = scratch.get<int32_t>(tab);
 			PGX_CHECK(cudaMemsetAsync(t_max, 0, tab * 4, st));
 			PGX_CHECK(cudaMemsetAsync(t_min, 0x7f, tab * 4, st));     // 0x7f7f7f7f: larger than any exon count
 			PGX_LAUNCH(k_fill_i32, grid_for((int64_t)tab, TB), TB, 0, st, t_r1, (int64_t)tab, INT32_MAX);
-			PGX_LAUNCH(k_fp_minmax, grid_for(N, TB), TB, 0, st, r_pid, r_nexon, r_gl, N, n_prot, t_max, t_min);
-			PGX_LAUNCH(k_fp_flag, grid_for(N, TB), TB, 0, st, r_pid, r_nexon, r_rank, r_gl, N, n_prot, t_max, t_min, t_r1, r_pseudo);
-			PGX_LAUNCH(k_fp_rank, grid_for(N, TB), TB, 0, st, r_pid, r_gl, N, n_prot, t_max, t_min, t_r1, r_rank);
+			PGX_LAUNCH(k_fp_minmax, grid_for(N, TB), TB, 0, st, raw.p, r_gl, N, n_prot, t_max, t_min);
+			PGX_LAUNCH(k_fp_flag, grid_for(N, TB), TB, 0, st, raw.p, r_rank, r_gl, N, n_prot, t_max, t_min, t_r1, r_pseudo);
+			PGX_LAUNCH(k_fp_rank, grid_for(N, TB), TB, 0, st, raw.p, r_gl, N, n_prot, t_max, t_min, t_r1, r_rank);
 			scratch.reset(m2);
 		}
 		check_err("upload");
@@ -233,7 +284,7 @@ struct Session {
 			PGX_CHECK(cudaMemcpyAsync(src.p, perm, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
 			scratch.reset(m2);
 		}
-		PGX_LAUNCH(k_gather, grid_for(N, TB), TB, 0, st, aos.p, src.p, N, hoff.p, coff.p, eoffg.p, r_rank, r_pseudo, r_gl, prot_gid.p, gene_pref.p, F);
+		PGX_LAUNCH(k_gather, grid_for(N, TB), TB, 0, st, raw.p, src.p, N, hoff.p, coff.p, eoffg.p, r_rank, r_pseudo, r_gl, prot_gid.p, gene_pref.p, F);
 		{
 			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(N));
 			exclusive_sum_u32(F.nex, F.eoff, N, agg, st);
@@ -601,20 +652,39 @@ struct Session {
 		if (d->n_genome != G) PGX_FATAL("download: pg_data_t does not match the uploaded one");
 		if (Nw) PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
 		if (N) {
-			DBuf<int32_t> out;
-			out.alloc((size_t)N * AOS_WORDS);
-			PGX_LAUNCH(k_materialize, grid_for((int64_t)N * AOS_WORDS, TB), TB, 0, st, aos.p, src.p, N, F, g2s.p, prot_rep.p, done_graph? 1 : 0, out.p);
+			DBuf<OutHit> out;
+			out.alloc((size_t)N + 1);
+			PGX_LAUNCH(k_pack_out, grid_for(N, TB), TB, 0, st, src.p, N, F, g2s.p, prot_rep.p, done_graph? 1 : 0, out.p);
+			ThreadPool &pool = ThreadPool::get();
 			std::vector<pg_hit_t*> fresh(G, nullptr);
 			for (int32_t j = 0; j < G; ++j) {
-				pg_genome_t *g = &d->genome[j];
-				int32_t n = h_hoff[j + 1] - h_hoff[j];
-				if (n != g->n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
-				fresh[j] = (pg_hit_t*)malloc(sizeof(pg_hit_t) * (n > 0? n : 1));
-				if (n) PGX_CHECK(cudaMemcpyAsync(fresh[j], out.p + (size_t)h_hoff[j] * AOS_WORDS, (size_t)n * sizeof(pg_hit_t), cudaMemcpyDeviceToHost, st));
+				if (h_hoff[j + 1] - h_hoff[j] != d->genome[j].n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
+				if (!host_sorted) fresh[j] = (pg_hit_t*)malloc(sizeof(pg_hit_t) * (d->genome[j].n_hit > 0? d->genome[j].n_hit : 1));
 			}
-			PGX_CHECK(cudaStreamSynchronize(st));
-			for (int32_t j = 0; j < G; ++j) { free(d->genome[j].hit); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = d->genome[j].n_hit; }   // hit.c:62-63
-			g_stats.d2h += (int64_t)N * 88;
+			const int64_t BLK = 1 << 14;
+			const bool in_place = host_sorted;
+			// only the 24 bytes per hit that changed cross the bus; host threads rebuild the 88-byte records from the caller's own copy
+			staged_d2h(out.p, (size_t)N * sizeof(OutHit), sizeof(OutHit), [&](size_t off, size_t len, const char *srcbuf) {
+				const int64_t h0 = (int64_t)(off / sizeof(OutHit)), h1 = h0 + (int64_t)(len / sizeof(OutHit));
+				pool.parallel_for((h1 - h0 + BLK - 1) / BLK, [&](int64_t b) {
+					const int64_t a = h0 + b * BLK, e = std::min(h1, a + BLK);
+					int g = (int)(std::upper_bound(h_hoff.begin(), h_hoff.end(), (int32_t)a) - h_hoff.begin()) - 1;
+					const OutHit *o = (const OutHit*)srcbuf + (a - h0);
+					for (int64_t t = a; t < e; ++t, ++o) {
+						while (t >= h_hoff[g + 1]) ++g;
+						const int64_t base = h_hoff[g];
+						pg_hit_t *dst = in_place? &d->genome[g].hit[t - base] : &fresh[g][t - base];
+						if (!in_place) *dst = d->genome[g].hit[(int64_t)o->src - base];
+						dst->rank = o->rank; dst->score_dom = o->sdom; dst->pid_dom = o->pdom; dst->pid_dom0 = o->pdom0;
+						memcpy((char*)dst + PG_HIT_BITS_OFFSET, &o->bits, 4);
+					}
+				});
+			}, st);
+			if (!host_sorted) {
+				pool.parallel_for(G, [&](int64_t j) { free(d->genome[j].hit); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = d->genome[j].n_hit; });   // hit.c:62-63
+				host_sorted = true;
+			}
+			g_stats.d2h += (int64_t)N * (int64_t)sizeof(OutHit);
 		}
 		for (int32_t i = 0; i < n_prot; ++i) {   // hit.c:206-207,215,230-237
 			d->prot[i].n = rep.prot_n[i]; d->prot[i].avg_score_adj = rep.prot_avg[i]; d->prot[i].rep = rep.prot_rep[i]; d->prot[i].max_score_ori = h_prot_max[i];

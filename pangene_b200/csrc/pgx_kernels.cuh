@@ -36,45 +36,47 @@ __device__ __forceinline__ int upper_bound_i32(const int32_t *a, int n, int32_t 
 // ------------------------------------------------------------------------------------------------
 // stage A: raw (file) order -- unpack, per-(genome,protein) pseudogene flags (hit.c:66-105)
 // ------------------------------------------------------------------------------------------------
+// what the device needs of a pg_hit_t, packed by the host while it fills the pinned upload chunks (pgx_hostpipe.hpp)
+struct RawHit { int32_t pid, cid, rank, sori, sadj, nexon, offexon, rev, cs, cm, ce, pad; };   // 48 bytes
+// what changed, packed by the device for the way back
+struct OutHit { uint32_t src; int32_t rank, sdom, pdom, pdom0; uint32_t bits; };               // 24 bytes
+
 // hoff[G+1]: hit offsets of the local genomes; coff[G+1]: contig-key offsets; one thread per raw hit.
-__global__ void k_unpack(const int32_t *__restrict__ aos, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff, int G,
-	int32_t *r_pid, int32_t *r_nexon, int32_t *r_rank, int32_t *r_gl, uint64_t *key, int32_t n_prot, uint32_t *err)
+__global__ void k_unpack(const RawHit *__restrict__ raw, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff, int G,
+	int32_t *r_rank, int32_t *r_gl, uint64_t *key, int32_t n_prot, uint32_t *err)
 {
 	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
-	const int32_t *w = aos + (size_t)t * AOS_WORDS;
+	RawHit h = raw[t];
 	int gl = upper_bound_i32(hoff, G + 1, t) - 1;
-	int32_t pid = w[W_PID], cid = w[W_CID];
-	int64_t cs = *(const int64_t*)(w + W_CS), cm = *(const int64_t*)(w + W_CM), ce = *(const int64_t*)(w + W_CE);
 	uint32_t bad = 0;
-	if (cs < 0 || ce > 0x7fffffffll || cm < 0 || cm > 0x7fffffffll || cs > ce) bad |= 1;   // this build keeps coordinates in int32
-	if (cid < 0 || cid >= coff[gl + 1] - coff[gl]) bad |= 2;
-	if (pid < 0 || pid >= n_prot) bad |= 4;
-	if (w[W_NEXON] < 1) bad |= 8;
-	if (bad) { atomicOr(err, bad); cid = 0; cs = 0; pid = 0; }
-	r_pid[t] = pid; r_nexon[t] = w[W_NEXON]; r_rank[t] = w[W_RANK]; r_gl[t] = gl;
-	key[t] = (uint64_t)(uint32_t)(coff[gl] + cid) << 32 | (uint32_t)cs;
+	if (h.cid < 0 || h.cid >= coff[gl + 1] - coff[gl]) bad |= 2;
+	if (h.pid < 0 || h.pid >= n_prot) bad |= 4;
+	if (h.nexon < 1) bad |= 8;
+	if (bad) { atomicOr(err, bad); h.cid = 0; h.cs = 0; }
+	r_rank[t] = h.rank; r_gl[t] = gl;
+	key[t] = (uint64_t)(uint32_t)(coff[gl] + h.cid) << 32 | (uint32_t)h.cs;
 }
 
-__global__ void k_fp_minmax(const int32_t *__restrict__ r_pid, const int32_t *__restrict__ r_nexon, const int32_t *__restrict__ r_gl, int32_t n, int32_t n_prot,
-	int32_t *t_max, int32_t *t_min)
+__global__ void k_fp_minmax(const RawHit *__restrict__ raw, const int32_t *__restrict__ r_gl, int32_t n, int32_t n_prot, int32_t *t_max, int32_t *t_min)
 {
 	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
-	size_t k = (size_t)r_gl[t] * n_prot + r_pid[t];
-	atomicMax(&t_max[k], r_nexon[t]);
-	atomicMin(&t_min[k], r_nexon[t]);
+	size_t k = (size_t)r_gl[t] * n_prot + raw[t].pid;
+	int32_t ne = raw[t].nexon;
+	atomicMax(&t_max[k], ne);
+	atomicMin(&t_min[k], ne);
 }
 
 __device__ __forceinline__ bool fp_group_flagged(int32_t M, int32_t m) { return M > 1 && (m == 1 || m * 2 <= M); }   // hit.c:84
 
-__global__ void k_fp_flag(const int32_t *__restrict__ r_pid, const int32_t *__restrict__ r_nexon, const int32_t *__restrict__ r_rank, const int32_t *__restrict__ r_gl,
+__global__ void k_fp_flag(const RawHit *__restrict__ raw, const int32_t *__restrict__ r_rank, const int32_t *__restrict__ r_gl,
 	int32_t n, int32_t n_prot, const int32_t *__restrict__ t_max, const int32_t *__restrict__ t_min, int32_t *t_r1, uint8_t *r_pseudo)
 {
 	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
-	size_t k = (size_t)r_gl[t] * n_prot + r_pid[t];
-	int32_t M = t_max[k], m = t_min[k], ne = r_nexon[t];
+	size_t k = (size_t)r_gl[t] * n_prot + raw[t].pid;
+	int32_t M = t_max[k], m = t_min[k], ne = raw[t].nexon;
 	uint8_t ps = 0;
 	if (fp_group_flagged(M, m)) {
 		if (ne == 1 || ne * 2 <= M) ps = 1;                 // hit.c:88-89
@@ -83,12 +85,12 @@ __global__ void k_fp_flag(const int32_t *__restrict__ r_pid, const int32_t *__re
 	r_pseudo[t] = ps;
 }
 
-__global__ void k_fp_rank(const int32_t *__restrict__ r_pid, const int32_t *__restrict__ r_gl, int32_t n, int32_t n_prot,
+__global__ void k_fp_rank(const RawHit *__restrict__ raw, const int32_t *__restrict__ r_gl, int32_t n, int32_t n_prot,
 	const int32_t *__restrict__ t_max, const int32_t *__restrict__ t_min, const int32_t *__restrict__ t_r1, int32_t *r_rank)
 {
 	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n) return;
-	size_t k = (size_t)r_gl[t] * n_prot + r_pid[t];
+	size_t k = (size_t)r_gl[t] * n_prot + raw[t].pid;
 	if (!fp_group_flagged(t_max[k], t_min[k])) return;
 	int32_t r1 = t_r1[k], r = r_rank[t];
 	if (r1 <= 0 || r1 == INT32_MAX) return;                 // hit.c:94
@@ -104,28 +106,28 @@ struct FullCols {            // all hits, (genome, contig, cs) order, packed int
 	uint64_t *key;
 };
 
-__global__ void k_gather(const int32_t *__restrict__ aos, const uint32_t *__restrict__ src, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff,
+__global__ void k_gather(const RawHit *__restrict__ raw, const uint32_t *__restrict__ src, int32_t n, const int32_t *__restrict__ hoff, const int32_t *__restrict__ coff,
 	const uint32_t *__restrict__ eoff_g, const int32_t *__restrict__ r_rank, const uint8_t *__restrict__ r_pseudo, const int32_t *__restrict__ r_gl,
 	const int32_t *__restrict__ prot_gid, const uint8_t *__restrict__ gene_pref, FullCols c)
 {
 	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t s = src[i];
-	const int32_t *w = aos + (size_t)s * AOS_WORDS;
+	RawHit h = raw[s];
 	int gl = r_gl[s];
-	int32_t pid = w[W_PID], gid = prot_gid[pid];
-	uint32_t b = (uint32_t)w[W_BITS] & PG_HB_REV;
+	int32_t gid = prot_gid[h.pid];
+	uint32_t b = (uint32_t)h.rev & PG_HB_REV;
 	if (r_pseudo[s]) b |= PG_HB_PSEUDO | PG_HB_FLT;          // read.c:246
 	if (i == hoff[gl]) b |= HB_FIRST;
-	c.ctg[i] = coff[gl] + w[W_CID];
-	c.cs[i] = (int32_t)*(const int64_t*)(w + W_CS); c.cm[i] = (int32_t)*(const int64_t*)(w + W_CM); c.ce[i] = (int32_t)*(const int64_t*)(w + W_CE);
-	c.pid[i] = pid; c.gidp[i] = gid << 1 | gene_pref[gid];
-	c.sadj[i] = w[W_SADJ]; c.sori[i] = w[W_SORI]; c.rank[i] = r_rank[s];
-	c.key[i] = score_key(w[W_SADJ], gid << 1 | gene_pref[gid], pid);
+	c.ctg[i] = coff[gl] + h.cid;
+	c.cs[i] = h.cs; c.cm[i] = h.cm; c.ce[i] = h.ce;
+	c.pid[i] = h.pid; c.gidp[i] = gid << 1 | gene_pref[gid];
+	c.sadj[i] = h.sadj; c.sori[i] = h.sori; c.rank[i] = r_rank[s];
+	c.key[i] = score_key(h.sadj, gid << 1 | gene_pref[gid], h.pid);
 	c.sdom[i] = 0; c.pdom0[i] = -1; c.pdom[i] = -1;          // parser state: read.c:133-134
 	c.bits[i] = b;
-	c.nex[i] = (uint32_t)w[W_NEXON];
-	c.esrc[i] = eoff_g[gl] + (uint32_t)w[W_OFFEXON];
+	c.nex[i] = (uint32_t)h.nexon;
+	c.esrc[i] = eoff_g[gl] + (uint32_t)h.offexon;
 }
 
 // copy each hit's exon list to its new home (contiguous in hit order) and sum the CDS length (overlap.c:45-51)
@@ -187,7 +189,7 @@ struct AccTile {
 	__device__ __forceinline__ int32_t pmax(int32_t p) const { return in(p)? s_pmax[p - lo] : c.pmax[p]; }
 	__device__ __forceinline__ uint32_t bits(int32_t p) const { return in(p)? s_bits[p - lo] : c.bits[p]; }
 	__device__ __forceinline__ int32_t gidp(int32_t p) const { return in(p)? s_gidp[p - lo] : c.gidp[p]; }
-	__device__ __forceinline__ int32_t rank(int32_t p) const { return in(p)? s_rank[p - lo] : c.rank[p]; }
+	__device__ __forceinline__ int32_t rank(int32_t p) const { return (s_rank && in(p))? s_rank[p - lo] : c.rank[p]; }
 	__device__ __forceinline__ int32_t cds(int32_t p) const { return in(p)? s_cds[p - lo] : c.cds[p]; }
 	__device__ __forceinline__ uint64_t key(int32_t p) const { return in(p)? s_key[p - lo] : c.key[p]; }
 	__device__ __forceinline__ uint32_t eoff(int32_t p) const { return (p >= lo && p <= hi)? s_eoff[p - lo] : c.eoff[p]; }
@@ -213,10 +215,9 @@ template<class Acc> __device__ __forceinline__ int32_t cds_overlap(const Acc &A,
 	return inter;
 }
 
-// Same walk, but only answers "are the two hits in relation?": overlap > 0 and, when `shorter` > 0 (different genes,
-// overlap.c:134-136), (double)overlap/shorter >= ratio.  The running overlap only grows, and x -> (double)x/shorter is
-// monotone, so the walk stops as soon as the answer is yes.
-template<class Acc> __device__ __forceinline__ bool cds_related(const Acc &A, uint32_t b0, uint32_t e0, int32_t cs0, int32_t ce0, uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1, int32_t shorter, double ratio)
+// Same walk, but only answers "are the two hits in relation?", i.e. "does the overlap reach `need`?".  The running
+// overlap only grows, so the walk stops as soon as the answer is yes.
+template<class Acc> __device__ __forceinline__ bool cds_related(const Acc &A, uint32_t b0, uint32_t e0, int32_t cs0, int32_t ce0, uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1, int32_t need)
 {
 	if (!(cs0 < ce1 && ce0 > cs1)) return false;
 	int32_t inter = 0;
@@ -231,10 +232,25 @@ template<class Acc> __device__ __forceinline__ bool cds_related(const Acc &A, ui
 			if (t1 < t0) { int32_t o = t1 - s0; inter += o > 0? o : 0; adv0 = false; }
 			else { inter += x0.y - x0.x; adv0 = true; }
 		}
-		if (inter > 0 && (shorter <= 0 || !((double)(uint64_t)inter / shorter < ratio))) return true;
+		if (inter >= need) return true;
 		if (adv0) { if (++b0 == e0) break; x0 = A.exon(b0); } else { if (++b1 == e1) break; x1 = A.exon(b1); }
 	}
 	return false;
+}
+
+// smallest overlap that puts two hits in relation: 1 for hits of one gene (overlap.c:81,132: any CDS overlap), else the
+// smallest integer ov with !((double)ov / shorter < ratio) (overlap.c:134-136) -- found with the SAME double division the
+// reference uses, so the predicate is reproduced exactly; two or three divisions per pair instead of one per walk step.
+__device__ __forceinline__ int32_t related_threshold(bool same_gene, int32_t cds_a, int32_t cds_b, double ratio)
+{
+	if (same_gene) return 1;
+	const int32_t shorter = cds_a < cds_b? cds_a : cds_b;
+	if (shorter <= 0) return 1;
+	double t = ceil(ratio * (double)shorter);
+	int32_t need = t < 1.0? 1 : (t > 2147483000.0? 2147483000 : (int32_t)t);
+	while (need > 1 && !((double)(uint64_t)(need - 1) / shorter < ratio)) --need;
+	while (need < 2147483000 && (double)(uint64_t)need / shorter < ratio) ++need;
+	return need;
 }
 
 // One hit against its window.  Every pair is visited from both members, but only the member that WOULD LOSE if the pair
@@ -293,11 +309,10 @@ template<int MODE, class Acc> __device__ __forceinline__ void sweep_hit(const Ac
 			const bool improves = pkey > best_key || (pkey == best_key && pkey > 0 && p < best_p);
 			if (MODE == SW_LOAD && pkey == best_key && pkey > 0 && A.cs(p) == A.cs(best_p)) atomicAdd(tie_cnt, 1u);
 			if (MODE != SW_ISO && lose && !improves) continue;
-			int32_t shorter = 0;
-			if (MODE != SW_ISO && !same_gene) { int32_t pcds = A.cds(p); shorter = mcds < pcds? mcds : pcds; }
+			const int32_t need = related_threshold(MODE == SW_ISO || same_gene, mcds, MODE == SW_ISO || same_gene? 0 : A.cds(p), o.min_ov_ratio);
 			const uint32_t pb = A.eoff(p), pe = A.eoff(p + 1);
-			const bool rel = side == 0? cds_related(A, pb, pe, pcs, pce, meb, mee, mcs, mce, shorter, o.min_ov_ratio)
-			                          : cds_related(A, meb, mee, mcs, mce, pb, pe, pcs, pce, shorter, o.min_ov_ratio);
+			const bool rel = side == 0? cds_related(A, pb, pe, pcs, pce, meb, mee, mcs, mce, need)
+			                          : cds_related(A, meb, mee, mcs, mce, pb, pe, pcs, pce, need);
 			if (!rel) continue;
 			lose = true;
 			if (MODE == SW_ISO) { side = 2; break; }                                      // one loss is all there is to know
@@ -398,6 +413,230 @@ template<int MODE> __global__ void __launch_bounds__(SWT_TILE) k_sweep_tile(Swee
 	A.c = c; A.lo = lo; A.hi = hi; A.elo = s_e[0]; A.ehi = s_e[1];
 	A.s_ctg = s_ctg; A.s_cs = s_cs; A.s_ce = s_ce; A.s_pmax = s_pmax; A.s_gidp = s_gidp; A.s_rank = s_rank; A.s_cds = s_cds; A.s_bits = s_bits; A.s_eoff = s_eoff; A.s_key = s_key; A.s_ex = s_ex;
 	sweep_hit<MODE>(A, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
+}
+
+// ---- pair-parallel tile sweep ---------------------------------------------------------------------
+// k_sweep_tile above still gives each thread one hit and lets it walk its whole window: ncu shows 5 of 32 lanes active
+// (windows of 4..23 partners, exon walks of 1..14 steps).  This variant splits the work into uniform pieces:
+//   phase 1  one thread per hit: the cheap part only -- window scan from shared memory, "would I lose to p?" from the two
+//            score keys; every (hit, partner) pair that could shadow the hit goes into a shared-memory queue;
+//   phase 2  one thread per QUEUED PAIR: the exon-list walk (with early exit), results folded into per-hit shared
+//            state with shared-memory atomics (any-loss flag, atomicMax on the 64-bit dominator key);
+//   phase 3  pairs whose key equals the winning key settle the smallest-partner-index rule (atomicMin);
+//   phase 4  one thread per hit writes the outputs; SW_LOAD walks its final dominator once more for the exact overlap.
+// Hits whose window leaves the staged range, or that hit a full queue, take the serial sweep_hit() path: same results.
+constexpr int SWQ_TILE = 256, SWQ_HALO = 64, SWQ_STG = SWQ_TILE + 2 * SWQ_HALO + 8, SWQ_EXCAP = 2560, SWQ_QCAP = 3072;
+
+struct AccStaged {           // hit columns: unchecked shared memory (callers stay inside [lo, hi)); exons: checked
+	SweepCols c;
+	int32_t lo; uint32_t elo, ehi;
+	const int32_t *s_ctg, *s_cs, *s_ce, *s_pmax, *s_gidp, *s_cds;
+	const uint32_t *s_bits, *s_eoff;
+	const uint64_t *s_key;
+	const int2 *s_ex;
+	__device__ __forceinline__ int32_t ctg(int32_t p) const { return s_ctg[p - lo]; }
+	__device__ __forceinline__ int32_t cs(int32_t p) const { return s_cs[p - lo]; }
+	__device__ __forceinline__ int32_t ce(int32_t p) const { return s_ce[p - lo]; }
+	__device__ __forceinline__ int32_t pmax(int32_t p) const { return s_pmax[p - lo]; }
+	__device__ __forceinline__ uint32_t bits(int32_t p) const { return s_bits[p - lo]; }
+	__device__ __forceinline__ int32_t gidp(int32_t p) const { return s_gidp[p - lo]; }
+	__device__ __forceinline__ int32_t cds(int32_t p) const { return s_cds[p - lo]; }
+	__device__ __forceinline__ uint64_t key(int32_t p) const { return s_key[p - lo]; }
+	__device__ __forceinline__ uint32_t eoff(int32_t p) const { return s_eoff[p - lo]; }
+	__device__ __forceinline__ int2 exon(uint32_t k) const { return (k >= elo && k < ehi)? s_ex[k - elo] : c.ex[k]; }
+};
+
+constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (size_t)(SWQ_STG + 4) * 4 + (size_t)SWQ_EXCAP * 8 + (size_t)SWQ_TILE * (8 + 4 + 4) + (size_t)SWQ_QCAP * 4 + 64;
+
+template<int MODE> __global__ void __launch_bounds__(SWQ_TILE) k_sweep_pairs(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	unsigned char *sp = smem_raw;
+	uint64_t *s_key = (uint64_t*)sp; sp += (size_t)SWQ_STG * 8;
+	int32_t *s_ctg = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	int32_t *s_cs = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	int32_t *s_ce = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	int32_t *s_pmax = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	int32_t *s_gidp = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	int32_t *s_cds = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	uint32_t *s_bits = (uint32_t*)sp; sp += (size_t)SWQ_STG * 4;
+	uint32_t *s_eoff = (uint32_t*)sp; sp += (size_t)(SWQ_STG + 4) * 4;
+	int2 *s_ex = (int2*)sp; sp += (size_t)SWQ_EXCAP * 8;
+	unsigned long long *st_key = (unsigned long long*)sp; sp += (size_t)SWQ_TILE * 8;   // best dominator key per tile hit
+	int32_t *st_p = (int32_t*)sp; sp += (size_t)SWQ_TILE * 4;                            // its partner index
+	uint32_t *st_flag = (uint32_t*)sp; sp += (size_t)SWQ_TILE * 4;                       // bit0: lost at least once, bit1: serial path
+	uint32_t *queue = (uint32_t*)sp; sp += (size_t)SWQ_QCAP * 4;
+	uint64_t *bar = (uint64_t*)sp; sp += 8;
+	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range, [2]: queue length
+
+	const int32_t t0 = blockIdx.x * SWQ_TILE, tid = threadIdx.x;
+	int32_t lo = t0 - SWQ_HALO; if (lo < 0) lo = 0;
+	lo &= ~3;
+	int32_t hi = t0 + SWQ_TILE + SWQ_HALO; if (hi > c.n) hi = c.n;
+	const int32_t cnt4 = (hi - lo + 3) & ~3, cnte = (hi - lo + 1 + 3) & ~3;
+	if (tid == 0) {
+		mbar_init(bar, 1);
+		fence_mbar_init();
+		uint32_t e0 = c.eoff[lo] & ~1u, e1 = c.eoff[hi];
+		uint32_t ne = (e1 - e0 + 1) & ~1u;
+		if (ne > SWQ_EXCAP) ne = SWQ_EXCAP;
+		s_misc[0] = e0; s_misc[1] = e0 + ne; s_misc[2] = 0;
+		fence_proxy_async();
+		mbar_expect_tx(bar, (uint32_t)cnt4 * 4u * 7u + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
+		bulk_g2s(s_ctg, c.ctg + lo, cnt4 * 4, bar); bulk_g2s(s_cs, c.cs + lo, cnt4 * 4, bar); bulk_g2s(s_ce, c.ce + lo, cnt4 * 4, bar);
+		bulk_g2s(s_pmax, c.pmax + lo, cnt4 * 4, bar); bulk_g2s(s_gidp, c.gidp + lo, cnt4 * 4, bar); bulk_g2s(s_cds, c.cds + lo, cnt4 * 4, bar);
+		bulk_g2s(s_bits, c.bits + lo, cnt4 * 4, bar); bulk_g2s(s_key, c.key + lo, cnt4 * 8, bar);
+		bulk_g2s(s_eoff, c.eoff + lo, cnte * 4, bar);
+		bulk_g2s(s_ex, c.ex + e0, ne * 8, bar);
+	}
+	st_key[tid] = 0; st_p[tid] = INT32_MAX; st_flag[tid] = 0;
+	__syncthreads();
+	while (!mbar_try_wait(bar, 0)) { }
+
+	AccStaged A;
+	A.c = c; A.lo = lo; A.elo = s_misc[0]; A.ehi = s_misc[1];
+	A.s_ctg = s_ctg; A.s_cs = s_cs; A.s_ce = s_ce; A.s_pmax = s_pmax; A.s_gidp = s_gidp; A.s_cds = s_cds; A.s_bits = s_bits; A.s_eoff = s_eoff; A.s_key = s_key; A.s_ex = s_ex;
+
+	const int32_t i = t0 + tid;
+	const bool live = i < c.n && !(s_bits[i < c.n? i - lo : 0] & PG_HB_FLT);
+	// ---- phase 1: candidate pairs.  The strongest candidate (largest key, then smallest index -- the would-be dominator)
+	// stays with the thread; the others go to the queue and are almost always pruned after phase 2a.
+	int32_t top_p = -1; uint64_t top_key = 0;
+	if (live) {
+		const int32_t mctg = A.ctg(i), mcs = A.cs(i), mce = A.ce(i), mgidp = A.gidp(i);
+		const uint32_t mbits = A.bits(i), mw = mbits & PG_HB_WBR_MASK;
+		const uint64_t mkey = A.key(i);
+		int32_t mrank = INT32_MIN;
+		bool slow = false;
+#pragma unroll 1
+		for (int side = 0; side < 2 && !slow; ++side) {
+#pragma unroll 1
+			for (int32_t p = side == 0? i - 1 : i + 1;; p += side == 0? -1 : 1) {
+				if (p < lo) { if (p >= 0) slow = true; break; }
+				if (p >= hi) { if (p < c.n) slow = true; break; }
+				if (A.ctg(p) != mctg) break;
+				if (side == 0) { if (A.pmax(p) <= mcs) break; if (A.ce(p) <= mcs) continue; }
+				else if (A.cs(p) >= mce) break;
+				const uint32_t pbits = A.bits(p);
+				if (pbits & PG_HB_FLT) continue;
+				const int32_t pgidp = A.gidp(p);
+				const bool same_gene = (pgidp >> 1) == (mgidp >> 1);
+				if (MODE == SW_ISO && !same_gene) continue;
+				if (o.check_strand && ((pbits ^ mbits) & PG_HB_REV)) continue;
+				const uint64_t pkey = A.key(p);
+				const uint32_t pw = pbits & PG_HB_WBR_MASK;
+				bool me_loses;
+				if (MODE == SW_ISO || same_gene || mw == pw) {
+					if (mkey != pkey) me_loses = mkey < pkey;
+					else {
+						if (mrank == INT32_MIN) mrank = c.rank[i];
+						int32_t prank = c.rank[p];
+						me_loses = side == 0? (mrank > prank) : !(prank > mrank);
+					}
+				} else me_loses = mw > pw;
+				if (!me_loses) continue;
+				int32_t q = p;
+				if (top_p < 0) { top_p = p; top_key = pkey; continue; }
+				if (pkey > top_key || (pkey == top_key && p < top_p)) { q = top_p; top_p = p; top_key = pkey; }   // the displaced one is queued
+				uint32_t slot = atomicAdd(&s_misc[2], 1u);
+				if (slot >= SWQ_QCAP) { slow = true; break; }
+				queue[slot] = (uint32_t)tid << 16 | (uint32_t)(q - lo);
+			}
+		}
+		if (slow) st_flag[tid] = 2;
+		else if (top_p >= 0) {
+			// ---- phase 2a: one walk per hit, against its strongest candidate
+			const int32_t need = related_threshold(MODE == SW_ISO || (A.gidp(top_p) >> 1) == (mgidp >> 1), A.cds(i), A.cds(top_p), o.min_ov_ratio);
+			const bool rel = top_p < i? cds_related(A, A.eoff(top_p), A.eoff(top_p + 1), A.cs(top_p), A.ce(top_p), A.eoff(i), A.eoff(i + 1), mcs, mce, need)
+			                          : cds_related(A, A.eoff(i), A.eoff(i + 1), mcs, mce, A.eoff(top_p), A.eoff(top_p + 1), A.cs(top_p), A.ce(top_p), need);
+			if (rel) { st_flag[tid] = 1; st_key[tid] = top_key; st_p[tid] = top_p; }
+		}
+	}
+	__syncthreads();
+	const uint32_t qn = s_misc[2] < SWQ_QCAP? s_misc[2] : SWQ_QCAP;
+	// ---- phase 2b: the queued (weaker) candidates; all of a hit's are skipped once its strongest candidate held
+#pragma unroll 1
+	for (uint32_t k = tid; k < qn; k += SWQ_TILE) {
+		const uint32_t ent = queue[k], il = ent >> 16, pl = ent & 0xffffu;
+		const uint32_t fl = ((volatile uint32_t*)st_flag)[il];
+		if (fl & 2) continue;
+		const uint64_t pkey = s_key[pl];
+		const int32_t ii = t0 + (int32_t)il, p = lo + (int32_t)pl;
+		if (MODE == SW_ISO) { if (fl & 1) continue; }
+		else if (fl & 1) {   // cannot become the dominator: weaker key, or same key with a larger index
+			const unsigned long long bk = ((volatile unsigned long long*)st_key)[il];
+			const int32_t bp = ((volatile int32_t*)st_p)[il];
+			if (pkey < bk || (pkey == bk && p > bp)) {
+				if (MODE == SW_LOAD && pkey == bk && bp != INT32_MAX && bp >= lo && bp < hi && s_cs[pl] == s_cs[bp - lo]) atomicAdd(tie_cnt, 1u);   // tie detector (conservative)
+				continue;
+			}
+		}
+		const int32_t need = related_threshold(MODE == SW_ISO || (A.gidp(ii) >> 1) == (A.gidp(p) >> 1), A.cds(ii), A.cds(p), o.min_ov_ratio);
+		const bool rel = p < ii? cds_related(A, A.eoff(p), A.eoff(p + 1), A.cs(p), A.ce(p), A.eoff(ii), A.eoff(ii + 1), A.cs(ii), A.ce(ii), need)
+		                       : cds_related(A, A.eoff(ii), A.eoff(ii + 1), A.cs(ii), A.ce(ii), A.eoff(p), A.eoff(p + 1), A.cs(p), A.ce(p), need);
+		if (!rel) continue;
+		atomicOr(&st_flag[il], 1u);
+		if (MODE != SW_ISO) { atomicMax(&st_key[il], (unsigned long long)pkey); queue[k] = ent | 0x80000000u; }
+	}
+	__syncthreads();
+	// ---- phase 3: smallest partner index among the related pairs that carry the winning key (overlap.c:150,153)
+	if (MODE != SW_ISO) {
+		// (a hit's own strongest candidate has the largest key of all its candidates, so if it held, st_key/st_p already name
+		// it and no queued pair can have raised st_key above it; otherwise st_p is still INT32_MAX here)
+#pragma unroll 1
+		for (uint32_t k = tid; k < qn; k += SWQ_TILE) {
+			const uint32_t ent = queue[k];
+			if (!(ent & 0x80000000u)) continue;
+			const uint32_t il = (ent >> 16) & 0x7fffu, pl = ent & 0xffffu;
+			const unsigned long long bk = st_key[il];
+			if (bk > 0 && s_key[pl] == bk) atomicMin(&st_p[il], lo + (int32_t)pl);
+		}
+		__syncthreads();
+		if (MODE == SW_LOAD) {   // tie detector: a second related partner with the winning key and the same start
+#pragma unroll 1
+			for (uint32_t k = tid; k < qn; k += SWQ_TILE) {
+				const uint32_t ent = queue[k];
+				if (!(ent & 0x80000000u)) continue;
+				const uint32_t il = (ent >> 16) & 0x7fffu, pl = ent & 0xffffu;
+				const int32_t bp = st_p[il];
+				if (st_key[il] > 0 && s_key[pl] == st_key[il] && lo + (int32_t)pl != bp && s_cs[pl] == s_cs[bp - lo]) atomicAdd(tie_cnt, 1u);
+			}
+		}
+	}
+	// ---- phase 4: outputs
+	if (i >= c.n) return;
+	const uint32_t mbits = s_bits[i - lo];
+	if (mbits & PG_HB_FLT) { bits_out[i] = mbits; return; }
+	const uint32_t fl = st_flag[tid];
+	if (fl & 2) {   // window left the staged range (or the queue was full): serial path, shared memory where possible
+		AccTile T;
+		T.c = c; T.lo = lo; T.hi = hi; T.elo = A.elo; T.ehi = A.ehi;
+		T.s_ctg = s_ctg; T.s_cs = s_cs; T.s_ce = s_ce; T.s_pmax = s_pmax; T.s_gidp = s_gidp; T.s_rank = nullptr; T.s_cds = s_cds; T.s_bits = s_bits; T.s_eoff = s_eoff; T.s_key = s_key; T.s_ex = s_ex;
+		sweep_hit<MODE>(T, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
+		return;
+	}
+	const bool lose = fl & 1;
+	const unsigned long long best_key = st_key[tid];
+	const int32_t best_p = st_p[tid];
+	if (MODE == SW_ISO) {
+		bits_out[i] = lose? (mbits | PG_HB_FLT_OV | PG_HB_FLT) : mbits;
+	} else if (MODE == SW_SHADOW) {
+		uint32_t b = mbits;
+		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;
+		if (lose) b |= PG_HB_SHADOW;
+		bits_out[i] = b;
+		pdom_out[i] = best_key > 0? c.pid[best_p] : -1;
+	} else {
+		bits_out[i] = mbits;
+		int32_t pd = -1, sd = -1;
+		if (best_key > 0) {
+			pd = c.pid[best_p];
+			const int32_t ov = best_p < i? cds_overlap(A, A.eoff(best_p), A.eoff(best_p + 1), A.cs(best_p), A.ce(best_p), A.eoff(i), A.eoff(i + 1), A.cs(i), A.ce(i))
+			                             : cds_overlap(A, A.eoff(i), A.eoff(i + 1), A.cs(i), A.ce(i), A.eoff(best_p), A.eoff(best_p + 1), A.cs(best_p), A.ce(best_p));
+			sd = (int32_t)(c.sori[i] * (1.0 - (double)ov / A.cds(i)) + c.sori[best_p] * ((double)ov / A.cds(best_p)) + .499);   // overlap.c:170
+		}
+		pdom_out[i] = pd; sdom_out[i] = sd;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -935,28 +1174,19 @@ __global__ void k_branch_hits(const uint32_t *__restrict__ sv, int32_t m, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// materialisation: pg_hit_t records in (contig, cs) order with every field final
+// the way back: only what changed.  The host rebuilds pg_hit_t records in (contig, cs) order from its own copy.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_materialize(const int32_t *__restrict__ aos, const uint32_t *__restrict__ src, int32_t n, FullCols c, const int32_t *__restrict__ g2s, const int32_t *__restrict__ prot_rep,
-	int32_t have_graph, int32_t *out)
+__global__ void k_pack_out(const uint32_t *__restrict__ src, int32_t n, FullCols c, const int32_t *__restrict__ g2s, const int32_t *__restrict__ prot_rep, int32_t have_graph, OutHit *out)
 {
-	// 22 consecutive threads cooperate on one record so that both the gather and the store are word-coalesced
-	int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t i = gt / AOS_WORDS; int w = (int)(gt % AOS_WORDS);
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	int32_t x = aos[(size_t)src[i] * AOS_WORDS + w];
-	if (w == W_RANK) x = c.rank[i];
-	else if (w == W_SDOM) x = c.sdom[i];
-	else if (w == W_PDOM) x = c.pdom[i];
-	else if (w == W_PDOM0) x = c.pdom0[i];
-	else if (w == W_BITS) {
-		uint32_t b = c.bits[i] & HB_ABI_MASK & ~(PG_HB_VTX | PG_HB_REP);
-		int32_t pid = c.pid[i];
-		if (prot_rep[pid]) b |= PG_HB_REP;                                              // hit.c:219-224
-		if (have_graph && g2s[c.gidp[i] >> 1] >= 0) b |= PG_HB_VTX;                     // graph.c:61-69 (last call)
-		x = (int32_t)b;
-	}
-	out[(size_t)i * AOS_WORDS + w] = x;
+	OutHit o;
+	o.src = src[i]; o.rank = c.rank[i]; o.sdom = c.sdom[i]; o.pdom = c.pdom[i]; o.pdom0 = c.pdom0[i];
+	uint32_t b = c.bits[i] & HB_ABI_MASK & ~(PG_HB_VTX | PG_HB_REP);
+	if (prot_rep[c.pid[i]]) b |= PG_HB_REP;                                             // hit.c:219-224
+	if (have_graph && g2s[c.gidp[i] >> 1] >= 0) b |= PG_HB_VTX;                         // graph.c:61-69 (last call)
+	o.bits = b;
+	out[i] = o;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -71,9 +71,40 @@ __global__ void k_scan_sum_add(uint32_t *out, const uint32_t *__restrict__ agg, 
 // scratch must hold ceil((n_in+1)/SCAN_TILE) uint32
 static inline size_t scan_scratch_elems(int64_t n_in) { return (size_t)((n_in + 1 + SCAN_TILE - 1) / SCAN_TILE); }
 
+// whole scan in ONE block (n_in up to a few hundred thousand): the many small per-round scans (segments, vertices, arc
+// groups) are launch-latency bound, three launches each hurt more than the serial chunk loop
+constexpr int SCAN_SMALL_B = 1024, SCAN_SMALL_MAX = 1 << 16;
+__global__ void __launch_bounds__(SCAN_SMALL_B) k_scan_sum_small(const uint32_t *__restrict__ in, uint32_t *out, int32_t n_in)
+{
+	__shared__ uint32_t wsum[32];
+	__shared__ uint32_t carry;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid == 0) carry = 0;
+	__syncthreads();
+	for (int32_t c0 = 0; c0 <= n_in; c0 += SCAN_SMALL_B) {
+		int32_t i = c0 + tid;
+		uint32_t x = i < n_in? in[i] : 0u, v = x;
+		for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+		if (lane == 31) wsum[warp] = v;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t w = wsum[lane], ws = w;
+			for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, ws, d); if (lane >= d) ws += t; }
+			wsum[lane] = ws - w;                       // exclusive prefix of the warp totals
+		}
+		__syncthreads();
+		uint32_t base = carry + wsum[warp];
+		if (i <= n_in) out[i] = base + v - x;
+		__syncthreads();
+		if (tid == SCAN_SMALL_B - 1) carry = base + v;
+		__syncthreads();
+	}
+}
+
 static void exclusive_sum_u32(const uint32_t *in, uint32_t *out, int64_t n_in, uint32_t *agg_scratch, cudaStream_t s)
 {
 	int64_t n_out = n_in + 1;
+	if (n_in <= SCAN_SMALL_MAX) { PGX_LAUNCH(k_scan_sum_small, 1, SCAN_SMALL_B, 0, s, in, out, (int32_t)n_in); return; }
 	int tiles = (int)((n_out + SCAN_TILE - 1) / SCAN_TILE);
 	PGX_LAUNCH(k_scan_sum_tiles, tiles, SCAN_B, 0, s, in, out, agg_scratch, n_in);
 	if (tiles > 1) {

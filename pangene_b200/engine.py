@@ -45,6 +45,7 @@ def lib():
         L.pgx_download.argtypes = [C.c_void_p, P(abi.pg_data_t), P(abi.pg_graph_t)]
         L.pgx_session_free.argtypes = [C.c_void_p]
         L.pgx_get_stats.argtypes = [P(pgx_stats_t)]
+        L.pgx_trim.restype = None
         L.pgx_test_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
         L.pgx_test_exclusive_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.pgx_test_segmented_max.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
