@@ -9,6 +9,9 @@
 #include <vector>
 #include <cstring>
 #include <cmath>
+#include <cstddef>
+#include <time.h>
+#include <sys/mman.h>
 #include "pgx.h"
 #include "pgx_util.cuh"
 #include "pgx_scan.cuh"
@@ -31,6 +34,21 @@ extern Stats g_stats;
 
 constexpr int TB = 256;   // default block size for the streaming kernels
 
+// fresh hit arrays for the caller (it will free() them): 2 MB-aligned and advised huge so that the ~430 k first-touch page
+// faults of a 1.8 GB result become ~900 where transparent huge pages are available (no effect otherwise)
+static inline pg_hit_t *alloc_hit_array(size_t n)
+{
+	const size_t bytes = sizeof(pg_hit_t) * (n > 0? n : 1), HP = (size_t)2 << 20;
+	if (bytes >= 4 * HP) {
+		void *p = nullptr;
+		const size_t sz = (bytes + HP - 1) / HP * HP;
+		if (posix_memalign(&p, HP, sz) == 0) { madvise(p, sz, MADV_HUGEPAGE); return (pg_hit_t*)p; }
+	}
+	return (pg_hit_t*)malloc(bytes);
+}
+
+static inline double wall_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
+
 struct Session {
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -41,6 +59,7 @@ struct Session {
 	std::vector<uint32_t> h_eoffg;
 	std::vector<uint8_t> h_gene_pref, h_gene_incl;
 	const pg_gene_t *h_gene_names = nullptr;
+	int32_t coord_bits = 32;             // bits needed for the largest cs/cm of this upload (fewer radix passes)
 	std::vector<int32_t> rank_G;         // local genome count of every rank (multi-GPU)
 	// ---- host-side results that go back into pg_data_t at download time
 	RepResult rep;
@@ -67,10 +86,12 @@ struct Session {
 	ActCols A;
 	int32_t m_sv = 0;
 	// ---- graph
-	int32_t n_seg = 0, n_arc = 0;
+	int32_t n_seg = 0, n_arc = 0, n_seg0 = 0;   // host copies; during the rounds the live values are in `dc`
+	size_t arc_cap = 0;
+	DBuf<DevCounts> dc;
 	DBuf<SegDev> seg, seg_alt;
 	DBuf<ArcDev> arc, arc_alt;
-	DBuf<int32_t> seg_ng, seg_tot;
+	DBuf<int32_t> seg_ng, seg_tot, arc_of_rec;
 	Arena scratch;
 	uint32_t *h_pin = nullptr;           // pinned word(s) for small read-backs
 	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_N = 8 };
@@ -158,6 +179,7 @@ struct Session {
 	{
 		ThreadPool &pool = ThreadPool::get();
 		std::atomic<uint32_t> bad{0};
+		std::atomic<int64_t> max_coord{0};
 		const int64_t BLK = 1 << 14;
 		if (N) staged_h2d(raw.p, (size_t)N * sizeof(RawHit), sizeof(RawHit), [&](size_t off, size_t len, char *dst) {
 			const int64_t h0 = (int64_t)(off / sizeof(RawHit)), h1 = h0 + (int64_t)(len / sizeof(RawHit));
@@ -166,17 +188,22 @@ struct Session {
 				int g = (int)(std::upper_bound(h_hoff.begin(), h_hoff.end(), (int32_t)a) - h_hoff.begin()) - 1;
 				RawHit *o = (RawHit*)dst + (a - h0);
 				uint32_t err = 0;
+				int64_t mc = 0;
 				for (int64_t t = a; t < e; ++t, ++o) {
 					while (t >= h_hoff[g + 1]) ++g;
 					const pg_hit_t &h = d->genome[g].hit[t - h_hoff[g]];
 					if (h.cs < 0 || h.ce > 0x7fffffffll || h.cm < 0 || h.cm > 0x7fffffffll || h.cs > h.ce) err = 1;
 					o->pid = h.pid; o->cid = h.cid; o->rank = h.rank; o->sori = h.score_ori; o->sadj = h.score_adj; o->nexon = h.n_exon; o->offexon = h.off_exon;
 					o->rev = h.rev; o->cs = (int32_t)h.cs; o->cm = (int32_t)h.cm; o->ce = (int32_t)h.ce; o->pad = 0;
+					if (h.cm > mc) mc = h.cm;
+					if (h.cs > mc) mc = h.cs;
 				}
 				if (err) bad.store(1);
+				for (int64_t cur = max_coord.load(); mc > cur && !max_coord.compare_exchange_weak(cur, mc);) { }
 			});
 		}, st);
 		if (bad.load()) PGX_FATAL("upload: a hit coordinate is outside [0, 2^31) or cs > ce -- this build keeps coordinates in int32");
+		coord_bits = bits_for((uint64_t)max_coord.load());
 		if (E) staged_h2d(ex_raw.p, (size_t)E * 8, 8, [&](size_t off, size_t len, char *dst) {
 			const int64_t e0 = (int64_t)(off / 8), e1 = e0 + (int64_t)(len / 8), EB = 1 << 17;
 			pool.parallel_for((e1 - e0 + EB - 1) / EB, [&](int64_t b) {
@@ -215,18 +242,22 @@ struct Session {
 	// one sweep launch; PGX_SWEEP=global selects the plain variant (debug / A-B timing), default is the TMA-tiled one
 	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out)
 	{
-		// PGX_SWEEP=global | tile | pairs (default): plain, TMA-staged thread-per-hit, TMA-staged pair-parallel
+		// PGX_SWEEP=global | tile | top (default): plain, TMA-staged thread-per-hit, TMA-staged strongest-candidate-first
 		static const int variant = []() { const char *e = getenv("PGX_SWEEP"); return (e && strcmp(e, "global") == 0)? 0 : (e && strcmp(e, "tile") == 0)? 1 : 2; }();
 		if (c.n <= 0) return;
 		if (variant == 2) {
 			static bool attr_set = false;
 			if (!attr_set) {
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_pairs<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_pairs<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_pairs<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				// five 36 KB CTAs per SM need the large shared-memory carve-out (ncu: the default left room for three)
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_LOAD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 				attr_set = true;
 			}
-			PGX_LAUNCH(k_sweep_pairs<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
+			PGX_LAUNCH(k_sweep_top<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 		} else if (variant == 1) PGX_LAUNCH(k_sweep_tile<MODE>, grid_for(c.n, SWT_TILE), SWT_TILE, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 		else PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 	}
@@ -280,7 +311,8 @@ struct Session {
 		// -- the one physical sort: (genome:contig, cs), stable => ties keep file order
 		{
 			size_t m2 = scratch.mark();
-			uint32_t *perm = sort_perm(key, N, 32 + bits_for((uint64_t)(n_ctg > 0? n_ctg - 1 : 0)));
+			PGX_LAUNCH(k_pack_sort_key, grid_for(N, TB), TB, 0, st, key, N, coord_bits);
+			uint32_t *perm = sort_perm(key, N, coord_bits + bits_for((uint64_t)(n_ctg > 0? n_ctg - 1 : 0)));
 			PGX_CHECK(cudaMemcpyAsync(src.p, perm, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
 			scratch.reset(m2);
 		}
@@ -392,7 +424,8 @@ struct Session {
 			// (contig, cm) order as a permutation; ties keep (contig, cs) order
 			uint64_t *key = scratch.get<uint64_t>((size_t)Nw + 1);
 			PGX_LAUNCH(k_make_cm_keys, grid_for(Nw, TB), TB, 0, st, A.ctg, A.cm, Nw, key);
-			uint32_t *perm = sort_perm(key, Nw, 32 + bits_for((uint64_t)(n_ctg > 0? n_ctg - 1 : 0)));
+			PGX_LAUNCH(k_pack_sort_key, grid_for(Nw, TB), TB, 0, st, key, Nw, coord_bits);
+			uint32_t *perm = sort_perm(key, Nw, coord_bits + bits_for((uint64_t)(n_ctg > 0? n_ctg - 1 : 0)));
 			PGX_CHECK(cudaMemcpyAsync(by_cm.p, perm, (size_t)Nw * 4, cudaMemcpyDeviceToDevice, st));
 		}
 		scratch.reset(mk);
@@ -406,7 +439,23 @@ struct Session {
 	void regen_g2s()
 	{
 		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
-		if (n_seg) PGX_LAUNCH(k_g2s_fill, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, g2s.p);
+		if (n_seg0) PGX_LAUNCH(k_g2s_fill, GS_GRID, TB, 0, st, seg.p, dc.p, g2s.p);
+	}
+	uint32_t *dcp(size_t field_off) { return (uint32_t*)((char*)dc.p + field_off); }
+	static constexpr int GS_GRID = 148 * 8;      // grid-stride kernels: 8 CTAs of 256 threads per SM
+	// exclusive scan of n flags into pos[n+1]; the total goes to a DevCounts field, not to the host
+	void scan_to_count(const uint32_t *flag, uint32_t *pos, int64_t n, size_t field_off)
+	{
+		uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(n));
+		exclusive_sum_u32(flag, pos, n, agg, st);
+		PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(field_off), pos + n);
+	}
+	DevCounts read_counts()
+	{
+		DevCounts h;
+		PGX_CHECK(cudaMemcpyAsync(&h, dc.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		return h;
 	}
 
 	void gen_vtx(const pg_opt_t *opt)   // vertex.c:6-100
@@ -422,23 +471,43 @@ struct Session {
 		int32_t *aux = aux_all + tab_max * g_comm.rank;
 		PGX_CHECK(cudaMemsetAsync(t_dom, 0, tab + 1, st));
 		PGX_LAUNCH(k_fill_i32, grid_for((int64_t)tab + 1, TB), TB, 0, st, t_first, (int64_t)tab + 1, INT32_MAX);
-		if (Nw) PGX_LAUNCH(k_vtx_mark, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, A.rank, A.bits, Nw, n_gene, t_dom, t_first);
+		if (Nw) PGX_LAUNCH(k_vtx_mark, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, A.rank, A.bits, Nw, G, t_dom, t_first);
 		if (tab) PGX_LAUNCH(k_vtx_resolve, grid_for((int64_t)tab, TB), TB, 0, st, t_dom, t_first, A.pdom, prot_gid.p, tab, aux, counters.p + C_ERR);
 		g_comm.allgather(aux, aux_all, tab_max * 4, st);
-		std::vector<int32_t> h_all(tab_max * g_comm.nranks + 1), h_aux((size_t)Gtot * n_gene + 1);
-		PGX_CHECK(cudaMemcpyAsync(h_all.data(), aux_all, tab_max * g_comm.nranks * 4, cudaMemcpyDeviceToHost, st));
+		double tv0 = wall_s();
+		// the table comes back through a pinned staging buffer when it fits (8 MB at 100 genomes x 20k genes)
+		const size_t all_bytes = tab_max * g_comm.nranks * 4;
+		std::vector<int32_t> h_all_v, h_aux_v;
+		const int32_t *h_all;
+		if (all_bytes <= PinnedRing::CAP) { h_all = (const int32_t*)PinnedRing::get().buf[0]; PGX_CHECK(cudaMemcpyAsync(PinnedRing::get().buf[0], aux_all, all_bytes, cudaMemcpyDeviceToHost, st)); }
+		else { h_all_v.resize(tab_max * g_comm.nranks + 1); h_all = h_all_v.data(); PGX_CHECK(cudaMemcpyAsync(h_all_v.data(), aux_all, all_bytes, cudaMemcpyDeviceToHost, st)); }
 		check_err("vertex selection");
-		{   // stitch the per-rank blocks into genome order (ranks hold consecutive genome ranges)
-			size_t o = 0;
-			for (int r = 0; r < g_comm.nranks; ++r) { size_t nr = (size_t)rank_G[r] * n_gene; memcpy(h_aux.data() + o, h_all.data() + tab_max * r, nr * 4); o += nr; }
-			if (o != (size_t)Gtot * n_gene) PGX_FATAL("genome partition inconsistent: %zu rows gathered, %d genomes expected", o / (n_gene? n_gene : 1), Gtot);
+		double tv1 = wall_s();
+		const int32_t *h_aux = h_all;
+		if (g_comm.nranks > 1) {   // stitch the per-rank [gene][local genome] blocks into [gene][genome] (ranks hold consecutive genome ranges)
+			h_aux_v.resize((size_t)Gtot * n_gene + 1);
+			int32_t jb = 0;
+			for (int r = 0; r < g_comm.nranks; ++r) {
+				const int32_t Gr = rank_G[r];
+				const int32_t *blk = h_all + tab_max * r;
+				for (int32_t g = 0; g < n_gene; ++g) memcpy(h_aux_v.data() + (size_t)g * Gtot + jb, blk + (size_t)g * Gr, (size_t)Gr * 4);
+				jb += Gr;
+			}
+			if (jb != Gtot) PGX_FATAL("genome partition inconsistent: %d genomes gathered, %d expected", jb, Gtot);
+			h_aux = h_aux_v.data();
 		}
-		elect_vertices(h_aux.data(), Gtot, n_gene, rep.gene_rep_pid.data(), rep.prot_avg.data(), h_gene_pref.data(), h_gene_incl.data(), opt->min_vertex_ratio,
+		elect_vertices(h_aux, Gtot, n_gene, rep.gene_rep_pid.data(), rep.prot_avg.data(), h_gene_pref.data(), h_gene_incl.data(), opt->min_vertex_ratio,
 			!!(opt->flag & PG_F_WRITE_VTX_SEL), h_gene_names, h_seg0);
-		n_seg = (int32_t)h_seg0.size();
+		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] gen_vtx: table D2H %.2f ms, host election %.2f ms\n", (tv1 - tv0) * 1e3, (wall_s() - tv1) * 1e3);
+		n_seg = n_seg0 = (int32_t)h_seg0.size();
 		std::vector<SegDev> hs(n_seg > 0? n_seg : 1);
 		for (int32_t i = 0; i < n_seg; ++i) { memset(&hs[i], 0, sizeof(SegDev)); hs[i].gid = h_seg0[i].gid; hs[i].n_dom = h_seg0[i].n_dom; hs[i].n_sub = h_seg0[i].n_sub; }
 		seg.alloc(hs.size()); seg_alt.alloc(hs.size()); seg_ng.alloc(hs.size()); seg_tot.alloc(hs.size()); idx.alloc(hs.size() * 2);
+		arc_cap = 2 * (size_t)(Nw > 0? Nw : 1);
+		arc.alloc(arc_cap + 1); arc_alt.alloc(arc_cap + 1);
+		dc.alloc(1);
+		DevCounts h0; memset(&h0, 0, sizeof(h0)); h0.n_seg = (uint32_t)n_seg0;
+		PGX_CHECK(cudaMemcpyAsync(dc.p, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
 		PGX_CHECK(cudaMemcpyAsync(seg.p, hs.data(), hs.size() * sizeof(SegDev), cudaMemcpyHostToDevice, st));
 		PGX_CHECK(cudaStreamSynchronize(st));
 		regen_g2s();
@@ -446,65 +515,73 @@ struct Session {
 		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::gen_vtx] selected %d vertices out of %d genes\n", n_seg, n_gene);
 	}
 
-	void gen_arc(const pg_opt_t *opt)   // graph.c:87-177
+	// graph.c:87-177.  No host round-trip in the single-GPU path: survivor count, group count and arc count stay on the device.
+	void gen_arc(const pg_opt_t *opt)
 	{
+		if (Nw == 0 || n_seg0 == 0) {   // nothing can survive: empty arc set, zero occupancy
+			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u);
+			if (n_seg0) {
+				PGX_CHECK(cudaMemsetAsync(seg_ng.p, 0, (size_t)n_seg0 * 4, st));
+				PGX_CHECK(cudaMemsetAsync(seg_tot.p, 0, (size_t)n_seg0 * 4, st));
+				PGX_LAUNCH(k_seg_store_occ, GS_GRID, TB, 0, st, seg.p, dc.p, seg_ng.p, seg_tot.p);
+			}
+			return;
+		}
 		size_t mk = scratch.mark();
 		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
-		n_arc = 0; m_sv = 0;
-		PGX_CHECK(cudaMemsetAsync(seg_ng.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 4, st));
-		PGX_CHECK(cudaMemsetAsync(seg_tot.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 4, st));
-		ArcPartial *part = nullptr; uint32_t n_part = 0;
-		if (Nw) {
-			launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits_alt, A.pdom, nullptr);
-			a_bits.swap(a_bits_alt); set_active();
+		PGX_CHECK(cudaMemsetAsync(seg_ng.p, 0, (size_t)n_seg0 * 4, st));
+		PGX_CHECK(cudaMemsetAsync(seg_tot.p, 0, (size_t)n_seg0 * 4, st));
+		launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits_alt, A.pdom, nullptr);
+		a_bits.swap(a_bits_alt); set_active();
+		{
 			uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *pos = scratch.get<uint32_t>((size_t)Nw + 2);
 			PGX_LAUNCH(k_flag_survivor_cm, grid_for(Nw, TB), TB, 0, st, A.bits, by_cm.p, Nw, flag);
-			m_sv = (int32_t)scan_flags(flag, pos, Nw);
-			if (m_sv) PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, Nw, sv.p);
+			scan_to_count(flag, pos, Nw, offsetof(DevCounts, m_sv));
+			PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, Nw, sv.p);
+			m_sv = (int32_t)read_u32(pos + Nw);      // one read-back per arc round: it sizes the record sort (survivors are ~half of the active set)
 		}
-		if (m_sv) {
-			size_t nr = 2 * (size_t)m_sv, bm = ((size_t)G * n_seg + 31) / 32 + 1;
-			uint64_t *key = scratch.get<uint64_t>(nr + 1);
-			int32_t *dist = scratch.get<int32_t>(nr), *s1 = scratch.get<int32_t>(nr), *s2 = scratch.get<int32_t>(nr);
-			uint32_t *seen = scratch.get<uint32_t>(bm);
-			PGX_CHECK(cudaMemsetAsync(seen, 0, bm * 4, st));
-			ArcEmit e; e.sv = sv.p; e.m = m_sv; e.ctg = A.ctg; e.cm = A.cm; e.gidp = A.gidp; e.sori = A.sori; e.sdom = A.sdom; e.pdom0 = A.pdom0; e.bits = A.bits;
-			e.g2s = g2s.p; e.prot_gid = prot_gid.p; e.ctg2g = ctg2g.p; e.use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH); e.n_seg = n_seg; e.gbits = bits_for((uint64_t)(G > 1? G - 1 : 1));
-			PGX_LAUNCH(k_arc_emit, grid_for(m_sv, TB), TB, 0, st, e, key, dist, s1, s2, seen, seg_ng.p, seg_tot.p, counters.p + C_TIE_CM, counters.p + C_ERR);
-			uint64_t nv = 2ull * n_seg, maxkey = ((nv * nv - 1) << e.gbits) | ((1ull << e.gbits) - 1);
-			uint32_t *rec = sort_perm(key, (int64_t)nr, bits_for(maxkey) + 1);      // +1: the all-ones "no arc" key sorts strictly last
-			uint32_t *flag = scratch.get<uint32_t>(nr + 1), *pos = scratch.get<uint32_t>(nr + 2);
-			PGX_LAUNCH(k_arc_heads, grid_for((int64_t)nr, TB), TB, 0, st, key, (int32_t)nr, e.gbits, flag);
-			n_part = scan_flags(flag, pos, (int64_t)nr);
-			part = scratch.get<ArcPartial>((size_t)n_part + 1);
-			if (n_part) {
-				uint32_t *start = scratch.get<uint32_t>((size_t)n_part + 1);
-				PGX_LAUNCH(k_compact_idx, grid_for((int64_t)nr, TB), TB, 0, st, pos, (const uint32_t*)nullptr, (int32_t)nr, start);
-				PGX_LAUNCH(k_arc_reduce, grid_for((int64_t)n_part * 32, TB), TB, 0, st, key, rec, dist, s1, s2, (int32_t)nr, e.gbits, n_seg, start, (int32_t)n_part, part);
-			}
+		if (m_sv == 0) {
+			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u);
+			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_part)), 0u);
+			if (g_comm.active()) merge_partials_across_ranks(nullptr);
+			g_comm.allreduce(seg_ng.p, n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
+			g_comm.allreduce(seg_tot.p, n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
+			PGX_LAUNCH(k_seg_store_occ, GS_GRID, TB, 0, st, seg.p, dc.p, seg_ng.p, seg_tot.p);
+			scratch.reset(mk);
+			return;
 		}
-		if (g_comm.active()) merge_partials_across_ranks(part, n_part);
-		else finalize_arcs(part, n_part);
-		g_comm.allreduce(seg_ng.p, n_seg, Comm::T_INT32, Comm::OP_SUM, st);
-		g_comm.allreduce(seg_tot.p, n_seg, Comm::T_INT32, Comm::OP_SUM, st);
-		if (n_seg) PGX_LAUNCH(k_seg_store_occ, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, seg_ng.p, seg_tot.p);
+		const size_t nr = 2 * (size_t)m_sv, bm = ((size_t)G * n_seg0 + 31) / 32 + 1;
+		uint64_t *key = scratch.get<uint64_t>(nr + 1);
+		int32_t *gen = scratch.get<int32_t>(nr), *dist = scratch.get<int32_t>(nr), *s1 = scratch.get<int32_t>(nr), *s2 = scratch.get<int32_t>(nr);
+		uint32_t *seen = scratch.get<uint32_t>(bm);
+		PGX_CHECK(cudaMemsetAsync(seen, 0, bm * 4, st));
+		ArcEmit e; e.sv = sv.p; e.cap = m_sv; e.ctg = A.ctg; e.cm = A.cm; e.gidp = A.gidp; e.sori = A.sori; e.sdom = A.sdom; e.pdom0 = A.pdom0; e.bits = A.bits;
+		e.g2s = g2s.p; e.prot_gid = prot_gid.p; e.ctg2g = ctg2g.p; e.use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH); e.n_seg = n_seg0; e.gbits = bits_for((uint64_t)(G > 1? G - 1 : 1));
+		PGX_LAUNCH(k_arc_emit, GS_GRID, TB, 0, st, e, dc.p, key, gen, dist, s1, s2, seen, seg_ng.p, seg_tot.p, counters.p + C_TIE_CM, counters.p + C_ERR);
+		uint64_t nv = 2ull * n_seg0;
+		uint32_t *rec = sort_perm(key, (int64_t)nr, bits_for(nv * nv - 1) + 1);     // +1: the all-ones "no arc" key sorts strictly last
+		uint32_t *flag = scratch.get<uint32_t>(nr + 1), *pos = scratch.get<uint32_t>(nr + 2), *start = scratch.get<uint32_t>(nr + 1);
+		PGX_LAUNCH(k_arc_heads, grid_for((int64_t)nr, TB), TB, 0, st, key, (int32_t)nr, flag);
+		scan_to_count(flag, pos, (int64_t)nr, offsetof(DevCounts, n_part));
+		PGX_LAUNCH(k_compact_idx, grid_for((int64_t)nr, TB), TB, 0, st, pos, (const uint32_t*)nullptr, (int32_t)nr, start);
+		ArcPartial *part = scratch.get<ArcPartial>(nr + 1);
+		arc_of_rec.ensure(nr + 2);
+		PGX_LAUNCH(k_arc_reduce, GS_GRID, TB, 0, st, key, rec, gen, dist, s1, s2, (int32_t)nr, n_seg0, start, dc.p, part, arc_of_rec.p);
+		if (g_comm.active()) merge_partials_across_ranks(part);
+		else {
+			PGX_LAUNCH(k_arc_finalize_direct, GS_GRID, TB, 0, st, part, dc.p, arc.p);
+			PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), dcp(offsetof(DevCounts, n_part)));
+		}
+		g_comm.allreduce(seg_ng.p, n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
+		g_comm.allreduce(seg_tot.p, n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
+		PGX_LAUNCH(k_seg_store_occ, GS_GRID, TB, 0, st, seg.p, dc.p, seg_ng.p, seg_tot.p);
 		scratch.reset(mk);
 	}
 
-	void finalize_arcs(const ArcPartial *part, uint32_t n_part)   // input sorted by x; equal x merged (graph.c:150-175)
+	// multi-GPU: every rank contributes its partial table (padded to the largest one); sort by key, merge equal keys (graph.c:150-175)
+	void merge_partials_across_ranks(const ArcPartial *part)
 	{
-		n_arc = 0;
-		if (!n_part) return;
-		uint32_t *flag = scratch.get<uint32_t>((size_t)n_part + 1), *pos = scratch.get<uint32_t>((size_t)n_part + 2);
-		PGX_LAUNCH(k_partial_heads, grid_for(n_part, TB), TB, 0, st, part, (int32_t)n_part, flag);
-		n_arc = (int32_t)scan_flags(flag, pos, n_part);
-		arc.ensure((size_t)n_arc + 1); arc_alt.ensure((size_t)n_arc + 1);
-		PGX_LAUNCH(k_arc_finalize, grid_for(n_part, TB), TB, 0, st, part, (int32_t)n_part, pos, arc.p);
-	}
-
-	void merge_partials_across_ranks(const ArcPartial *part, uint32_t n_part)
-	{
-		// every rank contributes its partial table, padded to the largest one; then sort by key and merge equal keys
+		uint32_t n_part = read_counts().n_part;
 		uint32_t *cnt = scratch.get<uint32_t>(g_comm.nranks + 1);
 		PGX_CHECK(cudaMemcpyAsync(cnt + g_comm.rank, &n_part, 4, cudaMemcpyHostToDevice, st));
 		g_comm.allgather(cnt + g_comm.rank, cnt, 4, st);
@@ -513,7 +590,8 @@ struct Session {
 		PGX_CHECK(cudaStreamSynchronize(st));
 		uint32_t mx = 0; uint64_t tot = 0;
 		for (uint32_t c : hc) { mx = c > mx? c : mx; tot += c; }
-		if (tot == 0) { n_arc = 0; return; }
+		if (tot == 0) { PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u); return; }
+		if (tot > arc_cap) PGX_FATAL("arc table overflow (%lu partial arcs)", (unsigned long)tot);
 		ArcPartial *all = scratch.get<ArcPartial>((size_t)mx * g_comm.nranks + 1), *mine = all + (size_t)mx * g_comm.rank;
 		if (n_part) PGX_CHECK(cudaMemcpyAsync(mine, part, (size_t)n_part * sizeof(ArcPartial), cudaMemcpyDeviceToDevice, st));
 		g_comm.allgather(mine, all, (size_t)mx * sizeof(ArcPartial), st);
@@ -521,30 +599,33 @@ struct Session {
 		uint64_t o = 0;
 		for (int r = 0; r < g_comm.nranks; ++r) { if (hc[r]) PGX_CHECK(cudaMemcpyAsync(packed + o, all + (size_t)mx * r, (size_t)hc[r] * sizeof(ArcPartial), cudaMemcpyDeviceToDevice, st)); o += hc[r]; }
 		uint64_t *key = scratch.get<uint64_t>(tot + 1);
-		PGX_LAUNCH(k_partial_keys, grid_for((int64_t)tot, TB), TB, 0, st, packed, (int32_t)tot, n_seg, key);
-		uint64_t nv = 2ull * n_seg;
+		PGX_LAUNCH(k_partial_keys, grid_for((int64_t)tot, TB), TB, 0, st, packed, (int32_t)tot, n_seg0, key);
+		uint64_t nv = 2ull * n_seg0;
 		uint32_t *perm = sort_perm(key, (int64_t)tot, bits_for(nv * nv - 1));
 		PGX_LAUNCH(k_partial_gather, grid_for((int64_t)tot, TB), TB, 0, st, packed, perm, (int32_t)tot, sorted);
-		finalize_arcs(sorted, (uint32_t)tot);
+		uint32_t *flag = scratch.get<uint32_t>((size_t)tot + 1), *pos = scratch.get<uint32_t>((size_t)tot + 2);
+		PGX_LAUNCH(k_partial_heads, grid_for((int64_t)tot, TB), TB, 0, st, sorted, (int32_t)tot, flag);
+		scan_to_count(flag, pos, (int64_t)tot, offsetof(DevCounts, n_arc));
+		PGX_LAUNCH(k_arc_finalize, grid_for((int64_t)tot, TB), TB, 0, st, sorted, (int32_t)tot, pos, arc.p);
 	}
 
 	void arc_index()   // graph.c:202-217
 	{
-		PGX_CHECK(cudaMemsetAsync(idx.p, 0, (size_t)(n_seg > 0? n_seg : 1) * 16, st));
-		if (n_arc) PGX_LAUNCH(k_arc_index, grid_for(n_arc, TB), TB, 0, st, arc.p, n_arc, idx.p);
+		PGX_CHECK(cudaMemsetAsync(idx.p, 0, (size_t)(n_seg0 > 0? n_seg0 : 1) * 16, st));
+		PGX_LAUNCH(k_arc_index, GS_GRID, TB, 0, st, arc.p, dc.p, idx.p);
 	}
 
 	void flt_high_occ(int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)   // graph.c:237-263
 	{
-		if (n_seg) {
+		if (n_seg0) {
 			size_t mk = scratch.mark();
-			uint32_t *keep = scratch.get<uint32_t>((size_t)n_seg + 1), *pos = scratch.get<uint32_t>((size_t)n_seg + 2);
-			PGX_LAUNCH(k_seg_mark_del, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, arc.p, n_arc, max_avg_occ * Gtot, max_degree, max_dist_loci, keep);
-			uint32_t k = scan_flags(keep, pos, n_seg);
-			PGX_LAUNCH(k_seg_compact, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg, pos, seg_alt.p);
+			uint32_t *keep = scratch.get<uint32_t>((size_t)n_seg0 + 1), *pos = scratch.get<uint32_t>((size_t)n_seg0 + 2);
+			PGX_LAUNCH(k_seg_mark_del, grid_for(n_seg0, TB), TB, 0, st, seg.p, n_seg0, dc.p, arc.p, max_avg_occ * Gtot, max_degree, max_dist_loci, keep);
+			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(n_seg0));
+			exclusive_sum_u32(keep, pos, n_seg0, agg, st);
+			PGX_LAUNCH(k_seg_compact, GS_GRID, TB, 0, st, seg.p, dc.p, pos, seg_alt.p);
+			PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_seg)), pos + n_seg0);
 			seg.swap(seg_alt);
-			if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::flt_high_occ] removed %d of %d segments\n", n_seg - (int32_t)k, n_seg);
-			n_seg = (int32_t)k;
 			scratch.reset(mk);
 		}
 		regen_g2s();
@@ -555,21 +636,18 @@ struct Session {
 	{
 		size_t mk = scratch.mark();
 		arc_index();
-		if (n_seg) PGX_LAUNCH(k_seg_zero_loci, grid_for(n_seg, TB), TB, 0, st, seg.p, n_seg);
-		int32_t n_vtx = 2 * n_seg;
-		if (Nw && n_vtx && n_arc) {
+		if (Nw && n_seg0) {
+			PGX_LAUNCH(k_seg_zero_loci, GS_GRID, TB, 0, st, seg.p, dc.p);
 			// representative position of every gene in every local genome (branch.c:6-29)
 			size_t tab = (size_t)n_gene * G;
 			uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *spos = scratch.get<uint32_t>((size_t)Nw + 2);
 			PGX_LAUNCH(k_flag_survivor_cs, grid_for(Nw, TB), TB, 0, st, A.bits, Nw, flag);
-			uint32_t m_cs = scan_flags(flag, spos, Nw);
+			scan_to_count(flag, spos, Nw, offsetof(DevCounts, m_cs));
 			{   // tie detector: two survivors with one (contig, cs)
 				size_t m2 = scratch.mark();
-				uint32_t *svcs = scratch.get<uint32_t>((size_t)m_cs + 1);
-				if (m_cs > 1) {
-					PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, spos, (const uint32_t*)nullptr, Nw, svcs);
-					PGX_LAUNCH(k_cs_tie_count, grid_for(m_cs, TB), TB, 0, st, A.ctg, A.cs, svcs, (int32_t)m_cs, counters.p + C_TIE_CS);
-				}
+				uint32_t *svcs = scratch.get<uint32_t>((size_t)Nw + 1);
+				PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, spos, (const uint32_t*)nullptr, Nw, svcs);
+				PGX_LAUNCH(k_cs_tie_count, GS_GRID, TB, 0, st, A.ctg, A.cs, svcs, dc.p, counters.p + C_TIE_CS);
 				scratch.reset(m2);
 			}
 			int32_t *t_last = scratch.get<int32_t>(tab + 1);
@@ -578,19 +656,20 @@ struct Session {
 			PGX_LAUNCH(k_pos_last, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, spos, Nw, G, t_last);
 			PGX_LAUNCH(k_pos_fill, grid_for((int64_t)tab, TB), TB, 0, st, t_last, tab, G, A.ctg, A.cm, spos, goff_act.p, gpos);
 			// n_local for every pair of out-arcs of every oriented vertex: local partial sums, one reduction, then the decisions
-			uint32_t *cnt = scratch.get<uint32_t>((size_t)n_vtx + 1), *off = scratch.get<uint32_t>((size_t)n_vtx + 2);
-			PGX_LAUNCH(k_branch_count, grid_for(n_vtx, TB), TB, 0, st, idx.p, n_vtx, cnt);
-			uint32_t n_nl = scan_flags(cnt, off, n_vtx);
-			int32_t *nl = scratch.get<int32_t>((size_t)n_nl + 1), *grp = scratch.get<int32_t>((size_t)n_arc + 1);
+			const int32_t cap_vtx = 2 * n_seg0;
+			uint32_t *cnt = scratch.get<uint32_t>((size_t)cap_vtx + 1), *off = scratch.get<uint32_t>((size_t)cap_vtx + 2);
+			PGX_LAUNCH(k_branch_count, grid_for(cap_vtx, TB), TB, 0, st, idx.p, cap_vtx, dc.p, cnt);
+			uint32_t n_nl = scan_flags(cnt, off, cap_vtx);       // the one host read-back of a round: it sizes the table below
+			int32_t *nl = scratch.get<int32_t>((size_t)n_nl + 1), *grp = scratch.get<int32_t>(arc_cap + 1);
 			BranchOpt bo; bo.local_dist = opt->local_dist; bo.local_count = opt->local_count; bo.frag_mode = !!(opt->flag & PG_F_FRAG_MODE);
 			bo.branch_diff = opt->branch_diff; bo.branch_diff_dist = opt->branch_diff_dist; bo.branch_diff_cut = opt->branch_diff_cut;
 			if (n_nl) {
-				PGX_LAUNCH(k_branch_nlocal, grid_for((int64_t)n_vtx * 32, TB), TB, 0, st, idx.p, n_vtx, arc.p, seg.p, gpos, G, off, bo, nl);
+				PGX_LAUNCH(k_branch_nlocal, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, gpos, G, off, (int32_t)n_nl, bo, nl);
 				g_comm.allreduce(nl, n_nl, Comm::T_INT32, Comm::OP_SUM, st);
 			}
-			PGX_LAUNCH(k_branch_decide, grid_for(n_vtx, 128), 128, 0, st, idx.p, n_vtx, arc.p, seg.p, off, nl, bo, grp);
+			PGX_LAUNCH(k_branch_decide, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, off, nl, bo, grp);
 			// hits inherit the weakness of the arcs they sit on; weak_br == 2 filters (branch.c:108-145, graph.c:309)
-			if (m_sv) PGX_LAUNCH(k_branch_hits, grid_for(m_sv, TB), TB, 0, st, sv.p, m_sv, A.ctg, A.gidp, A.bits, g2s.p, arc.p, n_arc);
+			PGX_LAUNCH(k_branch_hits, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, (const int32_t*)(g_comm.active()? nullptr : arc_of_rec.p));
 		}
 		scratch.reset(mk);
 	}
@@ -602,10 +681,8 @@ struct Session {
 		gen_vtx(opt);                                                                    // graph.c:286
 		flag_vtx();                                                                      // graph.c:287-288
 		gen_arc(opt);                                                                    // graph.c:289
-		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] round-1 graph: %d genes and %d arcs\n", n_seg, n_arc);
 		flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);     // graph.c:294-295
 		gen_arc(opt);                                                                    // graph.c:296
-		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] round-2 graph: %d genes and %d arcs\n", n_seg, n_arc);
 		for (int32_t i = 0; i < opt->n_branch_flt; ++i) {                                // graph.c:301-315
 			double r = 1.0 + (double)(opt->n_branch_flt - 1 - i) / opt->n_branch_flt;
 			int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
@@ -616,6 +693,8 @@ struct Session {
 			gen_arc(opt);
 		}
 		set_filter(SF_SHADOW);                                                           // graph.c:316
+		DevCounts hc = read_counts();
+		n_seg = (int32_t)hc.n_seg; n_arc = (int32_t)hc.n_arc;
 		if (opt->min_arc_cnt > 1 && n_arc) {                                             // graph.c:317-318
 			size_t mk = scratch.mark();
 			uint32_t *keep = scratch.get<uint32_t>((size_t)n_arc + 1), *pos = scratch.get<uint32_t>((size_t)n_arc + 2);
@@ -624,11 +703,12 @@ struct Session {
 			PGX_LAUNCH(k_arc_compact, grid_for(n_arc, TB), TB, 0, st, arc.p, n_arc, pos, arc_alt.p);
 			arc.swap(arc_alt);
 			n_arc = (int32_t)k;
+			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), (uint32_t)n_arc);
 			scratch.reset(mk);
 		}
 		arc_index();                                                                     // graph.c:319
 		check_err("graph generation");
-		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] round-3 graph: %d genes and %d arcs\n", n_seg, n_arc);
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] final graph: %d genes and %d arcs\n", n_seg, n_arc);
 		done_graph = true;
 		g_stats.n_seg = n_seg; g_stats.n_arc = n_arc;
 	}
@@ -659,7 +739,7 @@ struct Session {
 			std::vector<pg_hit_t*> fresh(G, nullptr);
 			for (int32_t j = 0; j < G; ++j) {
 				if (h_hoff[j + 1] - h_hoff[j] != d->genome[j].n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
-				if (!host_sorted) fresh[j] = (pg_hit_t*)malloc(sizeof(pg_hit_t) * (d->genome[j].n_hit > 0? d->genome[j].n_hit : 1));
+				if (!host_sorted) fresh[j] = alloc_hit_array((size_t)d->genome[j].n_hit);
 			}
 			const int64_t BLK = 1 << 14;
 			const bool in_place = host_sorted;

@@ -415,17 +415,16 @@ template<int MODE> __global__ void __launch_bounds__(SWT_TILE) k_sweep_tile(Swee
 	sweep_hit<MODE>(A, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
 }
 
-// ---- pair-parallel tile sweep ---------------------------------------------------------------------
-// k_sweep_tile above still gives each thread one hit and lets it walk its whole window: ncu shows 5 of 32 lanes active
-// (windows of 4..23 partners, exon walks of 1..14 steps).  This variant splits the work into uniform pieces:
-//   phase 1  one thread per hit: the cheap part only -- window scan from shared memory, "would I lose to p?" from the two
-//            score keys; every (hit, partner) pair that could shadow the hit goes into a shared-memory queue;
-//   phase 2  one thread per QUEUED PAIR: the exon-list walk (with early exit), results folded into per-hit shared
-//            state with shared-memory atomics (any-loss flag, atomicMax on the 64-bit dominator key);
-//   phase 3  pairs whose key equals the winning key settle the smallest-partner-index rule (atomicMin);
-//   phase 4  one thread per hit writes the outputs; SW_LOAD walks its final dominator once more for the exact overlap.
-// Hits whose window leaves the staged range, or that hit a full queue, take the serial sweep_hit() path: same results.
-constexpr int SWQ_TILE = 256, SWQ_HALO = 64, SWQ_STG = SWQ_TILE + 2 * SWQ_HALO + 8, SWQ_EXCAP = 2560, SWQ_QCAP = 3072;
+// ---- the production sweep: TMA-staged tile, strongest-candidate-first ------------------------------------------------
+// ncu on the thread-per-hit variants above: 5..8 of 32 lanes active and ~2900 thread-instructions per hit -- every thread walks
+// exon lists for several partners inside a branchy window loop.  What a hit needs from the sweep is (a) whether ANY related
+// partner beats it and (b) the related partner with the LARGEST key (smallest index on ties).  So:
+//   phase 1  scan the window from shared memory with straight-line predicated code and keep only the would-be dominator: the
+//            partner with the largest key among those the hit would lose to (no exon lists touched);
+//   phase 2  ONE exon walk per hit, against that partner.  If it is in relation, it is the dominator and the hit is shadowed:
+//            no other partner can have a larger key.  If it is not (a bounding-box overlap without a CDS overlap), or the
+//            window leaves the staged range, the hit takes the serial sweep_hit() path -- same results by construction.
+constexpr int SWQ_TILE = 256, SWQ_HALO = 64, SWQ_STG = SWQ_TILE + 2 * SWQ_HALO + 8, SWQ_EXCAP = 2560;
 
 struct AccStaged {           // hit columns: unchecked shared memory (callers stay inside [lo, hi)); exons: checked
 	SweepCols c;
@@ -446,9 +445,9 @@ struct AccStaged {           // hit columns: unchecked shared memory (callers st
 	__device__ __forceinline__ int2 exon(uint32_t k) const { return (k >= elo && k < ehi)? s_ex[k - elo] : c.ex[k]; }
 };
 
-constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (size_t)(SWQ_STG + 4) * 4 + (size_t)SWQ_EXCAP * 8 + (size_t)SWQ_TILE * (8 + 4 + 4) + (size_t)SWQ_QCAP * 4 + 64;
+constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (size_t)(SWQ_STG + 4) * 4 + (size_t)SWQ_EXCAP * 8 + 64;
 
-template<int MODE> __global__ void __launch_bounds__(SWQ_TILE) k_sweep_pairs(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_top(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	unsigned char *sp = smem_raw;
@@ -462,25 +461,21 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE) k_sweep_pairs(Swe
 	uint32_t *s_bits = (uint32_t*)sp; sp += (size_t)SWQ_STG * 4;
 	uint32_t *s_eoff = (uint32_t*)sp; sp += (size_t)(SWQ_STG + 4) * 4;
 	int2 *s_ex = (int2*)sp; sp += (size_t)SWQ_EXCAP * 8;
-	unsigned long long *st_key = (unsigned long long*)sp; sp += (size_t)SWQ_TILE * 8;   // best dominator key per tile hit
-	int32_t *st_p = (int32_t*)sp; sp += (size_t)SWQ_TILE * 4;                            // its partner index
-	uint32_t *st_flag = (uint32_t*)sp; sp += (size_t)SWQ_TILE * 4;                       // bit0: lost at least once, bit1: serial path
-	uint32_t *queue = (uint32_t*)sp; sp += (size_t)SWQ_QCAP * 4;
 	uint64_t *bar = (uint64_t*)sp; sp += 8;
-	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range, [2]: queue length
+	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range
 
 	const int32_t t0 = blockIdx.x * SWQ_TILE, tid = threadIdx.x;
 	int32_t lo = t0 - SWQ_HALO; if (lo < 0) lo = 0;
-	lo &= ~3;
+	lo &= ~3;                                                                            // 16-byte aligned column offsets
 	int32_t hi = t0 + SWQ_TILE + SWQ_HALO; if (hi > c.n) hi = c.n;
-	const int32_t cnt4 = (hi - lo + 3) & ~3, cnte = (hi - lo + 1 + 3) & ~3;
+	const int32_t cnt4 = (hi - lo + 3) & ~3, cnte = (hi - lo + 1 + 3) & ~3;              // columns are allocated with slack past n
 	if (tid == 0) {
 		mbar_init(bar, 1);
 		fence_mbar_init();
 		uint32_t e0 = c.eoff[lo] & ~1u, e1 = c.eoff[hi];
 		uint32_t ne = (e1 - e0 + 1) & ~1u;
 		if (ne > SWQ_EXCAP) ne = SWQ_EXCAP;
-		s_misc[0] = e0; s_misc[1] = e0 + ne; s_misc[2] = 0;
+		s_misc[0] = e0; s_misc[1] = e0 + ne;
 		fence_proxy_async();
 		mbar_expect_tx(bar, (uint32_t)cnt4 * 4u * 7u + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
 		bulk_g2s(s_ctg, c.ctg + lo, cnt4 * 4, bar); bulk_g2s(s_cs, c.cs + lo, cnt4 * 4, bar); bulk_g2s(s_ce, c.ce + lo, cnt4 * 4, bar);
@@ -489,151 +484,167 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE) k_sweep_pairs(Swe
 		bulk_g2s(s_eoff, c.eoff + lo, cnte * 4, bar);
 		bulk_g2s(s_ex, c.ex + e0, ne * 8, bar);
 	}
-	st_key[tid] = 0; st_p[tid] = INT32_MAX; st_flag[tid] = 0;
 	__syncthreads();
 	while (!mbar_try_wait(bar, 0)) { }
 
+	const int32_t i = t0 + tid;
+	const bool in_range = i < c.n;
+	const int32_t mq = in_range? i - lo : 0;
+	const uint32_t mbits = s_bits[mq];
 	AccStaged A;
 	A.c = c; A.lo = lo; A.elo = s_misc[0]; A.ehi = s_misc[1];
 	A.s_ctg = s_ctg; A.s_cs = s_cs; A.s_ce = s_ce; A.s_pmax = s_pmax; A.s_gidp = s_gidp; A.s_cds = s_cds; A.s_bits = s_bits; A.s_eoff = s_eoff; A.s_key = s_key; A.s_ex = s_ex;
-
-	const int32_t i = t0 + tid;
-	const bool live = i < c.n && !(s_bits[i < c.n? i - lo : 0] & PG_HB_FLT);
-	// ---- phase 1: candidate pairs.  The strongest candidate (largest key, then smallest index -- the would-be dominator)
-	// stays with the thread; the others go to the queue and are almost always pruned after phase 2a.
-	int32_t top_p = -1; uint64_t top_key = 0;
-	if (live) {
-		const int32_t mctg = A.ctg(i), mcs = A.cs(i), mce = A.ce(i), mgidp = A.gidp(i);
-		const uint32_t mbits = A.bits(i), mw = mbits & PG_HB_WBR_MASK;
-		const uint64_t mkey = A.key(i);
-		int32_t mrank = INT32_MIN;
-		bool slow = false;
+	const int32_t mctg = s_ctg[mq], mcs = s_cs[mq], mce = s_ce[mq], mgene = s_gidp[mq] >> 1;
+	const uint32_t mw = mbits & PG_HB_WBR_MASK;
+	const uint64_t mkey = s_key[mq];
+	int32_t top_p = INT32_MAX; uint64_t top_key = 0;
+	bool slow = false, lose = false, write_out = false;
+	if (in_range && (mbits & PG_HB_FLT)) bits_out[i] = mbits;                            // overlap.c:63,112
+	if (in_range && !(mbits & PG_HB_FLT)) {
+	// ---- phase 1: the would-be dominator
 #pragma unroll 1
-		for (int side = 0; side < 2 && !slow; ++side) {
+	for (int side = 0; side < 2; ++side) {
+		const int step = side == 0? -1 : 1;
 #pragma unroll 1
-			for (int32_t p = side == 0? i - 1 : i + 1;; p += side == 0? -1 : 1) {
-				if (p < lo) { if (p >= 0) slow = true; break; }
-				if (p >= hi) { if (p < c.n) slow = true; break; }
-				if (A.ctg(p) != mctg) break;
-				if (side == 0) { if (A.pmax(p) <= mcs) break; if (A.ce(p) <= mcs) continue; }
-				else if (A.cs(p) >= mce) break;
-				const uint32_t pbits = A.bits(p);
-				if (pbits & PG_HB_FLT) continue;
-				const int32_t pgidp = A.gidp(p);
-				const bool same_gene = (pgidp >> 1) == (mgidp >> 1);
-				if (MODE == SW_ISO && !same_gene) continue;
-				if (o.check_strand && ((pbits ^ mbits) & PG_HB_REV)) continue;
-				const uint64_t pkey = A.key(p);
-				const uint32_t pw = pbits & PG_HB_WBR_MASK;
-				bool me_loses;
-				if (MODE == SW_ISO || same_gene || mw == pw) {
-					if (mkey != pkey) me_loses = mkey < pkey;
-					else {
-						if (mrank == INT32_MIN) mrank = c.rank[i];
-						int32_t prank = c.rank[p];
-						me_loses = side == 0? (mrank > prank) : !(prank > mrank);
-					}
-				} else me_loses = mw > pw;
-				if (!me_loses) continue;
-				int32_t q = p;
-				if (top_p < 0) { top_p = p; top_key = pkey; continue; }
-				if (pkey > top_key || (pkey == top_key && p < top_p)) { q = top_p; top_p = p; top_key = pkey; }   // the displaced one is queued
-				uint32_t slot = atomicAdd(&s_misc[2], 1u);
-				if (slot >= SWQ_QCAP) { slow = true; break; }
-				queue[slot] = (uint32_t)tid << 16 | (uint32_t)(q - lo);
+		for (int32_t p = i + step;; p += step) {
+			if (p < lo) { slow = slow || p >= 0; break; }                // the window may continue outside the staged range
+			if (p >= hi) { slow = slow || p < c.n; break; }
+			const int32_t q = p - lo;
+			const int32_t pcs = s_cs[q], pce = s_ce[q];
+			if (s_ctg[q] != mctg) break;
+			if (side == 0? s_pmax[q] <= mcs : pcs >= mce) break;         // overlap.c:67-71,114-120: nothing further out can reach me
+			const uint32_t pbits = s_bits[q];
+			const int32_t pgene = s_gidp[q] >> 1;
+			const uint64_t pkey = s_key[q];
+			const bool same_gene = pgene == mgene;
+			bool ok = !(pbits & PG_HB_FLT) && pce > mcs;                 // overlap.c:70,118,122 (pce > mcs always holds on the forward side)
+			if (MODE == SW_ISO) ok = ok && same_gene;                    // overlap.c:77
+			if (o.check_strand) ok = ok && !((pbits ^ mbits) & PG_HB_REV);   // overlap.c:78,128
+			const uint32_t pw = pbits & PG_HB_WBR_MASK;
+			const bool key_rule = MODE == SW_ISO || same_gene || mw == pw;   // overlap.c:139-147
+			bool loses = key_rule? mkey < pkey : mw > pw;
+			if (ok && key_rule && mkey == pkey) {                        // same protein, same score: ranks decide (rare)
+				const int32_t mrank = c.rank[i], prank = c.rank[p];
+				loses = side == 0? (mrank > prank) : !(prank > mrank);
 			}
-		}
-		if (slow) st_flag[tid] = 2;
-		else if (top_p >= 0) {
-			// ---- phase 2a: one walk per hit, against its strongest candidate
-			const int32_t need = related_threshold(MODE == SW_ISO || (A.gidp(top_p) >> 1) == (mgidp >> 1), A.cds(i), A.cds(top_p), o.min_ov_ratio);
-			const bool rel = top_p < i? cds_related(A, A.eoff(top_p), A.eoff(top_p + 1), A.cs(top_p), A.ce(top_p), A.eoff(i), A.eoff(i + 1), mcs, mce, need)
-			                          : cds_related(A, A.eoff(i), A.eoff(i + 1), mcs, mce, A.eoff(top_p), A.eoff(top_p + 1), A.cs(top_p), A.ce(top_p), need);
-			if (rel) { st_flag[tid] = 1; st_key[tid] = top_key; st_p[tid] = top_p; }
-		}
-	}
-	__syncthreads();
-	const uint32_t qn = s_misc[2] < SWQ_QCAP? s_misc[2] : SWQ_QCAP;
-	// ---- phase 2b: the queued (weaker) candidates; all of a hit's are skipped once its strongest candidate held
-#pragma unroll 1
-	for (uint32_t k = tid; k < qn; k += SWQ_TILE) {
-		const uint32_t ent = queue[k], il = ent >> 16, pl = ent & 0xffffu;
-		const uint32_t fl = ((volatile uint32_t*)st_flag)[il];
-		if (fl & 2) continue;
-		const uint64_t pkey = s_key[pl];
-		const int32_t ii = t0 + (int32_t)il, p = lo + (int32_t)pl;
-		if (MODE == SW_ISO) { if (fl & 1) continue; }
-		else if (fl & 1) {   // cannot become the dominator: weaker key, or same key with a larger index
-			const unsigned long long bk = ((volatile unsigned long long*)st_key)[il];
-			const int32_t bp = ((volatile int32_t*)st_p)[il];
-			if (pkey < bk || (pkey == bk && p > bp)) {
-				if (MODE == SW_LOAD && pkey == bk && bp != INT32_MAX && bp >= lo && bp < hi && s_cs[pl] == s_cs[bp - lo]) atomicAdd(tie_cnt, 1u);   // tie detector (conservative)
-				continue;
-			}
-		}
-		const int32_t need = related_threshold(MODE == SW_ISO || (A.gidp(ii) >> 1) == (A.gidp(p) >> 1), A.cds(ii), A.cds(p), o.min_ov_ratio);
-		const bool rel = p < ii? cds_related(A, A.eoff(p), A.eoff(p + 1), A.cs(p), A.ce(p), A.eoff(ii), A.eoff(ii + 1), A.cs(ii), A.ce(ii), need)
-		                       : cds_related(A, A.eoff(ii), A.eoff(ii + 1), A.cs(ii), A.ce(ii), A.eoff(p), A.eoff(p + 1), A.cs(p), A.ce(p), need);
-		if (!rel) continue;
-		atomicOr(&st_flag[il], 1u);
-		if (MODE != SW_ISO) { atomicMax(&st_key[il], (unsigned long long)pkey); queue[k] = ent | 0x80000000u; }
-	}
-	__syncthreads();
-	// ---- phase 3: smallest partner index among the related pairs that carry the winning key (overlap.c:150,153)
-	if (MODE != SW_ISO) {
-		// (a hit's own strongest candidate has the largest key of all its candidates, so if it held, st_key/st_p already name
-		// it and no queued pair can have raised st_key above it; otherwise st_p is still INT32_MAX here)
-#pragma unroll 1
-		for (uint32_t k = tid; k < qn; k += SWQ_TILE) {
-			const uint32_t ent = queue[k];
-			if (!(ent & 0x80000000u)) continue;
-			const uint32_t il = (ent >> 16) & 0x7fffu, pl = ent & 0xffffu;
-			const unsigned long long bk = st_key[il];
-			if (bk > 0 && s_key[pl] == bk) atomicMin(&st_p[il], lo + (int32_t)pl);
-		}
-		__syncthreads();
-		if (MODE == SW_LOAD) {   // tie detector: a second related partner with the winning key and the same start
-#pragma unroll 1
-			for (uint32_t k = tid; k < qn; k += SWQ_TILE) {
-				const uint32_t ent = queue[k];
-				if (!(ent & 0x80000000u)) continue;
-				const uint32_t il = (ent >> 16) & 0x7fffu, pl = ent & 0xffffu;
-				const int32_t bp = st_p[il];
-				if (st_key[il] > 0 && s_key[pl] == st_key[il] && lo + (int32_t)pl != bp && s_cs[pl] == s_cs[bp - lo]) atomicAdd(tie_cnt, 1u);
+			if (ok && loses) {
+				if (MODE == SW_LOAD && pkey == top_key && top_p != INT32_MAX && pcs == s_cs[top_p - lo]) atomicAdd(tie_cnt, 1u);   // tie detector
+				if (pkey > top_key || (pkey == top_key && p < top_p)) { top_key = pkey; top_p = p; }
 			}
 		}
 	}
-	// ---- phase 4: outputs
-	if (i >= c.n) return;
-	const uint32_t mbits = s_bits[i - lo];
-	if (mbits & PG_HB_FLT) { bits_out[i] = mbits; return; }
-	const uint32_t fl = st_flag[tid];
-	if (fl & 2) {   // window left the staged range (or the queue was full): serial path, shared memory where possible
+	// ---- phase 2: one walk
+	if (!slow && top_p != INT32_MAX) {
+		const int32_t tq = top_p - lo;
+		const int32_t need = related_threshold(MODE == SW_ISO || (s_gidp[tq] >> 1) == mgene, s_cds[mq], s_cds[tq], o.min_ov_ratio);
+		const int32_t aq = top_p < i? tq : mq, bq = top_p < i? mq : tq;  // the earlier hit goes first (overlap.c:80)
+		lose = cds_related(A, s_eoff[aq], s_eoff[aq + 1], s_cs[aq], s_ce[aq], s_eoff[bq], s_eoff[bq + 1], s_cs[bq], s_ce[bq], need);
+		slow = !lose;                                                    // the strongest candidate did not hold: weaker ones must be tried
+	}
+	// ---- phase 3: the hits that could not be settled above (a few per cent) are parked and then taken one at a time by THEIR warp: the 32 lanes
+	// try 32 partners at once -- all would-be-loser pairs walk their exon lists in parallel, a shuffle reduction picks the
+	// related partner with the largest key (smallest index on ties).  Leaving such a hit to its own thread costs its whole warp
+	// ~3000 instruction slots (ncu: 2-4 of 32 lanes active for 42 % of the kernel's instructions).
+	write_out = !slow;
+	}   // (threads past n and filtered hits rejoin here: the ballot needs the whole warp)
+	{
+		uint32_t parked = __ballot_sync(0xffffffffu, slow);
+		const int lane = tid & 31;
 		AccTile T;
-		T.c = c; T.lo = lo; T.hi = hi; T.elo = A.elo; T.ehi = A.ehi;
+		T.c = c; T.lo = lo; T.hi = hi; T.elo = s_misc[0]; T.ehi = s_misc[1];
 		T.s_ctg = s_ctg; T.s_cs = s_cs; T.s_ce = s_ce; T.s_pmax = s_pmax; T.s_gidp = s_gidp; T.s_rank = nullptr; T.s_cds = s_cds; T.s_bits = s_bits; T.s_eoff = s_eoff; T.s_key = s_key; T.s_ex = s_ex;
-		sweep_hit<MODE>(T, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
-		return;
+#pragma unroll 1
+		while (parked) {
+			const int src_lane = __ffs(parked) - 1;
+			parked &= parked - 1;
+			const int32_t h = __shfl_sync(0xffffffffu, i, src_lane), hq = h - lo;
+			const int32_t hctg = s_ctg[hq], hcs = s_cs[hq], hce = s_ce[hq], hgene = s_gidp[hq] >> 1, hcds = s_cds[hq];
+			const uint32_t hbits = s_bits[hq], hw = hbits & PG_HB_WBR_MASK, heb = s_eoff[hq], hee = s_eoff[hq + 1];
+			const uint64_t hkey = s_key[hq];
+			bool w_lose = false; uint64_t w_key = 0; int32_t w_p = INT32_MAX;
+#pragma unroll 1
+			for (int side = 0; side < 2; ++side) {
+#pragma unroll 1
+				for (int32_t base = 1;; base += 32) {
+					const int32_t p = side == 0? h - base - lane : h + base + lane;
+					bool inwin = p >= 0 && p < c.n;
+					int32_t pcs = 0, pce = 0;
+					if (inwin) {
+						inwin = T.ctg(p) == hctg;
+						if (inwin) { pcs = T.cs(p); pce = T.ce(p); inwin = side == 0? T.pmax(p) > hcs : pcs < hce; }
+					}
+					if (inwin) {
+						const uint32_t pbits = T.bits(p);
+						const int32_t pgene = T.gidp(p) >> 1;
+						const uint64_t pkey = T.key(p);
+						const bool same_gene = pgene == hgene;
+						bool ok = !(pbits & PG_HB_FLT) && pce > hcs;
+						if (MODE == SW_ISO) ok = ok && same_gene;
+						if (o.check_strand) ok = ok && !((pbits ^ hbits) & PG_HB_REV);
+						const uint32_t pw = pbits & PG_HB_WBR_MASK;
+						const bool key_rule = MODE == SW_ISO || same_gene || hw == pw;
+						bool loses = key_rule? hkey < pkey : hw > pw;
+						if (ok && key_rule && hkey == pkey) { const int32_t r0 = c.rank[h], r1 = c.rank[p]; loses = side == 0? (r0 > r1) : !(r1 > r0); }
+						if (ok && loses) {
+							const int32_t need = related_threshold(MODE == SW_ISO || same_gene, hcds, T.cds(p), o.min_ov_ratio);
+							const uint32_t pb = T.eoff(p), pe = T.eoff(p + 1);
+							const bool rel = side == 0? cds_related(T, pb, pe, pcs, pce, heb, hee, hcs, hce, need) : cds_related(T, heb, hee, hcs, hce, pb, pe, pcs, pce, need);
+							if (rel) {
+								w_lose = true;
+								if (pkey > w_key || (pkey == w_key && p < w_p)) { w_key = pkey; w_p = p; }
+							}
+						}
+					}
+					if (!__any_sync(0xffffffffu, inwin && lane == 31)) break;   // the window predicate is monotone in distance: lane 31 is the farthest
+				}
+			}
+			// warp reduction: any loss; largest key, then smallest index (overlap.c:150,153)
+			w_lose = __any_sync(0xffffffffu, w_lose);
+#pragma unroll
+			for (int sft = 16; sft > 0; sft >>= 1) {
+				const uint64_t ok2 = __shfl_xor_sync(0xffffffffu, w_key, sft); const int32_t op = __shfl_xor_sync(0xffffffffu, w_p, sft);
+				if (ok2 > w_key || (ok2 == w_key && op < w_p)) { w_key = ok2; w_p = op; }
+			}
+			if (lane == 0) {
+				if (MODE == SW_ISO) bits_out[h] = w_lose? (hbits | PG_HB_FLT_OV | PG_HB_FLT) : hbits;
+				else if (MODE == SW_SHADOW) {
+					uint32_t b = hbits;
+					if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;
+					if (w_lose) b |= PG_HB_SHADOW;
+					bits_out[h] = b;
+					pdom_out[h] = (w_lose && w_key > 0)? c.pid[w_p] : -1;
+				} else {
+					bits_out[h] = hbits;
+					int32_t pd = -1, sd = -1;
+					if (w_lose && w_key > 0) {
+						pd = c.pid[w_p];
+						const int32_t ov = w_p < h? cds_overlap(T, T.eoff(w_p), T.eoff(w_p + 1), T.cs(w_p), T.ce(w_p), heb, hee, hcs, hce) : cds_overlap(T, heb, hee, hcs, hce, T.eoff(w_p), T.eoff(w_p + 1), T.cs(w_p), T.ce(w_p));
+						sd = (int32_t)(c.sori[h] * (1.0 - (double)ov / hcds) + c.sori[w_p] * ((double)ov / T.cds(w_p)) + .499);   // overlap.c:170
+					}
+					pdom_out[h] = pd; sdom_out[h] = sd;
+				}
+			}
+		}
 	}
-	const bool lose = fl & 1;
-	const unsigned long long best_key = st_key[tid];
-	const int32_t best_p = st_p[tid];
+	if (!write_out) return;
+	// ---- outputs
 	if (MODE == SW_ISO) {
-		bits_out[i] = lose? (mbits | PG_HB_FLT_OV | PG_HB_FLT) : mbits;
+		bits_out[i] = lose? (mbits | PG_HB_FLT_OV | PG_HB_FLT) : mbits;                  // overlap.c:85-91
 	} else if (MODE == SW_SHADOW) {
 		uint32_t b = mbits;
-		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;
+		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;                                          // overlap.c:108,113: hit 0 is never reset
 		if (lose) b |= PG_HB_SHADOW;
 		bits_out[i] = b;
-		pdom_out[i] = best_key > 0? c.pid[best_p] : -1;
+		pdom_out[i] = (lose && top_key > 0)? c.pid[top_p] : -1;                           // overlap.c:160-165
 	} else {
 		bits_out[i] = mbits;
 		int32_t pd = -1, sd = -1;
-		if (best_key > 0) {
-			pd = c.pid[best_p];
-			const int32_t ov = best_p < i? cds_overlap(A, A.eoff(best_p), A.eoff(best_p + 1), A.cs(best_p), A.ce(best_p), A.eoff(i), A.eoff(i + 1), A.cs(i), A.ce(i))
-			                             : cds_overlap(A, A.eoff(i), A.eoff(i + 1), A.cs(i), A.ce(i), A.eoff(best_p), A.eoff(best_p + 1), A.cs(best_p), A.ce(best_p));
-			sd = (int32_t)(c.sori[i] * (1.0 - (double)ov / A.cds(i)) + c.sori[best_p] * ((double)ov / A.cds(best_p)) + .499);   // overlap.c:170
+		if (lose && top_key > 0) {
+			const int32_t tq = top_p - lo;
+			pd = c.pid[top_p];
+			const int32_t ov = top_p < i? cds_overlap(A, s_eoff[tq], s_eoff[tq + 1], s_cs[tq], s_ce[tq], s_eoff[mq], s_eoff[mq + 1], mcs, mce)
+			                            : cds_overlap(A, s_eoff[mq], s_eoff[mq + 1], mcs, mce, s_eoff[tq], s_eoff[tq + 1], s_cs[tq], s_ce[tq]);
+			sd = (int32_t)(c.sori[i] * (1.0 - (double)ov / s_cds[mq]) + c.sori[top_p] * ((double)ov / s_cds[tq]) + .499);   // overlap.c:170
 		}
 		pdom_out[i] = pd; sdom_out[i] = sd;
 	}
@@ -804,15 +815,15 @@ __global__ void k_scatter_back(ActCols a, int32_t n, FullCols f)
 // ------------------------------------------------------------------------------------------------
 // vertex selection inputs (vertex.c:28-51)
 // ------------------------------------------------------------------------------------------------
-// t_dom[g*n_gene+gene] = 1 if an unshadowed rank-0 unfiltered hit exists; t_first = smallest index of a shadowed one
+// t_dom[gene*G+g] = 1 if an unshadowed rank-0 unfiltered hit exists; t_first = smallest index of a shadowed one
 __global__ void k_vtx_mark(const int32_t *__restrict__ ctg, const int32_t *__restrict__ ctg2g, const int32_t *__restrict__ gidp, const int32_t *__restrict__ rank,
-	const uint32_t *__restrict__ bits, int32_t n, int32_t n_gene, uint8_t *t_dom, int32_t *t_first)
+	const uint32_t *__restrict__ bits, int32_t n, int32_t G, uint8_t *t_dom, int32_t *t_first)
 {
 	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	uint32_t b = bits[i];
 	if ((b & PG_HB_FLT) || rank[i] != 0) return;
-	size_t k = (size_t)ctg2g[ctg[i]] * n_gene + (gidp[i] >> 1);
+	size_t k = (size_t)(gidp[i] >> 1) * G + ctg2g[ctg[i]];                              // gene-major: the host election reads rows
 	if (b & PG_HB_SHADOW) atomicMin(&t_first[k], i); else t_dom[k] = 1;
 }
 // aux[k] = -2 (dominant) | gene that shadows it | -1 (absent)
@@ -845,11 +856,18 @@ __global__ void k_compact_idx(const uint32_t *__restrict__ pos, const uint32_t *
 	if (k < n && pos[k + 1] != pos[k]) out[pos[k]] = src? src[k] : (uint32_t)k;
 }
 
+// Logical sizes that change from round to round live ON THE DEVICE: kernels read them through this struct and are launched
+// with capacity-sized (or fixed, grid-stride) grids, so a whole arc/branch round is enqueued without a host round-trip.
+struct DevCounts { uint32_t m_sv, n_part, n_arc, n_seg, n_nl, m_cs, pad0, pad1; };
+#define PGX_GS(i, n) for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x, gs_n_ = (int32_t)(n), gs_s_ = gridDim.x * blockDim.x; i < gs_n_; i += gs_s_)
+__global__ void k_copy_u32(uint32_t *dst, const uint32_t *src) { *dst = *src; }
+__global__ void k_set_u32(uint32_t *dst, uint32_t v) { *dst = v; }
+
 struct ArcEmit {
-	const uint32_t *sv; int32_t m;            // survivors in (contig, cm) order (indices into the active set)
+	const uint32_t *sv; int32_t cap;          // survivors in (contig, cm) order (indices into the active set); cap = capacity (active hits)
 	const int32_t *ctg, *cm, *gidp, *sori, *sdom, *pdom0; const uint32_t *bits;
 	const int32_t *g2s, *prot_gid, *ctg2g;
-	int32_t use_ori, n_seg, gbits;
+	int32_t use_ori, n_seg, gbits;         // n_seg: the segment count at vertex selection (fixed key/bitmap stride for the whole run)
 };
 __device__ __forceinline__ int32_t arc_score(const ArcEmit &e, uint32_t h)   // graph.c:82-85
 {
@@ -857,90 +875,99 @@ __device__ __forceinline__ int32_t arc_score(const ArcEmit &e, uint32_t h)   // 
 	return (e.use_ori || so > sd || p0 < 0 || e.g2s[e.prot_gid[p0]] >= 0)? so : sd;
 }
 // record t>0 with a predecessor on the same contig yields two keyed records (graph.c:115-120); others get the all-ones key
-// key = ((v * 2n_seg + w) << gbits) | local genome;  payload = (dist, s1, s2)
-__global__ void k_arc_emit(ArcEmit e, uint64_t *key, int32_t *dist, int32_t *s1, int32_t *s2, uint32_t *seg_seen, int32_t *seg_ng, int32_t *seg_tot, uint32_t *tie_cnt, uint32_t *err)
+// key = v * 2n_seg + w;  payload = (local genome, dist, s1, s2).  Records are emitted in genome order and the sort is
+// stable, so inside one key the records of a genome stay together -- no genome bits in the key, one radix pass fewer.
+__global__ void k_arc_emit(ArcEmit e, const DevCounts *__restrict__ dc, uint64_t *key, int32_t *gen, int32_t *dist, int32_t *s1, int32_t *s2, uint32_t *seg_seen, int32_t *seg_ng, int32_t *seg_tot, uint32_t *tie_cnt, uint32_t *err)
 {
-	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= e.m) return;
-	uint32_t h = e.sv[t];
-	int32_t sid = e.g2s[e.gidp[h] >> 1];
-	if (sid < 0) { atomicOr(err, 32u); sid = 0; }                                       // graph.c:111 assert
-	int32_t c = e.ctg[h], gl = e.ctg2g[c];
-	// seg occupancy (graph.c:113,125-126): first sighting of (genome, segment) bumps n_genome
-	{
-		size_t bit = (size_t)gl * e.n_seg + sid;
-		uint32_t old = atomicOr(&seg_seen[bit >> 5], 1u << (bit & 31));
-		if (!(old >> (bit & 31) & 1u)) atomicAdd(&seg_ng[sid], 1);
-		atomicAdd(&seg_tot[sid], 1);
-	}
-	uint64_t k0 = ~0ull, k1 = ~0ull;
-	int32_t d = 0, sa = 0, sp = 0;
-	if (t > 0) {
-		uint32_t hp = e.sv[t - 1];
-		if (e.ctg[hp] == c) {
-			uint32_t w = (uint32_t)sid << 1 | (e.bits[h] & PG_HB_REV);
-			uint32_t v = (uint32_t)e.g2s[e.gidp[hp] >> 1] << 1 | (e.bits[hp] & PG_HB_REV);
-			uint64_t nv = 2ull * e.n_seg;
-			d = e.cm[h] - e.cm[hp];
-			if (d == 0) atomicAdd(tie_cnt, 1u);
-			sp = arc_score(e, hp); sa = arc_score(e, h);
-			k0 = ((uint64_t)v * nv + w) << e.gbits | (uint32_t)gl;
-			k1 = ((uint64_t)(w ^ 1) * nv + (v ^ 1)) << e.gbits | (uint32_t)gl;
+	const int32_t m = (int32_t)dc->m_sv;
+	PGX_GS(t, e.cap) {
+		uint64_t k0 = ~0ull, k1 = ~0ull;
+		int32_t d = 0, sa = 0, sp = 0, gl = 0;
+		if (t < m) {
+			uint32_t h = e.sv[t];
+			int32_t sid = e.g2s[e.gidp[h] >> 1];
+			if (sid < 0) { atomicOr(err, 32u); sid = 0; }                               // graph.c:111 assert
+			int32_t c = e.ctg[h];
+			gl = e.ctg2g[c];
+			// seg occupancy (graph.c:113,125-126): first sighting of (genome, segment) bumps n_genome
+			{
+				size_t bit = (size_t)gl * e.n_seg + sid;
+				uint32_t old = atomicOr(&seg_seen[bit >> 5], 1u << (bit & 31));
+				if (!(old >> (bit & 31) & 1u)) atomicAdd(&seg_ng[sid], 1);
+				atomicAdd(&seg_tot[sid], 1);
+			}
+			if (t > 0) {
+				uint32_t hp = e.sv[t - 1];
+				if (e.ctg[hp] == c) {
+					uint32_t w = (uint32_t)sid << 1 | (e.bits[h] & PG_HB_REV);
+					uint32_t v = (uint32_t)e.g2s[e.gidp[hp] >> 1] << 1 | (e.bits[hp] & PG_HB_REV);
+					uint64_t nv = 2ull * e.n_seg;
+					d = e.cm[h] - e.cm[hp];
+					if (d == 0) atomicAdd(tie_cnt, 1u);
+					sp = arc_score(e, hp); sa = arc_score(e, h);
+					k0 = (uint64_t)v * nv + w;
+					k1 = (uint64_t)(w ^ 1) * nv + (v ^ 1);
+				}
+			}
 		}
+		key[2 * (size_t)t] = k0; gen[2 * (size_t)t] = gl; dist[2 * (size_t)t] = d; s1[2 * (size_t)t] = sp; s2[2 * (size_t)t] = sa;
+		key[2 * (size_t)t + 1] = k1; gen[2 * (size_t)t + 1] = gl; dist[2 * (size_t)t + 1] = d; s1[2 * (size_t)t + 1] = sa; s2[2 * (size_t)t + 1] = sp;
 	}
-	key[2 * (size_t)t] = k0; dist[2 * (size_t)t] = d; s1[2 * (size_t)t] = sp; s2[2 * (size_t)t] = sa;
-	key[2 * (size_t)t + 1] = k1; dist[2 * (size_t)t + 1] = d; s1[2 * (size_t)t + 1] = sa; s2[2 * (size_t)t + 1] = sp;
 }
 
 // partial arc = sums over the LOCAL genomes of one key (graph.c:128-145 per genome, then the additive part of 153-163)
 struct ArcPartial { uint64_t x; int64_t sum_dist, sum_s1, sum_s2; int32_t n_genome, tot_cnt; };
 
-__global__ void k_arc_heads(const uint64_t *__restrict__ key, int32_t n, int gbits, uint32_t *flag)
+__global__ void k_arc_heads(const uint64_t *__restrict__ key, int32_t n, uint32_t *flag)
 {
 	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n) return;
 	uint64_t k = key[p];
-	flag[p] = (k != ~0ull && (p == 0 || (key[p - 1] >> gbits) != (k >> gbits)))? 1u : 0u;
+	flag[p] = (k != ~0ull && (p == 0 || key[p - 1] != k))? 1u : 0u;
 }
 
 // one WARP per arc key: lanes stride over the key's records (sorted by key, then genome); a lane that sits on the first
 // record of a (key, genome) run folds that run (graph.c:128-145: count, mean distance, max scores) and adds it to its
 // private sums; a shuffle reduction finishes the key (the additive part of graph.c:153-163).
-__global__ void k_arc_reduce(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rec, const int32_t *__restrict__ dist, const int32_t *__restrict__ s1, const int32_t *__restrict__ s2,
-	int32_t n, int gbits, int32_t n_seg, const uint32_t *__restrict__ start, int32_t n_part, ArcPartial *out)
+__global__ void k_arc_reduce(const uint64_t *__restrict__ key, const uint32_t *__restrict__ rec, const int32_t *__restrict__ gen, const int32_t *__restrict__ dist, const int32_t *__restrict__ s1, const int32_t *__restrict__ s2,
+	int32_t n, int32_t n_seg, const uint32_t *__restrict__ start, const DevCounts *__restrict__ dc, ArcPartial *out, int32_t *arc_of_rec)
 {
-	int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (g >= n_part) return;
-	const int32_t b = start[g], e = g + 1 < n_part? (int32_t)start[g + 1] : n;
-	const uint64_t xk = key[b] >> gbits;
-	long long sum_dist = 0, sum_s1 = 0, sum_s2 = 0;
-	int32_t n_genome = 0, tot = 0;
-	for (int32_t q = b + lane; q < e; q += 32) {
-		uint64_t kg = key[q];
-		if (kg == ~0ull) break;
-		if (q > b && key[q - 1] == kg) continue;            // not the first record of its (key, genome) run
-		unsigned long long dsum = 0; int32_t m1 = 0, m2 = 0, cnt = 0;
-		for (int32_t r = q; r < e && key[r] == kg; ++r) {
-			uint32_t o = rec[r];
-			dsum += (unsigned long long)(long long)dist[o];
-			int32_t a1 = s1[o], a2 = s2[o];
-			m1 = m1 > a1? m1 : a1; m2 = m2 > a2? m2 : a2;
-			++cnt;
+	const int32_t n_part = (int32_t)dc->n_part, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (int32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_part; g += n_warps) {
+		const int32_t b = start[g];
+		int32_t e = g + 1 < n_part? (int32_t)start[g + 1] : n;
+		const uint64_t xk = key[b];
+		long long sum_dist = 0, sum_s1 = 0, sum_s2 = 0;
+		int32_t n_genome = 0, tot = 0;
+		for (int32_t q = b + lane; q < e; q += 32) {
+			if (key[q] != xk) break;                            // only the last group can run into the "no arc" tail
+			arc_of_rec[rec[q]] = g;                             // which arc a record went into (k_branch_hits, single-GPU)
+			const int32_t gq = gen[rec[q]];
+			if (q > b && gen[rec[q - 1]] == gq) continue;       // not the first record of its (key, genome) run
+			unsigned long long dsum = 0; int32_t m1 = 0, m2 = 0, cnt = 0;
+			for (int32_t r = q; r < e && key[r] == xk; ++r) {
+				uint32_t o = rec[r];
+				if (gen[o] != gq) break;
+				dsum += (unsigned long long)(long long)dist[o];
+				int32_t a1 = s1[o], a2 = s2[o];
+				m1 = m1 > a1? m1 : a1; m2 = m2 > a2? m2 : a2;
+				++cnt;
+			}
+			int32_t dg = (int32_t)((double)dsum / cnt + .499);                           // graph.c:141
+			n_genome += 1; tot += cnt;
+			sum_dist += (long long)((unsigned long long)(long long)dg * (unsigned long long)(long long)cnt);   // graph.c:160
+			sum_s1 += m1; sum_s2 += m2;
 		}
-		int32_t dg = (int32_t)((double)dsum / cnt + .499);                               // graph.c:141
-		n_genome += 1; tot += cnt;
-		sum_dist += (long long)((unsigned long long)(long long)dg * (unsigned long long)(long long)cnt);   // graph.c:160
-		sum_s1 += m1; sum_s2 += m2;
-	}
-	for (int s = 16; s > 0; s >>= 1) {
-		sum_dist += __shfl_xor_sync(0xffffffffu, sum_dist, s); sum_s1 += __shfl_xor_sync(0xffffffffu, sum_s1, s); sum_s2 += __shfl_xor_sync(0xffffffffu, sum_s2, s);
-		n_genome += __shfl_xor_sync(0xffffffffu, n_genome, s); tot += __shfl_xor_sync(0xffffffffu, tot, s);
-	}
-	if (lane == 0) {
-		ArcPartial a;
-		uint64_t nv = 2ull * n_seg, v = xk / nv, w = xk % nv;
-		a.x = v << 32 | w; a.sum_dist = sum_dist; a.sum_s1 = sum_s1; a.sum_s2 = sum_s2; a.n_genome = n_genome; a.tot_cnt = tot;
-		out[g] = a;
+		for (int s = 16; s > 0; s >>= 1) {
+			sum_dist += __shfl_xor_sync(0xffffffffu, sum_dist, s); sum_s1 += __shfl_xor_sync(0xffffffffu, sum_s1, s); sum_s2 += __shfl_xor_sync(0xffffffffu, sum_s2, s);
+			n_genome += __shfl_xor_sync(0xffffffffu, n_genome, s); tot += __shfl_xor_sync(0xffffffffu, tot, s);
+		}
+		if (lane == 0) {
+			ArcPartial a;
+			uint64_t nv = 2ull * n_seg, v = xk / nv, w = xk % nv;
+			a.x = v << 32 | w; a.sum_dist = sum_dist; a.sum_s1 = sum_s1; a.sum_s2 = sum_s2; a.n_genome = n_genome; a.tot_cnt = tot;
+			out[g] = a;
+		}
 	}
 }
 
@@ -967,56 +994,71 @@ __global__ void k_arc_finalize(const ArcPartial *__restrict__ in, int32_t n, con
 	arc[pos[p]] = o;
 }
 
+// single-GPU: every partial already is a complete arc (keys are unique after the reduction)
+__global__ void k_arc_finalize_direct(const ArcPartial *__restrict__ in, const DevCounts *__restrict__ dc, ArcDev *arc)
+{
+	PGX_GS(p, dc->n_part) {
+		ArcPartial a = in[p];
+		ArcDev o;
+		o.x = a.x; o.n_genome = a.n_genome; o.tot_cnt = a.tot_cnt; o.bits = 0;
+		o.avg_dist = (int32_t)(long long)((double)a.sum_dist / a.tot_cnt + .499);       // graph.c:170
+		o.s1 = (int32_t)((double)a.sum_s1 / a.n_genome + .499);                         // graph.c:171
+		o.s2 = (int32_t)((double)a.sum_s2 / a.n_genome + .499);                         // graph.c:172
+		arc[p] = o;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // small graph edits (graph.c:179-263)
 // ------------------------------------------------------------------------------------------------
 struct SegDev { int32_t gid, n_dom, n_sub, n_genome, tot_cnt; uint32_t del; int32_t n_dist_loci[2]; };   // == pg_seg_t
 
-__global__ void k_arc_index(const ArcDev *__restrict__ arc, int32_t n_arc, unsigned long long *idx)   // graph.c:202-211
+__global__ void k_arc_index(const ArcDev *__restrict__ arc, const DevCounts *__restrict__ dc, unsigned long long *idx)   // graph.c:202-211
 {
-	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= n_arc) return;
-	uint32_t v = (uint32_t)(arc[p].x >> 32);
-	if (p > 0 && (uint32_t)(arc[p - 1].x >> 32) == v) return;
-	int32_t q = p + 1;
-	while (q < n_arc && (uint32_t)(arc[q].x >> 32) == v) ++q;
-	idx[v] = (unsigned long long)p << 32 | (uint32_t)(q - p);
-}
-
-__global__ void k_seg_store_occ(SegDev *seg, int32_t n_seg, const int32_t *__restrict__ ng, const int32_t *__restrict__ tot)
-{
-	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s < n_seg) { seg[s].n_genome = ng[s]; seg[s].tot_cnt = tot[s]; }
-}
-
-// graph.c:237-256; degrees are taken from the arc list itself (idx may be stale or absent, as in the reference)
-__global__ void k_seg_mark_del(SegDev *seg, int32_t n_seg, const ArcDev *__restrict__ arc, int32_t n_arc, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, uint32_t *keep)
-{
-	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= n_seg) return;
-	bool del = seg[s].tot_cnt > max_occ_total;
-	for (int o = 0; o < 2 && !del; ++o) {
-		uint64_t v = (uint64_t)(2 * s + o) << 32;
-		int32_t lo = 0, hi = n_arc;                             // first arc with x >= v<<32
-		while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < v) lo = m + 1; else hi = m; }
-		int32_t a = lo; hi = n_arc;
-		uint64_t v1 = (uint64_t)(2 * s + o + 1) << 32;
-		while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < v1) lo = m + 1; else hi = m; }
-		if (lo - a > max_degree) del = true;
+	const int32_t n_arc = (int32_t)dc->n_arc;
+	PGX_GS(p, n_arc) {
+		uint32_t v = (uint32_t)(arc[p].x >> 32);
+		if (p > 0 && (uint32_t)(arc[p - 1].x >> 32) == v) continue;
+		int32_t q = p + 1;
+		while (q < n_arc && (uint32_t)(arc[q].x >> 32) == v) ++q;
+		idx[v] = (unsigned long long)p << 32 | (uint32_t)(q - p);
 	}
-	int32_t m = seg[s].n_dist_loci[0] > seg[s].n_dist_loci[1]? seg[s].n_dist_loci[0] : seg[s].n_dist_loci[1];
-	if (m > max_dist_loci) del = true;
-	keep[s] = del? 0u : 1u;
 }
-__global__ void k_seg_compact(const SegDev *__restrict__ in, int32_t n_seg, const uint32_t *__restrict__ pos, SegDev *out)
+
+__global__ void k_seg_store_occ(SegDev *seg, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ng, const int32_t *__restrict__ tot)
 {
-	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s < n_seg && pos[s + 1] != pos[s]) out[pos[s]] = in[s];
+	PGX_GS(s, dc->n_seg) { seg[s].n_genome = ng[s]; seg[s].tot_cnt = tot[s]; }
 }
-__global__ void k_g2s_fill(const SegDev *__restrict__ seg, int32_t n_seg, int32_t *g2s)
+
+// graph.c:237-256; degrees are taken from the arc list itself (idx may be stale or absent, as in the reference). keep[] covers the
+// capacity (segments at vertex selection); slots past the current count are 0
+__global__ void k_seg_mark_del(SegDev *seg, int32_t cap, const DevCounts *__restrict__ dc, const ArcDev *__restrict__ arc, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, uint32_t *keep)
 {
-	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s < n_seg) g2s[seg[s].gid] = s;
+	const int32_t n_seg = (int32_t)dc->n_seg, n_arc = (int32_t)dc->n_arc;
+	PGX_GS(s, cap) {
+		if (s >= n_seg) { keep[s] = 0u; continue; }
+		bool del = seg[s].tot_cnt > max_occ_total;
+		for (int o = 0; o < 2 && !del; ++o) {
+			uint64_t v = (uint64_t)(2 * s + o) << 32;
+			int32_t lo = 0, hi = n_arc;                             // first arc with x >= v<<32
+			while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < v) lo = m + 1; else hi = m; }
+			int32_t a = lo; hi = n_arc;
+			uint64_t v1 = (uint64_t)(2 * s + o + 1) << 32;
+			while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < v1) lo = m + 1; else hi = m; }
+			if (lo - a > max_degree) del = true;
+		}
+		int32_t m = seg[s].n_dist_loci[0] > seg[s].n_dist_loci[1]? seg[s].n_dist_loci[0] : seg[s].n_dist_loci[1];
+		if (m > max_dist_loci) del = true;
+		keep[s] = del? 0u : 1u;
+	}
+}
+__global__ void k_seg_compact(const SegDev *__restrict__ in, const DevCounts *__restrict__ dc, const uint32_t *__restrict__ pos, SegDev *out)
+{
+	PGX_GS(s, dc->n_seg) if (pos[s + 1] != pos[s]) out[pos[s]] = in[s];
+}
+__global__ void k_g2s_fill(const SegDev *__restrict__ seg, const DevCounts *__restrict__ dc, int32_t *g2s)
+{
+	PGX_GS(s, dc->n_seg) g2s[seg[s].gid] = s;
 }
 __global__ void k_arc_keep_min_cnt(const ArcDev *__restrict__ arc, int32_t n_arc, int32_t min_cnt, uint32_t *keep)
 {
@@ -1051,64 +1093,67 @@ __global__ void k_pos_fill(const int32_t *__restrict__ t_last, size_t n_tab, int
 	pos[k] = g;
 }
 
-__global__ void k_cs_tie_count(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, const uint32_t *__restrict__ sv_cs, int32_t m, uint32_t *tie_cnt)
+__global__ void k_cs_tie_count(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, const uint32_t *__restrict__ sv_cs, const DevCounts *__restrict__ dc, uint32_t *tie_cnt)
 {
-	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < 1 || t >= m) return;
-	uint32_t a = sv_cs[t - 1], b = sv_cs[t];
-	if (ctg[a] == ctg[b] && cs[a] == cs[b]) atomicAdd(tie_cnt, 1u);
+	PGX_GS(t, dc->m_cs) {
+		if (t < 1) continue;
+		uint32_t a = sv_cs[t - 1], b = sv_cs[t];
+		if (ctg[a] == ctg[b] && cs[a] == cs[b]) atomicAdd(tie_cnt, 1u);
+	}
 }
 
 // number of n_local values a vertex needs: all arc pairs (i <= k) of its out-list
-__global__ void k_branch_count(const unsigned long long *__restrict__ idx, int32_t n_vtx, uint32_t *cnt)
+__global__ void k_branch_count(const unsigned long long *__restrict__ idx, int32_t cap_vtx, const DevCounts *__restrict__ dc, uint32_t *cnt)
 {
-	int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= n_vtx) return;
-	uint32_t n = (uint32_t)idx[v];
-	cnt[v] = n >= 2? n * (n + 1) / 2 : 0u;
+	const int32_t n_vtx = 2 * (int32_t)dc->n_seg;
+	PGX_GS(v, cap_vtx) {
+		uint32_t n = v < n_vtx? (uint32_t)idx[v] : 0u;
+		cnt[v] = n >= 2? n * (n + 1) / 2 : 0u;
+	}
 }
 
 struct BranchOpt { int32_t local_dist, local_count, frag_mode; double branch_diff, branch_diff_dist, branch_diff_cut; };
 
 __device__ __forceinline__ uint32_t tri_index(uint32_t i, uint32_t k, uint32_t n) { return i * n - i * (i - 1) / 2 + (k - i); }   // i <= k
 
-// one warp per oriented vertex: partial n_local (branch.c:31-46) over the LOCAL genomes for every arc pair
-__global__ void k_branch_nlocal(const unsigned long long *__restrict__ idx, int32_t n_vtx, const ArcDev *__restrict__ arc, const SegDev *__restrict__ seg, const GenePos *__restrict__ pos, int32_t G,
-	const uint32_t *__restrict__ off, BranchOpt o, int32_t *nl)
+// one WARP per table entry = one (vertex, arc pair): partial n_local (branch.c:31-46) over the LOCAL genomes.  (A warp per
+// vertex leaves the few high-degree vertices -- 465 pairs at degree 30 -- as a serial tail: 264 us -> see profiles/README.md.)
+__global__ void k_branch_nlocal(const unsigned long long *__restrict__ idx, const DevCounts *__restrict__ dc, const ArcDev *__restrict__ arc, const SegDev *__restrict__ seg, const GenePos *__restrict__ pos, int32_t G,
+	const uint32_t *__restrict__ off, int32_t n_nl, BranchOpt o, int32_t *nl)
 {
-	int32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (v >= n_vtx) return;
-	unsigned long long e = idx[v];
-	uint32_t n = (uint32_t)e;
-	if (n < 2) return;
-	const ArcDev *a = arc + (e >> 32);
-	int32_t *out = nl + off[v];
-	for (uint32_t i = 0; i < n; ++i) {
-		const GenePos *p1 = pos + (size_t)seg[(uint32_t)a[i].x >> 1].gid * G;
-		for (uint32_t k = i; k < n; ++k) {
-			const GenePos *p2 = pos + (size_t)seg[(uint32_t)a[k].x >> 1].gid * G;
-			int32_t c = 0;
-			for (int32_t j = lane; j < G; j += 32) {
-				GenePos x = p1[j], y = p2[j];
-				if (x.cid < 0 || y.cid < 0) continue;
-				if (!o.frag_mode && x.cid != y.cid) continue;
-				long long dd = (long long)x.cm - y.cm; int32_t dc = x.ord - y.ord;
-				if ((dd >= -o.local_dist && dd <= o.local_dist) || (dc >= -o.local_count && dc <= o.local_count)) ++c;
-			}
-			for (int s = 16; s > 0; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
-			if (lane == 0) out[tri_index(i, k, n)] = c;
+	const int32_t n_vtx = 2 * (int32_t)dc->n_seg, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (int32_t ent = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ent < n_nl; ent += n_warps) {
+		// vertex owning this entry: last v with off[v] <= ent (off is the exclusive scan of the per-vertex pair counts)
+		int32_t lo = 0, hi = n_vtx;
+		while (lo < hi) { int32_t m = (lo + hi) >> 1; if (off[m] <= (uint32_t)ent) lo = m + 1; else hi = m; }
+		const int32_t v = lo - 1;
+		const unsigned long long e = idx[v];
+		const uint32_t n = (uint32_t)e;
+		uint32_t r = (uint32_t)ent - off[v], i = 0;
+		while (r >= n - i) { r -= n - i; ++i; }                 // row i of the upper triangle holds n - i entries (k = i .. n-1)
+		const uint32_t k = i + r;
+		const ArcDev *a = arc + (e >> 32);
+		const GenePos *p1 = pos + (size_t)seg[(uint32_t)a[i].x >> 1].gid * G, *p2 = pos + (size_t)seg[(uint32_t)a[k].x >> 1].gid * G;
+		int32_t c = 0;
+		for (int32_t j = lane; j < G; j += 32) {
+			GenePos x = p1[j], y = p2[j];
+			if (x.cid < 0 || y.cid < 0) continue;
+			if (!o.frag_mode && x.cid != y.cid) continue;
+			long long dd = (long long)x.cm - y.cm; int32_t dcnt = x.ord - y.ord;
+			if ((dd >= -o.local_dist && dd <= o.local_dist) || (dcnt >= -o.local_count && dcnt <= o.local_count)) ++c;
 		}
+		for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
+		if (lane == 0) nl[ent] = c;
 	}
 }
 
 // one thread per oriented vertex: branch.c:60-98 with the (summed) n_local table
-__global__ void k_branch_decide(const unsigned long long *__restrict__ idx, int32_t n_vtx, ArcDev *arc, SegDev *seg, const uint32_t *__restrict__ off, const int32_t *__restrict__ nl, BranchOpt o, int32_t *grp_scratch)
+__global__ void k_branch_decide(const unsigned long long *__restrict__ idx, const DevCounts *__restrict__ dc, ArcDev *arc, SegDev *seg, const uint32_t *__restrict__ off, const int32_t *__restrict__ nl, BranchOpt o, int32_t *grp_scratch)
 {
-	int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-	if (v >= n_vtx) return;
+	PGX_GS(v, 2 * (int32_t)dc->n_seg) {
 	unsigned long long e = idx[v];
 	int32_t n = (int32_t)(uint32_t)e;
-	if (n < 2) return;
+	if (n < 2) continue;
 	ArcDev *a = arc + (e >> 32);
 	const int32_t *t = nl + off[v];
 	int32_t best = 0;
@@ -1133,44 +1178,52 @@ __global__ void k_branch_decide(const unsigned long long *__restrict__ idx, int3
 			if (grp[k] == 0 && t[tri_index(i, k, n)] > 0) grp[k] = grp[i];
 	}
 	seg[v >> 1].n_dist_loci[v & 1] = n_grp;
+	}
 }
 
-// branch.c:108-145 + PG_SET_FILTER(weak_br == 2): survivors in (contig, cm) order look up the two arcs they sit on
+// branch.c:108-145 + PG_SET_FILTER(weak_br == 2): survivors in (contig, cm) order look up the two arcs they sit on.
+// Survivor t emitted records 2t (prev -> me) and 2t+1 (me^1 -> prev^1) in k_arc_emit; arc_of_rec (written by k_arc_reduce)
+// says which arc each record was folded into, so no search is needed.  With arc_of_rec == nullptr (multi-GPU: arcs are
+// re-numbered by the cross-rank merge) the arc is found by binary search on its key.
 __device__ __forceinline__ uint32_t arc_weak(const ArcDev *__restrict__ arc, int32_t n_arc, uint64_t x)
 {
 	int32_t lo = 0, hi = n_arc;
 	while (lo < hi) { int32_t m = (lo + hi) >> 1; if (arc[m].x < x) lo = m + 1; else hi = m; }
 	return (lo < n_arc && arc[lo].x == x)? (arc[lo].bits >> 1 & 3u) : 0u;
 }
-__global__ void k_branch_hits(const uint32_t *__restrict__ sv, int32_t m, const int32_t *__restrict__ ctg, const int32_t *__restrict__ gidp, uint32_t *bits, const int32_t *__restrict__ g2s,
-	const ArcDev *__restrict__ arc, int32_t n_arc)
+__global__ void k_branch_hits(const uint32_t *__restrict__ sv, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ctg, const int32_t *__restrict__ gidp, uint32_t *bits, const int32_t *__restrict__ g2s,
+	const ArcDev *__restrict__ arc, const int32_t *__restrict__ arc_of_rec)
 {
-	int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= m) return;
-	uint32_t h = sv[t], b = bits[h];
-	int32_t c = ctg[h];
-	uint32_t w = (uint32_t)g2s[gidp[h] >> 1] << 1 | (b & PG_HB_REV);
-	uint32_t wb = (b & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT;
-	if (t > 0) {                                            // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
-		uint32_t hp = sv[t - 1];
-		if (ctg[hp] == c) {
-			uint32_t v = (uint32_t)g2s[gidp[hp] >> 1] << 1 | (bits[hp] & PG_HB_REV);
-			uint32_t x = arc_weak(arc, n_arc, (uint64_t)(w ^ 1) << 32 | (v ^ 1));
+	const int32_t m = (int32_t)dc->m_sv, n_arc = (int32_t)dc->n_arc;
+	PGX_GS(t, m) {
+		uint32_t h = sv[t], b = bits[h];
+		int32_t c = ctg[h];
+		uint32_t wb = (b & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT;
+		if (t > 0 && ctg[sv[t - 1]] == c) {                 // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
+			uint32_t x;
+			if (arc_of_rec) x = arc[arc_of_rec[2 * (size_t)t + 1]].bits >> 1 & 3u;
+			else {
+				uint32_t hp = sv[t - 1];
+				uint32_t w = (uint32_t)g2s[gidp[h] >> 1] << 1 | (b & PG_HB_REV), v = (uint32_t)g2s[gidp[hp] >> 1] << 1 | (bits[hp] & PG_HB_REV);
+				x = arc_weak(arc, n_arc, (uint64_t)(w ^ 1) << 32 | (v ^ 1));
+			}
 			wb = wb > x? wb : x;
 		}
-	}
-	if (t + 1 < m) {                                        // I am the earlier hit of (me, next): arc (v -> w), branch.c:127-129
-		uint32_t hn = sv[t + 1];
-		if (ctg[hn] == c) {
-			uint32_t wn = (uint32_t)g2s[gidp[hn] >> 1] << 1 | (bits[hn] & PG_HB_REV);
-			uint32_t x = arc_weak(arc, n_arc, (uint64_t)w << 32 | wn);
+		if (t + 1 < m && ctg[sv[t + 1]] == c) {             // I am the earlier hit of (me, next): arc (v -> w), branch.c:127-129
+			uint32_t x;
+			if (arc_of_rec) x = arc[arc_of_rec[2 * (size_t)(t + 1)]].bits >> 1 & 3u;
+			else {
+				uint32_t hn = sv[t + 1];
+				uint32_t w = (uint32_t)g2s[gidp[h] >> 1] << 1 | (b & PG_HB_REV), wn = (uint32_t)g2s[gidp[hn] >> 1] << 1 | (bits[hn] & PG_HB_REV);
+				x = arc_weak(arc, n_arc, (uint64_t)w << 32 | wn);
+			}
 			wb = wb > x? wb : x;
 		}
+		// only the weak_br bits (and flt) of my own word change; neighbours read rev only, which never changes
+		b = (b & ~PG_HB_WBR_MASK) | wb << PG_HB_WBR_SHIFT;
+		if (wb == 2) b |= PG_HB_FLT;                             // graph.c:309
+		bits[h] = b;
 	}
-	// only the weak_br bits (and flt) of my own word change; neighbours read rev only, which never changes
-	b = (b & ~PG_HB_WBR_MASK) | wb << PG_HB_WBR_SHIFT;
-	if (wb == 2) b |= PG_HB_FLT;                             // graph.c:309
-	bits[h] = b;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1192,6 +1245,12 @@ __global__ void k_pack_out(const uint32_t *__restrict__ src, int32_t n, FullCols
 // ------------------------------------------------------------------------------------------------
 // odds and ends
 // ------------------------------------------------------------------------------------------------
+// (contig << 32 | coordinate) -> (contig << coord_bits | coordinate): same order, fewer significant bits, fewer radix passes
+__global__ void k_pack_sort_key(uint64_t *key, int32_t n, int coord_bits)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) { uint64_t k = key[i]; key[i] = (k >> 32) << coord_bits | (k & 0xffffffffull); }
+}
 __global__ void k_fill_i32(int32_t *a, int64_t n, int32_t v)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1202,10 +1261,9 @@ __global__ void k_gather_u32(const uint32_t *__restrict__ table, const uint32_t 
 	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) out[i] = table[index[i]];
 }
-__global__ void k_seg_zero_loci(SegDev *seg, int32_t n_seg)   // branch.c:56-57
+__global__ void k_seg_zero_loci(SegDev *seg, const DevCounts *__restrict__ dc)   // branch.c:56-57
 {
-	int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s < n_seg) seg[s].n_dist_loci[0] = seg[s].n_dist_loci[1] = 0;
+	PGX_GS(s, dc->n_seg) seg[s].n_dist_loci[0] = seg[s].n_dist_loci[1] = 0;
 }
 __global__ void k_partial_keys(const ArcPartial *__restrict__ in, int32_t n, int32_t n_seg, uint64_t *key)
 {
