@@ -487,9 +487,28 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_top(Sw
 	__syncthreads();
 	while (!mbar_try_wait(bar, 0)) { }
 
-	const int32_t i = t0 + tid;
-	const bool in_range = i < c.n;
-	const int32_t mq = in_range? i - lo : 0;
+	// filtered hits (25 % in the first sweep) do no work: compact the live ones so that they fill whole warps
+	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
+	int32_t i;
+	bool in_range;
+	{
+		const int32_t i0 = t0 + tid;
+		const bool r0 = i0 < c.n;
+		const uint32_t b0 = s_bits[r0? i0 - lo : 0];
+		if (r0 && (b0 & PG_HB_FLT)) bits_out[i0] = b0;                                   // overlap.c:63,112
+		const bool live0 = r0 && !(b0 & PG_HB_FLT);
+		const uint32_t bal = __ballot_sync(0xffffffffu, live0);
+		if ((tid & 31) == 0) s_wcnt[tid >> 5] = (uint16_t)__popc(bal);
+		__syncthreads();
+		int32_t base = 0, n_live = 0;
+#pragma unroll
+		for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
+		if (live0) s_live[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
+		__syncthreads();
+		in_range = tid < n_live;
+		i = in_range? t0 + (int32_t)s_live[tid] : t0;
+	}
+	const int32_t mq = i - lo;
 	const uint32_t mbits = s_bits[mq];
 	AccStaged A;
 	A.c = c; A.lo = lo; A.elo = s_misc[0]; A.ehi = s_misc[1];
@@ -499,20 +518,22 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_top(Sw
 	const uint64_t mkey = s_key[mq];
 	int32_t top_p = INT32_MAX; uint64_t top_key = 0;
 	bool slow = false, lose = false, write_out = false;
-	if (in_range && (mbits & PG_HB_FLT)) bits_out[i] = mbits;                            // overlap.c:63,112
-	if (in_range && !(mbits & PG_HB_FLT)) {
-	// ---- phase 1: the would-be dominator
+	if (in_range) {
+	// ---- phase 1: the would-be dominator.  One loop walks back, then forward: a lane whose backward window is short starts its
+	// forward window while its neighbours are still going back (the warp pays max(back + fwd), not max(back) + max(fwd)).
+	{
+		int side = 0, step = -1;
 #pragma unroll 1
-	for (int side = 0; side < 2; ++side) {
-		const int step = side == 0? -1 : 1;
-#pragma unroll 1
-		for (int32_t p = i + step;; p += step) {
-			if (p < lo) { slow = slow || p >= 0; break; }                // the window may continue outside the staged range
-			if (p >= hi) { slow = slow || p < c.n; break; }
-			const int32_t q = p - lo;
-			const int32_t pcs = s_cs[q], pce = s_ce[q];
-			if (s_ctg[q] != mctg) break;
-			if (side == 0? s_pmax[q] <= mcs : pcs >= mce) break;         // overlap.c:67-71,114-120: nothing further out can reach me
+		for (int32_t p = i - 1;; p += step) {
+			bool end = false;
+			int32_t q = 0, pcs = 0, pce = 0;
+			if (p < lo) { slow = slow || p >= 0; end = true; }           // the window may continue outside the staged range
+			else if (p >= hi) { slow = slow || p < c.n; end = true; }
+			else {
+				q = p - lo; pcs = s_cs[q]; pce = s_ce[q];
+				end = s_ctg[q] != mctg || (side == 0? s_pmax[q] <= mcs : pcs >= mce);   // overlap.c:67-71,114-120: nothing further out can reach me
+			}
+			if (end) { if (side == 1) break; side = 1; step = 1; p = i; continue; }
 			const uint32_t pbits = s_bits[q];
 			const int32_t pgene = s_gidp[q] >> 1;
 			const uint64_t pkey = s_key[q];
