@@ -69,7 +69,7 @@ struct Session {
 	// ---- device: constants and raw input
 	DBuf<int32_t> hoff, coff, ctg2g, prot_gid, prot_max, prot_rep, g2s;
 	DBuf<RawHit> raw;
-	bool host_sorted = false;            // the caller's hit arrays are already in (contig, cs) order (after a first download)
+	std::vector<const pg_hit_t*> installed;   // hit arrays this session handed to the caller (already in (contig, cs) order)
 	DBuf<uint32_t> eoffg, src, counters;
 	DBuf<uint8_t> gene_pref;
 	DBuf<int2> ex_raw, ex, wex;
@@ -170,7 +170,7 @@ struct Session {
 			scratch.reset(0);
 		} else rank_G.assign(1, G);
 		PGX_CHECK(cudaStreamSynchronize(st));
-		done_post = done_graph = false; host_sorted = false;
+		done_post = done_graph = false; installed.clear();
 	}
 
 	// host threads pack 48-byte RawHit records from the caller's pg_hit_t arrays into pinned chunks while the copy engine
@@ -518,12 +518,21 @@ struct Session {
 	// graph.c:87-177.  No host round-trip in the single-GPU path: survivor count, group count and arc count stay on the device.
 	void gen_arc(const pg_opt_t *opt)
 	{
+		struct Acc { double &a; double t0; ~Acc() { a += wall_s() - t0; } } acc_arc{t_arc, wall_s()};
 		if (Nw == 0 || n_seg0 == 0) {   // nothing can survive: empty arc set, zero occupancy
 			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u);
-			if (n_seg0) {
+			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_part)), 0u);
+			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, m_sv)), 0u);
+			m_sv = 0;
+			if (n_seg0) {   // n_seg0 is replicated: every rank takes the same branch, so the collectives below stay matched
+				size_t mk = scratch.mark();
 				PGX_CHECK(cudaMemsetAsync(seg_ng.p, 0, (size_t)n_seg0 * 4, st));
 				PGX_CHECK(cudaMemsetAsync(seg_tot.p, 0, (size_t)n_seg0 * 4, st));
+				if (g_comm.active()) merge_partials_across_ranks(nullptr);
+				g_comm.allreduce(seg_ng.p, n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
+				g_comm.allreduce(seg_tot.p, n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
 				PGX_LAUNCH(k_seg_store_occ, GS_GRID, TB, 0, st, seg.p, dc.p, seg_ng.p, seg_tot.p);
+				scratch.reset(mk);
 			}
 			return;
 		}
@@ -579,8 +588,11 @@ struct Session {
 	}
 
 	// multi-GPU: every rank contributes its partial table (padded to the largest one); sort by key, merge equal keys (graph.c:150-175)
+	double t_merge = 0, t_branch = 0, t_arc = 0, t_vtx = 0;   // host wall time per piece (PGX_TIMING)
 	void merge_partials_across_ranks(const ArcPartial *part)
 	{
+		double tm0 = wall_s();
+		struct Acc { double &a; double t0; ~Acc() { a += wall_s() - t0; } } acc{t_merge, tm0};
 		uint32_t n_part = read_counts().n_part;
 		uint32_t *cnt = scratch.get<uint32_t>(g_comm.nranks + 1);
 		PGX_CHECK(cudaMemcpyAsync(cnt + g_comm.rank, &n_part, 4, cudaMemcpyHostToDevice, st));
@@ -591,7 +603,7 @@ struct Session {
 		uint32_t mx = 0; uint64_t tot = 0;
 		for (uint32_t c : hc) { mx = c > mx? c : mx; tot += c; }
 		if (tot == 0) { PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u); return; }
-		if (tot > arc_cap) PGX_FATAL("arc table overflow (%lu partial arcs)", (unsigned long)tot);
+		if (tot + 1 > arc.n) { arc.alloc(tot + tot / 4 + 16); arc_alt.alloc(tot + tot / 4 + 16); arc_cap = arc.n - 1; }   // the merged table can exceed this rank's own capacity
 		ArcPartial *all = scratch.get<ArcPartial>((size_t)mx * g_comm.nranks + 1), *mine = all + (size_t)mx * g_comm.rank;
 		if (n_part) PGX_CHECK(cudaMemcpyAsync(mine, part, (size_t)n_part * sizeof(ArcPartial), cudaMemcpyDeviceToDevice, st));
 		g_comm.allgather(mine, all, (size_t)mx * sizeof(ArcPartial), st);
@@ -634,9 +646,10 @@ struct Session {
 
 	void branch_round(const pg_opt_t *opt)   // branch.c:48-145 + graph.c:309
 	{
+		struct Acc { double &a; double t0; ~Acc() { a += wall_s() - t0; } } acc_br{t_branch, wall_s()};
 		size_t mk = scratch.mark();
 		arc_index();
-		if (Nw && n_seg0) {
+		if (n_seg0) {   // (a rank without active hits still joins: the arc marks must come out identical everywhere)
 			PGX_LAUNCH(k_seg_zero_loci, GS_GRID, TB, 0, st, seg.p, dc.p);
 			// representative position of every gene in every local genome (branch.c:6-29)
 			size_t tab = (size_t)n_gene * G;
@@ -711,6 +724,8 @@ struct Session {
 		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] final graph: %d genes and %d arcs\n", n_seg, n_arc);
 		done_graph = true;
 		g_stats.n_seg = n_seg; g_stats.n_arc = n_arc;
+		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] rank %d stage 2 host wall: arc rounds %.2f ms (of which cross-rank merge %.2f), branch rounds %.2f ms\n", g_comm.rank, t_arc * 1e3, t_merge * 1e3, t_branch * 1e3);
+		t_arc = t_merge = t_branch = 0;
 	}
 
 	void collect_stats()
@@ -737,6 +752,10 @@ struct Session {
 			PGX_LAUNCH(k_pack_out, grid_for(N, TB), TB, 0, st, src.p, N, F, g2s.p, prot_rep.p, done_graph? 1 : 0, out.p);
 			ThreadPool &pool = ThreadPool::get();
 			std::vector<pg_hit_t*> fresh(G, nullptr);
+			// second download of a strict-mode run (after pg_graph_gen): the caller still holds the arrays we returned after
+			// pg_post_process, already permuted -> patch them in place.  Anything else is rebuilt from raw order.
+			bool host_sorted = (int32_t)installed.size() == G && G > 0;
+			for (int32_t j = 0; j < G && host_sorted; ++j) host_sorted = d->genome[j].hit == installed[j];
 			for (int32_t j = 0; j < G; ++j) {
 				if (h_hoff[j + 1] - h_hoff[j] != d->genome[j].n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
 				if (!host_sorted) fresh[j] = alloc_hit_array((size_t)d->genome[j].n_hit);
@@ -762,7 +781,7 @@ struct Session {
 			}, st);
 			if (!host_sorted) {
 				pool.parallel_for(G, [&](int64_t j) { free(d->genome[j].hit); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = d->genome[j].n_hit; });   // hit.c:62-63
-				host_sorted = true;
+				installed.assign(fresh.begin(), fresh.end());
 			}
 			g_stats.d2h += (int64_t)N * (int64_t)sizeof(OutHit);
 		}

@@ -6,6 +6,7 @@
 // compactions that are a small part of a round, see DESIGN.md.
 #pragma once
 #include "pgx_util.cuh"
+#include <cstring>
 
 namespace pgx {
 
@@ -68,9 +69,6 @@ __global__ void k_scan_sum_add(uint32_t *out, const uint32_t *__restrict__ agg, 
 	if (i < n_out) out[i] += agg[i / SCAN_TILE];
 }
 
-// scratch must hold ceil((n_in+1)/SCAN_TILE) uint32
-static inline size_t scan_scratch_elems(int64_t n_in) { return (size_t)((n_in + 1 + SCAN_TILE - 1) / SCAN_TILE); }
-
 // whole scan in ONE block (n_in up to a few hundred thousand): the many small per-round scans (segments, vertices, arc
 // groups) are launch-latency bound, three launches each hurt more than the serial chunk loop
 constexpr int SCAN_SMALL_B = 1024, SCAN_SMALL_MAX = 1 << 16;
@@ -101,11 +99,76 @@ __global__ void __launch_bounds__(SCAN_SMALL_B) k_scan_sum_small(const uint32_t 
 	}
 }
 
+// ---- single-pass variant (decoupled look-back): one launch instead of three -------------------------------------------
+// Every tile publishes (flag, value) in a 64-bit status word: AGG = "my own sum", PREFIX = "sum of everything up to and
+// including me".  A tile adds up the words of its predecessors, 32 at a time (one per lane), until it meets a PREFIX.  Tile
+// numbers come from an atomic ticket, so a tile only ever waits for tiles that are already running.
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PREFIX = 2ull << 62, LB_MASK = 3ull << 62;
+__global__ void __launch_bounds__(SCAN_B) k_scan_sum_lookback(const uint32_t *__restrict__ in, uint32_t *out, int64_t n_in, unsigned long long *status, uint32_t *ticket)
+{
+	__shared__ uint32_t sh[SCAN_B];
+	__shared__ uint32_t s_tile, s_prefix;
+	const int tid = threadIdx.x;
+	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)tid * SCAN_I;
+	uint32_t v[SCAN_I], sum = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) { int64_t i = base + k; v[k] = i < n_in? in[i] : 0u; sum += v[k]; }
+	sh[tid] = sum;
+	__syncthreads();
+	for (int d = 1; d < SCAN_B; d <<= 1) {
+		uint32_t t = tid >= d? sh[tid - d] : 0u;
+		__syncthreads();
+		sh[tid] += t;
+		__syncthreads();
+	}
+	const uint32_t tile_sum = sh[SCAN_B - 1];
+	if (tid < 32) {
+		if (tid == 0) { __threadfence(); atomicExch(&status[tile], (tile == 0? LB_PREFIX : LB_AGG) | tile_sum); }
+		uint32_t prefix = 0;
+		if (tile > 0) {
+			int64_t look = (int64_t)tile - 1;
+			for (;;) {
+				const int64_t p = look - tid;
+				unsigned long long w = LB_PREFIX;                    // lanes before the first tile: a zero-valued closed prefix
+				if (p >= 0) { do { w = *(volatile unsigned long long*)&status[p]; } while ((w & LB_MASK) == 0); }
+				const uint32_t closed = __ballot_sync(0xffffffffu, (w & LB_MASK) == LB_PREFIX);
+				const int first = closed? __ffs(closed) - 1 : 32;   // nearest predecessor that already knows its prefix
+				uint32_t add = tid <= first? (uint32_t)(w & 0xffffffffull) : 0u;
+				for (int sft = 16; sft > 0; sft >>= 1) add += __shfl_xor_sync(0xffffffffu, add, sft);
+				prefix += add;
+				if (closed) break;
+				look -= 32;
+			}
+			if (tid == 0) { __threadfence(); atomicExch(&status[tile], LB_PREFIX | (unsigned long long)(prefix + tile_sum)); }
+		}
+		if (tid == 0) s_prefix = prefix;
+	}
+	__syncthreads();
+	uint32_t run = s_prefix + sh[tid] - sum;
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) { int64_t i = base + k; if (i <= n_in) out[i] = run; run += v[k]; }
+}
+
+// scratch for the look-back variant: one status word per tile + the ticket, as uint32 elements
+static inline size_t scan_scratch_elems(int64_t n_in) { return (size_t)((n_in + 1 + SCAN_TILE - 1) / SCAN_TILE) * 2 + 4; }
+
 static void exclusive_sum_u32(const uint32_t *in, uint32_t *out, int64_t n_in, uint32_t *agg_scratch, cudaStream_t s)
 {
+	static const bool three_pass = []() { const char *e = getenv("PGX_SCAN"); return e && strcmp(e, "3pass") == 0; }();
 	int64_t n_out = n_in + 1;
 	if (n_in <= SCAN_SMALL_MAX) { PGX_LAUNCH(k_scan_sum_small, 1, SCAN_SMALL_B, 0, s, in, out, (int32_t)n_in); return; }
 	int tiles = (int)((n_out + SCAN_TILE - 1) / SCAN_TILE);
+	if (!three_pass) {
+		// status words must start 8-byte aligned: scratch comes from 256-byte aligned arena/cache blocks
+		unsigned long long *status = (unsigned long long*)agg_scratch;
+		uint32_t *ticket = agg_scratch + (size_t)tiles * 2;
+		PGX_CHECK(cudaMemsetAsync(agg_scratch, 0, ((size_t)tiles * 2 + 4) * 4, s));
+		PGX_LAUNCH(k_scan_sum_lookback, tiles, SCAN_B, 0, s, in, out, n_in, status, ticket);
+		return;
+	}
 	PGX_LAUNCH(k_scan_sum_tiles, tiles, SCAN_B, 0, s, in, out, agg_scratch, n_in);
 	if (tiles > 1) {
 		PGX_LAUNCH(k_scan_sum_agg, 1, SCAN_B, 0, s, agg_scratch, tiles);

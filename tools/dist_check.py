@@ -21,7 +21,8 @@ from pangene_b200 import dist as pgdist, engine, hostio
 
 CASES = [dict(config=2, n_genome=7, n_gene=1800, iso_per_gene=4, hits_per_genome=16000, args=[]),
          dict(config=2, n_genome=9, n_gene=2500, iso_per_gene=1, hits_per_genome=6000, args=["-S"]),
-         dict(config=5, n_genome=64, n_gene=1200, iso_per_gene=1, hits_per_genome=1000, args=["-p0", "-a2"])]
+         dict(config=5, n_genome=64, n_gene=1200, iso_per_gene=1, hits_per_genome=1000, args=["-p0", "-a2"]),
+         dict(config=2, n_genome=3, n_gene=900, iso_per_gene=4, hits_per_genome=8000, args=[])]   # fewer genomes than ranks at 4/8 GPUs: empty shards
 
 
 def main():
