@@ -17,6 +17,9 @@ static bool timing_on() { static const bool on = getenv("PGX_TIMING") != nullptr
 
 static void need_device()
 {
+	static int checked_dev = -2;          // the property query is slow (tens of ms with several GPUs on the box): once per device
+	if (g_device >= 0) PGX_CHECK(cudaSetDevice(g_device));
+	{ int cur = -1; if (cudaGetDevice(&cur) == cudaSuccess && cur == checked_dev) return; }
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
 	if (e != cudaSuccess || n < 1) PGX_FATAL("no CUDA device available (%s). libpgx has no CPU fallback.", cudaGetErrorString(e));
@@ -26,6 +29,7 @@ static void need_device()
 	PGX_CHECK(cudaGetDevice(&dev));
 	PGX_CHECK(cudaGetDeviceProperties(&p, dev));
 	if (p.major < 10) PGX_FATAL("device %d (%s, sm_%d%d) is not a Blackwell part; libpgx is built for sm_100a only", dev, p.name, p.major, p.minor);
+	checked_dev = dev;
 }
 
 static void timed_run(Session *s, const pg_opt_t *opt, int stage)
@@ -63,6 +67,7 @@ int pg_verbose = 3;
 
 void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 {
+	const double t_enter = wall();
 	need_device();
 	if (pg_verbose >= 3) fprintf(stderr, "[M::%s] %d genes and %d proteins\n", __func__, d->n_gene, d->n_prot);
 	auto it = g_sessions.find(d);
@@ -73,7 +78,7 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	double t1 = wall();
 	timed_run(s, opt, 1);
 	double t2 = wall();
-	if (timing_on()) fprintf(stderr, "[pgx timing] session+upload %.1f ms, stage 1 %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3);
+	if (timing_on()) fprintf(stderr, "[pgx timing] device check %.1f ms, session+upload %.1f ms, stage 1 %.1f ms\n", (t0 - t_enter) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
 	if (!g_lazy) s->download(d, nullptr);
 	else {   // the protein/gene tables are cheap and always current
 		for (int32_t i = 0; i < d->n_prot; ++i) { d->prot[i].n = s->rep.prot_n[i]; d->prot[i].avg_score_adj = s->rep.prot_avg[i]; d->prot[i].rep = s->rep.prot_rep[i]; d->prot[i].max_score_ori = s->h_prot_max[i]; }

@@ -35,15 +35,24 @@ __global__ void __launch_bounds__(RS_BLOCK) k_rs_hist(const uint64_t *__restrict
 	hist[(size_t)tid * n_tiles + blockIdx.x] = h[tid];
 }
 
-// vals_in == nullptr means "the value of element i is i" (first pass over fresh keys)
+// vals_in == nullptr means "the value of element i is i" (first pass over fresh keys).
+// After ranking, the tile is first permuted INSIDE shared memory (digit-major, stable), then written out: consecutive threads
+// store consecutive elements of a digit run, so every 32-byte sector written is fully used (a direct scatter of 8-byte keys to
+// 256 destinations touches one sector per key: ~4x write amplification, measured 96 us per pass on 3.6 M records).
+constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_TILE * 4 + (size_t)RS_WARPS * 256 * 4 + 256 * 4 * 2;
 __global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in, int64_t n, int shift,
 	const uint32_t *__restrict__ hist_scan, int n_tiles, uint64_t *keys_out, uint32_t *vals_out)
 {
-	__shared__ uint32_t wcnt[RS_WARPS][256];
+	extern __shared__ __align__(16) unsigned char rs_smem[];
+	uint64_t *skey = (uint64_t*)rs_smem;                                   // [RS_TILE] tile, digit-major
+	uint32_t *sval = (uint32_t*)(rs_smem + (size_t)RS_TILE * 8);           // [RS_TILE]
+	uint32_t (*wcnt)[256] = (uint32_t (*)[256])(rs_smem + (size_t)RS_TILE * 12);   // [RS_WARPS][256]
+	uint32_t *blk_off = (uint32_t*)(rs_smem + (size_t)RS_TILE * 12 + (size_t)RS_WARPS * 1024);   // [256] exclusive digit offsets inside the tile
+	uint32_t *gbase = blk_off + 256;                                       // [256] global base of (digit, tile)
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	for (int k = tid; k < RS_WARPS * 256; k += RS_BLOCK) (&wcnt[0][0])[k] = 0;
 	__syncthreads();
-	const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ITEMS);
+	const int64_t tbase = (int64_t)blockIdx.x * RS_TILE, wbase = tbase + (int64_t)warp * (32 * RS_ITEMS);
 	uint64_t key[RS_ITEMS];
 	uint32_t rank[RS_ITEMS];
 	const uint32_t lt = (1u << lane) - 1u;
@@ -61,11 +70,24 @@ __global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const uint64_t *__restr
 		rank[r] = before + __popc(peers & lt);
 	}
 	__syncthreads();
-	// digit `tid`: turn per-warp counts into per-warp exclusive bases, add the global base of (digit, tile)
+	// digit `tid`: per-warp counts -> per-warp exclusive bases inside the digit; digit total -> blk_off (scanned below)
 	{
-		uint32_t run = hist_scan[(size_t)tid * n_tiles + blockIdx.x];
+		uint32_t run = 0;
 #pragma unroll
 		for (int w = 0; w < RS_WARPS; ++w) { uint32_t c = wcnt[w][tid]; wcnt[w][tid] = run; run += c; }
+		blk_off[tid] = run;
+		gbase[tid] = hist_scan[(size_t)tid * n_tiles + blockIdx.x];
+	}
+	__syncthreads();
+	if (warp == 0) {   // exclusive scan of the 256 digit totals: 8 per lane + a warp scan
+		uint32_t v[8], sum = 0;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) { v[k] = blk_off[lane * 8 + k]; sum += v[k]; }
+		uint32_t inc = sum;
+		for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+		uint32_t run = inc - sum;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) { blk_off[lane * 8 + k] = run; run += v[k]; }
 	}
 	__syncthreads();
 #pragma unroll
@@ -73,10 +95,19 @@ __global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const uint64_t *__restr
 		int64_t i = wbase + r * 32 + lane;
 		if (i < n) {
 			uint32_t d = rs_digit(key[r], shift);
-			uint32_t pos = wcnt[warp][d] + rank[r];
-			keys_out[pos] = key[r];
-			vals_out[pos] = vals_in? vals_in[i] : (uint32_t)i;
+			uint32_t lp = blk_off[d] + wcnt[warp][d] + rank[r];
+			skey[lp] = key[r];
+			sval[lp] = vals_in? vals_in[i] : (uint32_t)i;
 		}
+	}
+	__syncthreads();
+	const int n_tile = (int)((n - tbase) < RS_TILE? (n - tbase) : RS_TILE);
+	for (int j = tid; j < n_tile; j += RS_BLOCK) {
+		uint64_t k = skey[j];
+		uint32_t d = rs_digit(k, shift);
+		uint32_t pos = gbase[d] + ((uint32_t)j - blk_off[d]);
+		keys_out[pos] = k;
+		vals_out[pos] = sval[j];
 	}
 }
 
@@ -90,6 +121,8 @@ struct RadixSortBuffers {          // caller-provided scratch (no allocation ins
 static void radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits, bool iota_vals, const RadixSortBuffers &b,
 	uint64_t **keys_res, uint32_t **vals_res, cudaStream_t s)
 {
+	static bool attr_set = false;
+	if (!attr_set) { PGX_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM)); attr_set = true; }
 	uint64_t *kin = keys, *kout = b.keys_alt;
 	uint32_t *vin = vals, *vout = b.vals_alt;
 	if (n > 0) {
@@ -100,7 +133,7 @@ static void radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int n_bi
 		for (int shift = 0; shift < n_bits; shift += 8) {
 			PGX_LAUNCH(k_rs_hist, n_tiles, RS_BLOCK, 0, s, kin, n, shift, b.hist, n_tiles);
 			exclusive_sum_u32(b.hist, b.hist, hn, b.scan_agg, s);
-			PGX_LAUNCH(k_rs_scatter, n_tiles, RS_BLOCK, 0, s, kin, (first && iota_vals)? (const uint32_t*)nullptr : vin, n, shift, b.hist, n_tiles, kout, vout);
+			PGX_LAUNCH(k_rs_scatter, n_tiles, RS_BLOCK, RS_SMEM, s, kin, (first && iota_vals)? (const uint32_t*)nullptr : vin, n, shift, b.hist, n_tiles, kout, vout);
 			uint64_t *tk = kin; kin = kout; kout = tk;
 			uint32_t *tv = vin; vin = vout; vout = tv;
 			first = false;
