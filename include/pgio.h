@@ -31,6 +31,11 @@ void pgio_data_destroy(pg_data_t *d);
  * Returns 0, or -1 if the file cannot be opened (then no genome is added), like the reference. */
 int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *fn);
 
+/* All files of a command line at once: each file is parsed by a worker thread with file-local ids, then the files are merged in
+ * argument order -- gene/protein ids, names, ranks and every hit come out exactly as from calling pgio_read_paf() file by file
+ * (tests/test_io.py).  n_threads 0 = hardware concurrency.  Returns the number of files opened. */
+int32_t pgio_read_pafs(const pg_opt_t *opt, pg_data_t *d, const char *const *fns, int32_t n_files, int32_t n_threads);
+
 /* read.c:305-318: name set for -X/-I/-P from "a,b,c" or "@file" */
 void *pgio_name_set(const char *spec);
 void pgio_name_set_destroy(void *set);

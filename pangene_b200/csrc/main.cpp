@@ -99,7 +99,7 @@ int main(int argc, char *argv[])
 	if (argc - optind < 1) return usage(stderr, &opt);
 
 	pg_data_t *d = pgio_data_init();
-	for (int i = optind; i < argc; ++i) pgio_read_paf(&opt, d, argv[i]);
+	pgio_read_pafs(&opt, d, (const char *const*)&argv[optind], argc - optind, 0);   // parallel parse, ids as in sequential order
 	double t1 = now();
 	pgx_set_lazy(!(opt.flag & PG_F_WRITE_BED_RAW));   // hits come back once, after pg_graph_gen
 	pg_post_process(&opt, d);

@@ -15,6 +15,8 @@
 #include <deque>
 #include <unordered_map>
 #include <algorithm>
+#include <thread>
+#include <atomic>
 #include <zlib.h>
 #include "pgio.h"
 #include "pgio_priv.hpp"
@@ -286,26 +288,36 @@ void pgio::push_hit(pg_genome_t *g, pg_hit_t &hit, const std::vector<pg_exon_t> 
 	g->hit[g->n_hit++] = hit;
 }
 
-extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *fn)
+// One PAF file parsed on its own, with FILE-LOCAL gene/protein ids (first-seen order inside the file).  Files are
+// independent except for the global id assignment (ids = dictionary size at first sight, read.c:151,161; hit.rank is a
+// per-file count, read.c:170), so they can be parsed in parallel and merged in command-line order afterwards
+// (SURVEY.md §8f rank 1): merging the per-file first-seen lists in file order reproduces the sequential ids exactly.
+namespace {
+struct LocalFile {
+	bool ok = false;
+	pg_genome_t g;
+	pgio::NameTable gene, prot, ctg;                  // local dictionaries (own their strings until the merge)
+	std::vector<int32_t> prot_gid, prot_len;          // per local protein: local gene id, length as left by its LAST line (read.c:166,174)
+	std::vector<int32_t> gene_len;                    // per local gene: max protein length seen (read.c:175)
+	std::vector<uint8_t> gene_pref, gene_incl;
+	int64_t n_lines = 0;
+	LocalFile() { memset(&g, 0, sizeof(g)); }
+};
+
+void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 {
 	std::string buf;
-	if (!read_whole(fn, buf)) return -1;                          // read.c:117-118
-	pgio::DataPriv *pv = (pgio::DataPriv*)d->d_ctg;
+	if (!read_whole(fn, buf)) return;                              // read.c:117-118
+	F.ok = true;
 	const pgio::NameTable *excl = (const pgio::NameTable*)opt->excl, *incl = (const pgio::NameTable*)opt->incl, *pref = (const pgio::NameTable*)opt->preferred;
-
-	grow0(d->genome, d->n_genome, d->m_genome);
-	pg_genome_t *g = &d->genome[d->n_genome++];
-	memset(g, 0, sizeof(*g));
+	pg_genome_t *g = &F.g;
 	g->label = fn && strcmp(fn, "-")? label_from_path(fn) : label_from_path("-");
-
-	std::unordered_map<std::string_view, int32_t> file_ctg;      // per-file contig ids, first-seen order
 	std::vector<int32_t> seen_cnt;                                // per-protein line count in THIS file (rank, read.c:170)
 	std::vector<pg_exon_t> tmp, ex;
 	std::vector<char*> fld;
-	int64_t n_tot = 0;
 
 	for_each_line(buf, [&](char *s, size_t) {
-		++n_tot;
+		++F.n_lines;
 		fld.clear();
 		for (char *p = s, *q = s;; ++p)
 			if (*p == '\t' || *p == 0) { int c = *p; *p = 0; fld.push_back(q); q = p + 1; if (c == 0) break; }
@@ -320,18 +332,14 @@ extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *
 			char *q = fld[0], *r = q;
 			if (excl && excl->find(q) >= 0) break;
 			while (*r && *r != opt->gene_delim) ++r;
-			bool has_delim = (*r == opt->gene_delim && *r != 0);
 			std::string_view gname(q, r - q);
 			if (excl && excl->find(gname) >= 0) break;
-			int preferred = pref && pref->find(gname) >= 0, included = incl && incl->find(gname) >= 0;
 			bool absent;
-			(void)has_delim;
-			const char *nm = pv->gene.intern(gname, &gid, &absent);
-			if (absent) { d->n_gene++; grow0(d->gene, gid, d->m_gene); }
-			d->gene[gid].name = nm; d->gene[gid].preferred = preferred; d->gene[gid].included = included;
-			nm = pv->prot.intern(q, &pid, &absent);
-			if (absent) { d->n_prot++; grow0(d->prot, pid, d->m_prot); }
-			d->prot[pid].name = nm; d->prot[pid].gid = gid; d->prot[pid].len = 0;
+			F.gene.intern(gname, &gid, &absent);
+			if (absent) { F.gene_len.push_back(0); F.gene_pref.push_back(pref && pref->find(gname) >= 0); F.gene_incl.push_back(incl && incl->find(gname) >= 0); }
+			F.prot.intern(q, &pid, &absent);
+			if (absent) { F.prot_gid.push_back(gid); F.prot_len.push_back(0); }
+			F.prot_gid[pid] = gid; F.prot_len[pid] = 0;
 			hit.pid = pid;
 			if ((size_t)pid >= seen_cnt.size()) seen_cnt.resize(pid + 1 + (pid >> 1), -1);
 			hit.rank = ++seen_cnt[pid];
@@ -339,27 +347,22 @@ extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *
 			// ---- columns 1..10 (read.c:172-211)
 			char *e;
 			int32_t len = (int32_t)strtol(fld[1], &e, 10);
-			d->prot[pid].len = len;
-			d->gene[gid].len = (int32_t)d->gene[gid].len > len? d->gene[gid].len : len;
+			F.prot_len[pid] = len;
+			if (F.gene_len[gid] < len) F.gene_len[gid] = len;
 			if (nf < 3) break;
 			hit.qs = (int32_t)strtol(fld[2], &e, 10);
 			if (nf < 4) break;
 			hit.qe = (int32_t)strtol(fld[3], &e, 10);
-			if (hit.qe - hit.qs < d->prot[pid].len * opt->min_prot_ratio) break;
+			if (hit.qe - hit.qs < len * opt->min_prot_ratio) break;
 			if (nf < 5) break;
 			if (fld[4][0] != '+' && fld[4][0] != '-') break;
 			hit.rev = fld[4][0] == '+'? 0 : 1;
 			if (nf < 6) break;
 			{
-				std::string_view cn(fld[5]);
-				auto it = file_ctg.find(cn);
-				if (it == file_ctg.end()) {
-					const char *gn = pv->ctg.intern(cn, 0, 0);
-					grow0(g->ctg, g->n_ctg, g->m_ctg);
-					g->ctg[g->n_ctg].name = gn;
-					hit.cid = g->n_ctg;
-					file_ctg.emplace(std::string_view(gn, cn.size()), g->n_ctg++);
-				} else hit.cid = it->second;
+				int32_t cid; bool cabs;
+				const char *cn = F.ctg.intern(fld[5], &cid, &cabs);
+				if (cabs) { grow0(g->ctg, g->n_ctg, g->m_ctg); g->ctg[g->n_ctg++].name = cn; }
+				hit.cid = cid;
 			}
 			if (nf < 7) break;
 			g->ctg[hit.cid].len = strtol(fld[6], &e, 10);
@@ -377,7 +380,7 @@ extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *
 				const char *t = fld[i];
 				if (strncmp(t, "ms:i:", 5) == 0) {
 					hit.score_ori = (int32_t)strtol(t + 5, &e, 10);
-					hit.score_adj = pgio::adjusted_score(opt, hit.score_ori, hit.mlen, hit.blen, hit.qs, hit.qe, d->prot[pid].len);
+					hit.score_adj = pgio::adjusted_score(opt, hit.score_ori, hit.mlen, hit.blen, hit.qs, hit.qe, len);
 				} else if (strncmp(t, "fs:i:", 5) == 0) n_fs = (int32_t)strtol(t + 5, &e, 10);
 				else if (strncmp(t, "st:i:", 5) == 0) n_stop = (int32_t)strtol(t + 5, &e, 10);
 				else if (strncmp(t, "cg:Z:", 5) == 0) {
@@ -389,9 +392,65 @@ extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *
 		} while (0);
 		if (have_exons) pgio::push_hit(g, hit, ex, cg_fs, n_fs, n_stop);
 	});
+}
+
+// fold one parsed file into the global tables, in command-line order (serial, cheap: names only), then rewrite its hits' ids
+void merge_file(pg_data_t *d, LocalFile &F)
+{
+	pgio::DataPriv *pv = (pgio::DataPriv*)d->d_ctg;
+	std::vector<int32_t> g2g(F.gene.names.size()), p2p(F.prot.names.size());
+	for (size_t lg = 0; lg < F.gene.names.size(); ++lg) {
+		int32_t gid; bool absent;
+		const char *nm = pv->gene.intern(F.gene.names[lg], &gid, &absent);
+		if (absent) { d->n_gene++; grow0(d->gene, gid, d->m_gene); }
+		d->gene[gid].name = nm; d->gene[gid].preferred = F.gene_pref[lg]; d->gene[gid].included = F.gene_incl[lg];
+		if ((int32_t)d->gene[gid].len < F.gene_len[lg]) d->gene[gid].len = F.gene_len[lg];
+		g2g[lg] = gid;
+	}
+	for (size_t lp = 0; lp < F.prot.names.size(); ++lp) {
+		int32_t pid; bool absent;
+		const char *nm = pv->prot.intern(F.prot.names[lp], &pid, &absent);
+		if (absent) { d->n_prot++; grow0(d->prot, pid, d->m_prot); }
+		d->prot[pid].name = nm; d->prot[pid].gid = g2g[F.prot_gid[lp]]; d->prot[pid].len = F.prot_len[lp];
+		p2p[lp] = pid;
+	}
+	grow0(d->genome, d->n_genome, d->m_genome);
+	pg_genome_t *g = &d->genome[d->n_genome++];
+	*g = F.g;
+	for (int32_t c = 0; c < g->n_ctg; ++c) g->ctg[c].name = pv->ctg.intern(g->ctg[c].name, 0, 0);   // global, stable storage
+	for (int32_t i = 0; i < g->n_hit; ++i) g->hit[i].pid = p2p[g->hit[i].pid];
+	memset(&F.g, 0, sizeof(F.g));
 	if (pgio_verbose >= 4)
-		fprintf(stderr, "[M::%s] [%d] %s: %ld lines parsed, %d hits kept\n", __func__, d->n_genome - 1, g->label? g->label : "*", (long)n_tot, g->n_hit);
+		fprintf(stderr, "[M::pgio_read_paf] [%d] %s: %ld lines parsed, %d hits kept\n", d->n_genome - 1, g->label? g->label : "*", (long)F.n_lines, g->n_hit);
+}
+} // namespace
+
+extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *fn)
+{
+	LocalFile F;
+	parse_file(opt, fn, F);
+	if (!F.ok) return -1;
+	merge_file(d, F);
 	return 0;
+}
+
+// All files of a command line: parsed by n_threads workers (0 = hardware concurrency, capped at the file count), merged in
+// order.  Returns the number of files that could be opened (the others are skipped, like main.c:120 ignores the error).
+extern "C" int32_t pgio_read_pafs(const pg_opt_t *opt, pg_data_t *d, const char *const *fns, int32_t n_files, int32_t n_threads)
+{
+	if (n_threads <= 0) n_threads = (int32_t)std::thread::hardware_concurrency();
+	if (n_threads > n_files) n_threads = n_files;
+	if (n_threads < 1) n_threads = 1;
+	std::vector<LocalFile> files(n_files > 0? n_files : 0);
+	std::atomic<int32_t> next(0);
+	auto worker = [&]() { for (int32_t i; (i = next.fetch_add(1)) < n_files;) parse_file(opt, fns[i], files[i]); };
+	std::vector<std::thread> th;
+	for (int32_t t = 1; t < n_threads; ++t) th.emplace_back(worker);
+	worker();
+	for (auto &t : th) t.join();
+	int32_t n_ok = 0;
+	for (int32_t i = 0; i < n_files; ++i) if (files[i].ok) { merge_file(d, files[i]); ++n_ok; }
+	return n_ok;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,6 +20,8 @@ def lib():
         L.pgio_data_destroy.argtypes = [P(abi.pg_data_t)]
         L.pgio_read_paf.argtypes = [P(abi.pg_opt_t), P(abi.pg_data_t), C.c_char_p]
         L.pgio_read_paf.restype = C.c_int32
+        L.pgio_read_pafs.argtypes = [P(abi.pg_opt_t), P(abi.pg_data_t), P(C.c_char_p), C.c_int32, C.c_int32]
+        L.pgio_read_pafs.restype = C.c_int32
         L.pgio_name_set.argtypes = [C.c_char_p]
         L.pgio_name_set.restype = C.c_void_p
         L.pgio_name_set_destroy.argtypes = [C.c_void_p]
@@ -52,10 +54,15 @@ def default_opt(**kw):
     return o
 
 
-def read_pafs(opt, files):
+def read_pafs(opt, files, threads=1):
+    """threads=1: file by file (pgio_read_paf); otherwise the parallel reader (pgio_read_pafs, 0 = all cores)"""
     d = lib().pgio_data_init()
-    for f in files:
-        lib().pgio_read_paf(C.byref(opt), d, os.fsencode(f))
+    if threads == 1:
+        for f in files:
+            lib().pgio_read_paf(C.byref(opt), d, os.fsencode(f))
+    else:
+        arr = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+        lib().pgio_read_pafs(C.byref(opt), d, arr, len(files), threads)
     return d
 
 

@@ -147,3 +147,16 @@ def test_tie_detector_reports_zero_on_goldens():
     st = engine.stats()
     assert st.tie[0] == 0 and st.tie[2] == 0
     engine.destroy(g); hostio.destroy(d)
+
+
+def test_cli_binary_prints_the_golden_gfa(tmp_path):
+    """`pangene *.paf > out.gfa` (our main(), parallel reader, libpgx, our writers) == the stock binary's output"""
+    import subprocess
+    files = common.c4_files(tmp_path)
+    exe = os.path.join(common.ROOT, "pangene_b200", "csrc", "pangene")
+    out = subprocess.run([exe, "-v1"] + files, check=True, stdout=subprocess.PIPE).stdout
+    assert out == open(os.path.join(common.GOLDEN, "C4.gfa"), "rb").read()
+    out = subprocess.run([exe, "-v1", "--bed=raw"] + files, check=True, stdout=subprocess.PIPE).stdout
+    assert out == open(os.path.join(common.GOLDEN, "C4.bed_raw"), "rb").read()
+    out = subprocess.run([exe, "-v1", "-w"] + files, check=True, stdout=subprocess.PIPE).stdout
+    assert out == open(os.path.join(common.GOLDEN, "C4_w.gfa"), "rb").read()

@@ -108,3 +108,37 @@ def test_host_side_radix_replay_of_libpgx_matches_oracle():
         engine.lib().pgx_test_flag_sort_replay(C.byref(A), n)
         pgoracle.lib().pgo_radix_replay128(C.byref(B), n)
         assert list(A) == list(B)
+
+
+def _same_data(d, d2):
+    assert (d.contents.n_genome, d.contents.n_gene, d.contents.n_prot) == (d2.contents.n_genome, d2.contents.n_gene, d2.contents.n_prot)
+    for j in range(d.contents.n_genome):
+        a, b = d.contents.genome[j], d2.contents.genome[j]
+        assert (a.n_hit, a.n_exon, a.n_ctg, a.label) == (b.n_hit, b.n_exon, b.n_ctg, b.label)
+        assert C.string_at(a.hit, a.n_hit * 88) == C.string_at(b.hit, b.n_hit * 88)
+        assert C.string_at(a.exon, a.n_exon * 8) == C.string_at(b.exon, b.n_exon * 8)
+        assert [(a.ctg[c].name, a.ctg[c].len) for c in range(a.n_ctg)] == [(b.ctg[c].name, b.ctg[c].len) for c in range(b.n_ctg)]
+    for i in range(d.contents.n_prot):
+        x, y = d.contents.prot[i], d2.contents.prot[i]
+        assert (x.name, x.len, x.gid) == (y.name, y.len, y.gid)
+    for i in range(d.contents.n_gene):
+        x, y = d.contents.gene[i], d2.contents.gene[i]
+        assert (x.name, x.bits) == (y.name, y.bits)
+
+
+def test_parallel_reader_reproduces_sequential_ids(tmp_path):
+    """per-file parsing with local ids + ordered merge == file-by-file parsing: ids, names, lengths, ranks, every hit byte"""
+    opt = hostio.default_opt()
+    files = common.c4_files(tmp_path)
+    for thr in (0, 3):
+        a, b = hostio.read_pafs(opt, files, threads=1), hostio.read_pafs(opt, files, threads=thr)
+        _same_data(a, b)
+        hostio.destroy(a); hostio.destroy(b)
+    # proteins first seen in LATER files, files listed in a scrambled order, one missing file in the middle
+    p = hostio.synth_params(2, n_genome=6, n_gene=500, iso_per_gene=4, hits_per_genome=4000, n_genome_total=6)
+    fs = hostio.synth_write_pafs(opt, p, str(tmp_path / "syn"))
+    order = [fs[3], fs[5], str(tmp_path / "does_not_exist.paf"), fs[0], fs[4], fs[1], fs[2]]
+    a, b = hostio.read_pafs(opt, order, threads=1), hostio.read_pafs(opt, order, threads=4)
+    assert a.contents.n_genome == 6
+    _same_data(a, b)
+    hostio.destroy(a); hostio.destroy(b)
