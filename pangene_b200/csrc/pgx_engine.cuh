@@ -431,6 +431,56 @@ struct Session {
 		scratch.reset(mk);
 	}
 
+	// Shrink the active set to the hits that are still unfiltered.  `flt` only grows and a filtered hit is never touched again
+	// (sweeps skip it, weak_br is only raised on survivors), so its state is final: it is written back to the full columns here
+	// and dropped.  After the vertex filter ~45 % of the active hits go; every later round (17 sweeps, 34 flag/scan passes,
+	// 15 position tables) runs on the smaller set.
+	void recompact_active()
+	{
+		if (Nw == 0) return;
+		size_t mk = scratch.mark();
+		uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *pos = scratch.get<uint32_t>((size_t)Nw + 2);
+		PGX_LAUNCH(k_flag_unfiltered, grid_for(Nw, TB), TB, 0, st, A.bits, Nw, flag);
+		const int32_t n2 = (int32_t)scan_flags(flag, pos, Nw);
+		if ((double)n2 > 0.85 * Nw) { scratch.reset(mk); return; }
+		PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
+		const size_t n1 = (size_t)n2 + 16;
+		DBuf<int32_t> b_ctg, b_cs, b_ce, b_cm, b_pid, b_gidp, b_sadj, b_rank, b_sori, b_sdom, b_pdom0, b_pdom, b_cds, b_pmax, b_full, b_goff;
+		DBuf<uint32_t> b_bits, b_bits_alt, b_nex, b_eoff, b_by_cm;
+		DBuf<uint64_t> b_key;
+		DBuf<int2> b_wex;
+		b_ctg.alloc(n1); b_cs.alloc(n1); b_ce.alloc(n1); b_cm.alloc(n1); b_pid.alloc(n1); b_gidp.alloc(n1); b_sadj.alloc(n1); b_rank.alloc(n1); b_sori.alloc(n1);
+		b_sdom.alloc(n1); b_pdom0.alloc(n1); b_pdom.alloc(n1); b_cds.alloc(n1); b_pmax.alloc(n1); b_full.alloc(n1); b_bits.alloc(n1); b_bits_alt.alloc(n1); b_nex.alloc(n1);
+		b_eoff.alloc(n1 + 16); b_by_cm.alloc(n1); b_key.alloc(n1); b_goff.alloc(G + 1);
+		ActCols B;
+		B.ctg = b_ctg.p; B.cs = b_cs.p; B.ce = b_ce.p; B.cm = b_cm.p; B.pid = b_pid.p; B.gidp = b_gidp.p; B.sadj = b_sadj.p; B.rank = b_rank.p; B.sori = b_sori.p;
+		B.sdom = b_sdom.p; B.pdom0 = b_pdom0.p; B.pdom = b_pdom.p; B.cds = b_cds.p; B.pmax = b_pmax.p; B.full = b_full.p; B.bits = b_bits.p; B.bits_alt = b_bits_alt.p; B.nex = b_nex.p; B.eoff = b_eoff.p; B.key = b_key.p;
+		int32_t *old_of_new = scratch.get<int32_t>(n1);
+		PGX_LAUNCH(k_recompact_active, grid_for(Nw, TB), TB, 0, st, A, pos, Nw, B, old_of_new);
+		PGX_LAUNCH(k_gather_u32, grid_for(G + 1, TB), TB, 0, st, pos, (const uint32_t*)goff_act.p, G + 1, (uint32_t*)b_goff.p);
+		if (n2) {
+			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(n2));
+			exclusive_sum_u32(B.nex, B.eoff, n2, agg, st);
+			uint32_t ne = read_u32(B.eoff + n2);
+			b_wex.alloc((size_t)ne + 16);
+			PGX_LAUNCH(k_copy_exons, grid_for(n2, 128), 128, 0, st, wex.p, A.eoff, old_of_new, B.eoff, n2, b_wex.p);
+			SegVal *sagg = scratch.get<SegVal>((size_t)(n2 / SCAN_TILE + 2));
+			segmented_running_max(B.ctg, B.ce, B.pmax, n2, sagg, st);
+			uint32_t *fcm = scratch.get<uint32_t>((size_t)Nw + 1), *pcm = scratch.get<uint32_t>((size_t)Nw + 2);
+			PGX_LAUNCH(k_flag_alive_cm, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, Nw, fcm);
+			uint32_t *agg2 = scratch.get<uint32_t>(scan_scratch_elems(Nw));
+			exclusive_sum_u32(fcm, pcm, Nw, agg2, st);
+			PGX_LAUNCH(k_renumber_cm, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, pcm, Nw, b_by_cm.p);
+		} else b_wex.alloc(16);
+		PGX_CHECK(cudaStreamSynchronize(st));   // the old buffers go back to the cache below
+		a_ctg.swap(b_ctg); a_cs.swap(b_cs); a_ce.swap(b_ce); a_cm.swap(b_cm); a_pid.swap(b_pid); a_gidp.swap(b_gidp); a_sadj.swap(b_sadj); a_rank.swap(b_rank); a_sori.swap(b_sori);
+		a_sdom.swap(b_sdom); a_pdom0.swap(b_pdom0); a_pdom.swap(b_pdom); a_cds.swap(b_cds); a_pmax.swap(b_pmax); a_full.swap(b_full); a_bits.swap(b_bits); a_bits_alt.swap(b_bits_alt);
+		a_nex.swap(b_nex); a_eoff.swap(b_eoff); by_cm.swap(b_by_cm); a_key.swap(b_key); wex.swap(b_wex); goff_act.swap(b_goff);
+		Nw = n2;
+		set_active();
+		scratch.reset(mk);
+	}
+
 	// ------------------------------------------------------------------------------------------------
 	// stage 2: pg_graph_gen (graph.c:280-322)
 	// ------------------------------------------------------------------------------------------------
@@ -693,8 +743,10 @@ struct Session {
 		set_filter(SF_PSEUDO);                                                           // graph.c:285
 		gen_vtx(opt);                                                                    // graph.c:286
 		flag_vtx();                                                                      // graph.c:287-288
+		recompact_active();
 		gen_arc(opt);                                                                    // graph.c:289
 		flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);     // graph.c:294-295
+		recompact_active();
 		gen_arc(opt);                                                                    // graph.c:296
 		for (int32_t i = 0; i < opt->n_branch_flt; ++i) {                                // graph.c:301-315
 			double r = 1.0 + (double)(opt->n_branch_flt - 1 - i) / opt->n_branch_flt;

@@ -487,6 +487,36 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_top(Sw
 	__syncthreads();
 	while (!mbar_try_wait(bar, 0)) { }
 
+	// ---- phase 0 (not for SW_ISO / -S): a sparse table over the staged score keys answers "which hit of an index range has the
+	// largest key (leftmost on ties)?" in two look-ups, so that phase 1 does not have to visit the ~10 partners of a window
+	// one by one.  Filtered hits count as key 0.  The table is only usable where the loser of a pair is decided by the keys
+	// alone, i.e. where no unfiltered hit of the tile carries a weak_br mark (overlap.c:139-147); otherwise s_mixed is set and
+	// the tile scans its windows as before.
+	__shared__ uint16_t s_st[6][SWQ_STG];          // s_st[j][q]: position of the maximum of [q, q + 2^(j+1)) (clipped)
+	__shared__ int s_mixed;
+	const int32_t S = hi - lo;
+	const bool rmq_mode = MODE == SW_LOAD && !o.check_strand;   // (the later sweeps run on the small active set: windows of 1-2 partners, the table would cost more than it saves)
+	if (rmq_mode) {
+		auto ekey = [&](int32_t q) -> uint64_t { return (s_bits[q] & PG_HB_FLT)? 0ull : s_key[q]; };
+		int mixed = 0;
+		for (int32_t q = tid; q < S; q += SWQ_TILE) {
+			const int32_t b = q + 1 < S? q + 1 : q;
+			s_st[0][q] = (uint16_t)(ekey(b) > ekey(q)? b : q);
+			const uint32_t bq = s_bits[q];
+			if (!(bq & PG_HB_FLT) && (bq & PG_HB_WBR_MASK)) mixed = 1;   // some unfiltered hit carries weak_br: keys alone do not decide
+		}
+		mixed = __syncthreads_or(mixed);
+		if (tid == 0) s_mixed = mixed;
+#pragma unroll 1
+		for (int j = 1; j < 6; ++j) {
+			for (int32_t q = tid; q < S; q += SWQ_TILE) {
+				const int32_t a = s_st[j - 1][q], q2 = q + (1 << j);
+				const int32_t b = q2 < S? (int32_t)s_st[j - 1][q2] : a;
+				s_st[j][q] = (uint16_t)(ekey(b) > ekey(a)? b : a);
+			}
+			__syncthreads();
+		}
+	}
 	// filtered hits (25 % in the first sweep) do no work: compact the live ones so that they fill whole warps
 	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
 	int32_t i;
@@ -519,9 +549,53 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_top(Sw
 	int32_t top_p = INT32_MAX; uint64_t top_key = 0;
 	bool slow = false, lose = false, write_out = false;
 	if (in_range) {
-	// ---- phase 1: the would-be dominator.  One loop walks back, then forward: a lane whose backward window is short starts its
-	// forward window while its neighbours are still going back (the warp pays max(back + fwd), not max(back) + max(fwd)).
-	{
+	// ---- phase 1a: the would-be dominator from the sparse table: window bounds by two light scans (one load per step), then two
+	// range-maximum queries.  Whatever the table cannot settle (a strongest hit that ended before my start, equal keys, windows
+	// longer than 64 or leaving the staged range) falls through to the partner-by-partner scan below.
+	bool scan = true;
+	if (rmq_mode && !s_mixed) {
+		auto ekey = [&](int32_t q) -> uint64_t { return (s_bits[q] & PG_HB_FLT)? 0ull : s_key[q]; };
+		auto rmq = [&](int32_t a, int32_t b) -> int32_t {   // leftmost maximum of ekey over [a, b), 1 <= b - a <= 64
+			const int32_t len = b - a;
+			if (len == 1) return a;
+			const int k = 31 - __clz(len);                  // 2^k <= len, k >= 1
+			const int32_t x = s_st[k - 1][a], y = s_st[k - 1][b - (1 << k)];
+			const uint64_t kx = ekey(x), ky = ekey(y);
+			return (ky > kx || (ky == kx && y < x))? y : x;
+		};
+		int32_t wb = mq, wf = mq + 1;
+		while (wb > 0 && s_ctg[wb - 1] == mctg && s_pmax[wb - 1] > mcs) --wb;          // overlap.c:67-71,114-120
+		while (wf < S && s_ctg[wf] == mctg && s_cs[wf] < mce) ++wf;
+		const bool open_back = wb == 0 && lo > 0, open_fwd = wf == S && hi < c.n;   // the window may continue outside the staged range
+		scan = false;
+		if (open_back || open_fwd) slow = true;
+		else if (mq - wb > 64 || wf - mq - 1 > 64) scan = true;
+		else {
+			int32_t tb = -1, tf = -1;
+			if (wb < mq) { tb = rmq(wb, mq); if (ekey(tb) == 0) tb = -1; else if (s_ce[tb] <= mcs) scan = true; }   // strongest in range is not a partner: a weaker one may be
+			if (mq + 1 < wf) { tf = rmq(mq + 1, wf); if (ekey(tf) == 0) tf = -1; }
+			if (!scan) {
+				const uint64_t kb = tb >= 0? s_key[tb] : 0ull, kf = tf >= 0? s_key[tf] : 0ull;
+				if ((tb >= 0 && kb == mkey) || (tf >= 0 && kf == mkey)) scan = true;       // same protein, same score: ranks decide (rare)
+				else {
+					if (tb >= 0 && kb > mkey) { top_key = kb; top_p = lo + tb; }
+					if (tf >= 0 && kf > mkey && kf > top_key) { top_key = kf; top_p = lo + tf; }   // equal keys: the backward one has the smaller index
+					if (MODE == SW_LOAD && top_p != INT32_MAX) {   // tie detector: a second partner with the winning key and the same start
+						const int32_t tq = top_p - lo;
+						int32_t r1 = -1, r2 = -1;
+						if (tq < mq) { if (wb < tq) r1 = rmq(wb, tq); if (tq + 1 < mq) r2 = rmq(tq + 1, mq); if (tf >= 0 && kf == top_key && s_cs[tf] == s_cs[tq]) atomicAdd(tie_cnt, 1u); }
+						else { if (mq + 1 < tq) r1 = rmq(mq + 1, tq); if (tq + 1 < wf) r2 = rmq(tq + 1, wf); }
+						if (r1 >= 0 && ekey(r1) == top_key && s_cs[r1] == s_cs[tq]) atomicAdd(tie_cnt, 1u);
+						if (r2 >= 0 && ekey(r2) == top_key && s_cs[r2] == s_cs[tq]) atomicAdd(tie_cnt, 1u);
+					}
+				}
+			}
+		}
+	}
+	// ---- phase 1b: the would-be dominator by scanning the window.  One loop walks back, then forward: a lane whose backward
+	// window is short starts its forward window while its neighbours are still going back (the warp pays max(back + fwd), not
+	// max(back) + max(fwd)).
+	if (scan && !slow) {
 		int side = 0, step = -1;
 #pragma unroll 1
 		for (int32_t p = i - 1;; p += step) {
@@ -808,6 +882,30 @@ __global__ void k_build_active(FullCols f, const uint32_t *__restrict__ pos, int
 	a.ctg[p] = f.ctg[i]; a.cs[p] = f.cs[i]; a.ce[p] = f.ce[i]; a.cm[p] = f.cm[i]; a.pid[p] = f.pid[i]; a.gidp[p] = f.gidp[i];
 	a.sadj[p] = f.sadj[i]; a.rank[p] = f.rank[i]; a.sori[p] = f.sori[i]; a.sdom[p] = f.sdom[i]; a.pdom0[p] = f.pdom0[i]; a.pdom[p] = -1;
 	a.cds[p] = f.cds[i]; a.full[p] = i; a.bits[p] = f.bits[i]; a.nex[p] = f.nex[i]; a.key[p] = f.key[i];
+}
+
+// shrink the active set to its unfiltered members (same order); pos = exclusive scan of the "still unfiltered" flags
+__global__ void k_recompact_active(ActCols a, const uint32_t *__restrict__ pos, int32_t n, ActCols b, int32_t *old_of_new)
+{
+	int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t p = pos[i];
+	if (pos[i + 1] == p) return;
+	b.ctg[p] = a.ctg[i]; b.cs[p] = a.cs[i]; b.ce[p] = a.ce[i]; b.cm[p] = a.cm[i]; b.pid[p] = a.pid[i]; b.gidp[p] = a.gidp[i];
+	b.sadj[p] = a.sadj[i]; b.rank[p] = a.rank[i]; b.sori[p] = a.sori[i]; b.sdom[p] = a.sdom[i]; b.pdom0[p] = a.pdom0[i]; b.pdom[p] = a.pdom[i];
+	b.cds[p] = a.cds[i]; b.full[p] = a.full[i]; b.bits[p] = a.bits[i]; b.nex[p] = a.nex[i]; b.key[p] = a.key[i];
+	old_of_new[p] = i;
+}
+// the (contig, cm) permutation of the shrunken set: keep the survivors of the old permutation, renumbered
+__global__ void k_flag_alive_cm(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ by_cm, int32_t n, uint32_t *flag)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) { uint32_t i = by_cm[k]; flag[k] = pos[i + 1] != pos[i]? 1u : 0u; }
+}
+__global__ void k_renumber_cm(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ by_cm, const uint32_t *__restrict__ pos_cm, int32_t n, uint32_t *out)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n && pos_cm[k + 1] != pos_cm[k]) out[pos_cm[k]] = pos[by_cm[k]];
 }
 
 __global__ void k_copy_exons(const int2 *__restrict__ ex_src, const uint32_t *__restrict__ eoff_src, const int32_t *__restrict__ full, const uint32_t *__restrict__ eoff_dst, int32_t n, int2 *ex_dst)
