@@ -94,3 +94,7 @@ PG_F_NO_JOINT_PSEUDO = 0x40
 PG_F_ORI_FOR_BRANCH = 0x80
 PG_F_CHECK_STRAND = 0x100
 PG_F_DROP_SGL_EXON = 0x200
+
+# bit-field word of pg_hit_t (include/pangene_abi.h PG_HB_*)
+PG_HB_REV, PG_HB_FLT, PG_HB_FLT_SUB, PG_HB_FLT_OV, PG_HB_FLT_CHAIN = 0x001, 0x002, 0x004, 0x008, 0x010
+PG_HB_PSEUDO, PG_HB_VTX, PG_HB_SHADOW, PG_HB_REP, PG_HB_WBR_SHIFT, PG_HB_WBR_MASK = 0x020, 0x040, 0x080, 0x100, 9, 0x600

@@ -160,3 +160,22 @@ def test_cli_binary_prints_the_golden_gfa(tmp_path):
     assert out == open(os.path.join(common.GOLDEN, "C4.bed_raw"), "rb").read()
     out = subprocess.run([exe, "-v1", "-w"] + files, check=True, stdout=subprocess.PIPE).stdout
     assert out == open(os.path.join(common.GOLDEN, "C4_w.gfa"), "rb").read()
+
+
+def test_config5_bacterial_with_matrix(tmp_path):
+    """BASELINE.json configs[4] shape (bacterial, -p0 -a2) at 300 of the 1000 genomes: bit-exact GFA vs the oracle and the
+    same presence/absence matrix (gfa2matrix, pangene.js:1168-1246) from both GFAs"""
+    opt = common.opt_from_args(["-p0", "-a2"])
+    p = hostio.synth_params(5, n_genome=300, n_genome_total=300)
+    d1, d2 = hostio.synth(opt, p), hostio.synth(opt, p)
+    g1 = pgoracle.hot_path(opt, d1)
+    g2 = engine.hot_path(opt, d2, lazy=True)
+    f1, f2 = str(tmp_path / "cpu.gfa"), str(tmp_path / "gpu.gfa")
+    hostio.write_gfa(g1, f1); hostio.write_gfa(g2, f2)
+    a, b = open(f1, "rb").read(), open(f2, "rb").read()
+    assert sorted(a.splitlines()) == sorted(b.splitlines()), common.first_diff(a, b)
+    m1, m2 = str(tmp_path / "cpu.tsv"), str(tmp_path / "gpu.tsv")
+    n1 = hostio.lib().pgio_gfa2matrix(os.fsencode(f1), os.fsencode(m1), 0)
+    n2 = hostio.lib().pgio_gfa2matrix(os.fsencode(f2), os.fsencode(m2), 0)
+    assert n1 == n2 > 4000 and open(m1, "rb").read() == open(m2, "rb").read()
+    engine.destroy(g2); pgoracle.destroy(g1); hostio.destroy(d1); hostio.destroy(d2)
