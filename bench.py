@@ -177,8 +177,11 @@ def main():
 
     # ---- value: device-resident ---------------------------------------------------------------------
     sess = L.pgx_upload(d0)
-    for _ in range(a.warmup):
+    L.pgx_set_sweep_stat(1)                       # the roofline numerator: counted once, in the first warm-up pass
+    for w in range(a.warmup):
         L.pgx_run(sess, C.byref(opt), 3)
+        L.pgx_set_sweep_stat(0)
+    L.pgx_set_sweep_stat(0)
     barrier()
     st0 = engine.stats()
     dev_ms, sweep_ms = [], []

@@ -67,7 +67,8 @@ void pgx_session_free(pgx_session_t *s);
 typedef struct {
 	uint64_t launches;            /* kernels launched by this library since the last reset */
 	double   sweep_ms;            /* device time of the FIRST (load-time) overlap sweep of the last run, CUDA events */
-	double   sweep_bytes;         /* its algorithmic bytes: sum_unfiltered(52 + 8 n_exon) + 4 n_filtered */
+	double   sweep_bytes;         /* its algorithmic bytes: sum_unfiltered(52 + 8 n_exon) + 4 n_filtered; counted by an
+	                               * extra kernel + read-back, only in runs made while pgx_set_sweep_stat(1) is in force (else kept) */
 	double   run_ms[3];           /* device time of stage 1, stage 2, total of the last pgx_run */
 	int64_t  n_hit, n_active;     /* hits uploaded / hits that survived the load-time filters */
 	int64_t  tie[4];              /* tie-order detector, same meaning as oracle pgo_tie_report() */
@@ -76,6 +77,7 @@ typedef struct {
 } pgx_stats_t;
 void pgx_get_stats(pgx_stats_t *out);
 void pgx_reset_stats(void);
+void pgx_set_sweep_stat(int on);              /* count sweep_bytes in the following runs (default off: it costs a pass over the hits) */
 void pgx_trim(void);                          /* give cached device memory back to the driver */
 
 /* test hooks for the device primitives (tests/test_gpu_primitives.py) */

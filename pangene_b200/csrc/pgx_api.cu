@@ -9,6 +9,7 @@ namespace pgx {
 LaunchStats g_launch;
 Stats g_stats;
 Comm g_comm;
+int g_sweep_stat = 0;
 static int g_device = -1, g_lazy = 0;
 static std::map<const pg_data_t*, Session*> g_sessions;   // pg_post_process() -> pg_graph_gen() hand-over
 
@@ -172,6 +173,7 @@ void pgx_get_stats(pgx_stats_t *o)
 	o->n_seg = g_stats.n_seg; o->n_arc = g_stats.n_arc; o->h2d_bytes = g_stats.h2d; o->d2h_bytes = g_stats.d2h;
 }
 void pgx_reset_stats(void) { g_launch.launches = 0; g_stats = Stats(); }
+void pgx_set_sweep_stat(int on) { g_sweep_stat = on; }
 void pgx_trim(void) { DevCache::get_cache().trim(); }
 
 // ---- test hooks -----------------------------------------------------------------------------------

@@ -37,6 +37,7 @@ def lib():
         L.pgx_device_count.restype = C.c_int
         L.pgx_set_device.argtypes = [C.c_int]
         L.pgx_set_lazy.argtypes = [C.c_int]
+        L.pgx_set_sweep_stat.argtypes = [C.c_int]
         L.pgx_comm_unique_id.argtypes = [C.c_void_p]
         L.pgx_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int32, C.c_int32]
         L.pgx_upload.argtypes = [P(abi.pg_data_t)]

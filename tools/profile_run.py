@@ -16,6 +16,7 @@ d = hostio.synth(opt, hostio.synth_params(3, n_genome=n, n_genome_total=n))
 L = engine.lib()
 engine.set_verbose(1)
 s = L.pgx_upload(d)
+L.pgx_set_sweep_stat(1 if os.environ.get("PGX_SWEEP_STAT") else 0)
 for _ in range(passes):
     L.pgx_run(s, C.byref(opt), 3)
 st = engine.stats()
