@@ -823,48 +823,15 @@ struct Session {
 			// pg_post_process, already permuted -> patch them in place.  Anything else is rebuilt from raw order.
 			bool host_sorted = (int32_t)installed.size() == G && G > 0;
 			for (int32_t j = 0; j < G && host_sorted; ++j) host_sorted = d->genome[j].hit == installed[j];
-			for (int32_t j = 0; j < G; ++j)
+			for (int32_t j = 0; j < G; ++j) {
 				if (h_hoff[j + 1] - h_hoff[j] != d->genome[j].n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
+				if (!host_sorted) fresh[j] = alloc_hit_array((size_t)d->genome[j].n_hit);
+			}
 			const int64_t BLK = 1 << 14;
 			const bool in_place = host_sorted;
-			// The sorted records go into arrays the caller will free() (hit.c:62-63 replaces the arrays the same way).  Allocating 1.8 GB
-			// afresh and freeing the caller's 1.8 GB costs ~860 k page faults/unmaps; instead the caller's array of a genome that has
-			// been consumed completely (all its hits lie in chunks already rebuilt) becomes the new array of a later genome when it is
-			// large enough.  Only the genomes of the first chunk get fresh memory and only the last few old arrays are freed.
-			static const bool recycle = []() { const char *e = getenv("PGX_RECYCLE"); return !(e && atoi(e) == 0); }();
-			const int64_t chunk_hits = (int64_t)(PinnedRing::CAP / sizeof(OutHit));
-			struct Donor { pg_hit_t *p; int32_t cap; int32_t from; };
-			std::vector<Donor> donors;
-			std::vector<pg_hit_t*> old_ptr(G, nullptr);
-			std::vector<int32_t> fresh_cap(G, 0);
-			std::vector<uint8_t> old_taken(G, 0);
-			for (int32_t j = 0; j < G; ++j) old_ptr[j] = d->genome[j].hit;
-			int32_t nxt_release = 0, nxt_assign = 0;
-			auto assign_until = [&](int64_t c) {   // called by the consumer thread before chunk c is rebuilt (c < 0: everything)
-				if (host_sorted) return;
-				while (recycle && c >= 0 && nxt_release < G) {
-					const int32_t k = nxt_release, nk = d->genome[k].n_hit;
-					if (nk > 0 && (int64_t)(h_hoff[k + 1] - 1) / chunk_hits >= c) break;           // still being read
-					if (nk > 0 && old_ptr[k] && d->genome[k].m_hit >= nk) donors.push_back(Donor{old_ptr[k], d->genome[k].m_hit, k});
-					++nxt_release;
-				}
-				while (nxt_assign < G) {
-					const int32_t j = nxt_assign, nj = d->genome[j].n_hit;
-					if (c >= 0 && nj > 0 && (int64_t)h_hoff[j] / chunk_hits > c) break;             // first needed by a later chunk
-					int best = -1;
-					for (size_t t = 0; t < donors.size(); ++t)
-						if (donors[t].cap >= nj && (best < 0 || donors[t].cap < donors[best].cap)) best = (int)t;
-					if (best >= 0 && nj > 0) {
-						fresh[j] = donors[best].p; fresh_cap[j] = donors[best].cap; old_taken[donors[best].from] = 1;
-						donors[best] = donors.back(); donors.pop_back();
-					} else { fresh[j] = alloc_hit_array((size_t)nj); fresh_cap[j] = nj; }
-					++nxt_assign;
-				}
-			};
 			// only the 24 bytes per hit that changed cross the bus; host threads rebuild the 88-byte records from the caller's own copy
 			staged_d2h(out.p, (size_t)N * sizeof(OutHit), sizeof(OutHit), [&](size_t off, size_t len, const char *srcbuf) {
 				const int64_t h0 = (int64_t)(off / sizeof(OutHit)), h1 = h0 + (int64_t)(len / sizeof(OutHit));
-				assign_until(h0 / chunk_hits);
 				pool.parallel_for((h1 - h0 + BLK - 1) / BLK, [&](int64_t b) {
 					const int64_t a = h0 + b * BLK, e = std::min(h1, a + BLK);
 					int g = (int)(std::upper_bound(h_hoff.begin(), h_hoff.end(), (int32_t)a) - h_hoff.begin()) - 1;
@@ -880,8 +847,7 @@ struct Session {
 				});
 			}, st);
 			if (!host_sorted) {
-				assign_until(-1);   // (genomes without hits past the last chunk)
-				pool.parallel_for(G, [&](int64_t j) { if (!old_taken[j]) free(old_ptr[j]); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = fresh_cap[j]; });   // hit.c:62-63
+				pool.parallel_for(G, [&](int64_t j) { free(d->genome[j].hit); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = d->genome[j].n_hit; });   // hit.c:62-63
 				installed.assign(fresh.begin(), fresh.end());
 			}
 			g_stats.d2h += (int64_t)N * (int64_t)sizeof(OutHit);
