@@ -244,9 +244,9 @@ struct Session {
 	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out)
 	{
 		// PGX_SWEEP=global | tile | top (default): plain, TMA-staged thread-per-hit, TMA-staged strongest-candidate-first
-		static const int variant = []() { const char *e = getenv("PGX_SWEEP"); return (e && strcmp(e, "global") == 0)? 0 : (e && strcmp(e, "tile") == 0)? 1 : (e && strcmp(e, "v2") == 0)? 3 : 2; }();
+		static const int variant = []() { const char *e = getenv("PGX_SWEEP"); return (e && strcmp(e, "global") == 0)? 0 : (e && strcmp(e, "tile") == 0)? 1 : (e && strcmp(e, "v2") == 0)? 3 : (e && strcmp(e, "v2l") == 0)? 4 : 2; }();
 		if (c.n <= 0) return;
-		if (variant == 3) {
+		if (variant == 3 || (variant == 4 && MODE == SW_LOAD)) {
 			static bool attr2_set = false;
 			if (!attr2_set) {
 				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
@@ -260,7 +260,7 @@ struct Session {
 			PGX_LAUNCH(k_sweep_v2<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 			return;
 		}
-		if (variant == 2) {
+		if (variant == 2 || variant == 4) {
 			static bool attr_set = false;
 			if (!attr_set) {
 				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
