@@ -240,41 +240,24 @@ struct Session {
 		c.bits = A.bits; c.eoff = A.eoff; c.ex = wex.p; return c;
 	}
 
-	// one sweep launch; PGX_SWEEP=global selects the plain variant (debug / A-B timing), default is the TMA-tiled one
+	// one sweep launch: the TMA-tiled kernel; PGX_SWEEP=global selects the plain thread-per-hit kernel (debugging / A-B timing)
 	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out)
 	{
-		// PGX_SWEEP=global | tile | top (default): plain, TMA-staged thread-per-hit, TMA-staged strongest-candidate-first
-		static const int variant = []() { const char *e = getenv("PGX_SWEEP"); return (e && strcmp(e, "global") == 0)? 0 : (e && strcmp(e, "tile") == 0)? 1 : (e && strcmp(e, "v2") == 0)? 3 : (e && strcmp(e, "v2l") == 0)? 4 : 2; }();
+		static const bool plain = []() { const char *e = getenv("PGX_SWEEP"); return e && strcmp(e, "global") == 0; }();
 		if (c.n <= 0) return;
-		if (variant == 3 || (variant == 4 && MODE == SW_LOAD)) {
-			static bool attr2_set = false;
-			if (!attr2_set) {
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_LOAD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_v2<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-				attr2_set = true;
-			}
-			PGX_LAUNCH(k_sweep_v2<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
-			return;
+		if (plain) { PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP); return; }
+		static bool attr_set = false;
+		if (!attr_set) {
+			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+			// five 42 KB CTAs per SM need the large shared-memory carve-out (ncu: the default left room for three)
+			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_LOAD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+			attr_set = true;
 		}
-		if (variant == 2 || variant == 4) {
-			static bool attr_set = false;
-			if (!attr_set) {
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-				// five 36 KB CTAs per SM need the large shared-memory carve-out (ncu: the default left room for three)
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_LOAD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-				PGX_CHECK(cudaFuncSetAttribute(k_sweep_top<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-				attr_set = true;
-			}
-			PGX_LAUNCH(k_sweep_top<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
-		} else if (variant == 1) PGX_LAUNCH(k_sweep_tile<MODE>, grid_for(c.n, SWT_TILE), SWT_TILE, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
-		else PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
+		PGX_LAUNCH(k_sweep_tiled<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
 	}
 
 	// stable radix sort of n (key, iota) pairs taken from the scratch arena; returns the permutation (device pointer valid until the arena is reset)

@@ -173,7 +173,6 @@ struct AccGlobal {
 	__device__ __forceinline__ int2 exon(uint32_t k) const { return c.ex[k]; }
 };
 
-constexpr int SWT_TILE = 256, SWT_HALO = 64, SWT_STG = SWT_TILE + 2 * SWT_HALO + 8, SWT_EXCAP = 3072;
 
 struct AccTile {
 	SweepCols c;
@@ -380,390 +379,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 }
 #endif
 
-// tiled variant: a CTA owns SWT_TILE consecutive hits; the ten packed columns of [tile - halo, tile + halo) and the exon
-// lists of those hits are pulled into shared memory by one thread issuing eleven cp.async.bulk copies (TMA, UBLKCP in SASS)
-// that complete on one mbarrier; several CTAs per SM overlap each other's copy and compute phases.  Windows that reach
-// past the halo (a hit with a megabase intron) fall through to global memory inside the accessor -- same results.
-template<int MODE> __global__ void __launch_bounds__(SWT_TILE) k_sweep_tile(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
-{
-	__shared__ __align__(16) uint64_t s_key[SWT_STG];
-	__shared__ __align__(16) int32_t s_ctg[SWT_STG], s_cs[SWT_STG], s_ce[SWT_STG], s_pmax[SWT_STG], s_gidp[SWT_STG], s_rank[SWT_STG], s_cds[SWT_STG];
-	__shared__ __align__(16) uint32_t s_bits[SWT_STG], s_eoff[SWT_STG + 4];
-	__shared__ __align__(16) int2 s_ex[SWT_EXCAP];
-	__shared__ __align__(8) uint64_t bar;
-	__shared__ uint32_t s_e[2];
-	const int32_t t0 = blockIdx.x * SWT_TILE;
-	int32_t lo = t0 - SWT_HALO; if (lo < 0) lo = 0;
-	lo &= ~3;                                                      // 16-byte aligned column offsets
-	int32_t hi = t0 + SWT_TILE + SWT_HALO; if (hi > c.n) hi = c.n;
-	const int32_t cnt4 = (hi - lo + 3) & ~3, cnte = (hi - lo + 1 + 3) & ~3;   // columns are allocated with slack past n
-	if (threadIdx.x == 0) {
-		mbar_init(&bar, 1);
-		fence_mbar_init();
-		uint32_t e0 = c.eoff[lo] & ~1u, e1 = c.eoff[hi];
-		uint32_t ne = (e1 - e0 + 1) & ~1u;
-		if (ne > SWT_EXCAP) ne = SWT_EXCAP;
-		s_e[0] = e0; s_e[1] = e0 + ne;
-		fence_proxy_async();
-		mbar_expect_tx(&bar, (uint32_t)cnt4 * 4u * 8u + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
-		bulk_g2s(s_ctg, c.ctg + lo, cnt4 * 4, &bar); bulk_g2s(s_cs, c.cs + lo, cnt4 * 4, &bar); bulk_g2s(s_ce, c.ce + lo, cnt4 * 4, &bar);
-		bulk_g2s(s_pmax, c.pmax + lo, cnt4 * 4, &bar); bulk_g2s(s_gidp, c.gidp + lo, cnt4 * 4, &bar); bulk_g2s(s_rank, c.rank + lo, cnt4 * 4, &bar);
-		bulk_g2s(s_cds, c.cds + lo, cnt4 * 4, &bar); bulk_g2s(s_bits, c.bits + lo, cnt4 * 4, &bar);
-		bulk_g2s(s_key, c.key + lo, cnt4 * 8, &bar);
-		bulk_g2s(s_eoff, c.eoff + lo, cnte * 4, &bar);
-		bulk_g2s(s_ex, c.ex + e0, ne * 8, &bar);
-	}
-	__syncthreads();
-	while (!mbar_try_wait(&bar, 0)) { }
-	const int32_t i = t0 + threadIdx.x;
-	if (i >= c.n) return;
-	const uint32_t mbits = s_bits[i - lo];
-	if (mbits & PG_HB_FLT) { bits_out[i] = mbits; return; }
-	AccTile A;
-	A.c = c; A.lo = lo; A.hi = hi; A.elo = s_e[0]; A.ehi = s_e[1];
-	A.s_ctg = s_ctg; A.s_cs = s_cs; A.s_ce = s_ce; A.s_pmax = s_pmax; A.s_gidp = s_gidp; A.s_rank = s_rank; A.s_cds = s_cds; A.s_bits = s_bits; A.s_eoff = s_eoff; A.s_key = s_key; A.s_ex = s_ex;
-	sweep_hit<MODE>(A, o, i, c.n, mbits, bits_out, pdom_out, sdom_out, tie_cnt);
-}
-
-// ---- the production sweep: TMA-staged tile, strongest-candidate-first ------------------------------------------------
-// ncu on the thread-per-hit variants above: 5..8 of 32 lanes active and ~2900 thread-instructions per hit -- every thread walks
-// exon lists for several partners inside a branchy window loop.  What a hit needs from the sweep is (a) whether ANY related
-// partner beats it and (b) the related partner with the LARGEST key (smallest index on ties).  So:
-//   phase 1  scan the window from shared memory with straight-line predicated code and keep only the would-be dominator: the
-//            partner with the largest key among those the hit would lose to (no exon lists touched);
-//   phase 2  ONE exon walk per hit, against that partner.  If it is in relation, it is the dominator and the hit is shadowed:
-//            no other partner can have a larger key.  If it is not (a bounding-box overlap without a CDS overlap), or the
-//            window leaves the staged range, the hit takes the serial sweep_hit() path -- same results by construction.
+// ---- the production sweep: a CTA owns SWQ_TILE consecutive hits of the (contig, cs) order ---------------------------------
+// Staging: the eight packed columns of [tile - halo, tile + halo) and the exon lists of those hits are pulled into shared memory
+// by one thread issuing ten cp.async.bulk copies (TMA, UBLKCP in SASS) that complete on one mbarrier; five CTAs per SM overlap
+// each other's copy and compute phases.
+// What a hit needs from the sweep is (a) whether ANY related partner beats it and (b) the related partner with the LARGEST key
+// (smallest index on ties).  ncu on the thread-per-hit kernel above: 5 of 32 lanes active, ~2900 thread-instructions per hit --
+// every thread walks exon lists for several partners inside a branchy window loop.  So:
+//   phase 0  (first sweep only) a sparse table over the staged keys: "strongest hit of an index range" in two look-ups;
+//   phase 1  the would-be dominator of every live hit -- the partner with the largest key among those the hit would lose to --
+//            from two binary searches for the window bounds (pmax and cs are monotone inside a contig) and two range-maximum
+//            queries (1a), or, where the table does not apply, from a straight-line scan of the window (1b); no exon list touched;
+//   phase 2  ONE exon walk per hit, against that partner.  If it is in relation, it is the dominator and the hit is shadowed: no
+//            other partner can have a larger key.  The (hit, candidate) pairs of the tile are bucketed by walk length (a counting
+//            sort in shared memory) and dealt out again longest first, one pair per thread, so that the lanes of a warp walk lists
+//            of about the same length; in SW_LOAD the exact overlap of overlap.c:170 comes out of the same walk;
+//   phase 3  what is left -- the strongest candidate was not in relation (a bounding-box overlap without enough CDS overlap), or
+//            the window leaves the staged range -- is parked and taken one hit at a time by a warp: 32 partners at once.
+// History of the design with the ncu numbers of every step: profiles/README.md.  tests/test_sweep_emu.py runs this kernel on the
+// CPU (SIMT shim) against the thread-per-hit kernel.
 constexpr int SWQ_TILE = 256, SWQ_HALO = 64, SWQ_STG = SWQ_TILE + 2 * SWQ_HALO + 8, SWQ_EXCAP = 2560;
-
-struct AccStaged {           // hit columns: unchecked shared memory (callers stay inside [lo, hi)); exons: checked
-	SweepCols c;
-	int32_t lo; uint32_t elo, ehi;
-	const int32_t *s_ctg, *s_cs, *s_ce, *s_pmax, *s_gidp, *s_cds;
-	const uint32_t *s_bits, *s_eoff;
-	const uint64_t *s_key;
-	const int2 *s_ex;
-	__device__ __forceinline__ int32_t ctg(int32_t p) const { return s_ctg[p - lo]; }
-	__device__ __forceinline__ int32_t cs(int32_t p) const { return s_cs[p - lo]; }
-	__device__ __forceinline__ int32_t ce(int32_t p) const { return s_ce[p - lo]; }
-	__device__ __forceinline__ int32_t pmax(int32_t p) const { return s_pmax[p - lo]; }
-	__device__ __forceinline__ uint32_t bits(int32_t p) const { return s_bits[p - lo]; }
-	__device__ __forceinline__ int32_t gidp(int32_t p) const { return s_gidp[p - lo]; }
-	__device__ __forceinline__ int32_t cds(int32_t p) const { return s_cds[p - lo]; }
-	__device__ __forceinline__ uint64_t key(int32_t p) const { return s_key[p - lo]; }
-	__device__ __forceinline__ uint32_t eoff(int32_t p) const { return s_eoff[p - lo]; }
-	__device__ __forceinline__ int2 exon(uint32_t k) const { return (k >= elo && k < ehi)? s_ex[k - elo] : c.ex[k]; }
-};
-
+constexpr int SWQ_LEVELS = 5, SWQ_WIN = 1 << SWQ_LEVELS;   // depth of the range-maximum table / the longest window it answers
 constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (size_t)(SWQ_STG + 4) * 4 + (size_t)SWQ_EXCAP * 8 + 64;
 
-template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_top(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	unsigned char *sp = smem_raw;
-	uint64_t *s_key = (uint64_t*)sp; sp += (size_t)SWQ_STG * 8;
-	int32_t *s_ctg = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	int32_t *s_cs = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	int32_t *s_ce = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	int32_t *s_pmax = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	int32_t *s_gidp = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	int32_t *s_cds = (int32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	uint32_t *s_bits = (uint32_t*)sp; sp += (size_t)SWQ_STG * 4;
-	uint32_t *s_eoff = (uint32_t*)sp; sp += (size_t)(SWQ_STG + 4) * 4;
-	int2 *s_ex = (int2*)sp; sp += (size_t)SWQ_EXCAP * 8;
-	uint64_t *bar = (uint64_t*)sp; sp += 8;
-	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range
-
-	const int32_t t0 = blockIdx.x * SWQ_TILE, tid = threadIdx.x;
-	int32_t lo = t0 - SWQ_HALO; if (lo < 0) lo = 0;
-	lo &= ~3;                                                                            // 16-byte aligned column offsets
-	int32_t hi = t0 + SWQ_TILE + SWQ_HALO; if (hi > c.n) hi = c.n;
-	const int32_t cnt4 = (hi - lo + 3) & ~3, cnte = (hi - lo + 1 + 3) & ~3;              // columns are allocated with slack past n
-	if (tid == 0) {
-		mbar_init(bar, 1);
-		fence_mbar_init();
-		uint32_t e0 = c.eoff[lo] & ~1u, e1 = c.eoff[hi];
-		uint32_t ne = (e1 - e0 + 1) & ~1u;
-		if (ne > SWQ_EXCAP) ne = SWQ_EXCAP;
-		s_misc[0] = e0; s_misc[1] = e0 + ne;
-		fence_proxy_async();
-		mbar_expect_tx(bar, (uint32_t)cnt4 * 4u * 7u + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
-		bulk_g2s(s_ctg, c.ctg + lo, cnt4 * 4, bar); bulk_g2s(s_cs, c.cs + lo, cnt4 * 4, bar); bulk_g2s(s_ce, c.ce + lo, cnt4 * 4, bar);
-		bulk_g2s(s_pmax, c.pmax + lo, cnt4 * 4, bar); bulk_g2s(s_gidp, c.gidp + lo, cnt4 * 4, bar); bulk_g2s(s_cds, c.cds + lo, cnt4 * 4, bar);
-		bulk_g2s(s_bits, c.bits + lo, cnt4 * 4, bar); bulk_g2s(s_key, c.key + lo, cnt4 * 8, bar);
-		bulk_g2s(s_eoff, c.eoff + lo, cnte * 4, bar);
-		bulk_g2s(s_ex, c.ex + e0, ne * 8, bar);
-	}
-	__syncthreads();
-	while (!mbar_try_wait(bar, 0)) { }
-
-	// ---- phase 0 (not for SW_ISO / -S): a sparse table over the staged score keys answers "which hit of an index range has the
-	// largest key (leftmost on ties)?" in two look-ups, so that phase 1 does not have to visit the ~10 partners of a window
-	// one by one.  Filtered hits count as key 0.  The table is only usable where the loser of a pair is decided by the keys
-	// alone, i.e. where no unfiltered hit of the tile carries a weak_br mark (overlap.c:139-147); otherwise s_mixed is set and
-	// the tile scans its windows as before.
-	__shared__ uint16_t s_st[6][SWQ_STG];          // s_st[j][q]: position of the maximum of [q, q + 2^(j+1)) (clipped)
-	__shared__ int s_mixed;
-	const int32_t S = hi - lo;
-	const bool rmq_mode = MODE == SW_LOAD && !o.check_strand;   // (the later sweeps run on the small active set: windows of 1-2 partners, the table would cost more than it saves)
-	if (rmq_mode) {
-		auto ekey = [&](int32_t q) -> uint64_t { return (s_bits[q] & PG_HB_FLT)? 0ull : s_key[q]; };
-		int mixed = 0;
-		for (int32_t q = tid; q < S; q += SWQ_TILE) {
-			const int32_t b = q + 1 < S? q + 1 : q;
-			s_st[0][q] = (uint16_t)(ekey(b) > ekey(q)? b : q);
-			const uint32_t bq = s_bits[q];
-			if (!(bq & PG_HB_FLT) && (bq & PG_HB_WBR_MASK)) mixed = 1;   // some unfiltered hit carries weak_br: keys alone do not decide
-		}
-		mixed = __syncthreads_or(mixed);
-		if (tid == 0) s_mixed = mixed;
-#pragma unroll 1
-		for (int j = 1; j < 6; ++j) {
-			for (int32_t q = tid; q < S; q += SWQ_TILE) {
-				const int32_t a = s_st[j - 1][q], q2 = q + (1 << j);
-				const int32_t b = q2 < S? (int32_t)s_st[j - 1][q2] : a;
-				s_st[j][q] = (uint16_t)(ekey(b) > ekey(a)? b : a);
-			}
-			__syncthreads();
-		}
-	}
-	// filtered hits (25 % in the first sweep) do no work: compact the live ones so that they fill whole warps
-	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
-	int32_t i;
-	bool in_range;
-	{
-		const int32_t i0 = t0 + tid;
-		const bool r0 = i0 < c.n;
-		const uint32_t b0 = s_bits[r0? i0 - lo : 0];
-		if (r0 && (b0 & PG_HB_FLT)) bits_out[i0] = b0;                                   // overlap.c:63,112
-		const bool live0 = r0 && !(b0 & PG_HB_FLT);
-		const uint32_t bal = __ballot_sync(0xffffffffu, live0);
-		if ((tid & 31) == 0) s_wcnt[tid >> 5] = (uint16_t)__popc(bal);
-		__syncthreads();
-		int32_t base = 0, n_live = 0;
-#pragma unroll
-		for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
-		if (live0) s_live[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
-		__syncthreads();
-		in_range = tid < n_live;
-		i = in_range? t0 + (int32_t)s_live[tid] : t0;
-	}
-	const int32_t mq = i - lo;
-	const uint32_t mbits = s_bits[mq];
-	AccStaged A;
-	A.c = c; A.lo = lo; A.elo = s_misc[0]; A.ehi = s_misc[1];
-	A.s_ctg = s_ctg; A.s_cs = s_cs; A.s_ce = s_ce; A.s_pmax = s_pmax; A.s_gidp = s_gidp; A.s_cds = s_cds; A.s_bits = s_bits; A.s_eoff = s_eoff; A.s_key = s_key; A.s_ex = s_ex;
-	const int32_t mctg = s_ctg[mq], mcs = s_cs[mq], mce = s_ce[mq], mgene = s_gidp[mq] >> 1;
-	const uint32_t mw = mbits & PG_HB_WBR_MASK;
-	const uint64_t mkey = s_key[mq];
-	int32_t top_p = INT32_MAX; uint64_t top_key = 0;
-	bool slow = false, lose = false, write_out = false;
-	if (in_range) {
-	// ---- phase 1a: the would-be dominator from the sparse table: window bounds by two light scans (one load per step), then two
-	// range-maximum queries.  Whatever the table cannot settle (a strongest hit that ended before my start, equal keys, windows
-	// longer than 64 or leaving the staged range) falls through to the partner-by-partner scan below.
-	bool scan = true;
-	if (rmq_mode && !s_mixed) {
-		auto ekey = [&](int32_t q) -> uint64_t { return (s_bits[q] & PG_HB_FLT)? 0ull : s_key[q]; };
-		auto rmq = [&](int32_t a, int32_t b) -> int32_t {   // leftmost maximum of ekey over [a, b), 1 <= b - a <= 64
-			const int32_t len = b - a;
-			if (len == 1) return a;
-			const int k = 31 - __clz(len);                  // 2^k <= len, k >= 1
-			const int32_t x = s_st[k - 1][a], y = s_st[k - 1][b - (1 << k)];
-			const uint64_t kx = ekey(x), ky = ekey(y);
-			return (ky > kx || (ky == kx && y < x))? y : x;
-		};
-		int32_t wb = mq, wf = mq + 1;
-		while (wb > 0 && s_ctg[wb - 1] == mctg && s_pmax[wb - 1] > mcs) --wb;          // overlap.c:67-71,114-120
-		while (wf < S && s_ctg[wf] == mctg && s_cs[wf] < mce) ++wf;
-		const bool open_back = wb == 0 && lo > 0, open_fwd = wf == S && hi < c.n;   // the window may continue outside the staged range
-		scan = false;
-		if (open_back || open_fwd) slow = true;
-		else if (mq - wb > 64 || wf - mq - 1 > 64) scan = true;
-		else {
-			int32_t tb = -1, tf = -1;
-			if (wb < mq) { tb = rmq(wb, mq); if (ekey(tb) == 0) tb = -1; else if (s_ce[tb] <= mcs) scan = true; }   // strongest in range is not a partner: a weaker one may be
-			if (mq + 1 < wf) { tf = rmq(mq + 1, wf); if (ekey(tf) == 0) tf = -1; }
-			if (!scan) {
-				const uint64_t kb = tb >= 0? s_key[tb] : 0ull, kf = tf >= 0? s_key[tf] : 0ull;
-				if ((tb >= 0 && kb == mkey) || (tf >= 0 && kf == mkey)) scan = true;       // same protein, same score: ranks decide (rare)
-				else {
-					if (tb >= 0 && kb > mkey) { top_key = kb; top_p = lo + tb; }
-					if (tf >= 0 && kf > mkey && kf > top_key) { top_key = kf; top_p = lo + tf; }   // equal keys: the backward one has the smaller index
-					if (MODE == SW_LOAD && top_p != INT32_MAX) {   // tie detector: a second partner with the winning key and the same start
-						const int32_t tq = top_p - lo;
-						int32_t r1 = -1, r2 = -1;
-						if (tq < mq) { if (wb < tq) r1 = rmq(wb, tq); if (tq + 1 < mq) r2 = rmq(tq + 1, mq); if (tf >= 0 && kf == top_key && s_cs[tf] == s_cs[tq]) atomicAdd(tie_cnt, 1u); }
-						else { if (mq + 1 < tq) r1 = rmq(mq + 1, tq); if (tq + 1 < wf) r2 = rmq(tq + 1, wf); }
-						if (r1 >= 0 && ekey(r1) == top_key && s_cs[r1] == s_cs[tq]) atomicAdd(tie_cnt, 1u);
-						if (r2 >= 0 && ekey(r2) == top_key && s_cs[r2] == s_cs[tq]) atomicAdd(tie_cnt, 1u);
-					}
-				}
-			}
-		}
-	}
-	// ---- phase 1b: the would-be dominator by scanning the window.  One loop walks back, then forward: a lane whose backward
-	// window is short starts its forward window while its neighbours are still going back (the warp pays max(back + fwd), not
-	// max(back) + max(fwd)).
-	if (scan && !slow) {
-		int side = 0, step = -1;
-#pragma unroll 1
-		for (int32_t p = i - 1;; p += step) {
-			bool end = false;
-			int32_t q = 0, pcs = 0, pce = 0;
-			if (p < lo) { slow = slow || p >= 0; end = true; }           // the window may continue outside the staged range
-			else if (p >= hi) { slow = slow || p < c.n; end = true; }
-			else {
-				q = p - lo; pcs = s_cs[q]; pce = s_ce[q];
-				end = s_ctg[q] != mctg || (side == 0? s_pmax[q] <= mcs : pcs >= mce);   // overlap.c:67-71,114-120: nothing further out can reach me
-			}
-			if (end) { if (side == 1) break; side = 1; step = 1; p = i; continue; }
-			const uint32_t pbits = s_bits[q];
-			const int32_t pgene = s_gidp[q] >> 1;
-			const uint64_t pkey = s_key[q];
-			const bool same_gene = pgene == mgene;
-			bool ok = !(pbits & PG_HB_FLT) && pce > mcs;                 // overlap.c:70,118,122 (pce > mcs always holds on the forward side)
-			if (MODE == SW_ISO) ok = ok && same_gene;                    // overlap.c:77
-			if (o.check_strand) ok = ok && !((pbits ^ mbits) & PG_HB_REV);   // overlap.c:78,128
-			const uint32_t pw = pbits & PG_HB_WBR_MASK;
-			const bool key_rule = MODE == SW_ISO || same_gene || mw == pw;   // overlap.c:139-147
-			bool loses = key_rule? mkey < pkey : mw > pw;
-			if (ok && key_rule && mkey == pkey) {                        // same protein, same score: ranks decide (rare)
-				const int32_t mrank = c.rank[i], prank = c.rank[p];
-				loses = side == 0? (mrank > prank) : !(prank > mrank);
-			}
-			if (ok && loses) {
-				if (MODE == SW_LOAD && pkey == top_key && top_p != INT32_MAX && pcs == s_cs[top_p - lo]) atomicAdd(tie_cnt, 1u);   // tie detector
-				if (pkey > top_key || (pkey == top_key && p < top_p)) { top_key = pkey; top_p = p; }
-			}
-		}
-	}
-	// ---- phase 2: one walk
-	if (!slow && top_p != INT32_MAX) {
-		const int32_t tq = top_p - lo;
-		const int32_t need = related_threshold(MODE == SW_ISO || (s_gidp[tq] >> 1) == mgene, s_cds[mq], s_cds[tq], o.min_ov_ratio);
-		const int32_t aq = top_p < i? tq : mq, bq = top_p < i? mq : tq;  // the earlier hit goes first (overlap.c:80)
-		lose = cds_related(A, s_eoff[aq], s_eoff[aq + 1], s_cs[aq], s_ce[aq], s_eoff[bq], s_eoff[bq + 1], s_cs[bq], s_ce[bq], need);
-		slow = !lose;                                                    // the strongest candidate did not hold: weaker ones must be tried
-	}
-	// ---- phase 3: the hits that could not be settled above (a few per cent) are parked and then taken one at a time by THEIR warp: the 32 lanes
-	// try 32 partners at once -- all would-be-loser pairs walk their exon lists in parallel, a shuffle reduction picks the
-	// related partner with the largest key (smallest index on ties).  Leaving such a hit to its own thread costs its whole warp
-	// ~3000 instruction slots (ncu: 2-4 of 32 lanes active for 42 % of the kernel's instructions).
-	write_out = !slow;
-	}   // (threads past n and filtered hits rejoin here: the ballot needs the whole warp)
-	{
-		uint32_t parked = __ballot_sync(0xffffffffu, slow);
-		const int lane = tid & 31;
-		AccTile T;
-		T.c = c; T.lo = lo; T.hi = hi; T.elo = s_misc[0]; T.ehi = s_misc[1];
-		T.s_ctg = s_ctg; T.s_cs = s_cs; T.s_ce = s_ce; T.s_pmax = s_pmax; T.s_gidp = s_gidp; T.s_rank = nullptr; T.s_cds = s_cds; T.s_bits = s_bits; T.s_eoff = s_eoff; T.s_key = s_key; T.s_ex = s_ex;
-#pragma unroll 1
-		while (parked) {
-			const int src_lane = __ffs(parked) - 1;
-			parked &= parked - 1;
-			const int32_t h = __shfl_sync(0xffffffffu, i, src_lane), hq = h - lo;
-			const int32_t hctg = s_ctg[hq], hcs = s_cs[hq], hce = s_ce[hq], hgene = s_gidp[hq] >> 1, hcds = s_cds[hq];
-			const uint32_t hbits = s_bits[hq], hw = hbits & PG_HB_WBR_MASK, heb = s_eoff[hq], hee = s_eoff[hq + 1];
-			const uint64_t hkey = s_key[hq];
-			bool w_lose = false; uint64_t w_key = 0; int32_t w_p = INT32_MAX;
-#pragma unroll 1
-			for (int side = 0; side < 2; ++side) {
-#pragma unroll 1
-				for (int32_t base = 1;; base += 32) {
-					const int32_t p = side == 0? h - base - lane : h + base + lane;
-					bool inwin = p >= 0 && p < c.n;
-					int32_t pcs = 0, pce = 0;
-					if (inwin) {
-						inwin = T.ctg(p) == hctg;
-						if (inwin) { pcs = T.cs(p); pce = T.ce(p); inwin = side == 0? T.pmax(p) > hcs : pcs < hce; }
-					}
-					if (inwin) {
-						const uint32_t pbits = T.bits(p);
-						const int32_t pgene = T.gidp(p) >> 1;
-						const uint64_t pkey = T.key(p);
-						const bool same_gene = pgene == hgene;
-						bool ok = !(pbits & PG_HB_FLT) && pce > hcs;
-						if (MODE == SW_ISO) ok = ok && same_gene;
-						if (o.check_strand) ok = ok && !((pbits ^ hbits) & PG_HB_REV);
-						const uint32_t pw = pbits & PG_HB_WBR_MASK;
-						const bool key_rule = MODE == SW_ISO || same_gene || hw == pw;
-						bool loses = key_rule? hkey < pkey : hw > pw;
-						if (ok && key_rule && hkey == pkey) { const int32_t r0 = c.rank[h], r1 = c.rank[p]; loses = side == 0? (r0 > r1) : !(r1 > r0); }
-						if (ok && loses) {
-							const int32_t need = related_threshold(MODE == SW_ISO || same_gene, hcds, T.cds(p), o.min_ov_ratio);
-							const uint32_t pb = T.eoff(p), pe = T.eoff(p + 1);
-							const bool rel = side == 0? cds_related(T, pb, pe, pcs, pce, heb, hee, hcs, hce, need) : cds_related(T, heb, hee, hcs, hce, pb, pe, pcs, pce, need);
-							if (rel) {
-								w_lose = true;
-								if (pkey > w_key || (pkey == w_key && p < w_p)) { w_key = pkey; w_p = p; }
-							}
-						}
-					}
-					if (!__any_sync(0xffffffffu, inwin && lane == 31)) break;   // the window predicate is monotone in distance: lane 31 is the farthest
-				}
-			}
-			// warp reduction: any loss; largest key, then smallest index (overlap.c:150,153)
-			w_lose = __any_sync(0xffffffffu, w_lose);
-#pragma unroll
-			for (int sft = 16; sft > 0; sft >>= 1) {
-				const uint64_t ok2 = __shfl_xor_sync(0xffffffffu, w_key, sft); const int32_t op = __shfl_xor_sync(0xffffffffu, w_p, sft);
-				if (ok2 > w_key || (ok2 == w_key && op < w_p)) { w_key = ok2; w_p = op; }
-			}
-			if (lane == 0) {
-				if (MODE == SW_ISO) bits_out[h] = w_lose? (hbits | PG_HB_FLT_OV | PG_HB_FLT) : hbits;
-				else if (MODE == SW_SHADOW) {
-					uint32_t b = hbits;
-					if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;
-					if (w_lose) b |= PG_HB_SHADOW;
-					bits_out[h] = b;
-					pdom_out[h] = (w_lose && w_key > 0)? c.pid[w_p] : -1;
-				} else {
-					bits_out[h] = hbits;
-					int32_t pd = -1, sd = -1;
-					if (w_lose && w_key > 0) {
-						pd = c.pid[w_p];
-						const int32_t ov = w_p < h? cds_overlap(T, T.eoff(w_p), T.eoff(w_p + 1), T.cs(w_p), T.ce(w_p), heb, hee, hcs, hce) : cds_overlap(T, heb, hee, hcs, hce, T.eoff(w_p), T.eoff(w_p + 1), T.cs(w_p), T.ce(w_p));
-						sd = (int32_t)(c.sori[h] * (1.0 - (double)ov / hcds) + c.sori[w_p] * ((double)ov / T.cds(w_p)) + .499);   // overlap.c:170
-					}
-					pdom_out[h] = pd; sdom_out[h] = sd;
-				}
-			}
-		}
-	}
-	if (!write_out) return;
-	// ---- outputs
-	if (MODE == SW_ISO) {
-		bits_out[i] = lose? (mbits | PG_HB_FLT_OV | PG_HB_FLT) : mbits;                  // overlap.c:85-91
-	} else if (MODE == SW_SHADOW) {
-		uint32_t b = mbits;
-		if (!(b & HB_FIRST)) b &= ~PG_HB_SHADOW;                                          // overlap.c:108,113: hit 0 is never reset
-		if (lose) b |= PG_HB_SHADOW;
-		bits_out[i] = b;
-		pdom_out[i] = (lose && top_key > 0)? c.pid[top_p] : -1;                           // overlap.c:160-165
-	} else {
-		bits_out[i] = mbits;
-		int32_t pd = -1, sd = -1;
-		if (lose && top_key > 0) {
-			const int32_t tq = top_p - lo;
-			pd = c.pid[top_p];
-			const int32_t ov = top_p < i? cds_overlap(A, s_eoff[tq], s_eoff[tq + 1], s_cs[tq], s_ce[tq], s_eoff[mq], s_eoff[mq + 1], mcs, mce)
-			                            : cds_overlap(A, s_eoff[mq], s_eoff[mq + 1], mcs, mce, s_eoff[tq], s_eoff[tq + 1], s_cs[tq], s_ce[tq]);
-			sd = (int32_t)(c.sori[i] * (1.0 - (double)ov / s_cds[mq]) + c.sori[top_p] * ((double)ov / s_cds[tq]) + .499);   // overlap.c:170
-		}
-		pdom_out[i] = pd; sdom_out[i] = sd;
-	}
-}
-
-// ---- sweep v2: same phases, three changes driven by the source-level ncu counters of k_sweep_top (profiles/README.md):
-//   (1) 58 % of the warp instructions were exon-list walks at ~7 of 32 lanes: a third of the lanes have no candidate and the
-//       walks of one warp have very different lengths.  The (hit, candidate) pairs of a tile are now bucketed by walk length
-//       (a counting sort in shared memory, ~25 instructions per thread) and handed out again, longest first, one pair per
-//       thread: the lanes of a warp walk lists of about the same length.  In SW_LOAD the "in relation?" walk and the
-//       exact-overlap walk of overlap.c:170 are one walk (the exact overlap decides both).
-//   (2) the window bounds are binary searches (pmax and cs are monotone inside a contig) instead of linear scans whose
-//       length the slowest lane of the warp dictates;
-//   (3) filtered hits get key 0 in the staged copy, so the range-maximum table reads one column instead of two.
 // One walk of two exon lists that live in ONE address space (both staged in shared memory, or both in global memory).
 // Adds up exactly what cds_overlap()/cds_related() add (overlap.c:6-42): in every one of the reference's four cases the
 // amount is min(t0,t1) - max(s0,s1), clipped at 0 where the reference clips (exon records have y >= x: read.c builds them
@@ -792,7 +430,7 @@ template<bool EARLY> __device__ __forceinline__ int32_t pair_overlap(const int2 
 	return walk_exons<EARLY>(g_ex + b0, g_ex + e0, cs0, g_ex + b1, g_ex + e1, cs1, need);
 }
 
-template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	unsigned char *sp = smem_raw;
@@ -808,7 +446,7 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 	int2 *s_ex = (int2*)sp; sp += (size_t)SWQ_EXCAP * 8;
 	uint64_t *bar = (uint64_t*)sp; sp += 8;
 	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range
-	__shared__ uint16_t s_st[6][SWQ_STG];          // s_st[j][q]: position of the maximum of [q, q + 2^(j+1)) (clipped)
+	__shared__ uint16_t s_st[SWQ_LEVELS][SWQ_STG]; // s_st[j][q]: position of the maximum of [q, q + 2^(j+1)) (clipped); windows up to SWQ_WIN hits
 	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
 	__shared__ uint32_t s_hist[64], s_job[SWQ_TILE], s_njob, s_flags;
 
@@ -844,6 +482,15 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 	// Flag 2: the staged range spans a contig boundary (then the window bounds are found by the linear scans).
 	const int32_t S = hi - lo;
 	const bool rmq_mode = MODE == SW_LOAD && !o.check_strand;   // (the later sweeps run on the small active set: windows of 1-2 partners, the table would cost more than it saves)
+	// filtered hits (25 % in the first sweep) do no work: the live ones are compacted so that they fill whole warps.  The two
+	// barriers of the compaction are the first two barriers of the table build.
+	const int32_t i0 = t0 + tid;
+	const bool r0 = i0 < c.n;
+	const uint32_t bits0 = s_bits[r0? i0 - lo : 0];
+	if (r0 && (bits0 & PG_HB_FLT)) bits_out[i0] = bits0;                                 // overlap.c:63,112
+	const bool live0 = r0 && !(bits0 & PG_HB_FLT);
+	const uint32_t bal = __ballot_sync(0xffffffffu, live0);
+	if ((tid & 31) == 0) s_wcnt[tid >> 5] = (uint16_t)__popc(bal);
 	if (rmq_mode) {
 		uint32_t flags = 0;
 		for (int32_t q = tid; q < S; q += SWQ_TILE) {
@@ -855,11 +502,20 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 			if (s_ctg[b] != s_ctg[q]) flags |= 2u;
 		}
 		if (flags) atomicOr(&s_flags, flags);
-		__syncthreads();
-		for (int32_t q = tid; q < S; q += SWQ_TILE) if (s_bits[q] & PG_HB_FLT) s_key[q] = 0ull;
-		__syncthreads();
+	}
+	__syncthreads();
+	int32_t n_live = 0;
+	{
+		int32_t base = 0;
+#pragma unroll
+		for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
+		if (live0) s_live[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
+	}
+	if (rmq_mode) for (int32_t q = tid; q < S; q += SWQ_TILE) if (s_bits[q] & PG_HB_FLT) s_key[q] = 0ull;
+	__syncthreads();
+	if (rmq_mode) {
 #pragma unroll 1
-		for (int j = 1; j < 6; ++j) {
+		for (int j = 1; j < SWQ_LEVELS; ++j) {
 			for (int32_t q = tid; q < S; q += SWQ_TILE) {
 				const int32_t a = s_st[j - 1][q], q2 = q + (1 << j);
 				const int32_t b = q2 < S? (int32_t)s_st[j - 1][q2] : a;
@@ -868,26 +524,8 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 			__syncthreads();
 		}
 	}
-	// filtered hits (25 % in the first sweep) do no work: compact the live ones so that they fill whole warps
-	int32_t i;
-	bool in_range;
-	{
-		const int32_t i0 = t0 + tid;
-		const bool r0 = i0 < c.n;
-		const uint32_t b0 = s_bits[r0? i0 - lo : 0];
-		if (r0 && (b0 & PG_HB_FLT)) bits_out[i0] = b0;                                   // overlap.c:63,112
-		const bool live0 = r0 && !(b0 & PG_HB_FLT);
-		const uint32_t bal = __ballot_sync(0xffffffffu, live0);
-		if ((tid & 31) == 0) s_wcnt[tid >> 5] = (uint16_t)__popc(bal);
-		__syncthreads();
-		int32_t base = 0, n_live = 0;
-#pragma unroll
-		for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
-		if (live0) s_live[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
-		__syncthreads();
-		in_range = tid < n_live;
-		i = in_range? t0 + (int32_t)s_live[tid] : t0;
-	}
+	const bool in_range = tid < n_live;
+	const int32_t i = in_range? t0 + (int32_t)s_live[tid] : t0;
 	const int32_t mq = i - lo;
 	const uint32_t mbits = s_bits[mq];
 	const uint32_t elo = s_misc[0], ehi = s_misc[1];
@@ -919,11 +557,11 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 
 	if (in_range) {
 	// ---- phase 1a: the would-be dominator from the sparse table: window bounds, then two range-maximum queries.  Whatever the
-	// table cannot settle (a strongest hit that ended before my start, equal keys, windows longer than 64 or leaving the
+	// table cannot settle (a strongest hit that ended before my start, equal keys, windows longer than SWQ_WIN or leaving the
 	// staged range) falls through to the partner-by-partner scan below.
 	bool scan = true;
 	if (rmq_mode && !(s_flags & 1u)) {
-		auto rmq = [&](int32_t a, int32_t b) -> int32_t {   // leftmost maximum of the key over [a, b), 1 <= b - a <= 64
+		auto rmq = [&](int32_t a, int32_t b) -> int32_t {   // leftmost maximum of the key over [a, b), 1 <= b - a <= SWQ_WIN
 			const int32_t len = b - a;
 			if (len == 1) return a;
 			const int k = 31 - __clz(len);                  // 2^k <= len, k >= 1
@@ -933,10 +571,10 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 		};
 		int32_t wb, wf;
 		if (!(s_flags & 2u)) {   // one contig: pmax (running maximum of ce) and cs are non-decreasing over the staged range
-			int32_t l = mq > 65? mq - 65 : 0, r = mq;
+			int32_t l = mq > SWQ_WIN + 1? mq - (SWQ_WIN + 1) : 0, r = mq;
 			while (l < r) { const int32_t m = (l + r) >> 1; if (s_pmax[m] > mcs) r = m; else l = m + 1; }   // overlap.c:67-71,114-120
 			wb = l;
-			l = mq + 1; r = S < mq + 66? S : mq + 66;
+			l = mq + 1; r = S < mq + SWQ_WIN + 2? S : mq + SWQ_WIN + 2;
 			while (l < r) { const int32_t m = (l + r) >> 1; if (s_cs[m] < mce) l = m + 1; else r = m; }
 			wf = l;
 		} else {
@@ -947,7 +585,7 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 		const bool open_back = wb == 0 && lo > 0, open_fwd = wf == S && hi < c.n;   // the window may continue outside the staged range
 		scan = false;
 		if (open_back || open_fwd) slow = true;
-		else if (mq - wb > 64 || wf - mq - 1 > 64) scan = true;
+		else if (mq - wb > SWQ_WIN || wf - mq - 1 > SWQ_WIN) scan = true;
 		else {
 			int32_t tb = -1, tf = -1;
 			if (wb < mq) { tb = rmq(wb, mq); if (s_key[tb] == 0) tb = -1; else if (s_ce[tb] <= mcs) scan = true; }   // strongest in range is not a partner: a weaker one may be
@@ -1011,38 +649,43 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_v2(Swe
 	// ---- phase 2: ONE walk per hit, against its would-be dominator; pairs bucketed by walk length and dealt out again
 	const bool has_job = in_range && !slow && top_p != INT32_MAX;
 	if (in_range && !slow && !has_job) emit(i, mq, mbits, false, false, 0, 0);       // nobody to lose to
-	uint32_t bin = 0, pos = 0;
-	if (has_job) {
-		const int32_t tq = top_p - lo;
-		const uint32_t len = (s_eoff[mq + 1] - s_eoff[mq]) + (s_eoff[tq + 1] - s_eoff[tq]);
-		bin = len >= 64u? 0u : 63u - len;                                            // longest first
-		pos = atomicAdd(&s_hist[bin], 1u);
-	}
-	__syncthreads();
-	if (tid < 32) {   // exclusive scan over the 64 buckets
-		const uint32_t a = s_hist[2 * tid], b = s_hist[2 * tid + 1];
-		uint32_t incl = a + b;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
-		const uint32_t excl = incl - (a + b);
-		s_hist[2 * tid] = excl; s_hist[2 * tid + 1] = excl + a;
-		if (tid == 31) s_njob = incl;
-	}
-	__syncthreads();
-	if (has_job) s_job[s_hist[bin] + pos] = (uint32_t)mq | (uint32_t)(top_p - lo) << 9 | (top_key > 0? 0x80000000u : 0u);
-	__syncthreads();
 	bool slow2 = false;
 	int32_t i2 = t0;
-	if (tid < (int32_t)s_njob) {
-		const uint32_t job = s_job[tid];
-		const int32_t jm = (int32_t)(job & 511u), jt = (int32_t)(job >> 9 & 511u);
-		const bool dom = (job >> 31) != 0;
+	auto run_job = [&](int32_t jm, int32_t jt, bool dom) {
 		i2 = lo + jm;
 		const int32_t need = related_threshold(MODE == SW_ISO || (s_gidp[jt] >> 1) == (s_gidp[jm] >> 1), s_cds[jm], s_cds[jt], o.min_ov_ratio);
 		const int32_t aq = jt < jm? jt : jm, bq = jt < jm? jm : jt;                  // the earlier hit goes first (overlap.c:80)
 		const int32_t ov = pair_overlap<MODE != SW_LOAD>(s_ex, elo, ehi, c.ex, s_eoff[aq], s_eoff[aq + 1], s_cs[aq], s_ce[aq], s_eoff[bq], s_eoff[bq + 1], s_cs[bq], s_ce[bq], need);
 		if (ov >= need) emit(i2, jm, s_bits[jm], true, dom, lo + jt, ov);
 		else slow2 = true;                                                           // the strongest candidate did not hold: weaker ones must be tried
+	};
+	if (MODE == SW_ISO) {   // isoforms of one gene: any CDS overlap counts, the walk stops at the first common base -- nothing to balance
+		if (has_job) run_job(mq, top_p - lo, top_key > 0);
+	} else {
+		uint32_t bin = 0, pos = 0;
+		if (has_job) {
+			const int32_t tq = top_p - lo;
+			const uint32_t len = (s_eoff[mq + 1] - s_eoff[mq]) + (s_eoff[tq + 1] - s_eoff[tq]);
+			bin = len >= 64u? 0u : 63u - len;                                        // longest first
+			pos = atomicAdd(&s_hist[bin], 1u);
+		}
+		__syncthreads();
+		if (tid < 32) {   // exclusive scan over the 64 buckets
+			const uint32_t a = s_hist[2 * tid], b = s_hist[2 * tid + 1];
+			uint32_t incl = a + b;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+			const uint32_t excl = incl - (a + b);
+			s_hist[2 * tid] = excl; s_hist[2 * tid + 1] = excl + a;
+			if (tid == 31) s_njob = incl;
+		}
+		__syncthreads();
+		if (has_job) s_job[s_hist[bin] + pos] = (uint32_t)mq | (uint32_t)(top_p - lo) << 9 | (top_key > 0? 0x80000000u : 0u);
+		__syncthreads();
+		if (tid < (int32_t)s_njob) {
+			const uint32_t job = s_job[tid];
+			run_job((int32_t)(job & 511u), (int32_t)(job >> 9 & 511u), (job >> 31) != 0);
+		}
 	}
 	// ---- phase 3: the hits that could not be settled above (a few per cent) are parked and then taken one at a time by a warp: the 32 lanes
 	// try 32 partners at once -- all would-be-loser pairs walk their exon lists in parallel, a shuffle reduction picks the

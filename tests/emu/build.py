@@ -19,10 +19,8 @@ extern "C" int sweep_emu(int variant, int mode, const EmuCols *e, double min_ov_
 	if (c.n <= 0) return 0;
 #define RUN(K, T) emu::launch((c.n + (T) - 1) / (T), (T), [&] { K(c, o, bits_out, pdom_out, sdom_out, tie_cnt); })
 #define BY_MODE(K, T) do { if (mode == 0) RUN(K<SW_LOAD>, T); else if (mode == 1) RUN(K<SW_SHADOW>, T); else RUN(K<SW_ISO>, T); } while (0)
-	if (variant == 0) BY_MODE(k_sweep, 128);
-	else if (variant == 1) BY_MODE(k_sweep_tile, SWT_TILE);
-	else if (variant == 2) BY_MODE(k_sweep_top, SWQ_TILE);
-	else if (variant == 3) BY_MODE(k_sweep_v2, SWQ_TILE);
+	if (variant == 0) BY_MODE(k_sweep, 128);                   // plain thread-per-hit kernel
+	else if (variant == 1) BY_MODE(k_sweep_tiled, SWQ_TILE);   // production kernel
 	else return -1;
 	return 0;
 }

@@ -1,7 +1,7 @@
 """The production sweep kernel's control flow, checked on the CPU: tests/emu/ compiles the sweep kernels of
 pangene_b200/csrc/pgx_kernels.cuh for the host (SIMT shim: one OS thread per CUDA thread) and this test runs every variant on the
 same hit columns.  The plain thread-per-hit kernel `k_sweep` is the restatement of overlap.c:58-178 that the GPU parity tests
-pin against the oracle; the tiled variants must reproduce its outputs bit for bit in all three modes."""
+pin against the oracle; the tiled production kernel `k_sweep_tiled` must reproduce its outputs bit for bit in all three modes."""
 import ctypes as C
 import os
 import sys
@@ -132,11 +132,9 @@ def test_tiled_sweeps_equal_plain_sweep(emu, case):
         n_dom = int((ref[1] >= 0).sum()) if mode != 2 else int((ref[0] & abi.PG_HB_FLT_OV != 0).sum())
         if mode != 2 or kw["iso_per_gene"] > 1:
             assert n_dom > cols["n"] // 50, "the case does not exercise the sweep"
-        for variant in (2, 3):
+        for variant in (1,):
             got = run(emu, variant, mode, cols, check_strand=strand)
             for k, what in enumerate(("bits", "pid_dom", "score_dom")):
                 bad = np.nonzero(ref[k] != got[k])[0]
                 assert len(bad) == 0, "%s: variant %d mode %d: %s differs at %s (plain %s, tiled %s)" % (name, variant, mode, what, bad[:5], ref[k][bad[:5]], got[k][bad[:5]])
-        # the two production variants share the tie detector
-        assert run(emu, 2, mode, cols, check_strand=strand)[3] == run(emu, 3, mode, cols, check_strand=strand)[3]
     hostio.destroy(d)

@@ -3,7 +3,7 @@ sys.path.insert(0,'/root/repo')
 from pangene_b200 import engine, hostio
 opt=hostio.default_opt()
 d0=hostio.synth(opt, hostio.synth_params(3))
-L=engine.lib(); engine.set_verbose(1); L.pgx_set_lazy(1)
+L=engine.lib(); engine.set_verbose(3 if os.environ.get("PGX_TIMING") else 1); L.pgx_set_lazy(1)
 for it in range(3):
     d=hostio.lib().pgio_data_clone(d0)
     t0=time.perf_counter()
