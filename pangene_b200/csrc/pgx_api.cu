@@ -1,7 +1,6 @@
 // pgx_api.cu -- the C-ABI surface of libpgx.so (include/pgx.h) over the device engine (pgx_engine.cuh).
 // Built for sm_100a only; there is no CPU path behind any of these entry points.
 #include <map>
-#include <sched.h>
 #include <time.h>
 #include <mutex>
 #include "pgx_engine.cuh"
@@ -16,57 +15,6 @@ static std::map<const pg_data_t*, Session*> g_sessions;   // pg_post_process() -
 
 static double wall() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 static bool timing_on() { static const bool on = getenv("PGX_TIMING") != nullptr; return on; }
-
-// Host threads next to the GPU: the staging pipeline moves ~2.4 GB per call through pinned buffers and the graph stage does ~35
-// small read-backs; from the far socket both get slower (a box in the pool showed 36 ms instead of 26 ms for stage 2 and
-// 230-290 ms instead of 180 ms end to end).  Once per process the calling thread -- and with it the thread pool and the pinned
-// ring, which are created afterwards -- is restricted to the CPUs the kernel lists as local to the GPU's PCI device, within
-// the affinity mask the process was started with.  PGX_NUMA=0 turns this off; PGX_NUMA_CPUS=<list> names the CPUs instead.
-static bool parse_cpulist(const char *s, cpu_set_t *set)
-{
-	CPU_ZERO(set);
-	int n = 0;
-	while (*s) {
-		char *e;
-		long a = strtol(s, &e, 10), b = a;
-		if (e == s) break;
-		if (*e == '-') { s = e + 1; b = strtol(s, &e, 10); if (e == s) break; }
-		for (long c = a; c <= b && c < CPU_SETSIZE; ++c) if (c >= 0) { CPU_SET((int)c, set); ++n; }
-		s = *e == ','? e + 1 : e;
-		if (*e != ',' ) break;
-	}
-	return n > 0;
-}
-
-static void bind_host_threads_near(int dev)
-{
-	static bool done = false;
-	if (done) return;
-	done = true;
-	const char *off = getenv("PGX_NUMA");
-	if (off && atoi(off) == 0) return;
-	cpu_set_t want, have, both;
-	const char *list = getenv("PGX_NUMA_CPUS");
-	char buf[4096] = "";
-	if (!list) {
-		char bus[64];
-		if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) { cudaGetLastError(); return; }
-		for (char *q = bus; *q; ++q) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
-		char path[160];
-		snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
-		FILE *f = fopen(path, "r");
-		if (!f) return;
-		if (!fgets(buf, (int)sizeof(buf), f)) buf[0] = 0;
-		fclose(f);
-		list = buf;
-	}
-	if (!parse_cpulist(list, &want)) return;
-	if (sched_getaffinity(0, sizeof(have), &have) != 0) return;
-	CPU_AND(&both, &want, &have);
-	if (CPU_COUNT(&both) == 0 || CPU_EQUAL(&both, &have)) return;
-	if (sched_setaffinity(0, sizeof(both), &both) == 0 && pg_verbose >= 3)
-		fprintf(stderr, "[M::pgx] host threads bound to %d CPUs local to GPU %d\n", CPU_COUNT(&both), dev);
-}
 
 static void need_device()
 {
@@ -83,7 +31,6 @@ static void need_device()
 	PGX_CHECK(cudaGetDeviceProperties(&p, dev));
 	if (p.major < 10) PGX_FATAL("device %d (%s, sm_%d%d) is not a Blackwell part; libpgx is built for sm_100a only", dev, p.name, p.major, p.minor);
 	checked_dev = dev;
-	bind_host_threads_near(dev);
 }
 
 static void timed_run(Session *s, const pg_opt_t *opt, int stage)
