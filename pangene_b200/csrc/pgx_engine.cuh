@@ -823,6 +823,10 @@ struct Session {
 						while (t >= h_hoff[g + 1]) ++g;
 						const int64_t base = h_hoff[g];
 						pg_hit_t *dst = in_place? &d->genome[g].hit[t - base] : &fresh[g][t - base];
+						if (!in_place && t + 12 < e) {   // the source records are visited in random order: ask for the one needed 12 hits from now
+							const char *pf = (const char*)&d->genome[g].hit[(int64_t)o[12].src - base];   // (past a genome boundary: a harmless wrong guess)
+							__builtin_prefetch(pf); __builtin_prefetch(pf + 64);
+						}
 						if (!in_place) *dst = d->genome[g].hit[(int64_t)o->src - base];
 						dst->rank = o->rank; dst->score_dom = o->sdom; dst->pid_dom = o->pdom; dst->pid_dom0 = o->pdom0;
 						memcpy((char*)dst + PG_HIT_BITS_OFFSET, &o->bits, 4);

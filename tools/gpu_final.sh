@@ -9,4 +9,5 @@ for m in lookback 3pass; do echo SCAN=$m; PGX_SCAN=$m python tools/stage_probe.p
 timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_final.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_final.csv python tools/profile_run.py 100 1 2>&1 | tail -1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_sweep_tiled -c 1 -o gpurun_out/sweep_final python tools/profile_run.py 100 1 2>&1 | tail -1
+timeout 300 bash tools/cli_compare.sh 16 2>&1 | tail -8 | tee gpurun_out/cli_compare_final.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv | tail -2
