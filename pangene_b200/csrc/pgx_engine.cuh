@@ -95,7 +95,7 @@ struct Session {
 	DBuf<int32_t> seg_ng, seg_tot, arc_of_rec;
 	Arena scratch;
 	uint32_t *h_pin = nullptr;           // pinned word(s) for small read-backs
-	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_N = 8 };
+	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_N = 8 };
 
 	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
 	~Session() { if (st) cudaStreamDestroy(st); for (auto &e : ev) if (e) cudaEventDestroy(e); if (h_pin) cudaFreeHost(h_pin); }
@@ -730,7 +730,7 @@ struct Session {
 			}
 			PGX_LAUNCH(k_branch_decide, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, off, nl, bo, grp);
 			// hits inherit the weakness of the arcs they sit on; weak_br == 2 filters (branch.c:108-145, graph.c:309)
-			PGX_LAUNCH(k_branch_hits, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, (const int32_t*)(g_comm.active()? nullptr : arc_of_rec.p));
+			PGX_LAUNCH(k_branch_hits, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, (const int32_t*)(g_comm.active()? nullptr : arc_of_rec.p), counters.p + C_BR_CHANGED);
 		}
 		scratch.reset(mk);
 	}
@@ -751,8 +751,16 @@ struct Session {
 			int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
 			int32_t max_degree = (int32_t)(opt->max_degree * r + .499);
 			int32_t max_dist_loci = (int32_t)(opt->max_dist_loci * r + .499);
+			static const bool trace = getenv("PGX_TIMING") != nullptr;
+			uint32_t seg_before = 0;
+			if (trace) { seg_before = read_counts().n_seg; PGX_CHECK(cudaMemsetAsync(counters.p + C_BR_CHANGED, 0, 4, st)); }
 			branch_round(opt);
 			if (i > 0) flt_high_occ(max_avg_occ, max_degree, max_dist_loci);
+			if (trace) {   // how much does a round change?  (a round that changes nothing could skip the pg_gen_arc below)
+				const uint32_t chg = read_u32(counters.p + C_BR_CHANGED);
+				DevCounts hc = read_counts();
+				fprintf(stderr, "[pgx timing] branch round %d: %u hit words changed, segments %u -> %u, arcs %u, survivors %u\n", i, chg, seg_before, hc.n_seg, hc.n_arc, hc.m_sv);
+			}
 			gen_arc(opt);
 		}
 		set_filter(SF_SHADOW);                                                           // graph.c:316

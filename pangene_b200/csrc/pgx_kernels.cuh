@@ -1347,11 +1347,12 @@ __device__ __forceinline__ uint32_t arc_weak(const ArcDev *__restrict__ arc, int
 	return (lo < n_arc && arc[lo].x == x)? (arc[lo].bits >> 1 & 3u) : 0u;
 }
 __global__ void k_branch_hits(const uint32_t *__restrict__ sv, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ctg, const int32_t *__restrict__ gidp, uint32_t *bits, const int32_t *__restrict__ g2s,
-	const ArcDev *__restrict__ arc, const int32_t *__restrict__ arc_of_rec)
+	const ArcDev *__restrict__ arc, const int32_t *__restrict__ arc_of_rec, uint32_t *n_changed)
 {
 	const int32_t m = (int32_t)dc->m_sv, n_arc = (int32_t)dc->n_arc;
 	PGX_GS(t, m) {
 		uint32_t h = sv[t], b = bits[h];
+		const uint32_t b_in = b;
 		int32_t c = ctg[h];
 		uint32_t wb = (b & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT;
 		if (t > 0 && ctg[sv[t - 1]] == c) {                 // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
@@ -1378,6 +1379,7 @@ __global__ void k_branch_hits(const uint32_t *__restrict__ sv, const DevCounts *
 		b = (b & ~PG_HB_WBR_MASK) | wb << PG_HB_WBR_SHIFT;
 		if (wb == 2) b |= PG_HB_FLT;                             // graph.c:309
 		bits[h] = b;
+		if (b != b_in) atomicAdd(n_changed, 1u);                 // (a round that changes no hit and deletes no segment leaves pg_gen_arc's input as it was)
 	}
 }
 
