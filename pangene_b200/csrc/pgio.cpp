@@ -515,47 +515,67 @@ static int32_t parse_sample(std::string &buf, const char *name)
 	return (r == p && hap >= 0)? (int32_t)hap : -1;
 }
 
-static void write_walk_lines(const pg_graph_t *q, Out &o)   // format.c:183-225
+// Per-genome text produced by worker threads, written in genome order: the W lines and the BED lines of one genome depend
+// on that genome alone (format.c:183-225, 78-118), and at 100 x 200 k hits formatting them single-threaded costs an order of
+// magnitude more than the whole hot path.  Batches of genomes bound the memory held in strings.
+template<class F> static void for_each_genome_text(int32_t n_genome, Out &o, F f)
 {
-	const pg_data_t *d = q->d;
+	int32_t n_thr = (int32_t)std::thread::hardware_concurrency();
+	if (const char *e = getenv("PGIO_THREADS")) n_thr = atoi(e);
+	if (n_thr > n_genome) n_thr = n_genome;
+	if (n_thr < 1) n_thr = 1;
+	const int32_t batch = n_thr * 2;
+	std::vector<std::string> text(batch);
+	for (int32_t j0 = 0; j0 < n_genome; j0 += batch) {
+		const int32_t nb = n_genome - j0 < batch? n_genome - j0 : batch;
+		std::atomic<int32_t> next(0);
+		auto worker = [&]() { for (int32_t k; (k = next.fetch_add(1)) < nb;) { text[k].clear(); f(j0 + k, text[k]); } };
+		std::vector<std::thread> th;
+		for (int32_t t = 1; t < n_thr && t < nb; ++t) th.emplace_back(worker);
+		worker();
+		for (auto &t : th) t.join();
+		o.flush();
+		for (int32_t k = 0; k < nb; ++k) if (!text[k].empty()) fwrite(text[k].data(), 1, text[k].size(), o.fp);
+	}
+}
+
+static inline void put_num(std::string &s, long v)
+{
+	char b[24]; int l = 0; bool neg = v < 0; unsigned long x = neg? 0ul - (unsigned long)v : (unsigned long)v;
+	do { b[l++] = '0' + x % 10; x /= 10; } while (x);
+	if (neg) b[l++] = '-';
+	while (l) s.push_back(b[--l]);
+}
+
+static void walk_lines_of_genome(const pg_data_t *d, int32_t j, std::string &s)   // format.c:183-225
+{
+	const pg_genome_t *g = &d->genome[j];
 	std::string sample;
+	// only unfiltered hits are printed (format.c:205,213): order THEM contig-major, then by CDS mid-point; ties keep the incoming
+	// (cid,cs) order (see DESIGN.md "tie order") -- a stable sort of the kept hits equals the stable sort of all hits with the rest removed
 	std::vector<int32_t> ord;
-	for (int32_t j = 0; j < d->n_genome; ++j) {
-		const pg_genome_t *g = &d->genome[j];
-		// contig-major, then CDS mid-point; ties keep the incoming (cid,cs) order (see DESIGN.md "tie order")
-		ord.resize(g->n_hit);
-		for (int32_t i = 0; i < g->n_hit; ++i) ord[i] = i;
-		std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
-			const pg_hit_t &x = g->hit[a], &y = g->hit[b];
-			return x.cid != y.cid? x.cid < y.cid : x.cm < y.cm; });
-		for (int32_t i0 = 0, i = 1; i <= g->n_hit; ++i) {
-			if (i == g->n_hit || g->hit[ord[i]].cid != g->hit[ord[i0]].cid) {
-				int32_t cid = g->hit[ord[i0]].cid, n = 0;
-				for (int32_t k = i0; k < i; ++k) n += !g->hit[ord[k]].flt;
-				if (n > 0) {
-					int32_t hap = parse_sample(sample, g->ctg[cid].name);
-					o.str("W\t");
-					if (hap >= 0) { o.str(sample.c_str()); o.ch('\t'); o.num(hap); }
-					else if (g->label) { o.str(g->label); o.str("\t0"); }
-					else { o.num(j); o.str("\t0"); }
-					o.ch('\t'); o.str(g->ctg[cid].name); o.str("\t*\t*\t");
-					for (int32_t k = i0; k < i; ++k) {
-						const pg_hit_t *a = &g->hit[ord[k]];
-						if (a->flt) continue;
-						o.ch("><"[a->rev]); o.str(d->gene[d->prot[a->pid].gid].name);
-					}
-					o.str("\tlf:B:i");
-					for (int32_t k = i0; k < i; ++k) {
-						const pg_hit_t *a = &g->hit[ord[k]];
-						if (a->flt) continue;
-						o.ch(','); o.num(a->lof);
-					}
-					o.ch('\n');
-					o.maybe_flush();
-				}
-				i0 = i;
-			}
+	for (int32_t i = 0; i < g->n_hit; ++i) if (!g->hit[i].flt) ord.push_back(i);
+	std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+		const pg_hit_t &x = g->hit[a], &y = g->hit[b];
+		return x.cid != y.cid? x.cid < y.cid : x.cm < y.cm; });
+	const size_t n = ord.size();
+	for (size_t i0 = 0, i = 1; i <= n; ++i) {
+		if (i < n && g->hit[ord[i]].cid == g->hit[ord[i0]].cid) continue;
+		const int32_t cid = g->hit[ord[i0]].cid;
+		const int32_t hap = parse_sample(sample, g->ctg[cid].name);
+		s += "W\t";
+		if (hap >= 0) { s += sample; s.push_back('\t'); put_num(s, hap); }
+		else if (g->label) { s += g->label; s += "\t0"; }
+		else { put_num(s, j); s += "\t0"; }
+		s.push_back('\t'); s += g->ctg[cid].name; s += "\t*\t*\t";
+		for (size_t k = i0; k < i; ++k) {
+			const pg_hit_t *a = &g->hit[ord[k]];
+			s.push_back("><"[a->rev]); s += d->gene[d->prot[a->pid].gid].name;
 		}
+		s += "\tlf:B:i";
+		for (size_t k = i0; k < i; ++k) { s.push_back(','); put_num(s, g->hit[ord[k]].lof); }
+		s.push_back('\n');
+		i0 = i;
 	}
 }
 
@@ -564,36 +584,38 @@ extern "C" int32_t pgio_write_gfa(const pg_graph_t *g, const char *path, int32_t
 	Out o(path);
 	if (o.fp == 0) return -1;
 	if (flags & 1) { write_seg_lines(g, o); write_arc_lines(g, o); }
-	if (flags & 2) write_walk_lines(g, o);
+	if (flags & 2) for_each_genome_text(g->d->n_genome, o, [&](int32_t j, std::string &s) { walk_lines_of_genome(g->d, j, s); });
 	return 0;
 }
 
-extern "C" int32_t pgio_write_bed(const pg_data_t *d, int32_t is_walk, const char *path)   // format.c:78-118
+static void bed_lines_of_genome(const pg_data_t *d, int32_t j, int32_t is_walk, std::string &s)   // format.c:78-118
+{
+	const pg_genome_t *g = &d->genome[j];
+	for (int32_t i = 0; i < g->n_hit; ++i) {
+		const pg_hit_t *a = &g->hit[i];
+		if (is_walk && a->flt) continue;
+		char idbuf[16];
+		// the reference's %ld formatter narrows through int (format.c:43-47); coordinates < 2^31 print identically
+		s += g->ctg[a->cid].name; s.push_back('\t'); put_num(s, (int)a->cs); s.push_back('\t'); put_num(s, (int)a->ce); s.push_back('\t');
+		s += d->prot[a->pid].name; s.push_back('\t'); put_num(s, a->score_ori); s.push_back('\t'); s.push_back("+-"[a->rev]); s.push_back('\t');
+		put_num(s, (int)a->cs); s.push_back('\t'); put_num(s, (int)a->ce); s += "\t0\t"; put_num(s, a->n_exon); s.push_back('\t');
+		for (int32_t k = 0; k < a->n_exon; ++k) { put_num(s, g->exon[a->off_exon + k].oe - g->exon[a->off_exon + k].os); s.push_back(','); }
+		s.push_back('\t');
+		for (int32_t k = 0; k < a->n_exon; ++k) { put_num(s, g->exon[a->off_exon + k].os); s.push_back(','); }
+		snprintf(idbuf, 15, "%.4f", (double)a->mlen / a->blen);
+		s += "\tft:i:"; put_num(s, a->flt);
+		s += "\tpf:Z:"; put_num(s, a->pseudo); put_num(s, a->flt_iso_ov); put_num(s, a->flt_chain); put_num(s, a->flt_iso_sub_self);
+		s += "\trk:i:"; put_num(s, a->rank); s += "\trp:i:"; put_num(s, a->rep); s += "\tsd:i:"; put_num(s, a->shadow);
+		s += "\tvt:i:"; put_num(s, a->vtx); s += "\tbr:i:"; put_num(s, a->weak_br); s += "\tcm:i:"; put_num(s, (int)a->cm);
+		s += "\tid:f:"; s += idbuf; s += "\tdm:Z:"; s += a->pid_dom0 < 0? "*" : d->prot[a->pid_dom0].name; s.push_back('\n');
+	}
+}
+
+extern "C" int32_t pgio_write_bed(const pg_data_t *d, int32_t is_walk, const char *path)
 {
 	Out o(path);
 	if (o.fp == 0) return -1;
-	for (int32_t j = 0; j < d->n_genome; ++j) {
-		const pg_genome_t *g = &d->genome[j];
-		for (int32_t i = 0; i < g->n_hit; ++i) {
-			const pg_hit_t *a = &g->hit[i];
-			if (is_walk && a->flt) continue;
-			char idbuf[16];
-			// the reference's %ld formatter narrows through int (format.c:43-47); coordinates < 2^31 print identically
-			o.str(g->ctg[a->cid].name); o.ch('\t'); o.num((int)a->cs); o.ch('\t'); o.num((int)a->ce); o.ch('\t');
-			o.str(d->prot[a->pid].name); o.ch('\t'); o.num(a->score_ori); o.ch('\t'); o.ch("+-"[a->rev]); o.ch('\t');
-			o.num((int)a->cs); o.ch('\t'); o.num((int)a->ce); o.str("\t0\t"); o.num(a->n_exon); o.ch('\t');
-			for (int32_t k = 0; k < a->n_exon; ++k) { o.num(g->exon[a->off_exon + k].oe - g->exon[a->off_exon + k].os); o.ch(','); }
-			o.ch('\t');
-			for (int32_t k = 0; k < a->n_exon; ++k) { o.num(g->exon[a->off_exon + k].os); o.ch(','); }
-			snprintf(idbuf, 15, "%.4f", (double)a->mlen / a->blen);
-			o.str("\tft:i:"); o.num(a->flt);
-			o.str("\tpf:Z:"); o.num(a->pseudo); o.num(a->flt_iso_ov); o.num(a->flt_chain); o.num(a->flt_iso_sub_self);
-			o.str("\trk:i:"); o.num(a->rank); o.str("\trp:i:"); o.num(a->rep); o.str("\tsd:i:"); o.num(a->shadow);
-			o.str("\tvt:i:"); o.num(a->vtx); o.str("\tbr:i:"); o.num(a->weak_br); o.str("\tcm:i:"); o.num((int)a->cm);
-			o.str("\tid:f:"); o.str(idbuf); o.str("\tdm:Z:"); o.str(a->pid_dom0 < 0? "*" : d->prot[a->pid_dom0].name); o.ch('\n');
-			o.maybe_flush();
-		}
-	}
+	for_each_genome_text(d->n_genome, o, [&](int32_t j, std::string &s) { bed_lines_of_genome(d, j, is_walk, s); });
 	return 0;
 }
 
