@@ -47,6 +47,11 @@ void pgx_set_device(int dev);                 /* default: current CUDA device */
  * materialises everything once.  0 (default): strict reference post-conditions after each call. */
 void pgx_set_lazy(int lazy);
 
+/* Optional: create the CUDA context, the pinned staging ring and the host thread pool now instead of inside the first
+ * pg_post_process().  May be called from a side thread while the caller parses its input (join before pg_post_process).
+ * Returns 1 if a device was initialised, 0 otherwise (never aborts). */
+int  pgx_warmup(void);
+
 /* Multi-GPU, one process per GPU.  Genomes are partitioned across ranks (this rank's pg_data_t holds genomes
  * [genome_begin, genome_begin + d->n_genome) of n_genome_total); gene/protein ids must be global.  The 128-byte
  * id comes from pgx_comm_unique_id() on rank 0 and is broadcast by the launcher (torch.distributed, MPI, ...).

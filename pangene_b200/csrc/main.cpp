@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <getopt.h>
+#include <thread>
 #include <sys/time.h>
 #include <sys/resource.h>
 #include "pgio.h"
@@ -99,7 +100,9 @@ int main(int argc, char *argv[])
 	if (argc - optind < 1) return usage(stderr, &opt);
 
 	pg_data_t *d = pgio_data_init();
+	std::thread warm([]() { pgx_warmup(); });   // CUDA context + pinned staging ring come up while the files are parsed
 	pgio_read_pafs(&opt, d, (const char *const*)&argv[optind], argc - optind, 0);   // parallel parse, ids as in sequential order
+	warm.join();
 	double t1 = now();
 	pgx_set_lazy(!(opt.flag & PG_F_WRITE_BED_RAW));   // hits come back once, after pg_graph_gen
 	pg_post_process(&opt, d);

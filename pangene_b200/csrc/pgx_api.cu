@@ -129,6 +129,20 @@ int pgx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 void pgx_set_device(int dev) { g_device = dev; PGX_CHECK(cudaSetDevice(dev)); }
 void pgx_set_lazy(int lazy) { g_lazy = lazy; }
 
+// Everything the first pg_post_process() would otherwise pay for on the caller's critical path -- CUDA context, the pinned
+// staging ring, the host thread pool -- done ahead of time; the CLI calls this on a side thread while the PAF files are parsed.
+// Never fatal: without a device it returns 0 and pg_post_process() reports the problem in its own words.
+int pgx_warmup(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) { cudaGetLastError(); return 0; }
+	if (g_device >= 0 && cudaSetDevice(g_device) != cudaSuccess) { cudaGetLastError(); return 0; }
+	if (cudaFree(0) != cudaSuccess) { cudaGetLastError(); return 0; }
+	PinnedRing::get();
+	ThreadPool::get();
+	return 1;
+}
+
 int pgx_comm_unique_id(void *out128)
 {
 	if (!g_comm.load()) PGX_FATAL("cannot load libnccl.so.2");
