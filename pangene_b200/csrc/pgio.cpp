@@ -18,6 +18,9 @@
 #include <thread>
 #include <atomic>
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include "pgio.h"
 #include "pgio_priv.hpp"
 
@@ -132,12 +135,32 @@ extern "C" void pgio_data_clone_destroy(pg_data_t *d)
 // ------------------------------------------------------------------------------------------------
 static bool read_whole(const char *fn, std::string &out)
 {
+	out.clear();
+	if (fn && strcmp(fn, "-")) {   // a regular, uncompressed file goes straight into the buffer (no zlib pass-through copy)
+		int fd = open(fn, O_RDONLY);
+		if (fd < 0) return false;
+		struct stat sb;
+		unsigned char magic[2] = {0, 0};
+		if (fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size >= 2 && pread(fd, magic, 2, 0) == 2 && !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+			out.resize((size_t)sb.st_size);
+			size_t got = 0;
+			while (got < out.size()) {
+				ssize_t r = read(fd, &out[got], out.size() - got);
+				if (r <= 0) break;
+				got += (size_t)r;
+			}
+			out.resize(got);
+			close(fd);
+			return true;
+		}
+		close(fd);
+	}
 	gzFile fp = (fn && strcmp(fn, "-"))? gzopen(fn, "r") : gzdopen(0, "r");
 	if (fp == 0) return false;
-	char buf[1 << 16];
+	gzbuffer(fp, 1 << 20);
+	std::vector<char> buf(1 << 20);
 	int n;
-	out.clear();
-	while ((n = gzread(fp, buf, sizeof(buf))) > 0) out.append(buf, n);
+	while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), n);
 	gzclose(fp);
 	return true;
 }
@@ -148,8 +171,8 @@ template<class F> static void for_each_line(std::string &buf, F f)
 {
 	size_t n = buf.size(), st = 0;
 	while (st < n) {
-		size_t en = st;
-		while (en < n && buf[en] != '\n') ++en;
+		const char *nl = (const char*)memchr(buf.data() + st, '\n', n - st);
+		size_t en = nl? (size_t)(nl - buf.data()) : n;
 		size_t e2 = en;
 		if (e2 > st && buf[e2 - 1] == '\r') --e2;
 		char saved = buf[e2]; // buf has a terminating 0 at buf[n] (std::string guarantee), so e2 <= n is fine
@@ -189,6 +212,17 @@ extern "C" void pgio_name_set_destroy(void *s) { delete (pgio::NameTable*)s; }
 // ------------------------------------------------------------------------------------------------
 // reader
 // ------------------------------------------------------------------------------------------------
+// strtol(p, &end, 10) for the common case "digits"; anything else (sign, blanks, 19+ digits) goes to strtol itself
+static inline long fast_l(const char *p, const char **end = 0)
+{
+	const char *q = p;
+	long v = 0;
+	while ((unsigned)(*q - '0') <= 9u) v = v * 10 + (*q++ - '0');
+	if (q == p || q - p > 18) { char *e; v = strtol(p, &e, 10); q = e; }
+	if (end) *end = q;
+	return v;
+}
+
 template<class T> static inline void grow0(T *&p, int64_t i, int32_t &m)   // pgpriv.h:28-36
 {
 	if (i >= m) {
@@ -225,8 +259,8 @@ int64_t pgio::cigar_to_exons(const char *cg, bool rev, std::vector<pg_exon_t> &t
 	tmp.push_back(pg_exon_t{0, 0});
 	const char *p = cg;
 	while (*p) {
-		char *r;
-		int64_t l = strtol(p, &r, 10);
+		const char *r;
+		int64_t l = fast_l(p, &r);
 		char op = *r;
 		if (op == 'N' || op == 'U' || op == 'V') {
 			int64_t st, en;
@@ -345,14 +379,13 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 			hit.rank = ++seen_cnt[pid];
 			if (nf < 2) break;
 			// ---- columns 1..10 (read.c:172-211)
-			char *e;
-			int32_t len = (int32_t)strtol(fld[1], &e, 10);
+			int32_t len = (int32_t)fast_l(fld[1]);
 			F.prot_len[pid] = len;
 			if (F.gene_len[gid] < len) F.gene_len[gid] = len;
 			if (nf < 3) break;
-			hit.qs = (int32_t)strtol(fld[2], &e, 10);
+			hit.qs = (int32_t)fast_l(fld[2]);
 			if (nf < 4) break;
-			hit.qe = (int32_t)strtol(fld[3], &e, 10);
+			hit.qe = (int32_t)fast_l(fld[3]);
 			if (hit.qe - hit.qs < len * opt->min_prot_ratio) break;
 			if (nf < 5) break;
 			if (fld[4][0] != '+' && fld[4][0] != '-') break;
@@ -365,25 +398,26 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 				hit.cid = cid;
 			}
 			if (nf < 7) break;
-			g->ctg[hit.cid].len = strtol(fld[6], &e, 10);
+			g->ctg[hit.cid].len = fast_l(fld[6]);
 			if (nf < 8) break;
-			hit.cs = strtol(fld[7], &e, 10);
+			hit.cs = fast_l(fld[7]);
 			if (nf < 9) break;
-			hit.ce = strtol(fld[8], &e, 10);
+			hit.ce = fast_l(fld[8]);
 			if (nf < 10) break;
-			hit.mlen = (int32_t)strtol(fld[9], &e, 10);
+			hit.mlen = (int32_t)fast_l(fld[9]);
 			if (nf < 11) break;
-			hit.blen = (int32_t)strtol(fld[10], &e, 10);
+			hit.blen = (int32_t)fast_l(fld[10]);
 			if (hit.mlen < hit.blen * opt->min_prot_iden) break;
 			// ---- tags (read.c:212-224)
 			for (int i = 12; i < nf; ++i) {
 				const char *t = fld[i];
-				if (strncmp(t, "ms:i:", 5) == 0) {
-					hit.score_ori = (int32_t)strtol(t + 5, &e, 10);
+				if (t[0] == 0 || t[1] == 0 || t[2] != ':' || t[3] == 0 || t[4] != ':') continue;   // none of ms:i: fs:i: st:i: cg:Z: (never reads past the field's terminator)
+				if (t[0] == 'm' && t[1] == 's' && t[3] == 'i') {
+					hit.score_ori = (int32_t)fast_l(t + 5);
 					hit.score_adj = pgio::adjusted_score(opt, hit.score_ori, hit.mlen, hit.blen, hit.qs, hit.qe, len);
-				} else if (strncmp(t, "fs:i:", 5) == 0) n_fs = (int32_t)strtol(t + 5, &e, 10);
-				else if (strncmp(t, "st:i:", 5) == 0) n_stop = (int32_t)strtol(t + 5, &e, 10);
-				else if (strncmp(t, "cg:Z:", 5) == 0) {
+				} else if (t[0] == 'f' && t[1] == 's' && t[3] == 'i') n_fs = (int32_t)fast_l(t + 5);
+				else if (t[0] == 's' && t[1] == 't' && t[3] == 'i') n_stop = (int32_t)fast_l(t + 5);
+				else if (t[0] == 'c' && t[1] == 'g' && t[3] == 'Z') {
 					int64_t x = pgio::cigar_to_exons(t + 5, hit.rev, tmp, ex, &cg_fs);
 					if (x != hit.ce - hit.cs) { fprintf(stderr, "[pgio] ERROR: CIGAR length %ld != ce-cs %ld\n", (long)x, (long)(hit.ce - hit.cs)); abort(); } // read.c:75
 					have_exons = true;

@@ -142,3 +142,32 @@ def test_parallel_reader_reproduces_sequential_ids(tmp_path):
     assert a.contents.n_genome == 6
     _same_data(a, b)
     hostio.destroy(a); hostio.destroy(b)
+
+
+def test_reader_line_ending_and_container_variants(tmp_path):
+    """the same records as plain text, gzip, CRLF text and text without a final newline parse to the same pg_data_t; odd trailing
+    fields (a short tag-like last field, non-numeric columns) are harmless"""
+    import gzip
+    opt = hostio.default_opt()
+    p = hostio.synth_params(2, n_genome=1, n_gene=300, iso_per_gene=4, hits_per_genome=2500, n_genome_total=1)
+    (plain,) = hostio.synth_write_pafs(opt, p, str(tmp_path / "v"))
+    text = open(plain, "rb").read()
+    name = os.path.basename(plain)
+    variants = {}
+    for tag, data in [("gz", None), ("crlf", text.replace(b"\n", b"\r\n")), ("nonl", text.rstrip(b"\n")), ("tail", text.rstrip(b"\n") + b"\tzz:\tab\tms:")]:
+        d = tmp_path / tag
+        d.mkdir()
+        if tag == "gz":
+            fn = str(d / (name + ".gz"))
+            with gzip.open(fn, "wb") as f:
+                f.write(text)
+        else:
+            fn = str(d / name)
+            open(fn, "wb").write(data)
+        variants[tag] = fn
+    a = hostio.read_pafs(opt, [plain])
+    for tag, fn in variants.items():
+        b = hostio.read_pafs(opt, [fn])
+        _same_data(a, b)
+        hostio.destroy(b)
+    hostio.destroy(a)
