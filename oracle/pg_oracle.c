@@ -111,6 +111,7 @@ typedef struct {
 	uint64_t *key;     /* score_adj<<33 | preferred<<32 | mix32(pid), overlap.c:82,137 */
 	int64_t *pmax;     /* running max of ce inside the contig: bounds the backward scan */
 	int32_t *by_cm;    /* permutation: contig-major, then cm; ties keep (contig, cs) order */
+	int32_t j;         /* genome index */
 } view_t;
 
 struct sort_ctx { const pg_hit_t *h; int by_cm; };
@@ -126,9 +127,23 @@ static int cmp_hit_idx(const void *pa, const void *pb, void *pc)
 	return a < b? -1 : a > b;
 }
 
+/* File position of every hit of every genome, in the (contig, cs) order the hits are kept in: the input the reference's
+ * sort chain starts from (replay_contig_order below).  Filled by pgo_post_process(), used by the pgo_graph_gen() that follows
+ * on the same pg_data_t (test infrastructure: one data set at a time). */
+static int32_t **g_file_pos, g_file_pos_n;
+
+static void file_pos_reset(int32_t n_genome)
+{
+	int32_t j;
+	for (j = 0; j < g_file_pos_n; ++j) free(g_file_pos[j]);
+	free(g_file_pos);
+	g_file_pos = NEW0(int32_t*, n_genome); g_file_pos_n = n_genome;
+}
+
 /* stable (contig, cs) order of one genome; stands in for the first pg_hit_sort(g,0) of read.c:247.
- * The reference's own tie order is history-dependent; ties here keep file order. */
-static void sort_by_cs(pg_genome_t *g)
+ * The reference's own tie order is history-dependent; ties here keep file order, and the places where the
+ * reference's order is observable replay its sort chain (replay_contig_order). */
+static void sort_by_cs(pg_genome_t *g, int32_t **file_pos)
 {
 	int32_t i, *idx = NEW(int32_t, g->n_hit);
 	struct sort_ctx c = { g->hit, 0 };
@@ -137,8 +152,57 @@ static void sort_by_cs(pg_genome_t *g)
 	qsort_r(idx, g->n_hit, sizeof(int32_t), cmp_hit_idx, &c);
 	a = NEW(pg_hit_t, g->n_hit);
 	for (i = 0; i < g->n_hit; ++i) a[i] = g->hit[idx[i]];
-	free(idx); free(g->hit);
+	if (file_pos) *file_pos = idx; else free(idx);
+	free(g->hit);
 	g->hit = a; g->m_hit = g->n_hit;
+}
+
+static int cmp_i64pair(const void *a, const void *b) { int64_t x = *(const int64_t*)a, y = *(const int64_t*)b; return x < y? -1 : x > y; }
+
+/* The reference re-sorts every genome's hit array with an UNSTABLE radix sort, alternating keys: once by cs when the file is
+ * loaded (read.c:247), then one (cm, cs) pair per pg_gen_arc (graph.c:103,123) and per pg_mark_branch_flt_hit
+ * (branch.c:116,140).  pg_hit_sort (hit.c:29-64) first buckets by contig, keeping the array order, then radix-sorts each
+ * contig's (key, index) pairs (radix_sort_pg128x) -- so where hits with equal keys end up depends only on the contig's key
+ * sequences and on the number of sorts so far, never on flags.  This replays that chain for the hits [lo, hi) of one contig
+ * (positions in OUR (contig, cs, file order) array) and returns rank[p - lo] = position of hit p inside the contig in the
+ * reference's array after `n_pairs` (cm, cs) pairs (by_cm = 0) or after one more sort by cm (by_cm = 1). */
+static void replay_contig_order(const pg_genome_t *g, const int32_t *file_pos, int32_t lo, int32_t hi, int32_t n_pairs, int by_cm, int32_t *rank)
+{
+	int32_t n = hi - lo, i, p;
+	int64_t *fo = NEW(int64_t, 2 * (size_t)n);
+	pg128_t *a = NEW(pg128_t, n);
+	for (i = 0; i < n; ++i) fo[2 * i] = file_pos[lo + i], fo[2 * i + 1] = lo + i;
+	qsort(fo, n, 16, cmp_i64pair);                                  /* the contig's hits in file order */
+	for (i = 0; i < n; ++i) a[i].y = (uint64_t)fo[2 * i + 1];
+	for (i = 0; i < n; ++i) a[i].x = (uint64_t)g->hit[a[i].y].cs;
+	pgo_radix_replay128(a, n);                                      /* read.c:247 */
+	for (p = 0; p < n_pairs + (by_cm? 1 : 0); ++p) {
+		for (i = 0; i < n; ++i) a[i].x = (uint64_t)g->hit[a[i].y].cm;
+		pgo_radix_replay128(a, n);
+		if (p == n_pairs) break;
+		for (i = 0; i < n; ++i) a[i].x = (uint64_t)g->hit[a[i].y].cs;
+		pgo_radix_replay128(a, n);
+	}
+	for (i = 0; i < n; ++i) rank[a[i].y - lo] = i;
+	free(a); free(fo);
+}
+
+static int32_t g_sort_pairs;   /* (cm, cs) sort pairs the reference has executed so far in pg_graph_gen */
+
+/* Which hit sits at position 0 of the reference's array right now?  pg_shadow (overlap.c:108) starts its loop at i = 1, so
+ * that hit's shadow bit is never reset.  It is a hit with the smallest cs of the first contig; when several share that cs, the
+ * reference's sort chain decides which of them is in front at this point -- replay it. */
+static int32_t ref_first_pos(const pg_genome_t *g, int32_t j)
+{
+	int32_t hi, i, first = 0, *rank;
+	if (g->n_hit < 2 || g->hit[1].cid != g->hit[0].cid || g->hit[1].cs != g->hit[0].cs) return 0;
+	if (g_file_pos == 0 || j >= g_file_pos_n || g_file_pos[j] == 0) return 0;
+	for (hi = 1; hi < g->n_hit && g->hit[hi].cid == g->hit[0].cid; ++hi) {}
+	rank = NEW(int32_t, hi);
+	replay_contig_order(g, g_file_pos[j], 0, hi, g_sort_pairs, 0, rank);
+	for (i = 0; i < hi; ++i) if (rank[i] == 0) first = i;
+	free(rank);
+	return first;
 }
 
 static void view_init(view_t *v, const pg_data_t *d, int32_t j)
@@ -146,7 +210,7 @@ static void view_init(view_t *v, const pg_data_t *d, int32_t j)
 	pg_genome_t *g = &d->genome[j];
 	int32_t i, k, n = g->n_hit;
 	struct sort_ctx c = { g->hit, 1 };
-	v->g = g; v->n = n;
+	v->g = g; v->n = n; v->j = j;
 	v->gid = NEW(int32_t, n); v->cds = NEW(int32_t, n); v->key = NEW(uint64_t, n);
 	v->pmax = NEW(int64_t, n); v->by_cm = NEW(int32_t, n);
 	for (i = 0; i < n; ++i) {
@@ -218,7 +282,7 @@ typedef struct { uint64_t key; int32_t partner, ov; } dom_t;
 static int32_t sweep(const pg_opt_t *opt, view_t *v, int mode, int cal_dom_sc, int check_strand)
 {
 	pg_hit_t *h = v->g->hit;
-	int32_t n = v->n, i, p, cnt = 0;
+	int32_t n = v->n, i, p, cnt = 0, first = mode == SWEEP_SHADOW? ref_first_pos(v->g, v->j) : 0;
 	uint8_t *lose = NEW0(uint8_t, n);
 	dom_t *best = NEW0(dom_t, n);
 	for (i = 0; i < n; ++i) {
@@ -251,8 +315,8 @@ static int32_t sweep(const pg_opt_t *opt, view_t *v, int mode, int cal_dom_sc, i
 		for (i = 0; i < n; ++i) {
 			pg_hit_t *a = &h[i];
 			if (a->flt) continue;
-			/* overlap.c:108,113: the sweep starts at i = 1, so the genome's first hit is never reset */
-			a->shadow = i == 0? (a->shadow | lose[i]) : lose[i];
+			/* overlap.c:108,113: the sweep starts at i = 1, so the hit at the front of the reference's array is never reset */
+			a->shadow = i == first? (a->shadow | lose[i]) : lose[i];
 			a->pid_dom = -1;
 			if (cal_dom_sc) a->score_dom = -1;
 			if (best[i].key > 0) {   /* overlap.c:162 */
@@ -345,7 +409,7 @@ static void load_time_block(const pg_opt_t *opt, pg_data_t *d, int32_t j)
 	view_t v;
 	flag_pseudo(d, g);                                                    /* read.c:245 */
 	for (i = 0; i < g->n_hit; ++i) if (g->hit[i].pseudo) g->hit[i].flt = 1; /* read.c:246 */
-	sort_by_cs(g);                                                        /* read.c:247 */
+	sort_by_cs(g, &g_file_pos[j]);                                        /* read.c:247 */
 	if (g->n_hit > 1 && g->hit[0].cid == g->hit[1].cid && g->hit[0].cs == g->hit[1].cs && !g->hit[0].flt && !g->hit[1].flt) ++g_tie[1];
 	view_init(&v, d, j);
 	sweep(opt, &v, SWEEP_SHADOW, 1, check_strand);                        /* read.c:248 */
@@ -433,6 +497,8 @@ void pgo_post_process(const pg_opt_t *opt, pg_data_t *d)
 {
 	int32_t j, check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
 	memset(g_tie, 0, sizeof(g_tie));
+	g_sort_pairs = 0;
+	file_pos_reset(d->n_genome);
 	for (j = 0; j < d->n_genome; ++j) load_time_block(opt, d, j);
 	cap_score_dom(d);
 	flag_representative(d);
@@ -685,14 +751,46 @@ static void mark_branch_arcs(const pg_opt_t *opt, pg_graph_t *q)
 	for (j = 0; j < d->n_genome; ++j) {
 		const pg_genome_t *g = &d->genome[j];
 		genepos_t *row = &pos[(size_t)j * ng];
-		int32_t r = 0, last = -1;
+		int32_t r = 0, last = -1, n_tied = 0;
 		for (i = 0; i < ng; ++i) row[i].cid = -1;
 		for (i = 0; i < g->n_hit; ++i) {   /* (contig, cs) order: the LAST survivor of a gene wins */
 			const pg_hit_t *b = &g->hit[i];
 			if (b->shadow || b->flt) continue;
-			if (last >= 0 && g->hit[last].cid == b->cid && g->hit[last].cs == b->cs) ++g_tie[1];
+			if (last >= 0 && g->hit[last].cid == b->cid && g->hit[last].cs == b->cs) ++g_tie[1], ++n_tied;
 			row[d->prot[b->pid].gid].cid = b->cid, row[d->prot[b->pid].gid].ord = r++, row[d->prot[b->pid].gid].cm = b->cm;
 			last = i;
+		}
+		/* Survivors with one (contig, cs): their ordinals follow the reference's array order at this point of its sort chain
+		 * (branch.c:18-25 walks the array as left by the last pg_hit_sort(g, 0)): replay the chain for those contigs. */
+		if (n_tied > 0 && g_file_pos && j < g_file_pos_n && g_file_pos[j]) {
+			int32_t i0, i1, lo, hi, *rank = 0, rank_lo = -1, rank_hi = -1;
+			for (i0 = 0, r = 0; i0 < g->n_hit; i0 = i1) {   /* groups of hits with one (contig, cs); r = survivors before the group */
+				int32_t n_sv = 0, t, u;
+				for (i1 = i0; i1 < g->n_hit && g->hit[i1].cid == g->hit[i0].cid && g->hit[i1].cs == g->hit[i0].cs; ++i1)
+					n_sv += !g->hit[i1].shadow && !g->hit[i1].flt;
+				if (n_sv >= 2) {
+					int32_t *sv = NEW(int32_t, n_sv);
+					if (!(i0 >= rank_lo && i0 < rank_hi)) {   /* a new contig: replay it */
+						for (lo = i0; lo > 0 && g->hit[lo - 1].cid == g->hit[i0].cid; --lo) {}
+						for (hi = i0; hi < g->n_hit && g->hit[hi].cid == g->hit[i0].cid; ++hi) {}
+						free(rank); rank = NEW(int32_t, hi - lo); rank_lo = lo, rank_hi = hi;
+						replay_contig_order(g, g_file_pos[j], lo, hi, g_sort_pairs, 0, rank);
+					}
+					for (t = i0, u = 0; t < i1; ++t) if (!g->hit[t].shadow && !g->hit[t].flt) sv[u++] = t;
+					for (t = 1; t < n_sv; ++t) {   /* insertion sort by the replayed position */
+						int32_t x = sv[t];
+						for (u = t; u > 0 && rank[sv[u - 1] - rank_lo] > rank[x - rank_lo]; --u) sv[u] = sv[u - 1];
+						sv[u] = x;
+					}
+					for (t = 0; t < n_sv; ++t) {   /* same walk as above, in the reference's order (the last survivor of a gene still wins) */
+						const pg_hit_t *b = &g->hit[sv[t]];
+						row[d->prot[b->pid].gid].cid = b->cid, row[d->prot[b->pid].gid].ord = r + t, row[d->prot[b->pid].gid].cm = b->cm;
+					}
+					free(sv);
+				}
+				r += n_sv;
+			}
+			free(rank);
 		}
 	}
 	for (i = 0; i < q->n_seg; ++i) q->seg[i].n_dist_loci[0] = q->seg[i].n_dist_loci[1] = 0;
@@ -758,15 +856,16 @@ void pgo_graph_gen(const pg_opt_t *opt, pg_graph_t *q)   /* graph.c:280-322 */
 	pg_data_t *d = q->d;
 	int32_t i, j, k;
 	view_t *views = NEW(view_t, d->n_genome);
+	g_sort_pairs = 0;
 	SET_FILTER(d, a->pseudo);
 	gen_vtx(opt, q);
 	flag_vtx(q);
 	SET_FILTER(d, !a->vtx);
 	for (j = 0; j < d->n_genome; ++j) view_init(&views[j], d, j);
-	gen_arc(opt, q, views);
+	gen_arc(opt, q, views); ++g_sort_pairs;                   /* graph.c:103,123 */
 	flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci, q);
 	SET_FILTER(d, !a->vtx);
-	gen_arc(opt, q, views);
+	gen_arc(opt, q, views); ++g_sort_pairs;
 	for (i = 0; i < opt->n_branch_flt; ++i) {
 		double r = 1.0 + (double)(opt->n_branch_flt - 1 - i) / opt->n_branch_flt;
 		int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
@@ -774,13 +873,13 @@ void pgo_graph_gen(const pg_opt_t *opt, pg_graph_t *q)   /* graph.c:280-322 */
 		int32_t max_dist_loci = (int32_t)(opt->max_dist_loci * r + .499);
 		arc_index(q);
 		mark_branch_arcs(opt, q);
-		mark_branch_hits(q, views);
+		mark_branch_hits(q, views); ++g_sort_pairs;               /* branch.c:116,140 */
 		SET_FILTER(d, a->weak_br == 2);
 		if (i > 0) {
 			flt_high_occ(max_avg_occ, max_degree, max_dist_loci, q);
 			SET_FILTER(d, !a->vtx);
 		}
-		gen_arc(opt, q, views);
+		gen_arc(opt, q, views); ++g_sort_pairs;
 	}
 	SET_FILTER(d, a->shadow);
 	if (opt->min_arc_cnt > 1) {   /* graph.c:179-200 */

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: randomized campaign of the oracle restatement against the compiled, unmodified reference
+(oracle/_ref/libpgref.so) -- many more shapes, seeds and option mixes than the CPU test suite has time for.
+Needs /root/reference (this container only).   usage: tools/fuzz_oracle.py [first_case] [n_cases]
+Prints one line per case; a mismatch that comes with a non-zero tie detector (DESIGN.md "tie order") is reported as TIE."""
+import os
+import random
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import common  # noqa: E402
+import refharness  # noqa: E402
+from oracle import pgoracle  # noqa: E402
+from pangene_b200 import hostio  # noqa: E402
+
+FLAGS = ["-S", "-J", "-E", "-F", "--ori-sc"]
+
+
+def random_case(k):
+    rnd = random.Random(777000 + k)
+    args = [f for f in FLAGS if rnd.random() < 0.2]
+    if rnd.random() < 0.5: args.append("-T%d" % rnd.choice([0, 1, 2, 3, 7, 15]))
+    if rnd.random() < 0.3: args.append("-p%s" % rnd.choice(["0", "0.01", "0.2", "0.5"]))
+    if rnd.random() < 0.3: args.append("-a%d" % rnd.choice([1, 2, 3]))
+    if rnd.random() < 0.3: args.append("-f%s" % rnd.choice(["0.1", "0.2", "0.5", "0.9"]))
+    if rnd.random() < 0.2: args.append("-c%d" % rnd.choice([1, 2, 4, 20]))
+    if rnd.random() < 0.2: args.append("-g%d" % rnd.choice([2, 4, 6, 30]))
+    if rnd.random() < 0.2: args.append("-r%d" % rnd.choice([0, 1, 3]))
+    if rnd.random() < 0.2: args.append("-b%s" % rnd.choice(["0.01", "0.1", "0.3"]))
+    if rnd.random() < 0.2: args.append("-y%s" % rnd.choice(["0.1", "0.3", "0.8"]))
+    if rnd.random() < 0.2: args.append("-B%s" % rnd.choice(["0.5", "0.9", "0.99"]))
+    if rnd.random() < 0.25:
+        case = dict(config=5, n_genome=rnd.randint(3, 80), n_gene=rnd.randint(100, 1200), iso_per_gene=1, args=args)
+        case["hits_per_genome"] = int(case["n_gene"] * rnd.uniform(0.5, 1.1))
+    else:
+        case = dict(config=2, n_genome=rnd.randint(1, 9), n_gene=rnd.randint(50, 2000), iso_per_gene=rnd.choice([1, 4]), args=args)
+        case["hits_per_genome"] = int(case["n_gene"] * case["iso_per_gene"] * rnd.uniform(1.2, 3.5))
+    case["seed"] = rnd.getrandbits(40)
+    case["n_ctg"] = rnd.choice([1, 2, 5, 24])
+    return case
+
+
+def data_for(case):
+    opt = common.opt_from_args(case["args"])
+    p = hostio.synth_params(case["config"], n_genome=case["n_genome"], n_gene=case["n_gene"], iso_per_gene=case["iso_per_gene"],
+                            hits_per_genome=case["hits_per_genome"], n_genome_total=case["n_genome"], seed=case["seed"], n_ctg=case["n_ctg"])
+    return opt, hostio.synth(opt, p)
+
+
+def main():
+    first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    rh = refharness.RefHot()
+    bad = 0
+    for k in range(first, first + n):
+        case = random_case(k)
+        opt, d1 = data_for(case)
+        _, d2 = data_for(case)
+        g1, _ = rh.hot_path(opt, d1)
+        g2 = pgoracle.hot_path(opt, d2)
+        tie = pgoracle.tie_report()
+        a, b = common.gfa_bytes(g1), common.gfa_bytes(g2)
+        ok_gfa = sorted(a.splitlines()) == sorted(b.splitlines())
+        ok_graph = common.graph_tuple(g1) == common.graph_tuple(g2)
+        ok_bed = sorted(common.bed_bytes(d1).splitlines()) == sorted(common.bed_bytes(d2).splitlines())
+        ok = ok_gfa and ok_graph and ok_bed
+        status = "ok" if ok else ("TIE" if (tie[0] or tie[2]) else "MISMATCH")
+        bad += status == "MISMATCH"
+        print("case %d %s hits=%d S=%d L=%d tie=%s gfa=%s graph=%s bed=%s %s" % (k, status, hostio.total_hits(d1), g1.contents.n_seg, g1.contents.n_arc, tie, ok_gfa, ok_graph, ok_bed,
+              {x: case[x] for x in ("config", "n_genome", "n_gene", "iso_per_gene", "hits_per_genome", "n_ctg", "seed", "args")}), flush=True)
+        if status == "MISMATCH":
+            print(common.first_diff(a, b), flush=True)
+        rh.destroy(g1); pgoracle.destroy(g2); hostio.destroy(d1); hostio.destroy(d2)
+    print("FUZZ %s (%d cases, %d mismatches)" % ("PASS" if bad == 0 else "FAIL", n, bad))
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
