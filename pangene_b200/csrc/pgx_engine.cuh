@@ -93,9 +93,13 @@ struct Session {
 	DBuf<SegDev> seg, seg_alt;
 	DBuf<ArcDev> arc, arc_alt;
 	DBuf<int32_t> seg_ng, seg_tot, arc_of_rec;
+	// ---- overlap.c:108 quirk, moving part (k_first_group / prepare_first_replay / k_set_first)
+	DBuf<FirstGroup> first_grp;
+	DBuf<int32_t> first_flagged, first_target;
+	int32_t n_first = 0, arc_call = 0;
 	Arena scratch;
 	uint32_t *h_pin = nullptr;           // pinned word(s) for small read-backs
-	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_N = 8 };
+	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_N = 8 };
 
 	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
 	~Session() { if (st) cudaStreamDestroy(st); for (auto &e : ev) if (e) cudaEventDestroy(e); if (h_pin) cudaFreeHost(h_pin); }
@@ -315,6 +319,8 @@ struct Session {
 			scratch.reset(m2);
 		}
 		PGX_LAUNCH(k_gather, grid_for(N, TB), TB, 0, st, raw.p, src.p, N, hoff.p, coff.p, eoffg.p, r_rank, r_pseudo, r_gl, prot_gid.p, gene_pref.p, F);
+		first_grp.alloc((size_t)G + 1);
+		PGX_LAUNCH(k_first_group, grid_for(G, TB), TB, 0, st, hoff.p, G, F.ctg, F.cs, first_grp.p, counters.p + C_FIRST_TIE);
 		{
 			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(N));
 			exclusive_sum_u32(F.nex, F.eoff, N, agg, st);
@@ -567,6 +573,7 @@ struct Session {
 	void gen_arc(const pg_opt_t *opt)
 	{
 		struct Acc { double &a; double t0; ~Acc() { a += wall_s() - t0; } } acc_arc{t_arc, wall_s()};
+		set_first_for_this_call();
 		if (Nw == 0 || n_seg0 == 0) {   // nothing can survive: empty arc set, zero occupancy
 			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u);
 			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_part)), 0u);
@@ -735,11 +742,77 @@ struct Session {
 		scratch.reset(mk);
 	}
 
+	// The hit at the front of the reference's array is never un-shadowed by pg_shadow (overlap.c:108).  Where a genome's first
+	// (contig, cs) is shared by several hits, the reference's sort chain -- one unstable radix sort by cs at load time, then a
+	// (cm, cs) pair per pg_gen_arc and per pg_mark_branch_flt_hit -- decides which of them is in front at each sweep.  The chain
+	// depends on the contig's cs/cm sequences only, so it is replayed here, once per run, for the first contig of the flagged
+	// genomes: target[m][k] = F index of the front hit of flagged genome k at the sweep of the m-th pg_gen_arc call.
+	void prepare_first_replay(const pg_opt_t *opt)
+	{
+		n_first = 0; arc_call = 0;
+		if (G == 0 || N == 0) return;
+		if (read_u32(counters.p + C_FIRST_TIE) == 0) return;
+		std::vector<FirstGroup> fg(G);
+		PGX_CHECK(cudaMemcpyAsync(fg.data(), first_grp.p, (size_t)G * sizeof(FirstGroup), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		std::vector<int32_t> flagged;
+		for (int32_t g = 0; g < G; ++g) if (fg[g].m >= 2) flagged.push_back(g);
+		if (flagged.empty()) return;
+		const int32_t nf = (int32_t)flagged.size(), n_calls = 2 + (opt->n_branch_flt > 0? opt->n_branch_flt : 0);
+		std::vector<std::vector<int32_t>> h_cs(nf), h_cm(nf);
+		std::vector<std::vector<uint32_t>> h_src(nf);
+		for (int32_t k = 0; k < nf; ++k) {
+			const FirstGroup &r = fg[flagged[k]];
+			h_cs[k].resize(r.len); h_cm[k].resize(r.len); h_src[k].resize(r.len);
+			PGX_CHECK(cudaMemcpyAsync(h_cs[k].data(), F.cs + r.i0, (size_t)r.len * 4, cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaMemcpyAsync(h_cm[k].data(), F.cm + r.i0, (size_t)r.len * 4, cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaMemcpyAsync(h_src[k].data(), src.p + r.i0, (size_t)r.len * 4, cudaMemcpyDeviceToHost, st));
+		}
+		PGX_CHECK(cudaStreamSynchronize(st));
+		// (cm, cs) sort pairs the reference has done when the m-th pg_gen_arc runs its sweep: 0, 1, then 3 + 2i in branch round i
+		std::vector<int32_t> pairs_at(n_calls);
+		for (int32_t m = 0; m < n_calls; ++m) pairs_at[m] = m < 2? m : 3 + 2 * (m - 2);
+		std::vector<int32_t> target((size_t)n_calls * nf);
+		ThreadPool::get().parallel_for(nf, [&](int64_t k) {
+			const FirstGroup &r = fg[flagged[k]];
+			const int32_t n = r.len;
+			std::vector<pg128_t> a(n);
+			std::vector<int32_t> ord(n);
+			for (int32_t i = 0; i < n; ++i) ord[i] = i;
+			std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return h_src[k][x] < h_src[k][y]; });   // the contig's hits in file order
+			for (int32_t i = 0; i < n; ++i) { a[i].y = (uint64_t)ord[i]; a[i].x = (uint64_t)h_cs[k][ord[i]]; }
+			FlagSortReplay::run(a.data(), n);                                                                       // read.c:247
+			int32_t m = 0;
+			for (int32_t p = 0;; ++p) {
+				while (m < n_calls && pairs_at[m] == p) target[(size_t)m++ * nf + k] = r.i0 + (int32_t)a[0].y;
+				if (m == n_calls) break;
+				for (int32_t i = 0; i < n; ++i) a[i].x = (uint64_t)h_cm[k][a[i].y];
+				FlagSortReplay::run(a.data(), n);                                                                   // graph.c:103, branch.c:116
+				for (int32_t i = 0; i < n; ++i) a[i].x = (uint64_t)h_cs[k][a[i].y];
+				FlagSortReplay::run(a.data(), n);                                                                   // graph.c:123, branch.c:140
+			}
+		});
+		first_flagged.alloc(nf); first_target.alloc(target.size());
+		PGX_CHECK(cudaMemcpyAsync(first_flagged.p, flagged.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaMemcpyAsync(first_target.p, target.data(), target.size() * 4, cudaMemcpyHostToDevice, st));
+		PGX_CHECK(cudaStreamSynchronize(st));   // `flagged` and `target` go out of scope
+		n_first = nf;
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::first_replay] %d genome(s) start with hits sharing one (contig, cs): sort chain replayed for their first contig\n", nf);
+	}
+	// called at the top of every gen_arc: moves HB_FIRST for the sweep of this call
+	void set_first_for_this_call()
+	{
+		const int32_t m = arc_call++;
+		if (n_first == 0 || Nw == 0) return;
+		PGX_LAUNCH(k_set_first, grid_for(n_first, TB), TB, 0, st, first_flagged.p, first_target.p + (size_t)m * n_first, n_first, first_grp.p, goff_act.p, A.full, A.bits);
+	}
+
 	void stage_graph(const pg_opt_t *opt)
 	{
 		if (!done_post) PGX_FATAL("pg_graph_gen() called before pg_post_process()");
 		set_filter(SF_PSEUDO);                                                           // graph.c:285
 		gen_vtx(opt);                                                                    // graph.c:286
+		prepare_first_replay(opt);
 		flag_vtx();                                                                      // graph.c:287-288
 		recompact_active();
 		gen_arc(opt);                                                                    // graph.c:289

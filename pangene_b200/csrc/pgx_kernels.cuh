@@ -141,6 +141,46 @@ __global__ void k_gather_exons(const int2 *__restrict__ ex_raw, const uint32_t *
 	cds[i] = len;
 }
 
+// ---- overlap.c:108 quirk, the moving part -------------------------------------------------------------------------------------
+// pg_shadow starts its loop at i = 1: the hit at the FRONT of the reference's array never has its shadow bit reset (HB_FIRST).  That
+// hit has the smallest cs of the genome's first contig; when several hits share that (contig, cs), which of them is in front changes
+// from sort to sort of the reference's unstable radix-sort chain.  k_first_group finds the genomes where that can
+// happen; Session::prepare_first_replay replays the chain for their first contig on the host (exact permutation, pgx_host.hpp) and
+// k_set_first moves HB_FIRST to the right hit before every later sweep.  Genomes without such a tie (the usual case) cost nothing.
+struct FirstGroup { int32_t i0, m, len; };   // first hit of the genome (F order); hits sharing its (contig, cs) -- 0 if alone; hits in that contig
+
+__global__ void k_first_group(const int32_t *__restrict__ hoff, int32_t G, const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, FirstGroup *out, uint32_t *n_flagged)
+{
+	int32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= G) return;
+	const int32_t i0 = hoff[g], e = hoff[g + 1];
+	FirstGroup r; r.i0 = i0; r.m = 0; r.len = 0;
+	if (e - i0 >= 2) {
+		const int32_t c = ctg[i0], s = cs[i0];
+		int32_t m = 1;
+		while (i0 + m < e && ctg[i0 + m] == c && cs[i0 + m] == s) ++m;
+		if (m >= 2) {
+			int32_t lo = i0 + m, hi = e;   // end of the contig: ctg is non-decreasing inside a genome
+			while (lo < hi) { const int32_t mid = (lo + hi) >> 1; if (ctg[mid] == c) lo = mid + 1; else hi = mid; }
+			r.m = m; r.len = lo - i0;
+			atomicAdd(n_flagged, 1u);
+		}
+	}
+	out[g] = r;
+}
+
+// one thread per flagged genome: the members of the first group that are still active sit at the head of the genome's active range
+__global__ void k_set_first(const int32_t *__restrict__ flagged_g, const int32_t *__restrict__ target, int32_t n_flagged, const FirstGroup *__restrict__ fg,
+	const int32_t *__restrict__ goff_act, const int32_t *__restrict__ full, uint32_t *bits)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_flagged) return;
+	const int32_t g = flagged_g[k], t = target[k];
+	const FirstGroup r = fg[g];
+	for (int32_t a = goff_act[g]; a < goff_act[g + 1] && full[a] < r.i0 + r.m; ++a)
+		bits[a] = full[a] == t? (bits[a] | HB_FIRST) : (bits[a] & ~HB_FIRST);
+}
+
 // ------------------------------------------------------------------------------------------------
 // the interval sweep (overlap.c:58-178) as a set of pairs, evaluated from both members of every pair
 // ------------------------------------------------------------------------------------------------

@@ -89,6 +89,20 @@ def test_randomized_vs_oracle(k):
     check_against(opt, lambda: common.synth_case_data(case)[1], "oracle", lazy=bool(k & 1))
 
 
+@pytest.mark.parametrize("k", [177, 179, 225, 463, 502])
+def test_first_hit_tie_cases(k):
+    """Genomes whose first (contig, cs) is shared by several hits: the front of the reference's array -- the one hit pg_shadow never
+    un-shadows (overlap.c:108) -- moves with the reference's unstable sort chain; libpgx replays the chain on the host for those
+    contigs (Session::prepare_first_replay).  Campaign cases of tools/fuzz_oracle.py on which a stable-order build differs."""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import fuzz_oracle
+    case = fuzz_oracle.random_case(k)
+    opt = common.opt_from_args(case["args"])
+    kind = "reference" if refharness.available() else "oracle"
+    check_against(opt, lambda: fuzz_oracle.data_for(case)[1], kind, lazy=bool(k & 1))
+
+
 @pytest.mark.skipif(not refharness.available(), reason="oracle/_ref did not travel")
 @pytest.mark.parametrize("cfg", ["euk", "bact"])
 def test_vs_compiled_reference(cfg):

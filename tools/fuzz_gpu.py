@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: randomized campaign of the CUDA path (through the C ABI) against the oracle restatement on a GPU box --
 the same case generator as tools/fuzz_oracle.py (which pins the oracle against the compiled reference in the build container).
-usage: tools/fuzz_gpu.py [first_case] [n_cases] [time_budget_s]"""
+usage: tools/fuzz_gpu.py [first_case | case,case,...] [n_cases] [time_budget_s]"""
 import os
 import sys
 import time
@@ -17,12 +17,16 @@ from pangene_b200 import engine, hostio  # noqa: E402
 
 
 def main():
-    first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    if len(sys.argv) > 1 and "," in sys.argv[1]:
+        cases = [int(x) for x in sys.argv[1].split(",")]
+    else:
+        first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+        cases = list(range(first, first + n))
     budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
     engine.set_verbose(1)
     t0, bad, done = time.time(), 0, 0
-    for k in range(first, first + n):
+    for k in cases:
         if time.time() - t0 > budget:
             break
         case = random_case(k)
