@@ -187,6 +187,25 @@ static void replay_contig_order(const pg_genome_t *g, const int32_t *file_pos, i
 	free(a); free(fo);
 }
 
+/* test hook (tests/test_oracle.py): the reference's array order of one genome, given in FILE order, after read.c:247 and
+ * `n_pairs` further (cm, cs) sort pairs (+ one sort by cm if by_cm): order_out[k] = file index of the hit at array position k.
+ * Checked against the compiled reference's own pg_hit_sort() chain. */
+void pgo_test_chain_order(const pg_genome_t *g0, int32_t n_pairs, int32_t by_cm, int32_t *order_out)
+{
+	pg_genome_t g = *g0;
+	int32_t *file_pos = 0, lo, hi, i, *rank;
+	g.hit = NEW(pg_hit_t, g0->n_hit);
+	memcpy(g.hit, g0->hit, sizeof(pg_hit_t) * g0->n_hit);
+	sort_by_cs(&g, &file_pos);
+	rank = NEW(int32_t, g.n_hit);
+	for (lo = 0; lo < g.n_hit; lo = hi) {
+		for (hi = lo; hi < g.n_hit && g.hit[hi].cid == g.hit[lo].cid; ++hi) {}
+		replay_contig_order(&g, file_pos, lo, hi, n_pairs, by_cm, rank + lo);
+		for (i = lo; i < hi; ++i) order_out[lo + rank[i]] = file_pos[i];
+	}
+	free(rank); free(file_pos); free(g.hit);
+}
+
 static int32_t g_sort_pairs;   /* (cm, cs) sort pairs the reference has executed so far in pg_graph_gen */
 
 /* Which hit sits at position 0 of the reference's array right now?  pg_shadow (overlap.c:108) starts its loop at i = 1, so
@@ -747,7 +766,7 @@ static void mark_branch_arcs(const pg_opt_t *opt, pg_graph_t *q)
 	int32_t j, i, k, ng = d->n_gene;
 	uint32_t v;
 	genepos_t *pos = NEW(genepos_t, (size_t)d->n_genome * ng);
-	int32_t *top = NEW(int32_t, q->n_arc), *grp = NEW(int32_t, q->n_arc);
+	int32_t *top = NEW(int32_t, q->n_arc), *grp = NEW(int32_t, q->n_arc), *owner = NEW(int32_t, ng);
 	for (j = 0; j < d->n_genome; ++j) {
 		const pg_genome_t *g = &d->genome[j];
 		genepos_t *row = &pos[(size_t)j * ng];
@@ -758,6 +777,7 @@ static void mark_branch_arcs(const pg_opt_t *opt, pg_graph_t *q)
 			if (b->shadow || b->flt) continue;
 			if (last >= 0 && g->hit[last].cid == b->cid && g->hit[last].cs == b->cs) ++g_tie[1], ++n_tied;
 			row[d->prot[b->pid].gid].cid = b->cid, row[d->prot[b->pid].gid].ord = r++, row[d->prot[b->pid].gid].cm = b->cm;
+			owner[d->prot[b->pid].gid] = i;
 			last = i;
 		}
 		/* Survivors with one (contig, cs): their ordinals follow the reference's array order at this point of its sort chain
@@ -782,10 +802,8 @@ static void mark_branch_arcs(const pg_opt_t *opt, pg_graph_t *q)
 						for (u = t; u > 0 && rank[sv[u - 1] - rank_lo] > rank[x - rank_lo]; --u) sv[u] = sv[u - 1];
 						sv[u] = x;
 					}
-					for (t = 0; t < n_sv; ++t) {   /* same walk as above, in the reference's order (the last survivor of a gene still wins) */
-						const pg_hit_t *b = &g->hit[sv[t]];
-						row[d->prot[b->pid].gid].cid = b->cid, row[d->prot[b->pid].gid].ord = r + t, row[d->prot[b->pid].gid].cm = b->cm;
-					}
+					for (t = 0; t < n_sv; ++t)   /* the ordinals of the group, in the reference's order (a gene keeps its LAST survivor: only its owner is renumbered) */
+						if (owner[d->prot[g->hit[sv[t]].pid].gid] == sv[t]) row[d->prot[g->hit[sv[t]].pid].gid].ord = r + t;
 					free(sv);
 				}
 				r += n_sv;
@@ -817,7 +835,7 @@ static void mark_branch_arcs(const pg_opt_t *opt, pg_graph_t *q)
 		}
 		q->seg[v >> 1].n_dist_loci[v & 1] = n_grp;
 	}
-	free(pos); free(top); free(grp);
+	free(pos); free(top); free(grp); free(owner);
 }
 
 static const pg_arc_t *find_arc(const pg_graph_t *q, uint32_t v, uint32_t w)   /* pgpriv.h:99-107 */

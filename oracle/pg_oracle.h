@@ -19,6 +19,7 @@ void pgo_graph_destroy(pg_graph_t *q);
 /* exact replay of the permutation produced by the reference's in-place MSD byte radix sort
  * (ksort.h:52-87) on 16-byte records keyed by .x */
 void pgo_radix_replay128(pg128_t *a, int64_t n);
+void pgo_test_chain_order(const pg_genome_t *g_in_file_order, int32_t n_pairs, int32_t by_cm, int32_t *order_out);
 
 /* tie-order detector (DESIGN.md "tie order"): out[0] = survivor pairs with equal (contig, cm),
  * out[1] = unfiltered pairs with equal (contig, cs), out[2] = duplicate-dominator ties in the load-time

@@ -97,9 +97,12 @@ struct Session {
 	DBuf<FirstGroup> first_grp;
 	DBuf<int32_t> first_flagged, first_target;
 	int32_t n_first = 0, arc_call = 0;
+	// ---- branch.c:18-25 ordinals of cs-tied survivors (k_cs_tie_mark / fix_tied_ordinals): the replayed sort chain of a contig, advanced round by round
+	struct TieChain { int32_t lo = 0, n = 0, pairs_done = 0; std::vector<int32_t> cs, cm; std::vector<pg128_t> a; };
+	std::map<int32_t, TieChain> tie_chains;
 	Arena scratch;
 	uint32_t *h_pin = nullptr;           // pinned word(s) for small read-backs
-	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_N = 8 };
+	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_TIE_ROUND = 8, C_LONG_RUN = 9, C_ORD_SENS = 10, C_N = 12 };
 
 	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
 	~Session() { if (st) cudaStreamDestroy(st); for (auto &e : ev) if (e) cudaEventDestroy(e); if (h_pin) cudaFreeHost(h_pin); }
@@ -699,6 +702,85 @@ struct Session {
 		flag_vtx();
 	}
 
+	// branch.c:18-25 numbers the survivors of a genome in array order; survivors that share one (contig, cs) sit in the order the
+	// reference's unstable sort chain left them in after `pairs` (cm, cs) sort pairs.  Replays the chain of the contigs concerned
+	// (cached and advanced from round to round) and shifts the ordinals of the tied hits accordingly.
+	int32_t branch_round_no = 0;
+	void fix_tied_ordinals(int32_t pairs, const uint32_t *tie_list, uint32_t n_ties, const uint32_t *svcs, const int32_t *t_last, GenePos *gpos)
+	{
+		size_t mk = scratch.mark();
+		TieRec *d_rec = scratch.get<TieRec>(n_ties + 1);
+		PGX_LAUNCH(k_tie_gather, grid_for(n_ties, TB), TB, 0, st, tie_list, (int32_t)n_ties, svcs, A.ctg, A.full, d_rec);
+		std::vector<TieRec> rec(n_ties);
+		PGX_CHECK(cudaMemcpyAsync(rec.data(), d_rec, (size_t)n_ties * sizeof(TieRec), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		std::sort(rec.begin(), rec.end(), [](const TieRec &x, const TieRec &y) { return x.t < y.t; });
+		std::vector<int32_t> ctgs, fresh;
+		for (const TieRec &r : rec) ctgs.push_back(r.ctg);
+		std::sort(ctgs.begin(), ctgs.end()); ctgs.erase(std::unique(ctgs.begin(), ctgs.end()), ctgs.end());
+		for (int32_t c : ctgs) if (!tie_chains.count(c)) fresh.push_back(c);
+		if (!fresh.empty()) {   // fetch (cs, cm, file position) of the contigs seen for the first time
+			int32_t *d_ids = scratch.get<int32_t>(fresh.size());
+			int2 *d_rng = scratch.get<int2>(fresh.size());
+			PGX_CHECK(cudaMemcpyAsync(d_ids, fresh.data(), fresh.size() * 4, cudaMemcpyHostToDevice, st));
+			PGX_LAUNCH(k_ctg_ranges, grid_for((int64_t)fresh.size(), TB), TB, 0, st, d_ids, (int32_t)fresh.size(), F.ctg, N, d_rng);
+			std::vector<int2> rng(fresh.size());
+			PGX_CHECK(cudaMemcpyAsync(rng.data(), d_rng, fresh.size() * sizeof(int2), cudaMemcpyDeviceToHost, st));
+			PGX_CHECK(cudaStreamSynchronize(st));
+			std::vector<std::vector<uint32_t>> h_src(fresh.size());
+			for (size_t k = 0; k < fresh.size(); ++k) {
+				TieChain &c = tie_chains[fresh[k]];
+				c.lo = rng[k].x; c.n = rng[k].y - rng[k].x; c.pairs_done = 0;
+				c.cs.resize(c.n); c.cm.resize(c.n); h_src[k].resize(c.n);
+				PGX_CHECK(cudaMemcpyAsync(c.cs.data(), F.cs + c.lo, (size_t)c.n * 4, cudaMemcpyDeviceToHost, st));
+				PGX_CHECK(cudaMemcpyAsync(c.cm.data(), F.cm + c.lo, (size_t)c.n * 4, cudaMemcpyDeviceToHost, st));
+				PGX_CHECK(cudaMemcpyAsync(h_src[k].data(), src.p + c.lo, (size_t)c.n * 4, cudaMemcpyDeviceToHost, st));
+			}
+			PGX_CHECK(cudaStreamSynchronize(st));
+			ThreadPool::get().parallel_for((int64_t)fresh.size(), [&](int64_t k) {
+				TieChain &c = tie_chains.find(fresh[k])->second;
+				std::vector<int32_t> ord(c.n);
+				for (int32_t i = 0; i < c.n; ++i) ord[i] = i;
+				std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return h_src[k][x] < h_src[k][y]; });   // file order
+				c.a.resize(c.n);
+				for (int32_t i = 0; i < c.n; ++i) { c.a[i].y = (uint64_t)ord[i]; c.a[i].x = (uint64_t)c.cs[ord[i]]; }
+				FlagSortReplay::run(c.a.data(), c.n);                                                                   // read.c:247
+			});
+		}
+		std::vector<std::vector<int32_t>> rank_of(ctgs.size());
+		ThreadPool::get().parallel_for((int64_t)ctgs.size(), [&](int64_t k) {
+			TieChain &c = tie_chains.find(ctgs[k])->second;
+			for (; c.pairs_done < pairs; ++c.pairs_done) {
+				for (int32_t i = 0; i < c.n; ++i) c.a[i].x = (uint64_t)c.cm[c.a[i].y];
+				FlagSortReplay::run(c.a.data(), c.n);                                                                   // graph.c:103, branch.c:116
+				for (int32_t i = 0; i < c.n; ++i) c.a[i].x = (uint64_t)c.cs[c.a[i].y];
+				FlagSortReplay::run(c.a.data(), c.n);                                                                   // graph.c:123, branch.c:140
+			}
+			rank_of[k].resize(c.n);
+			for (int32_t i = 0; i < c.n; ++i) rank_of[k][c.a[i].y] = i;
+		});
+		// groups of consecutive tied positions: members t0-1 .. tk hold the ordinals o .. o+m-1 in OUR order; hand them out in the reference's
+		std::vector<int2> patch;
+		for (size_t i0 = 0, i1; i0 < rec.size(); i0 = i1) {
+			for (i1 = i0 + 1; i1 < rec.size() && rec[i1].t == rec[i1 - 1].t + 1; ++i1) { }
+			const size_t kc = std::lower_bound(ctgs.begin(), ctgs.end(), rec[i0].ctg) - ctgs.begin();
+			const TieChain &c = tie_chains.find(rec[i0].ctg)->second;
+			struct Mem { int32_t act, rank, slot; };
+			std::vector<Mem> mem;
+			mem.push_back(Mem{rec[i0].a_prev, rank_of[kc][rec[i0].full_prev - c.lo], 0});
+			for (size_t i = i0; i < i1; ++i) mem.push_back(Mem{rec[i].a, rank_of[kc][rec[i].full - c.lo], (int32_t)(i - i0) + 1});
+			std::stable_sort(mem.begin(), mem.end(), [](const Mem &x, const Mem &y) { return x.rank < y.rank; });
+			for (size_t k = 0; k < mem.size(); ++k) if ((int32_t)k != mem[k].slot) patch.push_back(make_int2(mem[k].act, (int32_t)k - mem[k].slot));
+		}
+		if (!patch.empty()) {
+			int2 *d_patch = scratch.get<int2>(patch.size());
+			PGX_CHECK(cudaMemcpyAsync(d_patch, patch.data(), patch.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+			PGX_LAUNCH(k_patch_ord, grid_for((int64_t)patch.size(), TB), TB, 0, st, d_patch, (int32_t)patch.size(), A.ctg, A.gidp, ctg2g.p, G, t_last, gpos);
+			PGX_CHECK(cudaStreamSynchronize(st));   // `patch` goes out of scope
+		}
+		scratch.reset(mk);
+	}
+
 	void branch_round(const pg_opt_t *opt)   // branch.c:48-145 + graph.c:309
 	{
 		struct Acc { double &a; double t0; ~Acc() { a += wall_s() - t0; } } acc_br{t_branch, wall_s()};
@@ -711,28 +793,34 @@ struct Session {
 			uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *spos = scratch.get<uint32_t>((size_t)Nw + 2);
 			PGX_LAUNCH(k_flag_survivor_cs, grid_for(Nw, TB), TB, 0, st, A.bits, Nw, flag);
 			scan_to_count(flag, spos, Nw, offsetof(DevCounts, m_cs));
-			{   // tie detector: two survivors with one (contig, cs)
-				size_t m2 = scratch.mark();
-				uint32_t *svcs = scratch.get<uint32_t>((size_t)Nw + 1);
-				PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, spos, (const uint32_t*)nullptr, Nw, svcs);
-				PGX_LAUNCH(k_cs_tie_count, GS_GRID, TB, 0, st, A.ctg, A.cs, svcs, dc.p, counters.p + C_TIE_CS);
-				scratch.reset(m2);
-			}
+			uint32_t *svcs = scratch.get<uint32_t>((size_t)Nw + 1), *tie_list = scratch.get<uint32_t>((size_t)Nw + 1);
+			PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, spos, (const uint32_t*)nullptr, Nw, svcs);
 			int32_t *t_last = scratch.get<int32_t>(tab + 1);
 			GenePos *gpos = scratch.get<GenePos>(tab + 1);
 			PGX_CHECK(cudaMemsetAsync(t_last, 0xff, (tab + 1) * 4, st));
 			PGX_LAUNCH(k_pos_last, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, spos, Nw, G, t_last);
 			PGX_LAUNCH(k_pos_fill, grid_for((int64_t)tab, TB), TB, 0, st, t_last, tab, G, A.ctg, A.cm, spos, goff_act.p, gpos);
+			// tie detector: two survivors with one (contig, cs) -- counted, listed, their genes marked in the position table
+			PGX_CHECK(cudaMemsetAsync(counters.p + C_TIE_ROUND, 0, 12, st));
+			PGX_LAUNCH(k_cs_tie_mark, GS_GRID, TB, 0, st, A.ctg, A.cs, A.gidp, ctg2g.p, G, svcs, dc.p, t_last, gpos, counters.p + C_TIE_CS, counters.p + C_TIE_ROUND, tie_list, counters.p + C_LONG_RUN);
 			// n_local for every pair of out-arcs of every oriented vertex: local partial sums, one reduction, then the decisions
 			const int32_t cap_vtx = 2 * n_seg0;
 			uint32_t *cnt = scratch.get<uint32_t>((size_t)cap_vtx + 1), *off = scratch.get<uint32_t>((size_t)cap_vtx + 2);
 			PGX_LAUNCH(k_branch_count, grid_for(cap_vtx, TB), TB, 0, st, idx.p, cap_vtx, dc.p, cnt);
+			PGX_CHECK(cudaMemcpyAsync(h_pin + 1, counters.p + C_TIE_ROUND, 8, cudaMemcpyDeviceToHost, st));   // rides on the read-back below
 			uint32_t n_nl = scan_flags(cnt, off, cap_vtx);       // the one host read-back of a round: it sizes the table below
+			const uint32_t round_ties = h_pin[1], long_run = h_pin[2];
 			int32_t *nl = scratch.get<int32_t>((size_t)n_nl + 1), *grp = scratch.get<int32_t>(arc_cap + 1);
 			BranchOpt bo; bo.local_dist = opt->local_dist; bo.local_count = opt->local_count; bo.frag_mode = !!(opt->flag & PG_F_FRAG_MODE);
 			bo.branch_diff = opt->branch_diff; bo.branch_diff_dist = opt->branch_diff_dist; bo.branch_diff_cut = opt->branch_diff_cut;
 			if (n_nl) {
-				PGX_LAUNCH(k_branch_nlocal, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, gpos, G, off, (int32_t)n_nl, bo, nl);
+				PGX_LAUNCH(k_branch_nlocal, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, gpos, G, off, (int32_t)n_nl, bo, nl, counters.p + C_ORD_SENS);
+				// (rare) this round has cs-tied survivors AND one of their ordinals is within reach of the local_count threshold in a
+				// comparison it decides: renumber them as the reference does and count again
+				if (round_ties && (long_run || read_u32(counters.p + C_ORD_SENS))) {
+					fix_tied_ordinals(2 + 2 * branch_round_no, tie_list, round_ties, svcs, t_last, gpos);
+					PGX_LAUNCH(k_branch_nlocal, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, gpos, G, off, (int32_t)n_nl, bo, nl, counters.p + C_ORD_SENS);
+				}
 				g_comm.allreduce(nl, n_nl, Comm::T_INT32, Comm::OP_SUM, st);
 			}
 			PGX_LAUNCH(k_branch_decide, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, off, nl, bo, grp);
@@ -813,6 +901,7 @@ struct Session {
 		set_filter(SF_PSEUDO);                                                           // graph.c:285
 		gen_vtx(opt);                                                                    // graph.c:286
 		prepare_first_replay(opt);
+		tie_chains.clear();
 		flag_vtx();                                                                      // graph.c:287-288
 		recompact_active();
 		gen_arc(opt);                                                                    // graph.c:289
@@ -827,6 +916,7 @@ struct Session {
 			static const bool trace = getenv("PGX_TIMING") != nullptr;
 			uint32_t seg_before = 0;
 			if (trace) { seg_before = read_counts().n_seg; PGX_CHECK(cudaMemsetAsync(counters.p + C_BR_CHANGED, 0, 4, st)); }
+			branch_round_no = i;
 			branch_round(opt);
 			if (i > 0) flt_high_occ(max_avg_occ, max_degree, max_dist_loci);
 			if (trace) {   // how much does a round change?  (a round that changes nothing could skip the pg_gen_arc below)

@@ -1288,13 +1288,61 @@ __global__ void k_pos_fill(const int32_t *__restrict__ t_last, size_t n_tab, int
 	pos[k] = g;
 }
 
-__global__ void k_cs_tie_count(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, const uint32_t *__restrict__ sv_cs, const DevCounts *__restrict__ dc, uint32_t *tie_cnt)
+// Survivors that share one (contig, cs) with the survivor before them: counted (pgx_stats_t.tie[1]), listed
+// (list[] = position t in the survivor list of the LATER member of each tied pair) and their genes marked in the position table
+// (GenePos.pad) -- the reference numbers such hits in the order its unstable sort chain left them in (branch.c:18-25), which can
+// differ from ours by a permutation inside the group.  long_run: a group of more than 9 hits (the sensitivity window of
+// k_branch_nlocal assumes ordinals move by at most 8).
+__global__ void k_cs_tie_mark(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, const int32_t *__restrict__ gidp, const int32_t *__restrict__ ctg2g, int32_t G,
+	const uint32_t *__restrict__ sv_cs, const DevCounts *__restrict__ dc, const int32_t *__restrict__ t_last, GenePos *pos, uint32_t *tie_cnt, uint32_t *round_cnt, uint32_t *list, uint32_t *long_run)
 {
 	PGX_GS(t, dc->m_cs) {
 		if (t < 1) continue;
-		uint32_t a = sv_cs[t - 1], b = sv_cs[t];
-		if (ctg[a] == ctg[b] && cs[a] == cs[b]) atomicAdd(tie_cnt, 1u);
+		const uint32_t a = sv_cs[t - 1], b = sv_cs[t];
+		if (ctg[a] != ctg[b] || cs[a] != cs[b]) continue;
+		atomicAdd(tie_cnt, 1u);
+		list[atomicAdd(round_cnt, 1u)] = (uint32_t)t;
+		const size_t ka = (size_t)(gidp[a] >> 1) * G + ctg2g[ctg[a]], kb = (size_t)(gidp[b] >> 1) * G + ctg2g[ctg[b]];
+		if (t_last[ka] == (int32_t)a) pos[ka].pad = 1;
+		if (t_last[kb] == (int32_t)b) pos[kb].pad = 1;
+		if (t >= 9) { const uint32_t z = sv_cs[t - 9]; if (ctg[z] == ctg[b] && cs[z] == cs[b]) *long_run = 1u; }
 	}
+}
+
+struct TieRec { int32_t t, a_prev, a, ctg, full_prev, full; };   // one tied pair: survivor-list position, active indices, contig, F indices
+__global__ void k_tie_gather(const uint32_t *__restrict__ list, int32_t n, const uint32_t *__restrict__ sv_cs, const int32_t *__restrict__ ctg, const int32_t *__restrict__ full, TieRec *out)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	TieRec r;
+	r.t = (int32_t)list[k]; r.a_prev = (int32_t)sv_cs[r.t - 1]; r.a = (int32_t)sv_cs[r.t];
+	r.ctg = ctg[r.a]; r.full_prev = full[r.a_prev]; r.full = full[r.a];
+	out[k] = r;
+}
+
+// [lo, hi) of each listed contig in the (genome, contig, cs)-ordered full columns
+__global__ void k_ctg_ranges(const int32_t *__restrict__ ids, int32_t n_ids, const int32_t *__restrict__ f_ctg, int32_t N, int2 *out)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_ids) return;
+	const int32_t c = ids[k];
+	int32_t lo = 0, hi = N;
+	while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (f_ctg[m] < c) lo = m + 1; else hi = m; }
+	const int32_t b = lo;
+	hi = N;
+	while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (f_ctg[m] <= c) lo = m + 1; else hi = m; }
+	out[k] = make_int2(b, lo);
+}
+
+// ordinals of tied survivors, as the reference numbers them: only the hit that owns its gene's table entry is renumbered
+__global__ void k_patch_ord(const int2 *__restrict__ patch, int32_t n, const int32_t *__restrict__ ctg, const int32_t *__restrict__ gidp, const int32_t *__restrict__ ctg2g, int32_t G,
+	const int32_t *__restrict__ t_last, GenePos *pos)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	const int32_t a = patch[k].x;
+	const size_t key = (size_t)(gidp[a] >> 1) * G + ctg2g[ctg[a]];
+	if (t_last[key] == a) pos[key].ord += patch[k].y;
 }
 
 // number of n_local values a vertex needs: all arc pairs (i <= k) of its out-list
@@ -1314,7 +1362,7 @@ __device__ __forceinline__ uint32_t tri_index(uint32_t i, uint32_t k, uint32_t n
 // one WARP per table entry = one (vertex, arc pair): partial n_local (branch.c:31-46) over the LOCAL genomes.  (A warp per
 // vertex leaves the few high-degree vertices -- 465 pairs at degree 30 -- as a serial tail: 264 us -> see profiles/README.md.)
 __global__ void k_branch_nlocal(const unsigned long long *__restrict__ idx, const DevCounts *__restrict__ dc, const ArcDev *__restrict__ arc, const SegDev *__restrict__ seg, const GenePos *__restrict__ pos, int32_t G,
-	const uint32_t *__restrict__ off, int32_t n_nl, BranchOpt o, int32_t *nl)
+	const uint32_t *__restrict__ off, int32_t n_nl, BranchOpt o, int32_t *nl, uint32_t *ord_sensitive)
 {
 	const int32_t n_vtx = 2 * (int32_t)dc->n_seg, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
 	for (int32_t ent = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ent < n_nl; ent += n_warps) {
@@ -1336,6 +1384,12 @@ __global__ void k_branch_nlocal(const unsigned long long *__restrict__ idx, cons
 			if (!o.frag_mode && x.cid != y.cid) continue;
 			long long dd = (long long)x.cm - y.cm; int32_t dcnt = x.ord - y.ord;
 			if ((dd >= -o.local_dist && dd <= o.local_dist) || (dcnt >= -o.local_count && dcnt <= o.local_count)) ++c;
+			// an ordinal of a cs-tied survivor (k_cs_tie_mark) decides here and is within reach of the threshold: the round is redone
+			// with the reference's numbering of those hits (Session::fix_tied_ordinals)
+			if ((x.pad | y.pad) && !(dd >= -o.local_dist && dd <= o.local_dist)) {
+				const long long ac = dcnt < 0? -(long long)dcnt : dcnt;
+				if (ac > (long long)o.local_count - 8 && ac <= (long long)o.local_count + 8) *ord_sensitive = 1u;
+			}
 		}
 		for (int sft = 16; sft > 0; sft >>= 1) c += __shfl_xor_sync(0xffffffffu, c, sft);
 		if (lane == 0) nl[ent] = c;

@@ -103,6 +103,20 @@ def test_first_hit_tie_cases(k):
     check_against(opt, lambda: fuzz_oracle.data_for(case)[1], kind, lazy=bool(k & 1))
 
 
+@pytest.mark.parametrize("k", [1006, 2573, 176])
+def test_tied_survivor_ordinal_cases(k):
+    """local_dist = 1, local_count = k % 4: the locality test of branch.c:31-46 is decided by survivor ordinals, and survivors that
+    share one (contig, cs) are numbered in the order the reference's sort chain left them in (branch.c:18-25).  On 1006 and 2573 a
+    stable-order build differs from the reference; on 176 the stable order IS the reference's (a regression guard for the replay:
+    a tied hit that does not own its gene's table entry must not be renumbered).  libpgx: k_cs_tie_mark, Session::fix_tied_ordinals."""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import fuzz_oracle
+    case = fuzz_oracle.random_case(k, local=True)
+    kind = "reference" if refharness.available() else "oracle"
+    check_against(fuzz_oracle.data_for(case)[0], lambda: fuzz_oracle.data_for(case)[1], kind, lazy=bool(k & 1))
+
+
 @pytest.mark.skipif(not refharness.available(), reason="oracle/_ref did not travel")
 @pytest.mark.parametrize("cfg", ["euk", "bact"])
 def test_vs_compiled_reference(cfg):

@@ -116,15 +116,17 @@ def test_radix_permutation_replay_matches_reference_sort(n, key_bits):
 
 
 @needs_ref
-@pytest.mark.parametrize("k", [177, 179, 463, 502])
-def test_oracle_replays_the_reference_sort_chain_where_ties_are_observable(k):
-    """Campaign cases (tools/fuzz_oracle.py) whose first (contig, cs) of a genome is shared by several hits: the hit at the
-    front of the reference's array is never un-shadowed (overlap.c:108), and which hit that is changes from sort to sort of the
-    reference's unstable radix-sort chain.  A stable-order oracle differs from the reference on all four."""
+@pytest.mark.parametrize("k,local", [(177, False), (179, False), (463, False), (502, False), (1006, True), (2573, True), (176, True)])
+def test_oracle_replays_the_reference_sort_chain_where_ties_are_observable(k, local):
+    """Campaign cases (tools/fuzz_oracle.py).  177-502: the first (contig, cs) of a genome is shared by several hits -- the hit at
+    the front of the reference's array is never un-shadowed (overlap.c:108), and which hit that is changes from sort to sort of the
+    reference's unstable radix-sort chain; a stable-order oracle differs from the reference on all four.  1006, 2573 ("local"
+    mode: ordinals decide the locality test): survivors sharing one (contig, cs) take the reference's ordinals (branch.c:18-25);
+    176: the same situation where the stable order is the reference's."""
     import sys
     sys.path.insert(0, os.path.join(common.ROOT, "tools"))
     import fuzz_oracle
-    case = fuzz_oracle.random_case(k)
+    case = fuzz_oracle.random_case(k, local)
     opt, d1 = fuzz_oracle.data_for(case)
     _, d2 = fuzz_oracle.data_for(case)
     rh = refharness.RefHot()
@@ -136,3 +138,36 @@ def test_oracle_replays_the_reference_sort_chain_where_ties_are_observable(k):
     ba, bb = common.bed_bytes(d1), common.bed_bytes(d2)
     assert sorted(ba.splitlines()) == sorted(bb.splitlines()), common.first_diff(ba, bb)
     rh.destroy(g1); pgoracle.destroy(g2); hostio.destroy(d1); hostio.destroy(d2)
+
+
+@needs_ref
+@pytest.mark.parametrize("k", [176, 463])
+def test_sort_chain_replay_matches_reference_pg_hit_sort(k):
+    """pgo_test_chain_order (the replay behind the two tie fixes) against the compiled reference's own pg_hit_sort() applied
+    again and again to the same genome: identical array order after every cs sort and every cm sort of the chain."""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import fuzz_oracle
+    case = fuzz_oracle.random_case(k)
+    _, d = fuzz_oracle.data_for(case)
+    _, d2 = fuzz_oracle.data_for(case)
+    ref = C.CDLL(refharness.REF_LIB)
+    ref.pg_hit_sort.argtypes = [C.POINTER(abi.pg_genome_t), C.c_int32]
+    L = pgoracle.lib()
+    L.pgo_test_chain_order.argtypes = [C.POINTER(abi.pg_genome_t), C.c_int32, C.c_int32, C.c_void_p]
+    for j in range(min(d.contents.n_genome, 6)):
+        g, g2 = d.contents.genome[j], d2.contents.genome[j]
+        n = g.n_hit
+        for i in range(n):
+            g.hit[i].lof = i                     # tag every record with its file index
+        gp = C.pointer(g)
+        ref.pg_hit_sort(gp, 0)                   # read.c:247
+        for pairs in range(5):
+            out = (C.c_int32 * n)()
+            L.pgo_test_chain_order(C.byref(g2), pairs, 0, out)
+            assert list(out) == [g.hit[i].lof for i in range(n)], (j, pairs, "cs")
+            ref.pg_hit_sort(gp, 1)               # graph.c:103 / branch.c:116
+            L.pgo_test_chain_order(C.byref(g2), pairs, 1, out)
+            assert list(out) == [g.hit[i].lof for i in range(n)], (j, pairs, "cm")
+            ref.pg_hit_sort(gp, 0)               # graph.c:123 / branch.c:140
+    hostio.destroy(d); hostio.destroy(d2)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: randomized campaign of the CUDA path (through the C ABI) against the oracle restatement on a GPU box --
 the same case generator as tools/fuzz_oracle.py (which pins the oracle against the compiled reference in the build container).
-usage: tools/fuzz_gpu.py [first_case | case,case,...] [n_cases] [time_budget_s]"""
+usage: tools/fuzz_gpu.py [first_case | case,case,...] [n_cases] [time_budget_s] [local]      ("local": see tools/fuzz_oracle.py)"""
 import os
 import sys
 import time
@@ -24,12 +24,13 @@ def main():
         first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
         cases = list(range(first, first + n))
     budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
+    local = len(sys.argv) > 4 and sys.argv[4] == "local"
     engine.set_verbose(1)
     t0, bad, done = time.time(), 0, 0
     for k in cases:
         if time.time() - t0 > budget:
             break
-        case = random_case(k)
+        case = random_case(k, local)
         opt, d1 = data_for(case)
         _, d2 = data_for(case)
         g1 = pgoracle.hot_path(opt, d1)
@@ -44,7 +45,7 @@ def main():
         bad += not ok
         done += 1
         print("case %d %s hits=%d S=%d L=%d tie=%s gfa=%s graph=%s bed=%s tie_same=%s %s" % (k, "ok" if ok else "MISMATCH", hostio.total_hits(d1), g1.contents.n_seg, g1.contents.n_arc, list(st.tie), ok_gfa, ok_graph, ok_bed, ok_tie,
-              {x: case[x] for x in ("config", "n_genome", "n_gene", "iso_per_gene", "hits_per_genome", "n_ctg", "seed", "args")}), flush=True)
+              {x: case[x] for x in ("config", "n_genome", "n_gene", "iso_per_gene", "hits_per_genome", "n_ctg", "seed", "args", "local_count") if x in case}), flush=True)
         if not ok_gfa:
             print(common.first_diff(a, b), flush=True)
         pgoracle.destroy(g1); engine.destroy(g2); hostio.destroy(d1); hostio.destroy(d2)

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: randomized campaign of the oracle restatement against the compiled, unmodified reference
 (oracle/_ref/libpgref.so) -- many more shapes, seeds and option mixes than the CPU test suite has time for.
-Needs /root/reference (this container only).   usage: tools/fuzz_oracle.py [first_case] [n_cases]
+Needs /root/reference (this container only).   usage: tools/fuzz_oracle.py [first_case] [n_cases] [local]
+"local" runs every case with local_dist = 1 and local_count = case % 4 (pangene -D/-C): the locality test of branch.c:31-46 is
+then decided by survivor ordinals, which makes the reference's tie order among survivors with one (contig, cs) observable.
 Prints one line per case; a mismatch that comes with a non-zero tie detector (DESIGN.md "tie order") is reported as TIE."""
 import os
 import random
@@ -18,7 +20,7 @@ from pangene_b200 import hostio  # noqa: E402
 FLAGS = ["-S", "-J", "-E", "-F", "--ori-sc"]
 
 
-def random_case(k):
+def random_case(k, local=False):
     rnd = random.Random(777000 + k)
     args = [f for f in FLAGS if rnd.random() < 0.2]
     if rnd.random() < 0.5: args.append("-T%d" % rnd.choice([0, 1, 2, 3, 7, 15]))
@@ -39,11 +41,15 @@ def random_case(k):
         case["hits_per_genome"] = int(case["n_gene"] * case["iso_per_gene"] * rnd.uniform(1.2, 3.5))
     case["seed"] = rnd.getrandbits(40)
     case["n_ctg"] = rnd.choice([1, 2, 5, 24])
+    if local:
+        case["local_dist"], case["local_count"] = 1, k % 4
     return case
 
 
 def data_for(case):
     opt = common.opt_from_args(case["args"])
+    if "local_dist" in case:
+        opt.local_dist, opt.local_count = case["local_dist"], case["local_count"]
     p = hostio.synth_params(case["config"], n_genome=case["n_genome"], n_gene=case["n_gene"], iso_per_gene=case["iso_per_gene"],
                             hits_per_genome=case["hits_per_genome"], n_genome_total=case["n_genome"], seed=case["seed"], n_ctg=case["n_ctg"])
     return opt, hostio.synth(opt, p)
@@ -52,10 +58,11 @@ def data_for(case):
 def main():
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    local = len(sys.argv) > 3 and sys.argv[3] == "local"
     rh = refharness.RefHot()
     bad = 0
     for k in range(first, first + n):
-        case = random_case(k)
+        case = random_case(k, local)
         opt, d1 = data_for(case)
         _, d2 = data_for(case)
         g1, _ = rh.hot_path(opt, d1)
@@ -69,7 +76,7 @@ def main():
         status = "ok" if ok else ("TIE" if (tie[0] or tie[2]) else "MISMATCH")
         bad += status == "MISMATCH"
         print("case %d %s hits=%d S=%d L=%d tie=%s gfa=%s graph=%s bed=%s %s" % (k, status, hostio.total_hits(d1), g1.contents.n_seg, g1.contents.n_arc, tie, ok_gfa, ok_graph, ok_bed,
-              {x: case[x] for x in ("config", "n_genome", "n_gene", "iso_per_gene", "hits_per_genome", "n_ctg", "seed", "args")}), flush=True)
+              {x: case[x] for x in ("config", "n_genome", "n_gene", "iso_per_gene", "hits_per_genome", "n_ctg", "seed", "args", "local_count") if x in case}), flush=True)
         if status == "MISMATCH":
             print(common.first_diff(a, b), flush=True)
         rh.destroy(g1); pgoracle.destroy(g2); hostio.destroy(d1); hostio.destroy(d2)
