@@ -19,8 +19,11 @@
  *   - arcs (graph.c:87-177) are emitted as records and collapsed by a (key, genome) sort.
  * Where the reference's result depends on the exact permutation of its unstable radix sort and that is
  * observable in the GFA (hit.c:209, vertex.c:54: SURVEY.md H1 b,c), the permutation is replayed exactly
- * (pgo_radix_replay128).  Where it is observable only for coincident coordinates (H1 a), a detector
- * counts the cases (pgo_tie_report).
+ * (pgo_radix_replay128).  For coincident coordinates (H1 a) the reference's order follows from its whole chain of
+ * hit sorts; the chain is replayed per contig (replay_contig_order) in the two places where randomized campaigns
+ * against the compiled reference showed the order to be observable -- the never-reset hit at the front of the
+ * array (overlap.c:108: ref_first_pos) and the ordinals of cs-tied survivors (branch.c:18-25: mark_branch_arcs);
+ * the remaining coincidences are counted by a detector (pgo_tie_report).
  *
  * Every function cites the reference lines it restates.
  */
