@@ -10,6 +10,7 @@
 
 namespace pgx {
 
+// [emu-begin scan]  (tests/emu/build.py compiles the kernels up to [emu-end scan] for the host: tests/test_prim_emu.py)
 constexpr int SCAN_B = 256, SCAN_I = 8, SCAN_TILE = SCAN_B * SCAN_I;
 
 // ---- exclusive sum of uint32 -------------------------------------------------------------------
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(SCAN_B) k_scan_sum_lookback(const uint32_t *__
 	for (int k = 0; k < SCAN_I; ++k) { int64_t i = base + k; if (i <= n_in) out[i] = run; run += v[k]; }
 }
 
+// [emu-end scan]
 // scratch for the look-back variant: one status word per tile + the ticket, as uint32 elements
 static inline size_t scan_scratch_elems(int64_t n_in) { return (size_t)((n_in + 1 + SCAN_TILE - 1) / SCAN_TILE) * 2 + 4; }
 
@@ -178,6 +180,7 @@ static void exclusive_sum_u32(const uint32_t *in, uint32_t *out, int64_t n_in, u
 
 // ---- segmented inclusive running max -----------------------------------------------------------
 // out[i] = max(val[k] : k <= i, seg[k] == seg[i]);  seg must be non-decreasing (sorted contig keys)
+// [emu-begin segmax]
 struct SegVal { int32_t seg, val; };
 __device__ __forceinline__ SegVal seg_op(SegVal a, SegVal b) { SegVal r; r.seg = b.seg; r.val = (a.seg == b.seg && a.val > b.val)? a.val : b.val; return r; }
 
@@ -251,6 +254,7 @@ __global__ void k_segmax_apply(const int32_t *__restrict__ seg, int32_t *out, co
 	if (p.seg == seg[i] && p.val > out[i]) out[i] = p.val;
 }
 
+// [emu-end segmax]
 static void segmented_running_max(const int32_t *seg, const int32_t *val, int32_t *out, int64_t n, SegVal *agg_scratch, cudaStream_t s)
 {
 	if (n <= 0) return;

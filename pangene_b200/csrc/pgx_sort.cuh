@@ -15,6 +15,7 @@
 
 namespace pgx {
 
+// [emu-begin sort]  (tests/emu/build.py compiles the two kernels for the host: tests/test_prim_emu.py)
 constexpr int RS_WARPS = 8, RS_BLOCK = RS_WARPS * 32, RS_ITEMS = 16, RS_TILE = RS_BLOCK * RS_ITEMS;   // 4096 keys per tile
 
 __device__ __forceinline__ uint32_t rs_digit(uint64_t k, int shift) { return (uint32_t)(k >> shift) & 0xffu; }
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const uint64_t *__restr
 	}
 }
 
+// [emu-end sort]
 struct RadixSortBuffers {          // caller-provided scratch (no allocation inside the sort)
 	uint64_t *keys_alt; uint32_t *vals_alt; uint32_t *hist; uint32_t *scan_agg;
 	static size_t hist_elems(int64_t n) { int64_t t = (n + RS_TILE - 1) / RS_TILE; if (t < 1) t = 1; return (size_t)(256 * t + 1); }

@@ -1,4 +1,5 @@
-// simt_emu.hpp -- TEST INFRASTRUCTURE: a minimal SIMT execution shim that lets tests/emu/build.py compile the sweep kernels of
+// simt_emu.hpp -- TEST INFRASTRUCTURE: a minimal SIMT execution shim that lets tests/emu/build.py compile the sweep kernels (and, for
+// tests/test_prim_emu.py, the radix-sort / scan / segmented-max kernels of pgx_sort.cuh and pgx_scan.cuh) of
 // pangene_b200/csrc/pgx_kernels.cuh (the text between its [emu-begin sweep] / [emu-end sweep] markers, unchanged) for the host,
 // so that the control flow of the production kernel -- tile staging, sparse table, job bucketing, warp-cooperative parking --
 // can be checked against the plain thread-per-hit variant without a GPU (tests/test_sweep_emu.py).  One CTA runs at a time;
@@ -72,11 +73,18 @@ static inline bool __any_sync(uint32_t m, bool p) { return __ballot_sync(m, p) !
 template<class T> static inline T __shfl_sync(uint32_t, T v, int src) { return emu::exchange<T>(v, [src](const uint64_t *s, int) { return emu::from_u64<T>(s[src & 31]); }); }
 template<class T> static inline T __shfl_xor_sync(uint32_t, T v, int m) { return emu::exchange<T>(v, [m](const uint64_t *s, int lane) { return emu::from_u64<T>(s[(lane ^ m) & 31]); }); }
 template<class T> static inline T __shfl_up_sync(uint32_t, T v, int d) { return emu::exchange<T>(v, [d](const uint64_t *s, int lane) { return emu::from_u64<T>(s[lane >= d? lane - d : lane]); }); }
+static inline uint32_t __match_any_sync(uint32_t, uint32_t v)
+{
+	return emu::exchange<uint32_t>(v, [](const uint64_t *s, int lane) { uint32_t b = 0; for (int l = 0; l < 32; ++l) if ((uint32_t)s[l] == (uint32_t)s[lane]) b |= 1u << l; return b; });
+}
+static inline void __syncwarp() { emu::warp_sync(); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x == 0? 32 : __builtin_clz((uint32_t)x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 template<class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template<class T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template<class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 
 namespace emu {
 // run kernel(args...) over grid x block threads; one CTA at a time, the OS threads persist over the CTAs
