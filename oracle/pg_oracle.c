@@ -629,6 +629,38 @@ static void gen_vtx(const pg_opt_t *opt, pg_graph_t *q)
 	gen_g2s(q);
 }
 
+
+/* The surviving hits of one genome in the reference's (contig, cm) array order (graph.c:103, branch.c:116).  Ours is the stable
+ * one (ties keep (contig, cs) order); survivors that share one (contig, cm) are put in the order the reference's sort chain
+ * leaves them in at this point (replay_contig_order, by_cm = 1).  In every campaign case with such ties (tools/fuzz_oracle.py)
+ * the two orders were the same, so unlike the two replays above this one has never been observed to change a result. */
+static int32_t *survivors_in_ref_cm_order(const view_t *v, int32_t *n_out)
+{
+	const pg_hit_t *h = v->g->hit;
+	int32_t *sl = NEW(int32_t, v->n), n = 0, k, i0, i1, *rank = 0, rank_lo = -1, rank_hi = -1;
+	for (k = 0; k < v->n; ++k) if (!h[v->by_cm[k]].flt && !h[v->by_cm[k]].shadow) sl[n++] = v->by_cm[k];
+	for (i0 = 0; i0 < n && g_file_pos && v->j < g_file_pos_n && g_file_pos[v->j]; i0 = i1) {
+		int32_t t, u;
+		for (i1 = i0 + 1; i1 < n && h[sl[i1]].cid == h[sl[i0]].cid && h[sl[i1]].cm == h[sl[i0]].cm; ++i1) {}
+		if (i1 - i0 < 2) continue;
+		if (!(sl[i0] >= rank_lo && sl[i0] < rank_hi)) {
+			int32_t lo, hi;
+			for (lo = sl[i0]; lo > 0 && h[lo - 1].cid == h[sl[i0]].cid; --lo) {}
+			for (hi = sl[i0]; hi < v->n && h[hi].cid == h[sl[i0]].cid; ++hi) {}
+			free(rank); rank = NEW(int32_t, hi - lo); rank_lo = lo, rank_hi = hi;
+			replay_contig_order(v->g, g_file_pos[v->j], lo, hi, g_sort_pairs, 1, rank);
+		}
+		for (t = i0 + 1; t < i1; ++t) {   /* insertion sort of the group by the replayed position */
+			int32_t x = sl[t];
+			for (u = t; u > i0 && rank[sl[u - 1] - rank_lo] > rank[x - rank_lo]; --u) sl[u] = sl[u - 1];
+			sl[u] = x;
+		}
+	}
+	free(rank);
+	*n_out = n;
+	return sl;
+}
+
 typedef struct { uint64_t x; int32_t genome, dist, s1, s2; } arcrec_t;
 
 static int cmp_arcrec(const void *pa, const void *pb)
@@ -650,7 +682,7 @@ static void gen_arc(const pg_opt_t *opt, pg_graph_t *q, view_t *views)
 	int32_t j, i, k, use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH), check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
 	int64_t n_rec = 0, m_rec = 0, a0, a1;
 	arcrec_t *rec = 0;
-	int32_t *seg_cnt = NEW(int32_t, q->n_seg);
+	int32_t *seg_cnt = NEW(int32_t, q->n_seg), *sl, n_sl;
 	for (i = 0; i < q->n_seg; ++i) q->seg[i].n_genome = q->seg[i].tot_cnt = 0;
 	for (j = 0; j < d->n_genome; ++j) {
 		view_t *v = &views[j];
@@ -658,12 +690,12 @@ static void gen_arc(const pg_opt_t *opt, pg_graph_t *q, view_t *views)
 		uint32_t pv = 0;
 		sweep(opt, v, SWEEP_SHADOW, 0, check_strand);
 		memset(seg_cnt, 0, sizeof(int32_t) * q->n_seg);
-		for (k = 0; k < v->n; ++k) {   /* survivors in (contig, cm) order */
-			const pg_hit_t *a = &h[v->by_cm[k]];
+		sl = survivors_in_ref_cm_order(v, &n_sl);
+		for (k = 0; k < n_sl; ++k) {   /* survivors in (contig, cm) order */
+			const pg_hit_t *a = &h[sl[k]];
 			uint32_t w;
 			int32_t sid;
-			if (a->flt || a->shadow) continue;
-			sid = q->g2s[v->gid[v->by_cm[k]]];
+			sid = q->g2s[v->gid[sl[k]]];
 			if (sid < 0) { fprintf(stderr, "[pg_oracle] surviving hit without a segment\n"); abort(); }   /* graph.c:111 */
 			w = (uint32_t)sid << 1 | a->rev;
 			++seg_cnt[sid];
@@ -676,6 +708,7 @@ static void gen_arc(const pg_opt_t *opt, pg_graph_t *q, view_t *views)
 			}
 			prev = a, pv = w;
 		}
+		free(sl);
 		for (i = 0; i < q->n_seg; ++i) q->seg[i].n_genome += seg_cnt[i] > 0, q->seg[i].tot_cnt += seg_cnt[i];
 	}
 	free(seg_cnt);
@@ -857,18 +890,19 @@ static void mark_branch_hits(pg_graph_t *q, view_t *views)
 		view_t *v = &views[j];
 		pg_hit_t *h = v->g->hit, *prev = 0;
 		uint32_t pv = 0;
-		for (k = 0; k < v->n; ++k) {
-			pg_hit_t *a = &h[v->by_cm[k]];
+		int32_t n_sl, *sl = survivors_in_ref_cm_order(v, &n_sl);
+		for (k = 0; k < n_sl; ++k) {
+			pg_hit_t *a = &h[sl[k]];
 			const pg_arc_t *e;
 			uint32_t w;
-			if (a->flt || a->shadow) continue;
-			w = (uint32_t)q->g2s[v->gid[v->by_cm[k]]] << 1 | a->rev;
+			w = (uint32_t)q->g2s[v->gid[sl[k]]] << 1 | a->rev;
 			if (prev && prev->cid == a->cid) {
 				if ((e = find_arc(q, pv, w)) != 0 && e->weak_br > prev->weak_br) prev->weak_br = e->weak_br;
 				if ((e = find_arc(q, w ^ 1, pv ^ 1)) != 0 && e->weak_br > a->weak_br) a->weak_br = e->weak_br;
 			}
 			prev = a, pv = w;
 		}
+		free(sl);
 	}
 }
 

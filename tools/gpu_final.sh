@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final session of the round on the committed build: GPU tests, the bench line, and the ncu launch list of one pass.
+# Final session of a round on the committed build: GPU tests, the bench line, and the ncu launch list of one pass.
 mkdir -p gpurun_out
 timeout 200 python -m pytest tests -m gpu -q -n 2 -p no:cacheprovider > gpurun_out/tests_f.log 2>&1
 timeout 200 python bench.py > gpurun_out/bench_f.json 2> gpurun_out/bench_f.err
