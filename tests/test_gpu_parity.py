@@ -117,6 +117,29 @@ def test_tied_survivor_ordinal_cases(k):
     check_against(fuzz_oracle.data_for(case)[0], lambda: fuzz_oracle.data_for(case)[1], kind, lazy=bool(k & 1))
 
 
+@pytest.mark.parametrize("k", [0, 9, 17, 25])
+def test_perturbed_real_alignments(k, tmp_path):
+    """Cases of tools/fuzz_c4.py: the reference's test/C4 alignments with genomes subsampled and reordered, lines dropped,
+    duplicated (exact duplicate hits: equal keys, equal coordinates), re-scored or shuffled, under random option mixes."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import fuzz_c4
+    rnd = random.Random(424200 + k)
+    src = common.c4_files(tmp_path)
+    files = rnd.sample(src, rnd.randint(2, len(src)))
+    args = sorted(set(sum(rnd.sample(fuzz_c4.OPTS, rnd.randint(0, 3)), [])))
+    args = [a for a in args if not (a[:2] in ("-T", "-p", "-f") and sum(x[:2] == a[:2] for x in args) > 1 and a not in ("-T0", "-p0", "-f0.2"))]
+    mine = []
+    os.makedirs(str(tmp_path / "p"))
+    for f in files:
+        g = str(tmp_path / "p" / os.path.basename(f))
+        fuzz_c4.perturb(f, g, rnd)
+        mine.append(g)
+    opt = common.opt_from_args(args)
+    check_against(opt, lambda: hostio.read_pafs(opt, mine), "oracle", lazy=bool(k & 1))
+
+
 @pytest.mark.skipif(not refharness.available(), reason="oracle/_ref did not travel")
 @pytest.mark.parametrize("cfg", ["euk", "bact"])
 def test_vs_compiled_reference(cfg):
