@@ -18,6 +18,9 @@
 #include <thread>
 #include <atomic>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <time.h>
 #include <fcntl.h>
 #include <unistd.h>
@@ -45,23 +48,61 @@ extern "C" void pgio_opt_init(pg_opt_t *o)   // option.c:6-26
 // ------------------------------------------------------------------------------------------------
 // containers
 // ------------------------------------------------------------------------------------------------
+uint64_t pgio::NameTable::hash_of(std::string_view s)   // 8 bytes at a time, multiply-fold (names are 5-40 bytes)
+{
+	const char *p = s.data();
+	size_t n = s.size();
+	uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)n * 0xff51afd7ed558ccdull;
+	while (n >= 8) { uint64_t w; memcpy(&w, p, 8); h = (h ^ w) * 0x9fb21c651e98df25ull; h ^= h >> 29; p += 8; n -= 8; }
+	if (n) { uint64_t w = 0; memcpy(&w, p, n); h = (h ^ w) * 0x9fb21c651e98df25ull; h ^= h >> 29; }
+	h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 32;
+	return h;
+}
+void pgio::NameTable::grow()
+{
+	const size_t cap = slots.empty()? 1024 : slots.size() * 2;
+	std::vector<Slot> fresh(cap, Slot{0, -1});
+	for (const Slot &o : slots) {
+		if (o.id < 0) continue;
+		size_t k = o.hash & (cap - 1);
+		while (fresh[k].id >= 0) k = (k + 1) & (cap - 1);
+		fresh[k] = o;
+	}
+	slots.swap(fresh);
+}
 const char *pgio::NameTable::intern(std::string_view s, int32_t *id, bool *absent)
 {
-	auto it = map.find(s);
-	if (it != map.end()) { if (id) *id = it->second; if (absent) *absent = false; return names[it->second]; }
+	if ((names.size() + 1) * 2 > slots.size()) grow();   // load factor <= 1/2
+	const uint64_t h = hash_of(s);
+	const size_t mask = slots.size() - 1;
+	size_t k = h & mask;
+	for (; slots[k].id >= 0; k = (k + 1) & mask) {
+		const int32_t j = slots[k].id;
+		if (slots[k].hash == h && lens[j] == s.size() && memcmp(names[j], s.data(), s.size()) == 0) {
+			if (id) *id = j;
+			if (absent) *absent = false;
+			return names[j];
+		}
+	}
 	char *p = (char*)malloc(s.size() + 1);
 	memcpy(p, s.data(), s.size()); p[s.size()] = 0;
-	int32_t k = (int32_t)names.size();
-	names.push_back(p);
-	map.emplace(std::string_view(p, s.size()), k);
-	if (id) *id = k;
+	const int32_t j = (int32_t)names.size();
+	names.push_back(p); lens.push_back((uint32_t)s.size());
+	slots[k] = Slot{h, j};
+	if (id) *id = j;
 	if (absent) *absent = true;
 	return p;
 }
 int32_t pgio::NameTable::find(std::string_view s) const
 {
-	auto it = map.find(s);
-	return it == map.end()? -1 : it->second;
+	if (slots.empty()) return -1;
+	const uint64_t h = hash_of(s);
+	const size_t mask = slots.size() - 1;
+	for (size_t k = h & mask; slots[k].id >= 0; k = (k + 1) & mask) {
+		const int32_t j = slots[k].id;
+		if (slots[k].hash == h && lens[j] == s.size() && memcmp(names[j], s.data(), s.size()) == 0) return j;
+	}
+	return -1;
 }
 pgio::NameTable::~NameTable() { for (char *p : names) free(p); }
 
@@ -323,6 +364,24 @@ void pgio::push_hit(pg_genome_t *g, pg_hit_t &hit, const std::vector<pg_exon_t> 
 	g->hit[g->n_hit++] = hit;
 }
 
+// tab-separated fields of one NUL-terminated line, split in place (the tabs become terminators); like the reference's column
+// loop (read.c:135-137) the line ends at its first NUL byte
+static inline void split_tabs(char *s, size_t len, std::vector<char*> &fld)
+{
+	fld.clear();
+	fld.push_back(s);
+	if (const void *z = memchr(s, 0, len)) len = (size_t)((const char*)z - s);
+	size_t i = 0;
+#if defined(__SSE2__)
+	const __m128i tab = _mm_set1_epi8('\t');
+	for (; i + 16 <= len; i += 16) {
+		unsigned m = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)(s + i)), tab));
+		while (m) { const unsigned b = (unsigned)__builtin_ctz(m); m &= m - 1; s[i + b] = 0; fld.push_back(s + i + b + 1); }
+	}
+#endif
+	for (; i < len; ++i) if (s[i] == '\t') { s[i] = 0; fld.push_back(s + i + 1); }
+}
+
 // One PAF file parsed on its own, with FILE-LOCAL gene/protein ids (first-seen order inside the file).  Files are
 // independent except for the global id assignment (ids = dictionary size at first sight, read.c:151,161; hit.rank is a
 // per-file count, read.c:170), so they can be parsed in parallel and merged in command-line order afterwards
@@ -339,9 +398,11 @@ struct LocalFile {
 	LocalFile() { memset(&g, 0, sizeof(g)); }
 };
 
+std::string &file_buffer() { static thread_local std::string b; return b; }
+
 void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 {
-	std::string buf;
+	std::string &buf = file_buffer();                              // one per worker thread: the pages of the previous file are reused
 	if (!read_whole(fn, buf)) return;                              // read.c:117-118
 	F.ok = true;
 	const pgio::NameTable *excl = (const pgio::NameTable*)opt->excl, *incl = (const pgio::NameTable*)opt->incl, *pref = (const pgio::NameTable*)opt->preferred;
@@ -351,11 +412,9 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 	std::vector<pg_exon_t> tmp, ex;
 	std::vector<char*> fld;
 
-	for_each_line(buf, [&](char *s, size_t) {
+	for_each_line(buf, [&](char *s, size_t len) {
 		++F.n_lines;
-		fld.clear();
-		for (char *p = s, *q = s;; ++p)
-			if (*p == '\t' || *p == 0) { int c = *p; *p = 0; fld.push_back(q); q = p + 1; if (c == 0) break; }
+		split_tabs(s, len, fld);
 		pg_hit_t hit;
 		memset(&hit, 0, sizeof(hit));
 		hit.pid = hit.pid_dom = hit.cid = hit.off_exon = hit.n_exon = -1;
@@ -466,6 +525,7 @@ extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *
 	parse_file(opt, fn, F);
 	if (!F.ok) return -1;
 	merge_file(d, F);
+	if (file_buffer().capacity() > ((size_t)256 << 20)) std::string().swap(file_buffer());   // keep a modest buffer for the next file, not a huge one
 	return 0;
 }
 
@@ -486,6 +546,7 @@ extern "C" int32_t pgio_read_pafs(const pg_opt_t *opt, pg_data_t *d, const char 
 	for (int32_t t = 1; t < n_threads; ++t) th.emplace_back(worker);
 	worker();
 	for (auto &t : th) t.join();
+	std::string().swap(file_buffer());   // the calling thread's read buffer (the workers' went with their threads)
 	const double t1 = wall_now();
 	int32_t n_ok = 0;
 	for (int32_t i = 0; i < n_files; ++i) if (files[i].ok) { merge_file(d, files[i]); ++n_ok; }

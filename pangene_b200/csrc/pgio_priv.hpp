@@ -3,20 +3,25 @@
 #include <cstdint>
 #include <string_view>
 #include <vector>
-#include <unordered_map>
 #include "pangene_abi.h"
 
 namespace pgio {
 
-// name -> dense id in first-seen order; owns the strings (stands in for the reference's dict.c)
+// name -> dense id in first-seen order; owns the strings (stands in for the reference's dict.c).  Open addressing, linear probing,
+// the 64-bit hash kept next to the id: a look-up touches one cache line of the table and, on a hash match, the name itself.
 struct NameTable {
-	std::unordered_map<std::string_view, int32_t> map;
+	struct Slot { uint64_t hash; int32_t id; };          // id < 0: empty
+	std::vector<Slot> slots;
 	std::vector<char*> names;
+	std::vector<uint32_t> lens;
 	const char *intern(std::string_view s, int32_t *id, bool *absent);
 	int32_t find(std::string_view s) const;
 	NameTable() = default;
 	NameTable(const NameTable&) = delete;
 	~NameTable();
+private:
+	static uint64_t hash_of(std::string_view s);
+	void grow();
 };
 
 struct DataPriv {           // hangs off pg_data_t::d_ctg
