@@ -297,43 +297,54 @@ int64_t pgio::cigar_to_exons(const char *cg, bool rev, std::vector<pg_exon_t> &t
 {
 	int64_t x = 0;
 	int32_t fs = 0;
-	tmp.clear();
-	tmp.push_back(pg_exon_t{0, 0});
+	size_t n = 1;                                    // exons so far; tmp[n-1] is the open one
+	if (tmp.size() < 64) tmp.resize(64);
+	tmp[0] = pg_exon_t{0, 0};
 	const char *p = cg;
 	while (*p) {
-		const char *r;
-		int64_t l = fast_l(p, &r);
-		char op = *r;
-		if (op == 'N' || op == 'U' || op == 'V') {
+		int64_t l = 0;
+		const char *r = p;
+		while ((unsigned)(*r - '0') <= 9u) l = l * 10 + (*r++ - '0');
+		if (r == p || r - p > 18) l = fast_l(p, &r);   // sign, blanks, overflow: strtol's own answer
+		const char op = *r;
+		if (op == 'M' || op == 'X' || op == '=' || op == 'D') {
+			x += l * 3;
+		} else if (op == 'N' || op == 'U' || op == 'V') {
 			int64_t st, en;
 			if (op == 'N') st = x, en = x + l;
 			else if (op == 'U') st = x + 1, en = x + l - 2;
 			else st = x + 2, en = x + l - 1;
-			tmp.back().oe = (int32_t)st;
-			tmp.push_back(pg_exon_t{(int32_t)en, (int32_t)en});
+			tmp[n - 1].oe = (int32_t)st;
+			if (n == tmp.size()) tmp.resize(n * 2);
+			tmp[n++] = pg_exon_t{(int32_t)en, (int32_t)en};
 			x += l;
-		} else if (op == 'M' || op == 'X' || op == '=' || op == 'D') {
-			x += l * 3;
 		} else if (op == 'F' || op == 'G') {
 			x += l, ++fs;
 		}
 		if (op == 0) break;   // malformed tail; the reference would run off the string here
 		p = r + 1;
 	}
-	tmp.back().oe = (int32_t)x;
-	out.clear();
-	if (!rev) out = tmp;
-	else for (int32_t i = (int32_t)tmp.size() - 1; i >= 0; --i)
-		out.push_back(pg_exon_t{(int32_t)(x - tmp[i].oe), (int32_t)(x - tmp[i].os)});
+	tmp[n - 1].oe = (int32_t)x;
+	out.resize(n);
+	if (!rev) memcpy(out.data(), tmp.data(), n * sizeof(pg_exon_t));
+	else for (size_t i = 0; i < n; ++i) out[i] = pg_exon_t{(int32_t)(x - tmp[n - 1 - i].oe), (int32_t)(x - tmp[n - 1 - i].os)};
 	*n_fs = fs;
 	return x;
 }
 
 int32_t pgio::adjusted_score(const pg_opt_t *opt, int32_t ms, int32_t mlen, int32_t blen, int32_t qs, int32_t qe, int32_t plen)
-{   // read.c:212-216 -- long-double exp, same expression shape
+{   // read.c:212-216: (int32_t)(ms * expl(x) + .499), evaluated in long double
 	double div = 1.0 - (double)mlen / blen;
 	double uncov = 1.0 - (double)(qe - qs) / plen;
-	return (int32_t)(ms * expl(-opt->score_adj_coef * (div + uncov)) + .499);
+	const double x = -opt->score_adj_coef * (div + uncov);
+	// expl() costs ~250 cycles per line.  exp() is within 1 ulp (1.2e-16 relative), so for |ms * exp(x)| < 1e8 the double value is within
+	// ~5e-8 of the long-double one; unless it lands within 1e-6 of an integer, truncation gives the same int32.
+	if (ms > -4194304 && ms < 4194304 && x == x && x < 40.0 && x > -700.0) {
+		const double v = ms * exp(x) + .499;
+		const double r = nearbyint(v);
+		if (fabs(v - r) > 1e-6 && fabs(v) < 1e8) return (int32_t)v;
+	}
+	return (int32_t)(ms * expl(x) + .499);
 }
 
 static char *label_from_path(const char *fn)   // read.c:92-105
@@ -408,6 +419,19 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 	const pgio::NameTable *excl = (const pgio::NameTable*)opt->excl, *incl = (const pgio::NameTable*)opt->incl, *pref = (const pgio::NameTable*)opt->preferred;
 	pg_genome_t *g = &F.g;
 	g->label = fn && strcmp(fn, "-")? label_from_path(fn) : label_from_path("-");
+	{   // size the hit and exon arrays once from a sample of the text (calloc: untouched pages cost nothing; PG_GROW0-style growth stays as the fallback)
+		const size_t smp = buf.size() < ((size_t)1 << 16)? buf.size() : ((size_t)1 << 16);
+		size_t nl = 0, nn = 0;
+		for (size_t i = 0; i < smp; ++i) { nl += buf[i] == '\n'; nn += buf[i] == 'N'; }
+		if (nl > 0 && buf.size() / smp < 100000) {
+			const double lines = (double)buf.size() / smp * (double)nl;
+			const int64_t eh = (int64_t)(lines * 1.03) + 64, ee = (int64_t)(lines * 1.05 * (1.0 + (double)nn / nl)) + 64;
+			if (eh < 0x7fffffff && ee < 0x7fffffff) {
+				g->hit = (pg_hit_t*)calloc((size_t)eh, sizeof(pg_hit_t)); g->m_hit = g->hit? (int32_t)eh : 0;
+				g->exon = (pg_exon_t*)calloc((size_t)ee, sizeof(pg_exon_t)); g->m_exon = g->exon? (int32_t)ee : 0;
+			}
+		}
+	}
 	std::vector<int32_t> seen_cnt;                                // per-protein line count in THIS file (rank, read.c:170)
 	std::vector<pg_exon_t> tmp, ex;
 	std::vector<char*> fld;
