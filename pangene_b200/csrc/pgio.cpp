@@ -435,6 +435,8 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 	std::vector<int32_t> seen_cnt;                                // per-protein line count in THIS file (rank, read.c:170)
 	std::vector<pg_exon_t> tmp, ex;
 	std::vector<char*> fld;
+	int32_t last_pid = -1, last_gid = -1;
+	std::string_view last_pname, last_gname;                      // views into `buf` (earlier lines stay intact)
 
 	for_each_line(buf, [&](char *s, size_t len) {
 		++F.n_lines;
@@ -453,10 +455,20 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 			std::string_view gname(q, r - q);
 			if (excl && excl->find(gname) >= 0) break;
 			bool absent;
-			F.gene.intern(gname, &gid, &absent);
-			if (absent) { F.gene_len.push_back(0); F.gene_pref.push_back(pref && pref->find(gname) >= 0); F.gene_incl.push_back(incl && incl->find(gname) >= 0); }
-			F.prot.intern(q, &pid, &absent);
-			if (absent) { F.prot_gid.push_back(gid); F.prot_len.push_back(0); }
+			// (alignments of one protein, and of the isoforms of one gene, tend to sit on consecutive lines: remember the last of each)
+			const std::string_view pname(q);
+			if (last_pid >= 0 && pname == last_pname) pid = last_pid, gid = last_gid;
+			else {
+				if (last_gid >= 0 && gname == last_gname) gid = last_gid;
+				else {
+					F.gene.intern(gname, &gid, &absent);
+					if (absent) { F.gene_len.push_back(0); F.gene_pref.push_back(pref && pref->find(gname) >= 0); F.gene_incl.push_back(incl && incl->find(gname) >= 0); }
+					last_gid = gid; last_gname = gname;
+				}
+				F.prot.intern(pname, &pid, &absent);
+				if (absent) { F.prot_gid.push_back(gid); F.prot_len.push_back(0); }
+				last_pid = pid; last_pname = pname;
+			}
 			F.prot_gid[pid] = gid; F.prot_len[pid] = 0;
 			hit.pid = pid;
 			if ((size_t)pid >= seen_cnt.size()) seen_cnt.resize(pid + 1 + (pid >> 1), -1);
