@@ -258,8 +258,9 @@ extern "C" void pgio_name_set_destroy(void *s) { delete (pgio::NameTable*)s; }
 static inline long fast_l(const char *p, const char **end = 0)
 {
 	const char *q = p;
-	long v = 0;
-	while ((unsigned)(*q - '0') <= 9u) v = v * 10 + (*q++ - '0');
+	unsigned long u = 0;                                 // (unsigned: a run of 20+ digits wraps harmlessly before strtol takes over)
+	while ((unsigned)(*q - '0') <= 9u) u = u * 10 + (unsigned long)(*q++ - '0');
+	long v = (long)u;
 	if (q == p || q - p > 18) { char *e; v = strtol(p, &e, 10); q = e; }
 	if (end) *end = q;
 	return v;
@@ -302,9 +303,10 @@ int64_t pgio::cigar_to_exons(const char *cg, bool rev, std::vector<pg_exon_t> &t
 	tmp[0] = pg_exon_t{0, 0};
 	const char *p = cg;
 	while (*p) {
-		int64_t l = 0;
+		uint64_t lu = 0;
 		const char *r = p;
-		while ((unsigned)(*r - '0') <= 9u) l = l * 10 + (*r++ - '0');
+		while ((unsigned)(*r - '0') <= 9u) lu = lu * 10 + (uint64_t)(*r++ - '0');
+		int64_t l = (int64_t)lu;
 		if (r == p || r - p > 18) l = fast_l(p, &r);   // sign, blanks, overflow: strtol's own answer
 		const char op = *r;
 		if (op == 'M' || op == 'X' || op == '=' || op == 'D') {
