@@ -59,6 +59,21 @@ def build_cases(tmp):
     cases["ragged_T0_J"] = ([a, b, c, e], ["-T0", "-J"])
     cases["single_file"] = ([c], ["-p0"])
     cases["empty_only"] = ([b], [])
+    # reader corner cases (tools/asan/odd_lines.cpp runs the same lines under ASan/UBSan): fields ending on the 16-byte boundaries of
+    # the SSE2 tab split, a NUL inside a line (the reference stops the line there), CRLF, a 20-digit score, frameshift CIGAR
+    # operators, very long names, a last line without newline
+    o = os.path.join(d, "ODD.paf")
+    good = line("G1:P1", 100, 0, 100, "+", "s1#0#c1", 100000, 1000, "50M200N50M", 500)
+    with open(o, "wb") as f:
+        f.write(good.encode())
+        f.write(b"0123456789abcdef\n0123456789abcde\tx\n0123456789abcdef\t\n\t\t\t\t\t\t\t\t\t\t\t\t\t\t\t\t\t\t\n")
+        f.write(good[:40].encode() + b"\0" + good[41:].encode())
+        f.write(good.rstrip("\n").encode() + b"\r\n")
+        f.write(line("G3:P3", 50, 0, 50, "+", "ctg", 1000, 10, "50M", 0).replace("ms:i:0", "ms:i:99999999999999999999").encode())
+        f.write(line("G4:" + "x" * 5000, 50, 0, 50, "+", "c" * 3000, 1000, 10, "50M", 77).encode())
+        f.write(line("G5:P5", 60, 0, 60, "+", "s1#0#c1", 100000, 5000, "10M1F20M2G28M", 280, fs=2).encode())
+        f.write(line("G6:P6", 80, 0, 80, "-", "s1#0#c1", 100000, 7000, "20M100U20M100V40M", 300).rstrip("\n").encode())
+    cases["odd_lines"] = ([a, o], [])
     return cases
 
 
@@ -72,7 +87,7 @@ def run_ours(hot_path, destroy, files, args):
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["ragged", "ragged_S_p0", "ragged_T0_J", "single_file", "empty_only"])
+@pytest.mark.parametrize("name", ["ragged", "ragged_S_p0", "ragged_T0_J", "single_file", "empty_only", "odd_lines"])
 def test_oracle_matches_stock_cli_on_edge_cases(tmp_path, name):
     files, args = build_cases(tmp_path)[name]
     gfa, bed = run_ours(pgoracle.hot_path, pgoracle.destroy, files, args)
