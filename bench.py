@@ -19,10 +19,17 @@ per GPU, NCCL collectives inside libpgx.
   cpu_baseline the compiled, unmodified reference (oracle/_ref, 1 thread -- pangene is single-threaded) on a
                bounded sample of the same workload, timed on this box's host cores in the same run.
 
-  --impl reference   times only that CPU baseline and prints it in the same JSON shape.
+  parity       correctness gate on the graph the timed calls produced: S/L lines (replicated on every rank) and W lines (gathered in
+               rank order) are hashed and compared with tests/golden/c3_golden.json, which was printed by the UNMODIFIED reference
+               (stock binary and in-process objects, tests/golden/make_golden_c3.py).  "ok" or the process exits non-zero.
+
+  --impl reference   times the reference's own CPU implementation (oracle/_ref, unmodified, single thread) on the SAME configuration:
+                     ONE full pass over all 100 genomes (~95 s on one host core; K/W are not repeated, the line says steps 1).
 """
 import argparse
 import ctypes as C
+import faulthandler
+import hashlib
 import json
 import os
 import statistics
@@ -83,13 +90,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_sample(hostio, steps=1, warmup=0):
-    """hits/s of the reference's own CPU implementation (1 thread) on the first CPU_SAMPLE_GENOMES genomes of the workload"""
+def cpu_reference(hostio, n_genomes, steps=1, warmup=0):
+    """hits/s of the reference's own CPU implementation (1 thread) on the first n_genomes genomes of the workload (100 = all of it)"""
     import refharness
     opt = hostio.default_opt()
-    p = hostio.synth_params(3, n_genome=CPU_SAMPLE_GENOMES, n_genome_total=100)
+    p = hostio.synth_params(3, n_genome=n_genomes, n_genome_total=100)
     kind = "reference" if refharness.available() else "port"
-    times, hits = [], 0
+    times, hits, digest = [], 0, None
     for it in range(warmup + steps):
         d = hostio.synth(opt, p)
         hits = hostio.total_hits(d)
@@ -98,18 +105,47 @@ def cpu_reference_sample(hostio, steps=1, warmup=0):
             rh = refharness.RefHot()
             g, _ = rh.hot_path(opt, d)
             dt = time.perf_counter() - t0
+            if n_genomes == 100:
+                digest = hostio.gfa_digest(g)
             rh.destroy(g)
         else:
             from oracle import pgoracle
             g = pgoracle.hot_path(opt, d)
             dt = time.perf_counter() - t0
+            if n_genomes == 100:
+                digest = hostio.gfa_digest(g)
             pgoracle.destroy(g)
         hostio.destroy(d)
         if it >= warmup:
             times.append(dt)
     dt = sum(times) / len(times)
-    return {"value": hits / dt, "unit": "hits/s", "cores": 1, "kind": kind,
-            "sample": "%d of the 100 genomes of the same workload (%d hits), %.1f s per pass, single thread (the reference has no threads)" % (CPU_SAMPLE_GENOMES, hits, dt)}, dt
+    sample = ("none: all 100 genomes (%d hits), %.1f s per pass" % (hits, dt)) if n_genomes == 100 else \
+        ("%d of the 100 genomes of the same workload (%d hits), %.1f s per pass" % (n_genomes, hits, dt))
+    return {"value": hits / dt, "unit": "hits/s", "cores": 1, "kind": kind, "sample": sample + ", single thread (the reference has no threads)"}, dt, hits, digest
+
+
+def load_golden():
+    p = os.path.join(ROOT, "tests", "golden", "c3_golden.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def parity_verdict(sl_md5s, w_bytes, gold):
+    """sl_md5s: one S/L digest per rank (the graph is replicated); w_bytes: W lines of all ranks in rank (= genome) order"""
+    w_md5 = hashlib.md5(w_bytes).hexdigest()
+    out = {"golden": "tests/golden/c3_golden.json (unmodified reference: stock binary + in-process objects)", "sl_md5": sl_md5s[0], "w_md5": w_md5,
+           "n_W": w_bytes.count(b"\n"), "ranks_agree": len(set(sl_md5s)) == 1}
+    if gold is None:
+        out["status"] = "unchecked (golden file missing)"
+    else:
+        ok = out["ranks_agree"] and sl_md5s[0] == gold["sl_md5"] and w_md5 == gold["w_md5"] and out["n_W"] == gold["n_W"]
+        out["status"] = "ok" if ok else "FAIL"
+    return out
+
+
+def workload_config(n_total, G_total, world):
+    return {"workload": WORKLOAD if G_total == 100 else "DEBUG %d genomes" % G_total, "hits": n_total, "genomes": G_total,
+            "parallelism": "genomes sharded over %d rank(s)" % world,
+            "l2": "inputs (%.1f GB of hit columns + exons per step) exceed the 126 MB L2; no explicit flush" % ((n_total or 0) * 140 / 1e9)}
 
 
 def main():
@@ -120,20 +156,28 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genomes", type=int, default=100, help="override the genome count (debug; invalidates the number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=0, help="--impl reference on this many genomes instead of the full configuration (debug)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden comparison (debug)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     from pangene_b200 import hostio
 
+    faulthandler.enable()
     if a.impl == "reference":
         if rank != 0:
-            return
-        cb, dt = cpu_reference_sample(hostio, steps=max(1, a.steps), warmup=min(a.warmup, 1))
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "hits/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            return 0
+        full = a.genomes == 100 and not a.ref_sample
+        cb, dt, hits, digest = cpu_reference(hostio, 100 if full else (a.ref_sample or a.genomes))
+        par = parity_verdict([digest[0]], digest[1], load_golden()) if digest else {"status": "unchecked (sample run)"}
+        cfg = workload_config(hits if full else None, 100, a.gpus)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "hits/s", "n_gpus": a.gpus, "steps": 1, "warmup": 0,
+                          "steps_requested": a.steps, "warmup_requested": a.warmup,
                           "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-                          "config": {"workload": WORKLOAD, "sample": cb["sample"]}, "cpu_baseline": cb,
-                          "e2e": {"value": cb["value"], "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
-        return
+                          "config": cfg, "cpu_baseline": cb, "parity": par,
+                          "note": "one full pass of the whole configuration (K/W are not repeated: a pass takes ~1.5 min on the one core the reference can use)",
+                          "e2e": {"value": cb["value"], "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return 0
 
     import torch
     from pangene_b200 import engine
@@ -184,17 +228,18 @@ def main():
     L.pgx_set_sweep_stat(0)
     barrier()
     st0 = engine.stats()
-    dev_ms, sweep_ms = [], []
+    dev_ms, sweep_ms, st_ms = [], [], ([], [])
     with ClockSampler(local_rank) as clk:
         t0 = time.perf_counter()
         for _ in range(a.steps):
             L.pgx_run(sess, C.byref(opt), 3)
             s = engine.stats()
-            dev_ms.append(s.run_ms[2]); sweep_ms.append(s.sweep_ms)
+            dev_ms.append(s.run_ms[2]); sweep_ms.append(s.sweep_ms); st_ms[0].append(s.run_ms[0]); st_ms[1].append(s.run_ms[1])
         barrier()
         wall = time.perf_counter() - t0
     st1 = engine.stats()
     ms_step = max_over_ranks(sum(dev_ms) / len(dev_ms))
+    stage1_ms, stage2_ms = max_over_ranks(sum(st_ms[0]) / len(st_ms[0])), max_over_ranks(sum(st_ms[1]) / len(st_ms[1]))
     wall_step = max_over_ranks(wall / a.steps * 1e3)
     launches = (st1.launches - st0.launches) // a.steps
     sweep_bytes, sweep_t = st1.sweep_bytes, sum(sweep_ms) / len(sweep_ms)
@@ -203,8 +248,10 @@ def main():
 
     # ---- e2e: host pg_data_t in, host pg_data_t + pg_graph_t out --------------------------------------
     e2e_t, h2d, d2h = [], 0, 0
+    digest = None
     L.pgx_set_lazy(1)
-    for it in range(2 + 5):
+    n_e2e = 2 + 5
+    for it in range(n_e2e):
         d = hostio.lib().pgio_data_clone(d0)
         barrier()
         s0 = engine.stats()
@@ -218,12 +265,35 @@ def main():
         if it >= 2:
             e2e_t.append(max_over_ranks(dt))
         h2d, d2h = s1.h2d_bytes - s0.h2d_bytes, s1.d2h_bytes - s0.d2h_bytes
+        if it == n_e2e - 1 and not a.no_parity:
+            digest = hostio.gfa_digest(g)       # the graph and hits the LAST timed call returned (outside the timed region)
         L.pg_graph_destroy(g)
         hostio.lib().pgio_data_clone_destroy(d)
     e2e_s = statistics.median(e2e_t)           # median of 5 timed calls after 2 untimed ones (host page-fault/NUMA noise is +-30 %)
 
+    # ---- parity gate: every rank's replicated S/L lines + the W lines of all ranks in genome order, against the reference's golden
+    parity = {"status": "unchecked (--no-parity)"}
+    if digest is not None:
+        parts = [digest]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, digest)
+        if rank == 0:
+            parity = parity_verdict([x[0] for x in parts], b"".join(x[1] for x in parts), load_golden() if G_total == 100 else None)
+            if G_total != 100:
+                parity["status"] = "unchecked (debug genome count)"
+
+    # ---- teardown, the same on every rank: flush what we know first, then barrier -> libpgx communicator -> torch process group
+    def teardown():
+        if world > 1:
+            barrier()
+            L.pgx_comm_destroy()
+            dist.barrier()
+            dist.destroy_process_group()
+
     if rank != 0:
-        return
+        teardown()
+        return 0
     peak, peak_src = peaks()
     achieved = sweep_bytes / (sweep_t * 1e-3) / 1e9 if sweep_t > 0 else 0.0
     traffic = None
@@ -233,9 +303,9 @@ def main():
     out = {
         "metric": METRIC, "value": n_total / (ms_step * 1e-3), "unit": "hits/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-        "config": {"workload": WORKLOAD if a.genomes == 100 else "DEBUG %d genomes" % a.genomes, "hits": n_total, "genomes": G_total, "parallelism": "genomes sharded over %d rank(s)" % world,
-                   "l2": "inputs (%.1f GB of hit columns + exons per step) exceed the 126 MB L2; no explicit flush" % ((n_total * 140) / 1e9),
-                   "active_hits_after_load_filters_rank0": int(n_active), "wall_ms_per_step_incl_host": wall_step},
+        "config": workload_config(n_total, G_total, world),
+        "detail": {"active_hits_after_load_filters_rank0": int(n_active), "wall_ms_per_step_incl_host": wall_step, "stage_ms": [stage1_ms, stage2_ms]},
+        "parity": parity,
         "e2e": {"value": n_total / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "api": "pg_post_process + pg_graph_init + pg_graph_gen on malloc'd pg_data_t (lazy materialisation, as the CLI does); bytes are rank 0's, counted by the library: 48 B/hit + exons up, 24 B/hit + graph down"},
         "gpu_launches": int(launches),
@@ -244,11 +314,11 @@ def main():
         "clocks": clk.summary(),
     }
     if world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"], _ = cpu_reference_sample(hostio)
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+        out["cpu_baseline"] = cpu_reference(hostio, CPU_SAMPLE_GENOMES)[0]
+    print(json.dumps(out), flush=True)        # ONE line, flushed before the teardown below can go wrong
+    teardown()
+    return 0 if parity["status"] in ("ok",) or parity["status"].startswith("unchecked") else 1
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -23,31 +24,41 @@
 namespace pgx {
 
 class ThreadPool {
+	// One Job per parallel_for call.  A worker captures the shared_ptr of the job that is current when it wakes, under the mutex, and
+	// from then on touches only that object: a worker that wakes late finds either no job or a newer one, never the cursor of one call
+	// paired with the function of another (the function object lives on the caller's stack and dies when its call returns).
+	struct Job {
+		const std::function<void(int64_t)> *f;
+		int64_t n;
+		std::atomic<int64_t> next{0}, done{0};
+		Job(const std::function<void(int64_t)> *f_, int64_t n_) : f(f_), n(n_) { }
+	};
 	std::vector<std::thread> workers;
 	std::mutex mu;
 	std::condition_variable cv_work, cv_done;
-	const std::function<void(int64_t)> *job = nullptr;
-	int64_t n_items = 0;
-	std::atomic<int64_t> next{0};
-	int active = 0;
+	std::shared_ptr<Job> job;
 	uint64_t epoch = 0;
 	bool stop = false;
+	static void drain(Job &j)
+	{
+		int64_t mine = 0;
+		for (int64_t i; (i = j.next.fetch_add(1)) < j.n;) { (*j.f)(i); ++mine; }
+		if (mine) j.done.fetch_add(mine);
+	}
 	void loop()
 	{
 		uint64_t seen = 0;
 		for (;;) {
-			const std::function<void(int64_t)> *f;
+			std::shared_ptr<Job> j;
 			{
 				std::unique_lock<std::mutex> lk(mu);
 				cv_work.wait(lk, [&] { return stop || epoch != seen; });
 				if (stop) return;
-				seen = epoch; f = job; ++active;
+				seen = epoch; j = job;
 			}
-			for (int64_t i; (i = next.fetch_add(1)) < n_items;) (*f)(i);
-			{
-				std::unique_lock<std::mutex> lk(mu);
-				if (--active == 0) cv_done.notify_all();
-			}
+			if (!j) continue;
+			drain(*j);
+			if (j->done.load() >= j->n) { std::unique_lock<std::mutex> lk(mu); cv_done.notify_all(); }
 		}
 	}
 public:
@@ -66,21 +77,21 @@ public:
 		cv_work.notify_all();
 		for (auto &w : workers) w.join();
 	}
-	// run f(0..n-1) on the pool; the caller works too; returns when all items are done
+	// run f(0..n-1) on the pool; the caller works too; returns when every item has been executed (not merely claimed)
 	void parallel_for(int64_t n, const std::function<void(int64_t)> &f)
 	{
 		if (n <= 0) return;
 		if (n == 1 || workers.empty()) { for (int64_t i = 0; i < n; ++i) f(i); return; }
+		std::shared_ptr<Job> j = std::make_shared<Job>(&f, n);
 		{
 			std::unique_lock<std::mutex> lk(mu);
-			job = &f; n_items = n; next.store(0); ++epoch;
+			job = j; ++epoch;
 		}
 		cv_work.notify_all();
-		for (int64_t i; (i = next.fetch_add(1)) < n_items;) f(i);
+		drain(*j);
 		std::unique_lock<std::mutex> lk(mu);
-		// every worker that picked this epoch up has bumped `active`; workers that have not woken yet will find next >= n
-		cv_done.wait(lk, [&] { return active == 0; });
-		job = nullptr;
+		cv_done.wait(lk, [&] { return j->done.load() >= j->n; });
+		if (job == j) job.reset();
 	}
 	static ThreadPool &get() { static ThreadPool p; return p; }
 };

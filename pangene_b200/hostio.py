@@ -102,5 +102,18 @@ def write_bed(d, path, is_walk=False):
     return lib().pgio_write_bed(d, 1 if is_walk else 0, os.fsencode(path))
 
 
+def gfa_digest(graph):
+    """(md5 of the S and L lines in writer order, the W lines of the local genomes as bytes) -- what bench.py and the tests
+    compare with tests/golden/c3_golden.json; a sharded run concatenates the W bytes in rank order before hashing."""
+    import hashlib
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".gfa") as t:
+        write_gfa(graph, t.name, True, False)
+        sl = hashlib.md5(open(t.name, "rb").read()).hexdigest()
+        write_gfa(graph, t.name, False, True)
+        w = open(t.name, "rb").read()
+    return sl, w
+
+
 def destroy(d):
     lib().pgio_data_destroy(d)

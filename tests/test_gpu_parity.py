@@ -191,6 +191,24 @@ def test_full_size_properties():
     engine.destroy(g); hostio.destroy(d)
 
 
+def test_headline_config_matches_the_reference_golden():
+    """BASELINE.json configs[2] at FULL size (100 genomes x 200k hits, the configuration bench.py quotes its numbers on): the S/L
+    lines and the W lines of the GPU path, hashed, against tests/golden/c3_golden.json -- printed by the unmodified reference (stock
+    binary on the PAF files AND its objects in-process; tests/golden/make_golden_c3.py, ~6 min of one core).  Same gate as bench.py."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(common.GOLDEN, "c3_golden.json")))
+    opt = hostio.default_opt()
+    d = hostio.synth(opt, hostio.synth_params(3, n_genome=100, n_genome_total=100))
+    assert hostio.total_hits(d) == gold["n_hit"]
+    g = engine.hot_path(opt, d, lazy=True)
+    sl, w = hostio.gfa_digest(g)
+    assert (g.contents.n_seg, g.contents.n_arc, w.count(b"\n")) == (gold["n_S"], gold["n_L"], gold["n_W"])
+    assert sl == gold["sl_md5"]
+    assert hashlib.md5(w).hexdigest() == gold["w_md5"]
+    engine.destroy(g); hostio.destroy(d)
+
+
 def test_tie_detector_reports_zero_on_goldens():
     case = common.synth_golden()["euk_iso4"]
     opt, d = common.synth_case_data(case)
