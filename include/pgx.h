@@ -79,6 +79,8 @@ typedef struct {
 	int64_t  tie[4];              /* tie-order detector, same meaning as oracle pgo_tie_report() */
 	int32_t  n_seg, n_arc;
 	int64_t  h2d_bytes, d2h_bytes;
+	int32_t  fast_rounds;         /* pg_gen_arc calls of the last runs that took the sync-free path (pgx_round.cuh) */
+	int32_t  redo;                /* runs redone on the careful path (table overflow, or a round that needs the reference's tie order) */
 } pgx_stats_t;
 void pgx_get_stats(pgx_stats_t *out);
 void pgx_reset_stats(void);

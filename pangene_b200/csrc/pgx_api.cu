@@ -185,6 +185,7 @@ void pgx_get_stats(pgx_stats_t *o)
 	o->n_hit = g_stats.n_hit; o->n_active = g_stats.n_active;
 	for (int i = 0; i < 4; ++i) o->tie[i] = g_stats.tie[i];
 	o->n_seg = g_stats.n_seg; o->n_arc = g_stats.n_arc; o->h2d_bytes = g_stats.h2d; o->d2h_bytes = g_stats.d2h;
+	o->fast_rounds = g_stats.fast_rounds; o->redo = g_stats.redo;
 }
 void pgx_reset_stats(void) { g_launch.launches = 0; g_stats = Stats(); }
 void pgx_set_sweep_stat(int on) { g_sweep_stat = on; }

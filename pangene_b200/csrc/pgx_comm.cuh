@@ -19,8 +19,10 @@ struct Comm {
 	int (*CommDestroy)(void*) = nullptr;
 	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
 	int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(int) = nullptr;
-	enum { T_INT8 = 0, T_INT32 = 2, T_UINT32 = 3, T_INT64 = 4, T_UINT64 = 5 };   // ncclDataType_t
+	enum { T_INT8 = 0, T_UINT8 = 1, T_INT32 = 2, T_UINT32 = 3, T_INT64 = 4, T_UINT64 = 5 };   // ncclDataType_t
 	enum { OP_SUM = 0, OP_MAX = 2 };                                              // ncclRedOp_t
 
 	bool load()
@@ -35,10 +37,15 @@ struct Comm {
 		AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
 		AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
 		GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-		return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather;
+		GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+		GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
+		return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GroupStart && GroupEnd;
 	}
 	void check(int r, const char *what) { if (r != 0) PGX_FATAL("NCCL %s failed: %s", what, GetErrorString? GetErrorString(r) : "?"); }
 	bool active() const { return nranks > 1; }
+	// several collectives as one launch (ncclGroupStart/End)
+	void group_begin() { if (active()) check(GroupStart(), "group start"); }
+	void group_end() { if (active()) check(GroupEnd(), "group end"); }
 	void allreduce(void *buf, size_t count, int type, int op, cudaStream_t s) { if (active() && count) check(AllReduce(buf, buf, count, type, op, comm, s), "allreduce"); }
 	// every rank contributes `bytes` bytes; out holds nranks * bytes
 	void allgather(const void *in, void *out, size_t bytes, cudaStream_t s)

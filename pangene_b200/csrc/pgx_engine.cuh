@@ -17,6 +17,7 @@
 #include "pgx_scan.cuh"
 #include "pgx_sort.cuh"
 #include "pgx_kernels.cuh"
+#include "pgx_round.cuh"
 #include "pgx_comm.cuh"
 #include "pgx_host.hpp"
 #include "pgx_hostpipe.hpp"
@@ -28,7 +29,7 @@ namespace pgx {
 struct Stats {
 	double sweep_ms = 0, sweep_bytes = 0, run_ms[3] = {0, 0, 0};
 	int64_t n_hit = 0, n_active = 0, tie[4] = {0, 0, 0, 0}, h2d = 0, d2h = 0;
-	int32_t n_seg = 0, n_arc = 0;
+	int32_t n_seg = 0, n_arc = 0, fast_rounds = 0, redo = 0;
 };
 extern Stats g_stats;
 extern int g_sweep_stat;
@@ -248,7 +249,7 @@ struct Session {
 	}
 
 	// one sweep launch: the TMA-tiled kernel; PGX_SWEEP=global selects the plain thread-per-hit kernel (debugging / A-B timing)
-	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out)
+	template<int MODE> void launch_sweep(const SweepCols &c, const SweepOpt &so, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, const uint32_t *dirty = nullptr)
 	{
 		static const bool plain = []() { const char *e = getenv("PGX_SWEEP"); return e && strcmp(e, "global") == 0; }();
 		if (c.n <= 0) return;
@@ -264,7 +265,7 @@ struct Session {
 			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 			attr_set = true;
 		}
-		PGX_LAUNCH(k_sweep_tiled<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP);
+		PGX_LAUNCH(k_sweep_tiled<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
 	}
 
 	// stable radix sort of n (key, iota) pairs taken from the scratch arena; returns the permutation (device pointer valid until the arena is reset)
@@ -895,9 +896,194 @@ struct Session {
 		PGX_LAUNCH(k_set_first, grid_for(n_first, TB), TB, 0, st, first_flagged.p, first_target.p + (size_t)m * n_first, n_first, first_grp.p, goff_act.p, A.full, A.bits);
 	}
 
+
+	// ------------------------------------------------------------------------------------------------
+	// the sync-free rounds (pgx_round.cuh): buffers allocated once per run, pointers stable across rounds
+	// ------------------------------------------------------------------------------------------------
+	struct Fast {
+		bool on = false;
+		int32_t NV = 0, tiles_hit = 0, tiles_vtx = 0;
+		uint32_t H = 0, H2 = 0, ovf_cap = 0, arc_cap = 0, nl_cap = 0, part_cap = 0;
+		size_t bm_words = 0, lb_bytes = 0, seen_words = 0, dirty_words = 0;
+		DBuf<unsigned long long> lkey, gkey, l2key, l2dsum, lb, nl_total;
+		DBuf<ArcAcc> lacc, gacc;
+		DBuf<uint32_t> llist, glist, bm, l2n, l2list, degcur, off, nl_off, seg_seen, spos, svcs, tie_list, dirty;
+		DBuf<int32_t> l2m, segocc, t_last, grp;
+		DBuf<PairRec> rec; DBuf<OvfRec> ovf; DBuf<uint8_t> nl; DBuf<GenePos> gpos; DBuf<SegDev> seg_tmp; DBuf<ArcDev> arc_tmp; DBuf<ArcPartial> all;
+		ArcTable loc, glob; OvfTable l2;
+		unsigned long long *st_cm = nullptr, *st_vs = nullptr, *st_cs = nullptr; uint32_t *tk_cm = nullptr, *tk_vs = nullptr, *tk_cs = nullptr;
+		bool use_dirty = false;
+	} fast;
+	bool force_careful = false;
+
+	void clear_launch(const ClearList &c) { if (c.n) PGX_LAUNCH(k_round_clear, 148 * 4, 256, 0, st, c); }
+	DirtyCols dirty_cols() const
+	{
+		DirtyCols D; D.ctg = A.ctg; D.cs = A.cs; D.ce = A.ce; D.pmax = A.pmax; D.n = Nw; D.tiles = fast.use_dirty? fast.dirty.p : nullptr; D.tile = SWQ_TILE;
+		return D;
+	}
+
+	// Sizes the tables of the fast rounds from the round-2 graph (one read-back per run) and builds idx / degrees / pair offsets for
+	// the first branch round.  Every decision here depends on replicated values only, so all ranks decide alike.
+	bool setup_fast(const pg_opt_t *opt)
+	{
+		fast.on = false;
+		static const bool env_careful = []() { const char *e = getenv("PGX_ROUNDS"); return e && strcmp(e, "careful") == 0; }();
+		if (env_careful || force_careful || opt->n_branch_flt <= 0 || n_seg0 == 0) return false;
+		arc_index();                                                                     // graph.c:306 of the first round
+		const uint32_t n_arc2 = read_counts().n_arc;
+		Fast &f = fast;
+		f.NV = 2 * n_seg0;
+		uint64_t want = 3ull * n_arc2; if (want < (1u << 16)) want = 1u << 16;
+		uint32_t H = 1u << 16; while (H < want && H < (1u << 30)) H <<= 1;
+		int Gmax = 0; for (int g : rank_G) Gmax = g > Gmax? g : Gmax;
+		if ((uint64_t)H * (uint64_t)(Gmax > 0? Gmax : 1) / 8 > ((uint64_t)1 << 30)) return false;   // (key, genome) marks beyond 1 GB: stay on the sort path
+		f.H = H; f.H2 = 1u << 20; f.ovf_cap = 1u << 19;
+		f.bm_words = ((size_t)H * (size_t)(G > 0? G : 1) + 31) / 32;
+		f.bm_words = (f.bm_words + 3) & ~(size_t)3;
+		const bool multi = g_comm.active();
+		f.lkey.ensure(H); f.lacc.ensure(H); f.llist.ensure(H); f.bm.ensure(2 * f.bm_words);
+		f.loc.key = f.lkey.p; f.loc.acc = f.lacc.p; f.loc.list = f.llist.p; f.loc.bm1 = f.bm.p; f.loc.bm2 = f.bm.p + f.bm_words; f.loc.H = H;
+		f.glob = f.loc;
+		if (multi) {
+			f.gkey.ensure(H); f.gacc.ensure(H); f.glist.ensure(H);
+			f.glob.key = f.gkey.p; f.glob.acc = f.gacc.p; f.glob.list = f.glist.p; f.glob.bm1 = f.glob.bm2 = nullptr;
+			f.part_cap = n_arc2 + n_arc2 / 4 + 4096; if (f.part_cap > H / 2) f.part_cap = H / 2;
+			f.all.ensure((size_t)g_comm.nranks * (f.part_cap + 1));
+		}
+		f.l2key.ensure(f.H2); f.l2dsum.ensure(f.H2); f.l2n.ensure(f.H2); f.l2list.ensure(f.H2); f.l2m.ensure(2 * (size_t)f.H2);
+		f.l2.key = f.l2key.p; f.l2.dsum = f.l2dsum.p; f.l2.n = f.l2n.p; f.l2.list = f.l2list.p; f.l2.m1 = f.l2m.p; f.l2.m2 = f.l2m.p + f.H2; f.l2.H = f.H2;
+		PGX_CHECK(cudaMemsetAsync(f.l2key.p, 0xff, (size_t)f.H2 * 8, st)); PGX_CHECK(cudaMemsetAsync(f.l2dsum.p, 0, (size_t)f.H2 * 8, st));
+		PGX_CHECK(cudaMemsetAsync(f.l2n.p, 0, (size_t)f.H2 * 4, st)); PGX_CHECK(cudaMemsetAsync(f.l2m.p, 0, (size_t)f.H2 * 8, st));
+		const size_t nw1 = (size_t)Nw + 16, tab = (size_t)n_gene * (size_t)(G > 0? G : 1);
+		f.rec.ensure(nw1); f.ovf.ensure(f.ovf_cap); f.spos.ensure(nw1 + 2); f.svcs.ensure(nw1); f.tie_list.ensure(nw1);
+		f.degcur.ensure(2 * (size_t)f.NV + 8); f.off.ensure((size_t)f.NV + 8); f.nl_off.ensure((size_t)f.NV + 8); f.nl_total.ensure(2);
+		f.seen_words = (((size_t)(G > 0? G : 1) * n_seg0 + 31) / 32 + 4) & ~(size_t)3;
+		f.seg_seen.ensure(f.seen_words); f.segocc.ensure(2 * (size_t)n_seg0 + 4);
+		f.t_last.ensure(tab + 4); f.gpos.ensure(tab + 1); f.seg_tmp.ensure((size_t)n_seg0 + 1);
+		f.dirty_words = ((size_t)Nw / SWQ_TILE / 32 + 8) & ~(size_t)3;
+		f.dirty.ensure(f.dirty_words);
+		f.tiles_hit = (int32_t)(((size_t)Nw + 1 + SCAN_TILE - 1) / SCAN_TILE); f.tiles_vtx = (int32_t)(((size_t)f.NV + 1 + SCAN_TILE - 1) / SCAN_TILE);
+		const size_t lb_words = 2 * (size_t)f.tiles_hit + 2 * (size_t)f.tiles_vtx + 4;
+		f.lb.ensure(lb_words); f.lb_bytes = lb_words * 8;
+		f.st_cm = f.lb.p; f.st_cs = f.st_cm + f.tiles_hit; f.st_vs = f.st_cs + f.tiles_hit;
+		f.tk_cm = (uint32_t*)(f.st_vs + 2 * (size_t)f.tiles_vtx); f.tk_vs = f.tk_cm + 1; f.tk_cs = f.tk_cm + 2;
+		uint32_t need_arc = H / 2 > n_arc2 + 16? H / 2 : n_arc2 + 16;
+		if (arc.n < (size_t)need_arc + 1) {   // the merged graph of a sharded run can exceed this rank's own bound; keep the round-2 arcs
+			DBuf<ArcDev> bigger; bigger.alloc((size_t)need_arc + 1);
+			if (n_arc2) PGX_CHECK(cudaMemcpyAsync(bigger.p, arc.p, (size_t)n_arc2 * sizeof(ArcDev), cudaMemcpyDeviceToDevice, st));
+			PGX_CHECK(cudaStreamSynchronize(st));
+			arc.swap(bigger); arc_alt.alloc((size_t)need_arc + 1); arc_cap = arc.n - 1;
+		}
+		f.arc_cap = (uint32_t)(arc.n - 1);
+		f.arc_tmp.ensure((size_t)f.arc_cap + 1); f.grp.ensure((size_t)f.arc_cap + 1);
+		f.use_dirty = n_first == 0 && !(getenv("PGX_SWEEP") && strcmp(getenv("PGX_SWEEP"), "global") == 0) && !getenv("PGX_NO_DIRTY");
+		PGX_CHECK(cudaMemsetAsync(f.dirty.p, 0, f.dirty_words * 4, st));
+		PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, fallback)), 0u);
+		PGX_CHECK(cudaMemsetAsync(f.lb.p, 0, f.lb_bytes, st));
+		PGX_CHECK(cudaMemsetAsync(f.nl_total.p, 0, 16, st));
+		// degrees and pair offsets of the round-2 graph (the later rounds get them from their own arc build)
+		uint32_t *deg = f.degcur.p;
+		PGX_LAUNCH(k_deg_from_idx, GS_GRID, TB, 0, st, idx.p, f.NV, dc.p, deg);
+		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, 0xffffffffu, f.nl_total.p, f.st_vs, f.tk_vs);
+		unsigned long long h_tot = 0;
+		PGX_CHECK(cudaMemcpyAsync(&h_tot, f.nl_total.p, 8, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		if (h_tot > (1ull << 29)) return false;                                           // half a billion arc pairs: not the regime this path is for
+		f.nl_cap = (uint32_t)(2 * h_tot + (1u << 20));
+		f.nl.ensure((size_t)f.nl_cap + 16);
+		PGX_CHECK(cudaMemsetAsync(f.nl.p, 0, f.nl.n, st));
+		PGX_CHECK(cudaMemsetAsync(f.lb.p, 0, f.lb_bytes, st));
+		fast.on = true;
+		return true;
+	}
+
+	// graph.c:87-177 without sorting the records and without a host round trip (pgx_round.cuh)
+	void gen_arc_fast(const pg_opt_t *opt)
+	{
+		Fast &f = fast;
+		set_first_for_this_call();
+		const bool multi = g_comm.active();
+		uint32_t *deg = f.degcur.p, *cur = f.degcur.p + f.NV;
+		ClearList cl; cl.n = 0;
+		clear_add(cl, f.lb.p, f.lb_bytes, 0u);
+		clear_add(cl, f.segocc.p, 2 * (size_t)n_seg0 * 4, 0u);
+		clear_add(cl, f.seg_seen.p, f.seen_words * 4, 0u);
+		clear_add(cl, f.lkey.p, (size_t)f.H * 8, 0xffffffffu);
+		clear_add(cl, f.lacc.p, (size_t)f.H * sizeof(ArcAcc), 0u);
+		clear_add(cl, f.bm.p, 2 * f.bm_words * 4, 0u);
+		clear_add(cl, f.degcur.p, 2 * (size_t)f.NV * 4, 0u);
+		clear_add(cl, idx.p, (size_t)n_seg0 * 16, 0u);
+		clear_add(cl, f.nl_total.p, 16, 0u);
+		if (multi) { clear_add(cl, f.gkey.p, (size_t)f.H * 8, 0xffffffffu); clear_add(cl, f.gacc.p, (size_t)f.H * sizeof(ArcAcc), 0u); }
+		clear_launch(cl);
+		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
+		launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits, A.pdom, nullptr, f.use_dirty? f.dirty.p : nullptr);   // in place: a sweep reads flt / weak_br / rev of its partners, writes its own shadow bit
+		PGX_LAUNCH(k_compact_survivors, f.tiles_hit, SCAN_B, 0, st, A.bits, by_cm.p, Nw, (uint32_t*)nullptr, sv.p, dcp(offsetof(DevCounts, m_sv)), f.st_cm, f.tk_cm, dc.p);
+		ArcSrc e; e.sv = sv.p; e.ctg = A.ctg; e.cm = A.cm; e.gidp = A.gidp; e.sori = A.sori; e.sdom = A.sdom; e.pdom0 = A.pdom0; e.bits = A.bits;
+		e.g2s = g2s.p; e.prot_gid = prot_gid.p; e.ctg2g = ctg2g.p; e.use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH); e.n_seg0 = n_seg0; e.Gl = G > 0? G : 1;
+		int32_t *seg_ng_f = f.segocc.p, *seg_tot_f = f.segocc.p + n_seg0;
+		PGX_LAUNCH(k_arc_insert, GS_GRID, TB, 0, st, e, f.loc, dc.p, f.rec.p, f.seg_seen.p, seg_ng_f, seg_tot_f, multi? (uint32_t*)nullptr : deg, counters.p + C_TIE_CM, counters.p + C_ERR);
+		PGX_LAUNCH(k_arc_fold, GS_GRID, TB, 0, st, f.rec.p, f.loc, dc.p, e.Gl, f.ovf.p, f.ovf_cap);
+		PGX_LAUNCH(k_arc_ovf_insert, 148, TB, 0, st, f.ovf.p, f.ovf_cap, f.l2, dc.p);
+		PGX_LAUNCH(k_arc_ovf_fold, 148, TB, 0, st, f.l2, f.loc, dc.p);
+		if (multi) {
+			ArcPartial *mine = f.all.p + (size_t)g_comm.rank * (f.part_cap + 1);
+			PGX_LAUNCH(k_arc_pack, GS_GRID, TB, 0, st, f.loc, dc.p, mine, f.part_cap);
+			g_comm.group_begin();
+			g_comm.allgather(mine, f.all.p, (size_t)(f.part_cap + 1) * sizeof(ArcPartial), st);
+			g_comm.allreduce(f.segocc.p, 2 * (size_t)n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
+			g_comm.group_end();
+			PGX_LAUNCH(k_arc_merge, GS_GRID, TB, 0, st, f.all.p, g_comm.nranks, f.part_cap, f.glob, dc.p, deg);
+		}
+		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, f.arc_cap, f.nl_total.p, f.st_vs, f.tk_vs);
+		PGX_LAUNCH(k_arc_place, GS_GRID, TB, 0, st, f.glob, dcp(multi? offsetof(DevCounts, n_gpart) : offsetof(DevCounts, n_part)), f.off.p, cur, dc.p, f.arc_tmp.p);
+		PGX_LAUNCH(k_arc_rank, GS_GRID, TB, 0, st, f.arc_tmp.p, f.off.p, dc.p, arc.p, idx.p);
+		PGX_LAUNCH(k_seg_store_occ_fast, 148, TB, 0, st, seg.p, dc.p, seg_ng_f, seg_tot_f);
+		++g_stats.fast_rounds;
+	}
+
+	// branch.c:48-145 + graph.c:309-313, same rules as branch_round() below; idx / nl_off come from the preceding arc build
+	void branch_round_fast(const pg_opt_t *opt, int32_t round, int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)
+	{
+		Fast &f = fast;
+		const size_t tab = (size_t)n_gene * G;
+		ClearList cl; cl.n = 0;
+		clear_add(cl, f.t_last.p, (tab + 1) * 4, 0xffffffffu);
+		clear_add(cl, counters.p + C_TIE_ROUND, 16, 0u);
+		clear_add(cl, f.dirty.p, f.dirty_words * 4, 0u);
+		clear_launch(cl);
+		PGX_LAUNCH(k_compact_survivors, f.tiles_hit, SCAN_B, 0, st, A.bits, (const uint32_t*)nullptr, Nw, f.spos.p, f.svcs.p, dcp(offsetof(DevCounts, m_cs)), f.st_cs, f.tk_cs, (DevCounts*)nullptr);
+		if (Nw) PGX_LAUNCH(k_pos_last, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, f.spos.p, Nw, G, f.t_last.p);
+		if (tab) PGX_LAUNCH(k_pos_fill, grid_for((int64_t)tab, TB), TB, 0, st, f.t_last.p, tab, G, A.ctg, A.cm, f.spos.p, goff_act.p, f.gpos.p);
+		PGX_LAUNCH(k_cs_tie_mark, GS_GRID, TB, 0, st, A.ctg, A.cs, A.gidp, ctg2g.p, G, f.svcs.p, dc.p, f.t_last.p, f.gpos.p, counters.p + C_TIE_CS, counters.p + C_TIE_ROUND, f.tie_list.p, counters.p + C_LONG_RUN);
+		BranchOpt bo; bo.local_dist = opt->local_dist; bo.local_count = opt->local_count; bo.frag_mode = !!(opt->flag & PG_F_FRAG_MODE);
+		bo.branch_diff = opt->branch_diff; bo.branch_diff_dist = opt->branch_diff_dist; bo.branch_diff_cut = opt->branch_diff_cut;
+		PGX_LAUNCH(k_branch_local, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, f.gpos.p, G, f.nl_off.p, f.NV, f.nl_cap, f.nl_total.p, bo, f.nl.p, counters.p + C_ORD_SENS);
+		g_comm.allreduce(f.nl.p, f.nl_cap, Comm::T_UINT8, Comm::OP_SUM, st);
+		PGX_LAUNCH(k_branch_decide_fast, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, f.nl_off.p, f.nl.p, f.nl_cap, f.nl_total.p, bo, f.grp.p, counters.p + C_TIE_ROUND);
+		PGX_LAUNCH(k_branch_hits_fast, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, idx.p, dirty_cols(), counters.p + C_BR_CHANGED);
+		if (round > 0) {                                                                  // graph.c:310-313
+			PGX_LAUNCH(k_seg_filter, 1, SEGF_B, 0, st, seg.p, f.seg_tmp.p, dc.p, idx.p, max_avg_occ * Gtot, max_degree, max_dist_loci, g2s.p, n_gene);
+			if (Nw) PGX_LAUNCH(k_flag_vtx_fast, GS_GRID, TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols());
+		}
+	}
+
 	void stage_graph(const pg_opt_t *opt)
 	{
 		if (!done_post) PGX_FATAL("pg_graph_gen() called before pg_post_process()");
+		if (stage_graph_impl(opt, true)) return;
+		// a fixed-capacity table of the fast rounds overflowed, or a round needs the reference's order of cs-tied survivors: the same run again
+		// from the raw hits, every round on the careful path (host-sized sorts, per-round read-backs, chain replay)
+		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] redoing the run on the careful path\n");
+		++g_stats.redo;
+		PGX_CHECK(cudaMemsetAsync(counters.p, 0, C_N * 4, st));
+		stage_load(opt);
+		stage_post(opt);
+		if (!stage_graph_impl(opt, false)) PGX_FATAL("careful path asked for a redo");
+	}
+	bool stage_graph_impl(const pg_opt_t *opt, bool allow_fast)
+	{
 		set_filter(SF_PSEUDO);                                                           // graph.c:285
 		gen_vtx(opt);                                                                    // graph.c:286
 		prepare_first_replay(opt);
@@ -908,6 +1094,8 @@ struct Session {
 		flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);     // graph.c:294-295
 		recompact_active();
 		gen_arc(opt);                                                                    // graph.c:296
+		force_careful = !allow_fast;
+		const bool use_fast = setup_fast(opt);
 		for (int32_t i = 0; i < opt->n_branch_flt; ++i) {                                // graph.c:301-315
 			double r = 1.0 + (double)(opt->n_branch_flt - 1 - i) / opt->n_branch_flt;
 			int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
@@ -917,14 +1105,21 @@ struct Session {
 			uint32_t seg_before = 0;
 			if (trace) { seg_before = read_counts().n_seg; PGX_CHECK(cudaMemsetAsync(counters.p + C_BR_CHANGED, 0, 4, st)); }
 			branch_round_no = i;
-			branch_round(opt);
-			if (i > 0) flt_high_occ(max_avg_occ, max_degree, max_dist_loci);
-			if (trace) {   // how much does a round change?  (a round that changes nothing could skip the pg_gen_arc below)
+			if (use_fast) branch_round_fast(opt, i, max_avg_occ, max_degree, max_dist_loci);
+			else {
+				branch_round(opt);
+				if (i > 0) flt_high_occ(max_avg_occ, max_degree, max_dist_loci);
+			}
+			if (trace) {   // how much does a round change?
 				const uint32_t chg = read_u32(counters.p + C_BR_CHANGED);
 				DevCounts hc = read_counts();
-				fprintf(stderr, "[pgx timing] branch round %d: %u hit words changed, segments %u -> %u, arcs %u, survivors %u\n", i, chg, seg_before, hc.n_seg, hc.n_arc, hc.m_sv);
+				fprintf(stderr, "[pgx timing] branch round %d: %u hit words changed, segments %u -> %u, arcs %u, survivors %u, arc pairs %u, overflow records %u, fallback %u\n", i, chg, seg_before, hc.n_seg, hc.n_arc, hc.m_sv, hc.n_nl, hc.n_ovf, hc.fallback);
 			}
-			gen_arc(opt);
+			if (use_fast) gen_arc_fast(opt); else gen_arc(opt);
+		}
+		if (use_fast) {
+			if (g_comm.active()) g_comm.allreduce(dcp(offsetof(DevCounts, fallback)), 1, Comm::T_UINT32, Comm::OP_MAX, st);
+			if (read_counts().fallback) { fast.on = false; return false; }
 		}
 		set_filter(SF_SHADOW);                                                           // graph.c:316
 		DevCounts hc = read_counts();
@@ -947,6 +1142,7 @@ struct Session {
 		g_stats.n_seg = n_seg; g_stats.n_arc = n_arc;
 		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] rank %d stage 2 host wall: arc rounds %.2f ms (of which cross-rank merge %.2f), branch rounds %.2f ms\n", g_comm.rank, t_arc * 1e3, t_merge * 1e3, t_branch * 1e3);
 		t_arc = t_merge = t_branch = 0;
+		return true;
 	}
 
 	void collect_stats()

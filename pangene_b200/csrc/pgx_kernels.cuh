@@ -3,6 +3,7 @@
 // formulation they implement is spelled out (and pinned against the compiled reference) in oracle/pg_oracle.c.
 #pragma once
 #include "pgx_util.cuh"
+#include "pgx_graphtypes.cuh"
 #include "pangene_abi.h"
 
 namespace pgx {
@@ -470,8 +471,11 @@ template<bool EARLY> __device__ __forceinline__ int32_t pair_overlap(const int2 
 	return walk_exons<EARLY>(g_ex + b0, g_ex + e0, cs0, g_ex + b1, g_ex + e1, cs1, need);
 }
 
-template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt)
+// dirty (optional, SW_SHADOW with bits_out == c.bits): one bit per tile; a tile whose bit is clear holds no hit whose inputs changed since the
+// previous sweep (pgx_round.cuh: mark_dirty) and keeps its shadow bits and dominators.
+template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt, const uint32_t *dirty)
 {
+	if (dirty && !(dirty[blockIdx.x >> 5] >> (blockIdx.x & 31) & 1u)) return;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	unsigned char *sp = smem_raw;
 	uint64_t *s_key = (uint64_t*)sp; sp += (size_t)SWQ_STG * 8;
@@ -1051,10 +1055,7 @@ __global__ void k_compact_idx(const uint32_t *__restrict__ pos, const uint32_t *
 	if (k < n && pos[k + 1] != pos[k]) out[pos[k]] = src? src[k] : (uint32_t)k;
 }
 
-// Logical sizes that change from round to round live ON THE DEVICE: kernels read them through this struct and are launched
-// with capacity-sized (or fixed, grid-stride) grids, so a whole arc/branch round is enqueued without a host round-trip.
-struct DevCounts { uint32_t m_sv, n_part, n_arc, n_seg, n_nl, m_cs, pad0, pad1; };
-#define PGX_GS(i, n) for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x, gs_n_ = (int32_t)(n), gs_s_ = gridDim.x * blockDim.x; i < gs_n_; i += gs_s_)
+// (DevCounts, PGX_GS, ArcPartial, ArcDev, SegDev, GenePos, BranchOpt: pgx_graphtypes.cuh)
 __global__ void k_copy_u32(uint32_t *dst, const uint32_t *src) { *dst = *src; }
 __global__ void k_set_u32(uint32_t *dst, uint32_t v) { *dst = v; }
 
@@ -1110,8 +1111,6 @@ __global__ void k_arc_emit(ArcEmit e, const DevCounts *__restrict__ dc, uint64_t
 	}
 }
 
-// partial arc = sums over the LOCAL genomes of one key (graph.c:128-145 per genome, then the additive part of 153-163)
-struct ArcPartial { uint64_t x; int64_t sum_dist, sum_s1, sum_s2; int32_t n_genome, tot_cnt; };
 
 __global__ void k_arc_heads(const uint64_t *__restrict__ key, int32_t n, uint32_t *flag)
 {
@@ -1172,7 +1171,6 @@ __global__ void k_partial_heads(const ArcPartial *__restrict__ in, int32_t n, ui
 	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p < n) flag[p] = (p == 0 || in[p - 1].x != in[p].x)? 1u : 0u;
 }
-struct ArcDev { uint64_t x; int32_t n_genome, tot_cnt, avg_dist, s1, s2; uint32_t bits; };   // == pg_arc_t
 __global__ void k_arc_finalize(const ArcPartial *__restrict__ in, int32_t n, const uint32_t *__restrict__ pos, ArcDev *arc)
 {
 	int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1181,32 +1179,20 @@ __global__ void k_arc_finalize(const ArcPartial *__restrict__ in, int32_t n, con
 	for (int32_t q = p + 1; q < n && in[q].x == a.x; ++q) {
 		a.sum_dist += in[q].sum_dist; a.sum_s1 += in[q].sum_s1; a.sum_s2 += in[q].sum_s2; a.n_genome += in[q].n_genome; a.tot_cnt += in[q].tot_cnt;
 	}
-	ArcDev o;
-	o.x = a.x; o.n_genome = a.n_genome; o.tot_cnt = a.tot_cnt; o.bits = 0;
-	o.avg_dist = (int32_t)(long long)((double)a.sum_dist / a.tot_cnt + .499);           // graph.c:170
-	o.s1 = (int32_t)((double)a.sum_s1 / a.n_genome + .499);                             // graph.c:171
-	o.s2 = (int32_t)((double)a.sum_s2 / a.n_genome + .499);                             // graph.c:172
-	arc[pos[p]] = o;
+	arc[pos[p]] = arc_finalize(a);
 }
 
 // single-GPU: every partial already is a complete arc (keys are unique after the reduction)
 __global__ void k_arc_finalize_direct(const ArcPartial *__restrict__ in, const DevCounts *__restrict__ dc, ArcDev *arc)
 {
 	PGX_GS(p, dc->n_part) {
-		ArcPartial a = in[p];
-		ArcDev o;
-		o.x = a.x; o.n_genome = a.n_genome; o.tot_cnt = a.tot_cnt; o.bits = 0;
-		o.avg_dist = (int32_t)(long long)((double)a.sum_dist / a.tot_cnt + .499);       // graph.c:170
-		o.s1 = (int32_t)((double)a.sum_s1 / a.n_genome + .499);                         // graph.c:171
-		o.s2 = (int32_t)((double)a.sum_s2 / a.n_genome + .499);                         // graph.c:172
-		arc[p] = o;
+		arc[p] = arc_finalize(in[p]);
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
 // small graph edits (graph.c:179-263)
 // ------------------------------------------------------------------------------------------------
-struct SegDev { int32_t gid, n_dom, n_sub, n_genome, tot_cnt; uint32_t del; int32_t n_dist_loci[2]; };   // == pg_seg_t
 
 __global__ void k_arc_index(const ArcDev *__restrict__ arc, const DevCounts *__restrict__ dc, unsigned long long *idx)   // graph.c:202-211
 {
@@ -1276,7 +1262,6 @@ __global__ void k_pos_last(const int32_t *__restrict__ ctg, const int32_t *__res
 	if (i >= n || surv_pos[i + 1] == surv_pos[i]) return;
 	atomicMax(&t_last[(size_t)(gidp[i] >> 1) * G + ctg2g[ctg[i]]], i);                 // layout [gene][genome]: n_local reads are contiguous
 }
-struct GenePos { int32_t cid, ord, cm, pad; };                  // cid < 0: absent
 __global__ void k_pos_fill(const int32_t *__restrict__ t_last, size_t n_tab, int32_t G, const int32_t *__restrict__ ctg, const int32_t *__restrict__ cm, const uint32_t *__restrict__ surv_pos,
 	const int32_t *__restrict__ goff_act, GenePos *pos)
 {
@@ -1355,7 +1340,6 @@ __global__ void k_branch_count(const unsigned long long *__restrict__ idx, int32
 	}
 }
 
-struct BranchOpt { int32_t local_dist, local_count, frag_mode; double branch_diff, branch_diff_dist, branch_diff_cut; };
 
 __device__ __forceinline__ uint32_t tri_index(uint32_t i, uint32_t k, uint32_t n) { return i * n - i * (i - 1) / 2 + (k - i); }   // i <= k
 

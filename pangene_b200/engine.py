@@ -16,7 +16,7 @@ class pgx_stats_t(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("sweep_ms", C.c_double), ("sweep_bytes", C.c_double),
                 ("run_ms", C.c_double * 3), ("n_hit", C.c_int64), ("n_active", C.c_int64),
                 ("tie", C.c_int64 * 4), ("n_seg", C.c_int32), ("n_arc", C.c_int32),
-                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("fast_rounds", C.c_int32), ("redo", C.c_int32)]
 
 
 def lib():

@@ -17,10 +17,11 @@ extern "C" int sweep_emu(int variant, int mode, const EmuCols *e, double min_ov_
 	c.key = e->key; c.bits = e->bits; c.eoff = e->eoff; c.ex = (const int2*)e->ex;
 	SweepOpt o; o.min_ov_ratio = min_ov_ratio; o.check_strand = check_strand;
 	if (c.n <= 0) return 0;
-#define RUN(K, T) emu::launch((c.n + (T) - 1) / (T), (T), [&] { K(c, o, bits_out, pdom_out, sdom_out, tie_cnt); })
-#define BY_MODE(K, T) do { if (mode == 0) RUN(K<SW_LOAD>, T); else if (mode == 1) RUN(K<SW_SHADOW>, T); else RUN(K<SW_ISO>, T); } while (0)
+#define RUN(K, T, ...) emu::launch((c.n + (T) - 1) / (T), (T), [&] { K(c, o, bits_out, pdom_out, sdom_out, tie_cnt __VA_ARGS__); })
+#define BY_MODE(K, T, ...) do { if (mode == 0) RUN(K<SW_LOAD>, T, __VA_ARGS__); else if (mode == 1) RUN(K<SW_SHADOW>, T, __VA_ARGS__); else RUN(K<SW_ISO>, T, __VA_ARGS__); } while (0)
+#define COMMA ,
 	if (variant == 0) BY_MODE(k_sweep, 128);                   // plain thread-per-hit kernel
-	else if (variant == 1) BY_MODE(k_sweep_tiled, SWQ_TILE);   // production kernel
+	else if (variant == 1) BY_MODE(k_sweep_tiled, SWQ_TILE, COMMA (const uint32_t*)nullptr);   // production kernel (no tile skipping)
 	else return -1;
 	return 0;
 }
@@ -138,6 +139,137 @@ def build_prim():
     return so
 
 
+ROUND_DRIVER = r'''
+// host driver in the shape of Session::gen_arc_fast (pgx_engine.cuh): one arc build of `ranks` virtual ranks that own consecutive genome
+// ranges of the same survivor list; the allgather between k_arc_pack and k_arc_merge is a memcpy
+struct EmuArcIn {
+	int32_t n_hit, n_sv, n_seg0, n_gene, G, use_ori, grid, H, H2, ovf_cap, arc_cap, ranks;
+	const uint32_t *sv, *bits; const int32_t *ctg, *cm, *gidp, *sori, *sdom, *pdom0, *g2s, *prot_gid, *ctg2g;
+	pgx::ArcDev *arc; unsigned long long *idx; int32_t *seg_ng, *seg_tot; uint32_t *nl_off; uint32_t *out_counts;   // out_counts: n_arc, n_nl, fallback, n_ovf
+};
+extern "C" int round_emu_arc_build(const EmuArcIn *in)
+{
+	using namespace pgx;
+	const int NV = 2 * in->n_seg0, R = in->ranks, TBk = 256, grid = in->grid;
+	std::vector<DevCounts> dcs(R);
+	std::vector<std::vector<unsigned long long>> lkey(R), gkey(R);
+	std::vector<std::vector<ArcAcc>> lacc(R), gacc(R);
+	std::vector<std::vector<uint32_t>> llist(R), glist(R), bm(R), degcur(R), seen(R);
+	std::vector<std::vector<int32_t>> segocc(R);
+	const uint32_t part_cap = in->H / 2;
+	std::vector<ArcPartial> all((size_t)R * (part_cap + 1));
+	std::vector<ArcTable> loc(R), glob(R);
+	// which survivors belong to which rank: genomes [G*r/R, G*(r+1)/R); every rank sees its own slice of sv as ITS list, genome ids made local
+	for (int r = 0; r < R; ++r) {
+		const int g0 = in->G * r / R, g1 = in->G * (r + 1) / R, Gl = g1 - g0 > 0? g1 - g0 : 1;
+		std::vector<uint32_t> sv;
+		for (int t = 0; t < in->n_sv; ++t) { int g = in->ctg2g[in->ctg[in->sv[t]]]; if (g >= g0 && g < g1) sv.push_back(in->sv[t]); }
+		std::vector<int32_t> ctg2g_loc;
+		int n_ctg = 0; for (int i = 0; i < in->n_hit; ++i) n_ctg = std::max(n_ctg, in->ctg[i] + 1);
+		ctg2g_loc.resize(n_ctg);
+		for (int i = 0; i < in->n_hit; ++i) ctg2g_loc[in->ctg[i]] = in->ctg2g[in->ctg[i]] - g0;
+		memset(&dcs[r], 0, sizeof(DevCounts));
+		dcs[r].m_sv = (uint32_t)sv.size(); dcs[r].n_seg = in->n_seg0;
+		lkey[r].assign(in->H, KEY_EMPTY); lacc[r].assign(in->H, ArcAcc{0, 0, 0, 0}); llist[r].assign(in->H, 0);
+		const size_t bmw = (((size_t)in->H * Gl + 31) / 32 + 3) & ~(size_t)3;
+		bm[r].assign(2 * bmw, 0); degcur[r].assign(2 * (size_t)NV + 8, 0); seen[r].assign(((size_t)Gl * in->n_seg0 + 31) / 32 + 4, 0); segocc[r].assign(2 * (size_t)in->n_seg0 + 4, 0);
+		loc[r].key = lkey[r].data(); loc[r].acc = lacc[r].data(); loc[r].list = llist[r].data(); loc[r].bm1 = bm[r].data(); loc[r].bm2 = bm[r].data() + bmw; loc[r].H = in->H;
+		glob[r] = loc[r];
+		if (R > 1) { gkey[r].assign(in->H, KEY_EMPTY); gacc[r].assign(in->H, ArcAcc{0, 0, 0, 0}); glist[r].assign(in->H, 0); glob[r].key = gkey[r].data(); glob[r].acc = gacc[r].data(); glob[r].list = glist[r].data(); glob[r].bm1 = glob[r].bm2 = nullptr; }
+		std::vector<unsigned long long> l2key(in->H2, KEY_EMPTY), l2d(in->H2, 0); std::vector<uint32_t> l2n(in->H2, 0), l2list(in->H2, 0); std::vector<int32_t> l2m(2 * (size_t)in->H2, 0);
+		OvfTable L; L.key = l2key.data(); L.dsum = l2d.data(); L.n = l2n.data(); L.list = l2list.data(); L.m1 = l2m.data(); L.m2 = l2m.data() + in->H2; L.H = in->H2;
+		std::vector<PairRec> rec(sv.size() + 1); std::vector<OvfRec> ovf(in->ovf_cap + 1);
+		uint32_t tie = 0, err = 0;
+		ArcSrc e; e.sv = sv.data(); e.ctg = in->ctg; e.cm = in->cm; e.gidp = in->gidp; e.sori = in->sori; e.sdom = in->sdom; e.pdom0 = in->pdom0; e.bits = in->bits;
+		e.g2s = in->g2s; e.prot_gid = in->prot_gid; e.ctg2g = ctg2g_loc.data(); e.use_ori = in->use_ori; e.n_seg0 = in->n_seg0; e.Gl = Gl;
+		DevCounts *dc = &dcs[r];
+		uint32_t *deg = degcur[r].data();
+		int32_t *ng = segocc[r].data(), *tot = segocc[r].data() + in->n_seg0;
+		emu::launch(grid, TBk, [&] { k_arc_insert(e, loc[r], dc, rec.data(), seen[r].data(), ng, tot, R > 1? (uint32_t*)nullptr : deg, &tie, &err); });
+		emu::launch(grid, TBk, [&] { k_arc_fold(rec.data(), loc[r], dc, Gl, ovf.data(), (uint32_t)in->ovf_cap); });
+		emu::launch(2, TBk, [&] { k_arc_ovf_insert(ovf.data(), (uint32_t)in->ovf_cap, L, dc); });
+		emu::launch(2, TBk, [&] { k_arc_ovf_fold(L, loc[r], dc); });
+		for (uint32_t j = 0; j < L.H; ++j) if (l2key[j] != KEY_EMPTY || l2n[j] || l2d[j] || l2m[j] || l2m[j + in->H2]) return -2;   // the overflow table hands itself back clean
+		if (err) return -3;
+		if (R > 1) { ArcPartial *mine = all.data() + (size_t)r * (part_cap + 1); emu::launch(grid, TBk, [&] { k_arc_pack(loc[r], dc, mine, part_cap); }); }
+	}
+	// "allreduce" of the segment occupancy, then every rank merges and finalises; rank 0's result is returned, the others must agree
+	std::vector<int32_t> occ(2 * (size_t)in->n_seg0 + 4, 0);
+	for (int r = 0; r < R; ++r) for (size_t i = 0; i < occ.size(); ++i) occ[i] += segocc[r][i];
+	std::vector<ArcDev> first;
+	for (int r = 0; r < R; ++r) {
+		DevCounts *dc = &dcs[r];
+		uint32_t *deg = degcur[r].data(), *cur = deg + NV;
+		if (R > 1) emu::launch(grid, TBk, [&] { k_arc_merge(all.data(), R, part_cap, glob[r], dc, deg); });
+		const int tiles = (NV + 1 + SCAN_TILE - 1) / SCAN_TILE;
+		std::vector<unsigned long long> status(2 * (size_t)tiles + 2, 0ull); uint32_t ticket = 0; unsigned long long nl_total = 0;
+		std::vector<uint32_t> off(NV + 8), nl_off(NV + 8);
+		std::vector<ArcDev> tmp(in->arc_cap + 1), arc(in->arc_cap + 1);
+		std::vector<unsigned long long> idx(NV + 2, 0ull);
+		emu::launch(tiles, SCAN_B, [&] { k_vertex_scan(deg, NV, off.data(), nl_off.data(), dc, (uint32_t)in->arc_cap, &nl_total, status.data(), &ticket); });
+		emu::launch(grid, TBk, [&] { k_arc_place(glob[r], R > 1? &dc->n_gpart : &dc->n_part, off.data(), cur, dc, tmp.data()); });
+		emu::launch(grid, TBk, [&] { k_arc_rank(tmp.data(), off.data(), dc, arc.data(), idx.data()); });
+		if (nl_total != dc->n_nl) return -4;
+		if (r == 0) {
+			memcpy(in->arc, arc.data(), (size_t)dc->n_arc * sizeof(ArcDev)); memcpy(in->idx, idx.data(), (size_t)NV * 8); memcpy(in->nl_off, nl_off.data(), (size_t)(NV + 1) * 4);
+			memcpy(in->seg_ng, occ.data(), (size_t)in->n_seg0 * 4); memcpy(in->seg_tot, occ.data() + in->n_seg0, (size_t)in->n_seg0 * 4);
+			in->out_counts[0] = dc->n_arc; in->out_counts[1] = dc->n_nl; in->out_counts[3] = dc->n_ovf;
+			first.assign(arc.begin(), arc.begin() + dc->n_arc);
+		} else if (dc->n_arc != first.size() || memcmp(first.data(), arc.data(), first.size() * sizeof(ArcDev)) != 0) return -5;
+		in->out_counts[2] |= dc->fallback;
+	}
+	return 0;
+}
+
+extern "C" int round_emu_compact(const uint32_t *bits, const uint32_t *perm, int32_t n, uint32_t *pos, uint32_t *list, uint32_t *count)
+{
+	using namespace pgx;
+	const int tiles = (n + 1 + SCAN_TILE - 1) / SCAN_TILE;
+	std::vector<unsigned long long> status(tiles + 1, 0ull); uint32_t ticket = 0;
+	DevCounts dc; memset(&dc, 0xff, sizeof(dc));
+	emu::launch(tiles, SCAN_B, [&] { k_compact_survivors(bits, perm, n, pos, list, count, status.data(), &ticket, &dc); });
+	return (dc.n_part | dc.n_ovf | dc.n_l2 | dc.n_gpart) == 0? 0 : -1;
+}
+
+extern "C" int round_emu_seg_filter(pgx::SegDev *seg, int32_t *n_seg, const unsigned long long *idx, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, int32_t *g2s, int32_t n_gene)
+{
+	using namespace pgx;
+	DevCounts dc; memset(&dc, 0, sizeof(dc)); dc.n_seg = *n_seg;
+	std::vector<SegDev> tmp(*n_seg + 1);
+	emu::launch(1, SEGF_B, [&] { k_seg_filter(seg, tmp.data(), &dc, idx, max_occ_total, max_degree, max_dist_loci, g2s, n_gene); });
+	*n_seg = dc.n_seg;
+	return 0;
+}
+
+extern "C" int round_emu_dirty(const int32_t *ctg, const int32_t *cs, const int32_t *ce, const int32_t *pmax, int32_t n, int32_t tile, const int32_t *changed, int32_t n_changed, uint32_t *tiles)
+{
+	using namespace pgx;
+	DirtyCols D; D.ctg = ctg; D.cs = cs; D.ce = ce; D.pmax = pmax; D.n = n; D.tiles = tiles; D.tile = tile;
+	for (int i = 0; i < n_changed; ++i) mark_dirty(D, changed[i]);
+	return 0;
+}
+'''
+
+
+def build_round():
+    """tests/emu/_build/libround_emu.so: the kernels of pgx_round.cuh (the sync-free arc build and friends) on the SIMT shim"""
+    csrc = os.path.join(ROOT, "pangene_b200", "csrc")
+    scan = open(os.path.join(csrc, "pgx_scan.cuh")).read()
+    types = open(os.path.join(csrc, "pgx_graphtypes.cuh")).read()
+    rnd = open(os.path.join(csrc, "pgx_round.cuh")).read()
+    body = _between(scan, "scan") + "\n" + _between(types, "graphtypes") + "\n" + _between(rnd, "round")
+    os.makedirs(OUT, exist_ok=True)
+    cpp = os.path.join(OUT, "round_emu.cpp")
+    src = '#include "simt_emu.hpp"\n#include <algorithm>\n#include "pangene_abi.h"\nnamespace pgx {\n' + body + "\n}\n" + ROUND_DRIVER
+    so = os.path.join(OUT, "libround_emu.so")
+    if os.path.exists(cpp) and os.path.exists(so) and open(cpp).read() == src and os.path.getmtime(so) >= os.path.getmtime(os.path.join(HERE, "simt_emu.hpp")):
+        return so
+    open(cpp, "w").write(src)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-I", HERE, "-I", os.path.join(ROOT, "include"), cpp, "-o", so])
+    return so
+
+
 if __name__ == "__main__":
     print(build())
     print(build_prim())
+    print(build_round())

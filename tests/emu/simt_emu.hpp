@@ -28,6 +28,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct int2 { int32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
 struct emu_dim3 { int x = 0, y = 0, z = 0; };
 static thread_local emu_dim3 threadIdx, blockIdx;
 static emu_dim3 blockDim, gridDim;
@@ -85,6 +86,9 @@ static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 template<class T> static inline T atomicAdd(T *p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 template<class T> static inline T atomicOr(T *p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template<class T> static inline T atomicExch(T *p, T v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+template<class T> static inline T atomicCAS(T *p, T cmp, T v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+template<class T> static inline T atomicMax(T *p, T v) { T old = __atomic_load_n(p, __ATOMIC_RELAXED); while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) { } return old; }
+template<class T> static inline T atomicMin(T *p, T v) { T old = __atomic_load_n(p, __ATOMIC_RELAXED); while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) { } return old; }
 
 namespace emu {
 // run kernel(args...) over grid x block threads; one CTA at a time, the OS threads persist over the CTAs
