@@ -169,15 +169,18 @@ struct Session {
 		prot_max.alloc(n_prot); prot_rep.alloc(n_prot); z.alloc(n_prot); cs4.alloc((size_t)n_prot * 4); g2s.alloc(n_gene);
 		prot_rep.zero(st);
 		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
-		if (g_comm.active()) {   // every rank learns every rank's local genome count
-			int32_t *tmp = scratch.get<int32_t>(g_comm.nranks);
-			PGX_CHECK(cudaMemcpyAsync(tmp + g_comm.rank, &G, 4, cudaMemcpyHostToDevice, st));
-			g_comm.allgather(tmp + g_comm.rank, tmp, 4, st);
-			rank_G.resize(g_comm.nranks);
-			PGX_CHECK(cudaMemcpyAsync(rank_G.data(), tmp, 4 * g_comm.nranks, cudaMemcpyDeviceToHost, st));
+		if (g_comm.active()) {   // every rank learns every rank's local genome and hit counts
+			int32_t *tmp = scratch.get<int32_t>(2 * (size_t)g_comm.nranks);
+			const int32_t mine[2] = {G, N};
+			PGX_CHECK(cudaMemcpyAsync(tmp + 2 * g_comm.rank, mine, 8, cudaMemcpyHostToDevice, st));
+			g_comm.allgather(tmp + 2 * g_comm.rank, tmp, 8, st);
+			std::vector<int32_t> h2(2 * (size_t)g_comm.nranks);
+			PGX_CHECK(cudaMemcpyAsync(h2.data(), tmp, 8 * (size_t)g_comm.nranks, cudaMemcpyDeviceToHost, st));
 			PGX_CHECK(cudaStreamSynchronize(st));
+			rank_G.resize(g_comm.nranks); rank_N.resize(g_comm.nranks);
+			for (int r = 0; r < g_comm.nranks; ++r) { rank_G[r] = h2[2 * r]; rank_N[r] = h2[2 * r + 1]; }
 			scratch.reset(0);
-		} else rank_G.assign(1, G);
+		} else { rank_G.assign(1, G); rank_N.assign(1, N); }
 		PGX_CHECK(cudaStreamSynchronize(st));
 		done_post = done_graph = false; installed.clear();
 	}
@@ -901,54 +904,62 @@ struct Session {
 	// the sync-free rounds (pgx_round.cuh): buffers allocated once per run, pointers stable across rounds
 	// ------------------------------------------------------------------------------------------------
 	struct Fast {
-		bool on = false;
-		int32_t NV = 0, tiles_hit = 0, tiles_vtx = 0;
+		bool on = false, use_dirty = false;
+		int32_t NV = 0, tiles_hit = 0, tiles_vtx = 0, tiles_seg = 0;
 		uint32_t H = 0, H2 = 0, ovf_cap = 0, arc_cap = 0, nl_cap = 0, part_cap = 0;
 		size_t bm_words = 0, lb_bytes = 0, seen_words = 0, dirty_words = 0;
 		DBuf<unsigned long long> lkey, gkey, l2key, l2dsum, lb, nl_total;
 		DBuf<ArcAcc> lacc, gacc;
-		DBuf<uint32_t> llist, glist, bm, l2n, l2list, degcur, off, nl_off, seg_seen, spos, svcs, tie_list, dirty;
+		DBuf<uint32_t> llist, glist, bm, l2n, l2list, degcur, off, nl_off, seg_seen, spos, svcs, tie_list, dirty, rec, pos_of, seg_pos;
 		DBuf<int32_t> l2m, segocc, t_last, grp;
-		DBuf<PairRec> rec; DBuf<OvfRec> ovf; DBuf<uint8_t> nl; DBuf<GenePos> gpos; DBuf<SegDev> seg_tmp; DBuf<ArcDev> arc_tmp; DBuf<ArcPartial> all;
+		DBuf<SvInfo> info; DBuf<OvfRec> ovf; DBuf<uint8_t> nl; DBuf<GenePos> gpos; DBuf<ArcDev> arc_tmp; DBuf<ArcWire> all; DBuf<int2> reach;
 		ArcTable loc, glob; OvfTable l2;
-		unsigned long long *st_cm = nullptr, *st_vs = nullptr, *st_cs = nullptr; uint32_t *tk_cm = nullptr, *tk_vs = nullptr, *tk_cs = nullptr;
-		bool use_dirty = false;
+		unsigned long long *st_cm = nullptr, *st_vs = nullptr, *st_cs = nullptr, *st_sg = nullptr; uint32_t *tk_cm = nullptr, *tk_vs = nullptr, *tk_cs = nullptr, *tk_sg = nullptr, *n_keep = nullptr;
 	} fast;
 	bool force_careful = false;
+	std::vector<int64_t> rank_N;          // hits of every rank (multi-GPU)
 
 	void clear_launch(const ClearList &c) { if (c.n) PGX_LAUNCH(k_round_clear, 148 * 4, 256, 0, st, c); }
-	DirtyCols dirty_cols() const
+	DirtyCols dirty_cols() const { DirtyCols D; D.reach = fast.reach.p; D.tiles = fast.use_dirty? fast.dirty.p : nullptr; return D; }
+	ArcSrc arc_src(const pg_opt_t *opt) const
 	{
-		DirtyCols D; D.ctg = A.ctg; D.cs = A.cs; D.ce = A.ce; D.pmax = A.pmax; D.n = Nw; D.tiles = fast.use_dirty? fast.dirty.p : nullptr; D.tile = SWQ_TILE;
-		return D;
+		ArcSrc e; e.sv = sv.p; e.ctg = A.ctg; e.cm = A.cm; e.gidp = A.gidp; e.sori = A.sori; e.sdom = A.sdom; e.pdom0 = A.pdom0; e.bits = A.bits;
+		e.g2s = g2s.p; e.prot_gid = prot_gid.p; e.ctg2g = ctg2g.p; e.use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH); e.n_seg0 = n_seg0; e.Gl = G > 0? G : 1;
+		return e;
 	}
 
-	// Sizes the tables of the fast rounds from the round-2 graph (one read-back per run) and builds idx / degrees / pair offsets for
-	// the first branch round.  Every decision here depends on replicated values only, so all ranks decide alike.
+	// Sizes the tables of the fast rounds from the round-2 graph (one read-back per run) and builds, for the first branch round, what the
+	// later rounds get from their own arc build: survivor records, the key table over the round-2 arcs, degrees and pair offsets.
+	// Every decision here depends on replicated values only, so all ranks decide alike.
 	bool setup_fast(const pg_opt_t *opt)
 	{
 		fast.on = false;
 		static const bool env_careful = []() { const char *e = getenv("PGX_ROUNDS"); return e && strcmp(e, "careful") == 0; }();
 		if (env_careful || force_careful || opt->n_branch_flt <= 0 || n_seg0 == 0) return false;
+		// the packed sums of ArcAcc: counts below 2^26, score sums below 2^38
+		int64_t n_hits_all = 0, s_max = 0;
+		for (int64_t x : rank_N) n_hits_all += x;
+		for (int32_t x : h_prot_max) s_max = x > s_max? x : s_max;
+		if (n_hits_all >= (1ll << 26) || Gtot >= (1 << 26) || (double)s_max * (double)Gtot >= (double)(1ll << ACC_SHIFT)) return false;
 		arc_index();                                                                     // graph.c:306 of the first round
 		const uint32_t n_arc2 = read_counts().n_arc;
 		Fast &f = fast;
 		f.NV = 2 * n_seg0;
-		uint64_t want = 3ull * n_arc2; if (want < (1u << 16)) want = 1u << 16;
-		uint32_t H = 1u << 16; while (H < want && H < (1u << 30)) H <<= 1;
+		uint64_t want = 2ull * n_arc2; if (want < (1u << 16)) want = 1u << 16;           // canonical keys: half the arcs; load factor <= 1/4 at the start
+		uint32_t H = 1u << 16; while (H < want && H < (1u << 29)) H <<= 1;
 		int Gmax = 0; for (int g : rank_G) Gmax = g > Gmax? g : Gmax;
 		if ((uint64_t)H * (uint64_t)(Gmax > 0? Gmax : 1) / 8 > ((uint64_t)1 << 30)) return false;   // (key, genome) marks beyond 1 GB: stay on the sort path
 		f.H = H; f.H2 = 1u << 20; f.ovf_cap = 1u << 19;
 		f.bm_words = ((size_t)H * (size_t)(G > 0? G : 1) + 31) / 32;
 		f.bm_words = (f.bm_words + 3) & ~(size_t)3;
 		const bool multi = g_comm.active();
-		f.lkey.ensure(H); f.lacc.ensure(H); f.llist.ensure(H); f.bm.ensure(2 * f.bm_words);
+		f.lkey.ensure(H); f.lacc.ensure(H); f.llist.ensure(H); f.bm.ensure(2 * f.bm_words); f.pos_of.ensure(2 * (size_t)H);
 		f.loc.key = f.lkey.p; f.loc.acc = f.lacc.p; f.loc.list = f.llist.p; f.loc.bm1 = f.bm.p; f.loc.bm2 = f.bm.p + f.bm_words; f.loc.H = H;
 		f.glob = f.loc;
 		if (multi) {
 			f.gkey.ensure(H); f.gacc.ensure(H); f.glist.ensure(H);
 			f.glob.key = f.gkey.p; f.glob.acc = f.gacc.p; f.glob.list = f.glist.p; f.glob.bm1 = f.glob.bm2 = nullptr;
-			f.part_cap = n_arc2 + n_arc2 / 4 + 4096; if (f.part_cap > H / 2) f.part_cap = H / 2;
+			f.part_cap = n_arc2 / 2 + n_arc2 / 4 + 4096; if (f.part_cap > H / 2) f.part_cap = H / 2;
 			f.all.ensure((size_t)g_comm.nranks * (f.part_cap + 1));
 		}
 		f.l2key.ensure(f.H2); f.l2dsum.ensure(f.H2); f.l2n.ensure(f.H2); f.l2list.ensure(f.H2); f.l2m.ensure(2 * (size_t)f.H2);
@@ -956,19 +967,20 @@ struct Session {
 		PGX_CHECK(cudaMemsetAsync(f.l2key.p, 0xff, (size_t)f.H2 * 8, st)); PGX_CHECK(cudaMemsetAsync(f.l2dsum.p, 0, (size_t)f.H2 * 8, st));
 		PGX_CHECK(cudaMemsetAsync(f.l2n.p, 0, (size_t)f.H2 * 4, st)); PGX_CHECK(cudaMemsetAsync(f.l2m.p, 0, (size_t)f.H2 * 8, st));
 		const size_t nw1 = (size_t)Nw + 16, tab = (size_t)n_gene * (size_t)(G > 0? G : 1);
-		f.rec.ensure(nw1); f.ovf.ensure(f.ovf_cap); f.spos.ensure(nw1 + 2); f.svcs.ensure(nw1); f.tie_list.ensure(nw1);
-		f.degcur.ensure(2 * (size_t)f.NV + 8); f.off.ensure((size_t)f.NV + 8); f.nl_off.ensure((size_t)f.NV + 8); f.nl_total.ensure(2);
+		f.rec.ensure(nw1); f.info.ensure(nw1); f.ovf.ensure((size_t)f.ovf_cap + 2); f.spos.ensure(nw1 + 2); f.svcs.ensure(nw1); f.tie_list.ensure(nw1); f.reach.ensure(nw1);
+		f.degcur.ensure(2 * (size_t)f.NV + 8); f.off.ensure((size_t)f.NV + 8); f.nl_off.ensure((size_t)f.NV + 8); f.nl_total.ensure(2); f.seg_pos.ensure((size_t)n_seg0 + 8);
 		f.seen_words = (((size_t)(G > 0? G : 1) * n_seg0 + 31) / 32 + 4) & ~(size_t)3;
 		f.seg_seen.ensure(f.seen_words); f.segocc.ensure(2 * (size_t)n_seg0 + 4);
-		f.t_last.ensure(tab + 4); f.gpos.ensure(tab + 1); f.seg_tmp.ensure((size_t)n_seg0 + 1);
+		f.t_last.ensure(tab + 4); f.gpos.ensure(tab + 1);
 		f.dirty_words = ((size_t)Nw / SWQ_TILE / 32 + 8) & ~(size_t)3;
 		f.dirty.ensure(f.dirty_words);
 		f.tiles_hit = (int32_t)(((size_t)Nw + 1 + SCAN_TILE - 1) / SCAN_TILE); f.tiles_vtx = (int32_t)(((size_t)f.NV + 1 + SCAN_TILE - 1) / SCAN_TILE);
-		const size_t lb_words = 2 * (size_t)f.tiles_hit + 2 * (size_t)f.tiles_vtx + 4;
-		f.lb.ensure(lb_words); f.lb_bytes = lb_words * 8;
-		f.st_cm = f.lb.p; f.st_cs = f.st_cm + f.tiles_hit; f.st_vs = f.st_cs + f.tiles_hit;
-		f.tk_cm = (uint32_t*)(f.st_vs + 2 * (size_t)f.tiles_vtx); f.tk_vs = f.tk_cm + 1; f.tk_cs = f.tk_cm + 2;
-		uint32_t need_arc = H / 2 > n_arc2 + 16? H / 2 : n_arc2 + 16;
+		f.tiles_seg = (int32_t)(((size_t)n_seg0 + 1 + SCAN_TILE - 1) / SCAN_TILE);
+		const size_t lb_words = 2 * (size_t)f.tiles_hit + 2 * (size_t)f.tiles_vtx + (size_t)f.tiles_seg + 4;
+		f.lb.ensure(lb_words + 2); f.lb_bytes = ((lb_words * 8) + 15) & ~(size_t)15;
+		f.st_cm = f.lb.p; f.st_cs = f.st_cm + f.tiles_hit; f.st_vs = f.st_cs + f.tiles_hit; f.st_sg = f.st_vs + 2 * (size_t)f.tiles_vtx;
+		f.tk_cm = (uint32_t*)(f.st_sg + f.tiles_seg); f.tk_vs = f.tk_cm + 1; f.tk_cs = f.tk_cm + 2; f.tk_sg = f.tk_cm + 3; f.n_keep = f.tk_cm + 4;
+		uint32_t need_arc = H > n_arc2 + 16? H : n_arc2 + 16;                             // up to H / 2 canonical keys -> H arcs
 		if (arc.n < (size_t)need_arc + 1) {   // the merged graph of a sharded run can exceed this rank's own bound; keep the round-2 arcs
 			DBuf<ArcDev> bigger; bigger.alloc((size_t)need_arc + 1);
 			if (n_arc2) PGX_CHECK(cudaMemcpyAsync(bigger.p, arc.p, (size_t)n_arc2 * sizeof(ArcDev), cudaMemcpyDeviceToDevice, st));
@@ -979,10 +991,16 @@ struct Session {
 		f.arc_tmp.ensure((size_t)f.arc_cap + 1); f.grp.ensure((size_t)f.arc_cap + 1);
 		f.use_dirty = n_first == 0 && !(getenv("PGX_SWEEP") && strcmp(getenv("PGX_SWEEP"), "global") == 0) && !getenv("PGX_NO_DIRTY");
 		PGX_CHECK(cudaMemsetAsync(f.dirty.p, 0, f.dirty_words * 4, st));
-		PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, fallback)), 0u);
 		PGX_CHECK(cudaMemsetAsync(f.lb.p, 0, f.lb_bytes, st));
 		PGX_CHECK(cudaMemsetAsync(f.nl_total.p, 0, 16, st));
-		// degrees and pair offsets of the round-2 graph (the later rounds get them from their own arc build)
+		PGX_CHECK(cudaMemsetAsync(f.glob.key, 0xff, (size_t)H * 8, st));
+		PGX_CHECK(cudaMemsetAsync(f.segocc.p, 0, 2 * (size_t)n_seg0 * 4, st)); PGX_CHECK(cudaMemsetAsync(f.seg_seen.p, 0, f.seen_words * 4, st));
+		PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, fallback)), 0u);
+		PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_gpart)), 0u);
+		if (f.use_dirty && Nw) PGX_LAUNCH(k_reach, GS_GRID, TB, 0, st, A.ctg, A.cs, A.ce, A.pmax, Nw, (int32_t)SWQ_TILE, f.reach.p);
+		// the round-2 graph as the first branch round needs it: survivor records, key table + arc positions, degrees, pair offsets
+		PGX_LAUNCH(k_survivor_info, GS_GRID, TB, 0, st, arc_src(opt), dc.p, f.info.p, f.seg_seen.p, f.segocc.p, f.segocc.p + n_seg0, counters.p + C_ERR);
+		PGX_LAUNCH(k_table_from_arcs, GS_GRID, TB, 0, st, arc.p, dc.p, f.glob, f.pos_of.p);
 		uint32_t *deg = f.degcur.p;
 		PGX_LAUNCH(k_deg_from_idx, GS_GRID, TB, 0, st, idx.p, f.NV, dc.p, deg);
 		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, 0xffffffffu, f.nl_total.p, f.st_vs, f.tk_vs);
@@ -1020,30 +1038,30 @@ struct Session {
 		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
 		launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits, A.pdom, nullptr, f.use_dirty? f.dirty.p : nullptr);   // in place: a sweep reads flt / weak_br / rev of its partners, writes its own shadow bit
 		PGX_LAUNCH(k_compact_survivors, f.tiles_hit, SCAN_B, 0, st, A.bits, by_cm.p, Nw, (uint32_t*)nullptr, sv.p, dcp(offsetof(DevCounts, m_sv)), f.st_cm, f.tk_cm, dc.p);
-		ArcSrc e; e.sv = sv.p; e.ctg = A.ctg; e.cm = A.cm; e.gidp = A.gidp; e.sori = A.sori; e.sdom = A.sdom; e.pdom0 = A.pdom0; e.bits = A.bits;
-		e.g2s = g2s.p; e.prot_gid = prot_gid.p; e.ctg2g = ctg2g.p; e.use_ori = !!(opt->flag & PG_F_ORI_FOR_BRANCH); e.n_seg0 = n_seg0; e.Gl = G > 0? G : 1;
+		const ArcSrc e = arc_src(opt);
 		int32_t *seg_ng_f = f.segocc.p, *seg_tot_f = f.segocc.p + n_seg0;
-		PGX_LAUNCH(k_arc_insert, GS_GRID, TB, 0, st, e, f.loc, dc.p, f.rec.p, f.seg_seen.p, seg_ng_f, seg_tot_f, multi? (uint32_t*)nullptr : deg, counters.p + C_TIE_CM, counters.p + C_ERR);
-		PGX_LAUNCH(k_arc_fold, GS_GRID, TB, 0, st, f.rec.p, f.loc, dc.p, e.Gl, f.ovf.p, f.ovf_cap);
+		PGX_LAUNCH(k_survivor_info, GS_GRID, TB, 0, st, e, dc.p, f.info.p, f.seg_seen.p, seg_ng_f, seg_tot_f, counters.p + C_ERR);
+		PGX_LAUNCH(k_arc_insert, GS_GRID, TB, 0, st, f.info.p, ctg2g.p, e.Gl, f.loc, dc.p, f.rec.p, multi? (uint32_t*)nullptr : deg, counters.p + C_TIE_CM);
+		PGX_LAUNCH(k_arc_fold, GS_GRID, TB, 0, st, f.info.p, f.rec.p, ctg2g.p, f.loc, dc.p, e.Gl, f.ovf.p, f.ovf_cap);
 		PGX_LAUNCH(k_arc_ovf_insert, 148, TB, 0, st, f.ovf.p, f.ovf_cap, f.l2, dc.p);
 		PGX_LAUNCH(k_arc_ovf_fold, 148, TB, 0, st, f.l2, f.loc, dc.p);
 		if (multi) {
-			ArcPartial *mine = f.all.p + (size_t)g_comm.rank * (f.part_cap + 1);
+			ArcWire *mine = f.all.p + (size_t)g_comm.rank * (f.part_cap + 1);
 			PGX_LAUNCH(k_arc_pack, GS_GRID, TB, 0, st, f.loc, dc.p, mine, f.part_cap);
 			g_comm.group_begin();
-			g_comm.allgather(mine, f.all.p, (size_t)(f.part_cap + 1) * sizeof(ArcPartial), st);
+			g_comm.allgather(mine, f.all.p, (size_t)(f.part_cap + 1) * sizeof(ArcWire), st);
 			g_comm.allreduce(f.segocc.p, 2 * (size_t)n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
 			g_comm.group_end();
 			PGX_LAUNCH(k_arc_merge, GS_GRID, TB, 0, st, f.all.p, g_comm.nranks, f.part_cap, f.glob, dc.p, deg);
 		}
 		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, f.arc_cap, f.nl_total.p, f.st_vs, f.tk_vs);
 		PGX_LAUNCH(k_arc_place, GS_GRID, TB, 0, st, f.glob, dcp(multi? offsetof(DevCounts, n_gpart) : offsetof(DevCounts, n_part)), f.off.p, cur, dc.p, f.arc_tmp.p);
-		PGX_LAUNCH(k_arc_rank, GS_GRID, TB, 0, st, f.arc_tmp.p, f.off.p, dc.p, arc.p, idx.p);
+		PGX_LAUNCH(k_arc_rank, GS_GRID, TB, 0, st, f.arc_tmp.p, f.off.p, dc.p, arc.p, idx.p, f.pos_of.p);
 		PGX_LAUNCH(k_seg_store_occ_fast, 148, TB, 0, st, seg.p, dc.p, seg_ng_f, seg_tot_f);
 		++g_stats.fast_rounds;
 	}
 
-	// branch.c:48-145 + graph.c:309-313, same rules as branch_round() below; idx / nl_off come from the preceding arc build
+	// branch.c:48-145 + graph.c:309-313, same rules as branch_round() below; idx / nl_off / the key table come from the preceding arc build
 	void branch_round_fast(const pg_opt_t *opt, int32_t round, int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)
 	{
 		Fast &f = fast;
@@ -1062,10 +1080,14 @@ struct Session {
 		PGX_LAUNCH(k_branch_local, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, f.gpos.p, G, f.nl_off.p, f.NV, f.nl_cap, f.nl_total.p, bo, f.nl.p, counters.p + C_ORD_SENS);
 		g_comm.allreduce(f.nl.p, f.nl_cap, Comm::T_UINT8, Comm::OP_SUM, st);
 		PGX_LAUNCH(k_branch_decide_fast, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, f.nl_off.p, f.nl.p, f.nl_cap, f.nl_total.p, bo, f.grp.p, counters.p + C_TIE_ROUND);
-		PGX_LAUNCH(k_branch_hits_fast, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, idx.p, dirty_cols(), counters.p + C_BR_CHANGED);
+		PGX_LAUNCH(k_branch_hits_fast, GS_GRID, TB, 0, st, sv.p, f.info.p, dc.p, A.bits, arc.p, f.glob, f.pos_of.p, dirty_cols(), counters.p + C_BR_CHANGED);
 		if (round > 0) {                                                                  // graph.c:310-313
-			PGX_LAUNCH(k_seg_filter, 1, SEGF_B, 0, st, seg.p, f.seg_tmp.p, dc.p, idx.p, max_avg_occ * Gtot, max_degree, max_dist_loci, g2s.p, n_gene);
-			if (Nw) PGX_LAUNCH(k_flag_vtx_fast, GS_GRID, TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols());
+			PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
+			PGX_LAUNCH(k_seg_keep_scan, f.tiles_seg, SCAN_B, 0, st, seg.p, dc.p, idx.p, max_avg_occ * Gtot, max_degree, max_dist_loci, f.seg_pos.p, f.n_keep, f.st_sg, f.tk_sg);
+			PGX_LAUNCH(k_seg_compact_fast, 148, TB, 0, st, seg.p, seg_alt.p, dc.p, f.seg_pos.p, f.n_keep, g2s.p);
+			PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_seg)), f.n_keep);
+			seg.swap(seg_alt);
+			if (Nw) PGX_LAUNCH(k_flag_vtx_fast, grid_for(Nw, TB), TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols());
 		}
 	}
 

@@ -142,15 +142,22 @@ __global__ void __launch_bounds__(SCAN_B) k_compact_survivors(const uint32_t *__
 }
 
 // ---- the arc table ------------------------------------------------------------------------------------------------------
-struct ArcAcc { unsigned long long cnt, sum_dist, sum_s1, sum_s2; };   // cnt = n_genome << 32 | tot_cnt; all zero at the start of a round
+// Every adjacency yields the arc (v -> w) and its mirror (w^1 -> v^1) with the two scores swapped (graph.c:115-120), always together, so the
+// whole multiset is mirror-symmetric: only the CANONICAL key of a pair -- the smaller of the two -- is stored and summed; the mirror arc
+// is written out from the same sums when the table is turned into arc[] (same n_genome, tot_cnt, avg_dist; s1 and s2 exchanged).  An arc
+// that is its own mirror (w == v^1) receives both records of its pair: a (key, genome) group of two, handled by the overflow path.
+constexpr int ACC_SHIFT = 38;                                    // packed sums: [count : 26 bits][score sum : 38 bits] (the engine checks the bounds)
+constexpr unsigned long long ACC_MASK = (1ull << ACC_SHIFT) - 1;
+struct ArcAcc { unsigned long long a, b, dist; };              // a = n_genome << 38 | sum_s1, b = tot_cnt << 38 | sum_s2, dist = sum(dist * n); zero at the start of a round
 struct ArcTable {
-	unsigned long long *key;     // [H] arc key x = v << 32 | w, KEY_EMPTY when free
+	unsigned long long *key;     // [H] canonical arc key x = v << 32 | w, KEY_EMPTY when free
 	ArcAcc *acc;                 // [H]
 	uint32_t *list;              // [H] slots in creation order
 	uint32_t *bm1, *bm2;         // [H * Gl bits] (key, local genome): seen once / seen more than once
 	uint32_t H;                  // power of two
 };
-struct PairRec { uint32_t s0, s1; int32_t d, sp, sa, gl; };   // what one adjacent survivor pair contributes: the slots of (v -> w) and (w^1 -> v^1), distance, scores, genome
+struct SvInfo { uint32_t w; int32_t sc, cm, ctg; };             // a survivor as the arc walk sees it: oriented vertex (graph.c:112), score (graph.c:82-85), position, contig
+constexpr uint32_t REC_SWAP = 0x40000000u, REC_SELF = 0x80000000u, REC_SLOT = 0x3fffffffu;   // pair record: slot of the canonical key | canonical is the mirror | arc is its own mirror
 struct OvfRec { uint32_t slot; int32_t gl, d, a1, a2; };
 struct OvfTable { unsigned long long *key; uint32_t *n; unsigned long long *dsum; int32_t *m1, *m2; uint32_t *list; uint32_t H; };   // groups (slot, genome) of the overflow records
 
@@ -159,8 +166,10 @@ __device__ __forceinline__ uint32_t hash_u64(unsigned long long k)
 	k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
 	return (uint32_t)k;
 }
+__device__ __forceinline__ unsigned long long arc_mirror(unsigned long long x) { return (unsigned long long)((uint32_t)x ^ 1u) << 32 | ((uint32_t)(x >> 32) ^ 1u); }
 
-// slot of key k, created if new.  n_created: running count of distinct keys (list position); deg (optional): out-degree of the source vertex
+// slot of canonical key k, created if new.  n_created: running count of distinct keys (list position); deg (optional): out-degrees, bumped
+// for the key's source vertex and for its mirror's
 __device__ __forceinline__ uint32_t arc_slot(const ArcTable &T, unsigned long long k, uint32_t *n_created, uint32_t *deg, uint32_t *fallback)
 {
 	uint32_t i = hash_u64(k) & (T.H - 1);
@@ -173,7 +182,11 @@ __device__ __forceinline__ uint32_t arc_slot(const ArcTable &T, unsigned long lo
 				const uint32_t id = atomicAdd(n_created, 1u);
 				if (id < T.H) T.list[id] = i;
 				if (2ull * id >= T.H) *fallback = 1u;      // load factor 1/2: the engine sized the table from the previous round with a wide margin
-				if (deg) atomicAdd(&deg[(uint32_t)(k >> 32)], 1u);
+				if (deg) {
+					const unsigned long long m = arc_mirror(k);
+					atomicAdd(&deg[(uint32_t)(k >> 32)], 1u);
+					if (m != k) atomicAdd(&deg[(uint32_t)(m >> 32)], 1u);
+				}
 				return i;
 			}
 			if (cur == k) return i;
@@ -182,6 +195,17 @@ __device__ __forceinline__ uint32_t arc_slot(const ArcTable &T, unsigned long lo
 	*fallback = 1u;
 	return 0;
 }
+// read-only look-up; ARC_NONE if absent
+__device__ __forceinline__ uint32_t arc_find(const ArcTable &T, unsigned long long k)
+{
+	uint32_t i = hash_u64(k) & (T.H - 1);
+	for (uint32_t probe = 0; probe < T.H; ++probe, i = (i + 1) & (T.H - 1)) {
+		const unsigned long long cur = T.key[i];
+		if (cur == k) return i;
+		if (cur == KEY_EMPTY) return ARC_NONE;
+	}
+	return ARC_NONE;
+}
 
 struct ArcSrc {      // the arc walk's input: survivors in (contig, cm) order (indices into the active columns) and those columns
 	const uint32_t *sv;
@@ -189,44 +213,46 @@ struct ArcSrc {      // the arc walk's input: survivors in (contig, cm) order (i
 	const int32_t *g2s, *prot_gid, *ctg2g;
 	int32_t use_ori, n_seg0, Gl;
 };
-__device__ __forceinline__ int32_t arc_src_score(const ArcSrc &e, uint32_t h)   // graph.c:82-85
-{
-	const int32_t so = e.sori[h], sd = e.sdom[h], p0 = e.pdom0[h];
-	return (e.use_ori || so > sd || p0 < 0 || e.g2s[e.prot_gid[p0]] >= 0)? so : sd;
-}
 
-// graph.c:106-122: survivor t and its predecessor on the same contig give (v -> w) and (w^1 -> v^1); segment occupancy (graph.c:113,125-126)
-__global__ void k_arc_insert(ArcSrc e, ArcTable T, DevCounts *dc, PairRec *rec, uint32_t *seg_seen, int32_t *seg_ng, int32_t *seg_tot, uint32_t *deg, uint32_t *tie_cnt, uint32_t *err)
+// one thread per survivor: everything the walk needs of it in 16 contiguous bytes, and the segment occupancy (graph.c:113,125-126)
+__global__ void k_survivor_info(ArcSrc e, const DevCounts *__restrict__ dc, SvInfo *info, uint32_t *seg_seen, int32_t *seg_ng, int32_t *seg_tot, uint32_t *err)
 {
 	const int32_t m = (int32_t)dc->m_sv;
 	PGX_GS(t, m) {
 		const uint32_t h = e.sv[t];
+		const int32_t c = e.ctg[h], so = e.sori[h], sd = e.sdom[h], p0 = e.pdom0[h];
+		const uint32_t b = e.bits[h];
 		int32_t sid = e.g2s[e.gidp[h] >> 1];
 		if (sid < 0) { atomicOr(err, 32u); sid = 0; }                               // graph.c:111 assert
-		const int32_t c = e.ctg[h], gl = e.ctg2g[c];
-		{
-			const size_t bit = (size_t)gl * e.n_seg0 + sid;
-			const uint32_t mk = 1u << (bit & 31);
-			if (!(atomicOr(&seg_seen[bit >> 5], mk) & mk)) atomicAdd(&seg_ng[sid], 1);
-			atomicAdd(&seg_tot[sid], 1);
-		}
-		PairRec r; r.s0 = r.s1 = ARC_NONE; r.d = 0; r.sp = r.sa = 0; r.gl = gl;
+		SvInfo r;
+		r.w = (uint32_t)sid << 1 | (b & PG_HB_REV); r.cm = e.cm[h]; r.ctg = c;
+		r.sc = (e.use_ori || so > sd || p0 < 0 || e.g2s[e.prot_gid[p0]] >= 0)? so : sd;   // graph.c:82-85
+		info[t] = r;
+		const size_t bit = (size_t)e.ctg2g[c] * e.n_seg0 + sid;
+		const uint32_t mk = 1u << (bit & 31);
+		if (!(atomicOr(&seg_seen[bit >> 5], mk) & mk)) atomicAdd(&seg_ng[sid], 1);
+		atomicAdd(&seg_tot[sid], 1);
+	}
+}
+
+// graph.c:106-122: survivor t and its predecessor on the same contig give (v -> w) and (w^1 -> v^1); here: the canonical one of the two
+__global__ void k_arc_insert(const SvInfo *__restrict__ info, const int32_t *__restrict__ ctg2g, int32_t Gl, ArcTable T, DevCounts *dc, uint32_t *rec, uint32_t *deg, uint32_t *tie_cnt)
+{
+	const int32_t m = (int32_t)dc->m_sv;
+	PGX_GS(t, m) {
+		uint32_t r = ARC_NONE;
 		if (t > 0) {
-			const uint32_t hp = e.sv[t - 1];
-			if (e.ctg[hp] == c) {
-				const uint32_t w = (uint32_t)sid << 1 | (e.bits[h] & PG_HB_REV);
-				const uint32_t v = (uint32_t)e.g2s[e.gidp[hp] >> 1] << 1 | (e.bits[hp] & PG_HB_REV);
-				r.d = e.cm[h] - e.cm[hp];
-				if (r.d == 0) atomicAdd(tie_cnt, 1u);
-				r.sp = arc_src_score(e, hp); r.sa = arc_src_score(e, h);
-				r.s0 = arc_slot(T, (unsigned long long)v << 32 | w, &dc->n_part, deg, &dc->fallback);
-				r.s1 = arc_slot(T, (unsigned long long)(w ^ 1u) << 32 | (v ^ 1u), &dc->n_part, deg, &dc->fallback);
-#pragma unroll
-				for (int q = 0; q < 2; ++q) {
-					const size_t bit = (size_t)(q? r.s1 : r.s0) * e.Gl + gl;
-					const uint32_t mk = 1u << (bit & 31);
-					if (atomicOr(&T.bm1[bit >> 5], mk) & mk) atomicOr(&T.bm2[bit >> 5], mk);
-				}
+			const SvInfo a = info[t - 1], b = info[t];
+			if (a.ctg == b.ctg) {
+				if (b.cm == a.cm) atomicAdd(tie_cnt, 1u);
+				const unsigned long long k0 = (unsigned long long)a.w << 32 | b.w, k1 = arc_mirror(k0);
+				const unsigned long long kc = k0 < k1? k0 : k1;
+				const uint32_t slot = arc_slot(T, kc, &dc->n_part, deg, &dc->fallback);
+				r = slot | (k1 < k0? REC_SWAP : 0u) | (k1 == k0? REC_SELF : 0u);
+				const size_t bit = (size_t)slot * Gl + ctg2g[b.ctg];
+				const uint32_t mk = 1u << (bit & 31);
+				if (k1 == k0) { atomicOr(&T.bm1[bit >> 5], mk); atomicOr(&T.bm2[bit >> 5], mk); }   // two records of one (key, genome) group
+				else if (atomicOr(&T.bm1[bit >> 5], mk) & mk) atomicOr(&T.bm2[bit >> 5], mk);
 			}
 		}
 		rec[t] = r;
@@ -234,29 +260,29 @@ __global__ void k_arc_insert(ArcSrc e, ArcTable T, DevCounts *dc, PairRec *rec, 
 }
 
 // graph.c:128-145 for the groups of one record, graph.c:153-163 (the additive part) for all of them
-__global__ void k_arc_fold(const PairRec *__restrict__ rec, ArcTable T, DevCounts *dc, int32_t Gl, OvfRec *ovf, uint32_t ovf_cap)
+__global__ void k_arc_fold(const SvInfo *__restrict__ info, const uint32_t *__restrict__ rec, const int32_t *__restrict__ ctg2g, ArcTable T, DevCounts *dc, int32_t Gl, OvfRec *ovf, uint32_t ovf_cap)
 {
 	const int32_t m = (int32_t)dc->m_sv;
 	PGX_GS(t, m) {
-		const PairRec r = rec[t];
-		if (r.s0 == ARC_NONE) continue;
-#pragma unroll
-		for (int q = 0; q < 2; ++q) {
-			const uint32_t slot = q? r.s1 : r.s0;
-			const int32_t a1 = q? r.sa : r.sp, a2 = q? r.sp : r.sa;                  // graph.c:116,118: (s1, s2) of the record
-			const size_t bit = (size_t)slot * Gl + r.gl;
-			if (T.bm2[bit >> 5] >> (bit & 31) & 1u) {
-				const uint32_t id = atomicAdd(&dc->n_ovf, 1u);
-				if (id < ovf_cap) { OvfRec o; o.slot = slot; o.gl = r.gl; o.d = r.d; o.a1 = a1; o.a2 = a2; ovf[id] = o; }
-				else dc->fallback = 1u;
-			} else {
-				// one record: n = 1, dist = (int32)((double)d / 1 + .499) = d (d >= 0: survivors are in cm order), max scores start at 0 (graph.c:131)
-				ArcAcc *a = &T.acc[slot];
-				atomicAdd(&a->cnt, 1ull << 32 | 1ull);
-				if (r.d) atomicAdd(&a->sum_dist, (unsigned long long)(long long)r.d);
-				if (a1 > 0) atomicAdd(&a->sum_s1, (unsigned long long)a1);
-				if (a2 > 0) atomicAdd(&a->sum_s2, (unsigned long long)a2);
-			}
+		const uint32_t r = rec[t];
+		if (r == ARC_NONE) continue;
+		const SvInfo a = info[t - 1], b = info[t];
+		const uint32_t slot = r & REC_SLOT;
+		const int32_t d = b.cm - a.cm, gl = ctg2g[b.ctg];
+		const int32_t s1 = (r & REC_SWAP)? b.sc : a.sc, s2 = (r & REC_SWAP)? a.sc : b.sc;   // graph.c:116,118: (s1, s2) of the canonical record
+		const size_t bit = (size_t)slot * Gl + gl;
+		if (T.bm2[bit >> 5] >> (bit & 31) & 1u) {
+			const uint32_t cnt = (r & REC_SELF)? 2u : 1u, id = atomicAdd(&dc->n_ovf, cnt);
+			if (id + cnt <= ovf_cap) {
+				OvfRec o; o.slot = slot; o.gl = gl; o.d = d; o.a1 = s1; o.a2 = s2; ovf[id] = o;
+				if (cnt == 2u) { o.a1 = s2; o.a2 = s1; ovf[id + 1] = o; }
+			} else dc->fallback = 1u;
+		} else {
+			// one record: n = 1, dist = (int32)((double)d / 1 + .499) = d (d >= 0: survivors are in cm order), max scores start at 0 (graph.c:131)
+			ArcAcc *acc = &T.acc[slot];
+			atomicAdd(&acc->a, 1ull << ACC_SHIFT | (unsigned long long)(s1 > 0? s1 : 0));
+			atomicAdd(&acc->b, 1ull << ACC_SHIFT | (unsigned long long)(s2 > 0? s2 : 0));
+			if (d) atomicAdd(&acc->dist, (unsigned long long)(long long)d);
 		}
 	}
 }
@@ -299,50 +325,43 @@ __global__ void k_arc_ovf_fold(OvfTable L, ArcTable T, DevCounts *dc)
 		const unsigned long long dsum = L.dsum[j];
 		const int32_t m1 = L.m1[j], m2 = L.m2[j];
 		const int32_t dg = (int32_t)((double)dsum / cnt + .499);                      // graph.c:141
-		ArcAcc *a = &T.acc[slot];
-		atomicAdd(&a->cnt, 1ull << 32 | (unsigned long long)cnt);
-		atomicAdd(&a->sum_dist, (unsigned long long)(long long)dg * (unsigned long long)cnt);   // graph.c:160
-		atomicAdd(&a->sum_s1, (unsigned long long)(long long)m1);
-		atomicAdd(&a->sum_s2, (unsigned long long)(long long)m2);
+		ArcAcc *acc = &T.acc[slot];
+		atomicAdd(&acc->a, 1ull << ACC_SHIFT | (unsigned long long)m1);
+		atomicAdd(&acc->b, (unsigned long long)cnt << ACC_SHIFT | (unsigned long long)m2);
+		atomicAdd(&acc->dist, (unsigned long long)(long long)dg * (unsigned long long)cnt);   // graph.c:160
 		L.key[j] = KEY_EMPTY; L.n[j] = 0; L.dsum[j] = 0; L.m1[j] = 0; L.m2[j] = 0;
 	}
 }
 
-__device__ __forceinline__ ArcPartial acc_to_partial(unsigned long long x, const ArcAcc &a)
+__device__ __forceinline__ ArcPartial acc_to_partial(unsigned long long x, const ArcAcc &c)
 {
 	ArcPartial p;
-	p.x = x; p.n_genome = (int32_t)(a.cnt >> 32); p.tot_cnt = (int32_t)(uint32_t)a.cnt;
-	p.sum_dist = (int64_t)a.sum_dist; p.sum_s1 = (int64_t)a.sum_s1; p.sum_s2 = (int64_t)a.sum_s2;
+	p.x = x; p.n_genome = (int32_t)(c.a >> ACC_SHIFT); p.tot_cnt = (int32_t)(c.b >> ACC_SHIFT);
+	p.sum_dist = (int64_t)c.dist; p.sum_s1 = (int64_t)(c.a & ACC_MASK); p.sum_s2 = (int64_t)(c.b & ACC_MASK);
 	return p;
 }
 
 // ---- N ranks: every rank's table travels as [header, records...]; the sums are integers, so adding them in any order is exact -------
-// header: x = number of records, sum_dist = the sender's fallback flag
-__global__ void k_arc_pack(ArcTable T, DevCounts *dc, ArcPartial *send, uint32_t cap)
+struct ArcWire { unsigned long long x, a, b, dist; };          // header: x = number of records, a = the sender's fallback flag
+__global__ void k_arc_pack(ArcTable T, DevCounts *dc, ArcWire *send, uint32_t cap)
 {
 	uint32_t n = dc->n_part;
 	if (n > cap) { n = cap; if (blockIdx.x == 0 && threadIdx.x == 0) dc->fallback = 1u; }
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		ArcPartial h; h.x = n; h.sum_dist = (dc->fallback || dc->n_part > cap)? 1 : 0; h.sum_s1 = h.sum_s2 = 0; h.n_genome = h.tot_cnt = 0;
-		send[0] = h;
-	}
-	PGX_GS(i, n) { const uint32_t s = T.list[i]; send[1 + i] = acc_to_partial(T.key[s], T.acc[s]); }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { ArcWire h; h.x = n; h.a = (dc->fallback || dc->n_part > cap)? 1 : 0; h.b = h.dist = 0; send[0] = h; }
+	PGX_GS(i, n) { const uint32_t s = T.list[i]; const ArcAcc c = T.acc[s]; ArcWire w; w.x = T.key[s]; w.a = c.a; w.b = c.b; w.dist = c.dist; send[1 + i] = w; }
 }
-__global__ void k_arc_merge(const ArcPartial *__restrict__ all, int32_t nranks, uint32_t cap, ArcTable G, DevCounts *dc, uint32_t *deg)
+__global__ void k_arc_merge(const ArcWire *__restrict__ all, int32_t nranks, uint32_t cap, ArcTable G, DevCounts *dc, uint32_t *deg)
 {
 	const unsigned long long total = (unsigned long long)nranks * cap;
 	for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (unsigned long long)gridDim.x * blockDim.x) {
 		const uint32_t r = (uint32_t)(j / cap), i = (uint32_t)(j % cap);
-		const ArcPartial *blk = all + (size_t)r * (cap + 1);
-		if (i == 0 && blk[0].sum_dist) dc->fallback = 1u;
+		const ArcWire *blk = all + (size_t)r * (cap + 1);
+		if (i == 0 && blk[0].a) dc->fallback = 1u;
 		if (i >= (uint32_t)blk[0].x) continue;
-		const ArcPartial p = blk[1 + i];
-		const uint32_t s = arc_slot(G, p.x, &dc->n_gpart, deg, &dc->fallback);
-		ArcAcc *a = &G.acc[s];
-		atomicAdd(&a->cnt, (unsigned long long)(uint32_t)p.n_genome << 32 | (unsigned long long)(uint32_t)p.tot_cnt);
-		atomicAdd(&a->sum_dist, (unsigned long long)p.sum_dist);
-		atomicAdd(&a->sum_s1, (unsigned long long)p.sum_s1);
-		atomicAdd(&a->sum_s2, (unsigned long long)p.sum_s2);
+		const ArcWire p = blk[1 + i];
+		ArcAcc *acc = &G.acc[arc_slot(G, p.x, &dc->n_gpart, deg, &dc->fallback)];
+		atomicAdd(&acc->a, p.a); atomicAdd(&acc->b, p.b);
+		if (p.dist) atomicAdd(&acc->dist, p.dist);
 	}
 }
 
@@ -392,51 +411,78 @@ __global__ void __launch_bounds__(SCAN_B) k_vertex_scan(const uint32_t *__restri
 	}
 }
 
+// every canonical key gives its arc and the mirror arc (scores exchanged); tmp.bits remembers where it came from: slot << 1 | is_mirror
 __global__ void k_arc_place(ArcTable T, const uint32_t *__restrict__ n_created, const uint32_t *__restrict__ off, uint32_t *cur, const DevCounts *__restrict__ dc, ArcDev *tmp)
 {
 	if (dc->n_arc == 0) return;                           // nothing, or more than the arrays hold (fallback raised by k_vertex_scan)
 	const uint32_t n = *n_created < T.H? *n_created : T.H;
 	PGX_GS(i, n) {
 		const uint32_t s = T.list[i];
-		const unsigned long long x = T.key[s];
+		const unsigned long long x = T.key[s], xm = arc_mirror(x);
+		ArcDev a = arc_finalize(acc_to_partial(x, T.acc[s]));
+		a.bits = s << 1;
 		const uint32_t v = (uint32_t)(x >> 32);
-		tmp[off[v] + atomicAdd(&cur[v], 1u)] = arc_finalize(acc_to_partial(x, T.acc[s]));
+		tmp[off[v] + atomicAdd(&cur[v], 1u)] = a;
+		if (xm != x) {
+			const uint32_t vm = (uint32_t)(xm >> 32);
+			const int32_t t = a.s1; a.s1 = a.s2; a.s2 = t; a.x = xm; a.bits = s << 1 | 1u;
+			tmp[off[vm] + atomicAdd(&cur[vm], 1u)] = a;
+		}
 	}
 }
-__global__ void k_arc_rank(const ArcDev *__restrict__ tmp, const uint32_t *__restrict__ off, const DevCounts *__restrict__ dc, ArcDev *arc, unsigned long long *idx)
+// pos_of[slot * 2 + is_mirror] = where the arc ended up (k_branch_hits_fast finds an adjacency's arcs through it)
+__global__ void k_arc_rank(const ArcDev *__restrict__ tmp, const uint32_t *__restrict__ off, const DevCounts *__restrict__ dc, ArcDev *arc, unsigned long long *idx, uint32_t *pos_of)
 {
 	PGX_GS(p, dc->n_arc) {
-		const ArcDev a = tmp[p];
+		ArcDev a = tmp[p];
 		const uint32_t v = (uint32_t)(a.x >> 32), b = off[v], e = off[v + 1];
 		uint32_t rank = 0;
 		for (uint32_t q = b; q < e; ++q) rank += tmp[q].x < a.x? 1u : 0u;                // keys are distinct
+		pos_of[a.bits] = b + rank;
+		a.bits = 0;
 		arc[b + rank] = a;
 		if (rank == 0) idx[v] = (unsigned long long)b << 32 | (e - b);                  // graph.c:202-211
 	}
 }
-// first branch round of a run: the arcs come from the round-1 path, which leaves idx[] but no degree table
+// first branch round of a run: the arcs come from the round-1 path, which leaves idx[] but no table: build one over the arc keys
 __global__ void k_deg_from_idx(const unsigned long long *__restrict__ idx, int32_t NV, const DevCounts *__restrict__ dc, uint32_t *deg)
 {
 	const int32_t n_vtx = 2 * (int32_t)dc->n_seg;
 	PGX_GS(v, NV) deg[v] = v < n_vtx? (uint32_t)idx[v] : 0u;
 }
+__global__ void k_table_from_arcs(const ArcDev *__restrict__ arc, DevCounts *dc, ArcTable T, uint32_t *pos_of)
+{
+	PGX_GS(p, dc->n_arc) {
+		const unsigned long long x = arc[p].x, xm = arc_mirror(x);
+		const uint32_t slot = arc_slot(T, x < xm? x : xm, &dc->n_gpart, (uint32_t*)nullptr, &dc->fallback);
+		pos_of[slot * 2 + (xm < x? 1u : 0u)] = (uint32_t)p;
+	}
+}
 
 // ---- which tiles of the next overlap sweep can a changed hit influence? ---------------------------------------------------------------
 // A hit's sweep result (shadow bit, pid_dom; overlap.c:101-178) depends on its own flag word and on the flag words of its window partners,
 // nothing else that changes after the load-time block.  When hit h changes its flt / weak_br bits, the hits that have h in their window
-// are: later ones that start before h ends, earlier ones that end after h starts -- index ranges, because cs and the running maximum of
-// ce are monotone inside a contig.  Their 256-hit sweep tiles are marked; k_sweep_tiled<SW_SHADOW> skips every unmarked tile.
-struct DirtyCols { const int32_t *ctg, *cs, *ce, *pmax; int32_t n; uint32_t *tiles; int32_t tile; };
+// are: later ones that start before h ends, earlier ones that end after h starts -- an index range, because cs and the running maximum of
+// ce are monotone inside a contig.  The range (in 256-hit sweep tiles) depends on coordinates only: k_reach computes it once per active
+// set; a changed hit marks its tiles; k_sweep_tiled<SW_SHADOW> skips every unmarked tile.
+struct DirtyCols { const int2 *reach; uint32_t *tiles; };
+__global__ void k_reach(const int32_t *__restrict__ ctg, const int32_t *__restrict__ cs, const int32_t *__restrict__ ce, const int32_t *__restrict__ pmax, int32_t n, int32_t tile, int2 *reach)
+{
+	PGX_GS(h, n) {
+		const int32_t c = ctg[h], hs = cs[h], he = ce[h];
+		int32_t lo = 0, hi = h;                                 // contig start: first index with ctg >= c (ctg is non-decreasing)
+		while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (ctg[m] < c) lo = m + 1; else hi = m; }
+		int32_t first = lo; hi = h;                             // first hit of the contig whose running max of ce exceeds my start
+		while (first < hi) { const int32_t m = (first + hi) >> 1; if (pmax[m] > hs) hi = m; else first = m + 1; }
+		lo = h + 1; hi = n;                                     // first index past h that is on another contig or starts at/after my end
+		while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (ctg[m] == c && cs[m] < he) lo = m + 1; else hi = m; }
+		reach[h] = make_int2(first / tile, (lo - 1) / tile);
+	}
+}
 __device__ __forceinline__ void mark_dirty(const DirtyCols &D, int32_t h)
 {
-	const int32_t c = D.ctg[h], hs = D.cs[h], he = D.ce[h];
-	int32_t lo = 0, hi = h;                                 // contig start: first index with ctg >= c (ctg is non-decreasing)
-	while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (D.ctg[m] < c) lo = m + 1; else hi = m; }
-	int32_t first = lo; hi = h;                             // first hit of the contig whose running max of ce exceeds my start
-	while (first < hi) { const int32_t m = (first + hi) >> 1; if (D.pmax[m] > hs) hi = m; else first = m + 1; }
-	lo = h + 1; hi = D.n;                                   // first index past h that is on another contig or starts at/after my end
-	while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (D.ctg[m] == c && D.cs[m] < he) lo = m + 1; else hi = m; }
-	for (int32_t t = first / D.tile; t <= (lo - 1) / D.tile; ++t) atomicOr(&D.tiles[t >> 5], 1u << (t & 31));
+	const int2 r = D.reach[h];
+	for (int32_t t = r.x; t <= r.y; ++t) atomicOr(&D.tiles[t >> 5], 1u << (t & 31));
 }
 
 // ---- branch round -----------------------------------------------------------------------------------------------------------
@@ -525,42 +571,38 @@ __global__ void k_branch_decide_fast(const unsigned long long *__restrict__ idx,
 	}
 }
 
-// pgpriv.h:99-107: the arc (v -> w), found through idx[]
-__device__ __forceinline__ uint32_t arc_weak_by_idx(const ArcDev *__restrict__ arc, const unsigned long long *__restrict__ idx, uint32_t v, uint32_t w)
+// branch.c:108-145 + PG_SET_FILTER(weak_br == 2) (graph.c:309).  The two arcs an adjacency sits on (pg_get_arc, pgpriv.h:99-107) are found
+// through the table of canonical keys and pos_of[]; a hit whose flt / weak_br bits change marks the sweep tiles it can influence.
+__device__ __forceinline__ uint32_t arc_weak_of(const ArcTable &T, const uint32_t *__restrict__ pos_of, const ArcDev *__restrict__ arc, unsigned long long x)
 {
-	const unsigned long long e = idx[v];
-	const ArcDev *a = arc + (e >> 32);
-	for (uint32_t i = 0, n = (uint32_t)e; i < n; ++i) if ((uint32_t)a[i].x == w) return a[i].bits >> 1 & 3u;
-	return 0u;
+	const unsigned long long xm = arc_mirror(x);
+	const uint32_t s = arc_find(T, x < xm? x : xm);
+	if (s == ARC_NONE) return 0u;
+	return arc[pos_of[s * 2 + (xm < x? 1u : 0u)]].bits >> 1 & 3u;
 }
-// branch.c:108-145 + PG_SET_FILTER(weak_br == 2) (graph.c:309); a hit whose flt / weak_br bits change marks the sweep tiles it can influence
-__global__ void k_branch_hits_fast(const uint32_t *__restrict__ sv, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ctg, const int32_t *__restrict__ gidp, uint32_t *bits, const int32_t *__restrict__ g2s,
-	const ArcDev *__restrict__ arc, const unsigned long long *__restrict__ idx, DirtyCols D, uint32_t *n_changed)
+__global__ void k_branch_hits_fast(const uint32_t *__restrict__ sv, const SvInfo *__restrict__ info, const DevCounts *__restrict__ dc, uint32_t *bits,
+	const ArcDev *__restrict__ arc, ArcTable T, const uint32_t *__restrict__ pos_of, DirtyCols D, uint32_t *n_changed)
 {
 	const int32_t m = (int32_t)dc->m_sv;
 	PGX_GS(t, m) {
 		const uint32_t h = sv[t], b_in = bits[h];
-		uint32_t b = b_in;
-		const int32_t c = ctg[h];
-		uint32_t wb = (b & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT;
-		const uint32_t w = (uint32_t)g2s[gidp[h] >> 1] << 1 | (b & PG_HB_REV);
+		const SvInfo me = info[t];
+		uint32_t wb = (b_in & PG_HB_WBR_MASK) >> PG_HB_WBR_SHIFT;
 		if (t > 0) {
-			const uint32_t hp = sv[t - 1];
-			if (ctg[hp] == c) {                                 // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
-				const uint32_t v = (uint32_t)g2s[gidp[hp] >> 1] << 1 | (bits[hp] & PG_HB_REV);
-				const uint32_t x = arc_weak_by_idx(arc, idx, w ^ 1u, v ^ 1u);
+			const SvInfo p = info[t - 1];
+			if (p.ctg == me.ctg) {                              // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
+				const uint32_t x = arc_weak_of(T, pos_of, arc, (unsigned long long)(me.w ^ 1u) << 32 | (p.w ^ 1u));
 				wb = wb > x? wb : x;
 			}
 		}
 		if (t + 1 < m) {
-			const uint32_t hn = sv[t + 1];
-			if (ctg[hn] == c) {                                 // I am the earlier hit of (me, next): arc (v -> w), branch.c:127-129
-				const uint32_t wn = (uint32_t)g2s[gidp[hn] >> 1] << 1 | (bits[hn] & PG_HB_REV);
-				const uint32_t x = arc_weak_by_idx(arc, idx, w, wn);
+			const SvInfo nx = info[t + 1];
+			if (nx.ctg == me.ctg) {                             // I am the earlier hit of (me, next): arc (v -> w), branch.c:127-129
+				const uint32_t x = arc_weak_of(T, pos_of, arc, (unsigned long long)me.w << 32 | nx.w);
 				wb = wb > x? wb : x;
 			}
 		}
-		b = (b & ~PG_HB_WBR_MASK) | wb << PG_HB_WBR_SHIFT;
+		uint32_t b = (b_in & ~PG_HB_WBR_MASK) | wb << PG_HB_WBR_SHIFT;
 		if (wb == 2) b |= PG_HB_FLT;                               // graph.c:309
 		if (b != b_in) { bits[h] = b; atomicAdd(n_changed, 1u); if (D.tiles) mark_dirty(D, (int32_t)h); }
 	}
@@ -568,49 +610,57 @@ __global__ void k_branch_hits_fast(const uint32_t *__restrict__ sv, const DevCou
 // graph.c:61-69 + PG_SET_FILTER(vtx == 0) (graph.c:312)
 __global__ void k_flag_vtx_fast(const int32_t *__restrict__ gidp, uint32_t *bits, int32_t n, const int32_t *__restrict__ g2s, DirtyCols D)
 {
-	PGX_GS(i, n) {
-		const uint32_t b_in = bits[i];
-		uint32_t b = b_in;
-		if (g2s[gidp[i] >> 1] >= 0) b |= PG_HB_VTX; else { b &= ~PG_HB_VTX; b |= PG_HB_FLT; }
-		if (b != b_in) { bits[i] = b; if (D.tiles && ((b ^ b_in) & PG_HB_FLT)) mark_dirty(D, i); }
-	}
+	const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t b_in = bits[i];
+	uint32_t b = b_in;
+	if (g2s[gidp[i] >> 1] >= 0) b |= PG_HB_VTX; else { b &= ~PG_HB_VTX; b |= PG_HB_FLT; }
+	if (b != b_in) { bits[i] = b; if (D.tiles && ((b ^ b_in) & PG_HB_FLT)) mark_dirty(D, i); }
 }
 
-// graph.c:237-263 in ONE CTA: delete marks (occupancy, out-degree from idx[], distant loci), order-preserving compaction (pg_hard_delete),
-// gene -> segment map (pg_gen_g2s).  tmp: scratch for n_seg records.
-constexpr int SEGF_B = 1024;
-__global__ void __launch_bounds__(SEGF_B) k_seg_filter(SegDev *seg, SegDev *tmp, DevCounts *dc, const unsigned long long *__restrict__ idx, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci,
-	int32_t *g2s, int32_t n_gene)
+// graph.c:237-263 in two launches: delete marks (occupancy, out-degree from idx[], distant loci) scanned in one pass, then the
+// order-preserving compaction (pg_hard_delete) with the gene -> segment map (pg_gen_g2s; g2s is filled with -1 beforehand).
+__global__ void __launch_bounds__(SCAN_B) k_seg_keep_scan(const SegDev *__restrict__ seg, const DevCounts *__restrict__ dc, const unsigned long long *__restrict__ idx,
+	int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, uint32_t *pos, uint32_t *n_keep, unsigned long long *status, uint32_t *ticket)
 {
 	__shared__ uint32_t wsum[33];
-	__shared__ uint32_t s_carry;
+	__shared__ uint32_t s_tile, s_prefix;
 	const int tid = threadIdx.x;
-	const int32_t n_seg = (int32_t)dc->n_seg;
-	if (tid == 0) s_carry = 0;
-	for (int32_t g = tid; g < n_gene; g += SEGF_B) g2s[g] = -1;
+	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
 	__syncthreads();
-	for (int32_t c0 = 0; c0 < n_seg; c0 += SEGF_B) {
-		const int32_t s = c0 + tid;
-		uint32_t keep = 0;
-		SegDev r;
+	const uint32_t tile = s_tile;
+	const int32_t n_seg = (int32_t)dc->n_seg;
+	const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)tid * SCAN_I;
+	uint32_t fl = 0, sum = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) {
+		const int64_t s = base + k;
 		if (s < n_seg) {
-			r = seg[s];
+			const SegDev r = seg[s];
 			bool del = r.tot_cnt > max_occ_total;                                            // graph.c:241
 			del = del || (int32_t)(uint32_t)idx[2 * s] > max_degree || (int32_t)(uint32_t)idx[2 * s + 1] > max_degree;   // graph.c:244-248
 			const int32_t m = r.n_dist_loci[0] > r.n_dist_loci[1]? r.n_dist_loci[0] : r.n_dist_loci[1];
 			del = del || m > max_dist_loci;                                                  // graph.c:251-255
-			keep = del? 0u : 1u;
+			if (!del) { fl |= 1u << k; ++sum; }
 		}
-		uint32_t tot;
-		const uint32_t ex = block_exclusive_scan<SEGF_B>(keep, tot, wsum);
-		if (keep) tmp[s_carry + ex] = r;
-		__syncthreads();
-		if (tid == 0) s_carry += tot;
-		__syncthreads();
 	}
-	const int32_t n_new = (int32_t)s_carry;
-	for (int32_t s = tid; s < n_new; s += SEGF_B) { const SegDev r = tmp[s]; seg[s] = r; g2s[r.gid] = s; }
-	if (tid == 0) dc->n_seg = (uint32_t)n_new;
+	uint32_t tile_sum;
+	const uint32_t excl = block_exclusive_scan<SCAN_B>(sum, tile_sum, wsum);
+	if (tid < 32) { const uint32_t p = lookback_prefix(status, tile, tile_sum); if (tid == 0) s_prefix = p; }
+	__syncthreads();
+	uint32_t run = s_prefix + excl;
+#pragma unroll
+	for (int k = 0; k < SCAN_I; ++k) {
+		const int64_t s = base + k;
+		if (s < n_seg) pos[s] = (fl >> k & 1u)? run : ARC_NONE;
+		if (s == n_seg) *n_keep = run;
+		run += fl >> k & 1u;
+	}
+}
+__global__ void k_seg_compact_fast(const SegDev *__restrict__ in, SegDev *out, DevCounts *dc, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ n_keep, int32_t *g2s)
+{
+	const int32_t n_seg = (int32_t)dc->n_seg;                  // (the count is replaced by the LAST block to finish reading it: a separate launch does it)
+	PGX_GS(s, n_seg) { const uint32_t p = pos[s]; if (p != ARC_NONE) { const SegDev r = in[s]; out[p] = r; g2s[r.gid] = (int32_t)p; } }
 }
 __global__ void k_seg_store_occ_fast(SegDev *seg, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ng, const int32_t *__restrict__ tot)
 {

@@ -157,7 +157,7 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 	std::vector<std::vector<uint32_t>> llist(R), glist(R), bm(R), degcur(R), seen(R);
 	std::vector<std::vector<int32_t>> segocc(R);
 	const uint32_t part_cap = in->H / 2;
-	std::vector<ArcPartial> all((size_t)R * (part_cap + 1));
+	std::vector<ArcWire> all((size_t)R * (part_cap + 1));
 	std::vector<ArcTable> loc(R), glob(R);
 	// which survivors belong to which rank: genomes [G*r/R, G*(r+1)/R); every rank sees its own slice of sv as ITS list, genome ids made local
 	for (int r = 0; r < R; ++r) {
@@ -170,28 +170,29 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 		for (int i = 0; i < in->n_hit; ++i) ctg2g_loc[in->ctg[i]] = in->ctg2g[in->ctg[i]] - g0;
 		memset(&dcs[r], 0, sizeof(DevCounts));
 		dcs[r].m_sv = (uint32_t)sv.size(); dcs[r].n_seg = in->n_seg0;
-		lkey[r].assign(in->H, KEY_EMPTY); lacc[r].assign(in->H, ArcAcc{0, 0, 0, 0}); llist[r].assign(in->H, 0);
+		lkey[r].assign(in->H, KEY_EMPTY); lacc[r].assign(in->H, ArcAcc{0, 0, 0}); llist[r].assign(in->H, 0);
 		const size_t bmw = (((size_t)in->H * Gl + 31) / 32 + 3) & ~(size_t)3;
 		bm[r].assign(2 * bmw, 0); degcur[r].assign(2 * (size_t)NV + 8, 0); seen[r].assign(((size_t)Gl * in->n_seg0 + 31) / 32 + 4, 0); segocc[r].assign(2 * (size_t)in->n_seg0 + 4, 0);
 		loc[r].key = lkey[r].data(); loc[r].acc = lacc[r].data(); loc[r].list = llist[r].data(); loc[r].bm1 = bm[r].data(); loc[r].bm2 = bm[r].data() + bmw; loc[r].H = in->H;
 		glob[r] = loc[r];
-		if (R > 1) { gkey[r].assign(in->H, KEY_EMPTY); gacc[r].assign(in->H, ArcAcc{0, 0, 0, 0}); glist[r].assign(in->H, 0); glob[r].key = gkey[r].data(); glob[r].acc = gacc[r].data(); glob[r].list = glist[r].data(); glob[r].bm1 = glob[r].bm2 = nullptr; }
+		if (R > 1) { gkey[r].assign(in->H, KEY_EMPTY); gacc[r].assign(in->H, ArcAcc{0, 0, 0}); glist[r].assign(in->H, 0); glob[r].key = gkey[r].data(); glob[r].acc = gacc[r].data(); glob[r].list = glist[r].data(); glob[r].bm1 = glob[r].bm2 = nullptr; }
 		std::vector<unsigned long long> l2key(in->H2, KEY_EMPTY), l2d(in->H2, 0); std::vector<uint32_t> l2n(in->H2, 0), l2list(in->H2, 0); std::vector<int32_t> l2m(2 * (size_t)in->H2, 0);
 		OvfTable L; L.key = l2key.data(); L.dsum = l2d.data(); L.n = l2n.data(); L.list = l2list.data(); L.m1 = l2m.data(); L.m2 = l2m.data() + in->H2; L.H = in->H2;
-		std::vector<PairRec> rec(sv.size() + 1); std::vector<OvfRec> ovf(in->ovf_cap + 1);
+		std::vector<uint32_t> rec(sv.size() + 1); std::vector<SvInfo> info(sv.size() + 1); std::vector<OvfRec> ovf(in->ovf_cap + 2);
 		uint32_t tie = 0, err = 0;
 		ArcSrc e; e.sv = sv.data(); e.ctg = in->ctg; e.cm = in->cm; e.gidp = in->gidp; e.sori = in->sori; e.sdom = in->sdom; e.pdom0 = in->pdom0; e.bits = in->bits;
 		e.g2s = in->g2s; e.prot_gid = in->prot_gid; e.ctg2g = ctg2g_loc.data(); e.use_ori = in->use_ori; e.n_seg0 = in->n_seg0; e.Gl = Gl;
 		DevCounts *dc = &dcs[r];
 		uint32_t *deg = degcur[r].data();
 		int32_t *ng = segocc[r].data(), *tot = segocc[r].data() + in->n_seg0;
-		emu::launch(grid, TBk, [&] { k_arc_insert(e, loc[r], dc, rec.data(), seen[r].data(), ng, tot, R > 1? (uint32_t*)nullptr : deg, &tie, &err); });
-		emu::launch(grid, TBk, [&] { k_arc_fold(rec.data(), loc[r], dc, Gl, ovf.data(), (uint32_t)in->ovf_cap); });
+		emu::launch(grid, TBk, [&] { k_survivor_info(e, dc, info.data(), seen[r].data(), ng, tot, &err); });
+		emu::launch(grid, TBk, [&] { k_arc_insert(info.data(), ctg2g_loc.data(), Gl, loc[r], dc, rec.data(), R > 1? (uint32_t*)nullptr : deg, &tie); });
+		emu::launch(grid, TBk, [&] { k_arc_fold(info.data(), rec.data(), ctg2g_loc.data(), loc[r], dc, Gl, ovf.data(), (uint32_t)in->ovf_cap); });
 		emu::launch(2, TBk, [&] { k_arc_ovf_insert(ovf.data(), (uint32_t)in->ovf_cap, L, dc); });
 		emu::launch(2, TBk, [&] { k_arc_ovf_fold(L, loc[r], dc); });
 		for (uint32_t j = 0; j < L.H; ++j) if (l2key[j] != KEY_EMPTY || l2n[j] || l2d[j] || l2m[j] || l2m[j + in->H2]) return -2;   // the overflow table hands itself back clean
 		if (err) return -3;
-		if (R > 1) { ArcPartial *mine = all.data() + (size_t)r * (part_cap + 1); emu::launch(grid, TBk, [&] { k_arc_pack(loc[r], dc, mine, part_cap); }); }
+		if (R > 1) { ArcWire *mine = all.data() + (size_t)r * (part_cap + 1); emu::launch(grid, TBk, [&] { k_arc_pack(loc[r], dc, mine, part_cap); }); }
 	}
 	// "allreduce" of the segment occupancy, then every rank merges and finalises; rank 0's result is returned, the others must agree
 	std::vector<int32_t> occ(2 * (size_t)in->n_seg0 + 4, 0);
@@ -203,13 +204,24 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 		if (R > 1) emu::launch(grid, TBk, [&] { k_arc_merge(all.data(), R, part_cap, glob[r], dc, deg); });
 		const int tiles = (NV + 1 + SCAN_TILE - 1) / SCAN_TILE;
 		std::vector<unsigned long long> status(2 * (size_t)tiles + 2, 0ull); uint32_t ticket = 0; unsigned long long nl_total = 0;
-		std::vector<uint32_t> off(NV + 8), nl_off(NV + 8);
+		std::vector<uint32_t> off(NV + 8), nl_off(NV + 8), pos_of(2 * (size_t)in->H, 0xffffffffu);
 		std::vector<ArcDev> tmp(in->arc_cap + 1), arc(in->arc_cap + 1);
 		std::vector<unsigned long long> idx(NV + 2, 0ull);
 		emu::launch(tiles, SCAN_B, [&] { k_vertex_scan(deg, NV, off.data(), nl_off.data(), dc, (uint32_t)in->arc_cap, &nl_total, status.data(), &ticket); });
 		emu::launch(grid, TBk, [&] { k_arc_place(glob[r], R > 1? &dc->n_gpart : &dc->n_part, off.data(), cur, dc, tmp.data()); });
-		emu::launch(grid, TBk, [&] { k_arc_rank(tmp.data(), off.data(), dc, arc.data(), idx.data()); });
+		emu::launch(grid, TBk, [&] { k_arc_rank(tmp.data(), off.data(), dc, arc.data(), idx.data(), pos_of.data()); });
 		if (nl_total != dc->n_nl) return -4;
+		// every arc is found again through the key table (what k_branch_hits_fast does), and a table rebuilt from the arcs (first round of a run) agrees
+		std::vector<unsigned long long> tkey(in->H, KEY_EMPTY); std::vector<uint32_t> tlist(in->H, 0), tpos(2 * (size_t)in->H, 0xffffffffu);
+		ArcTable T2 = glob[r]; T2.key = tkey.data(); T2.list = tlist.data();
+		DevCounts dc2 = *dc; dc2.n_gpart = 0;
+		emu::launch(grid, TBk, [&] { k_table_from_arcs(arc.data(), &dc2, T2, tpos.data()); });
+		for (uint32_t p = 0; p < dc->n_arc && !dc->fallback; ++p) {
+			const unsigned long long x = arc[p].x, xm = arc_mirror(x);
+			const uint32_t s = arc_find(glob[r], x < xm? x : xm), s2 = arc_find(T2, x < xm? x : xm);
+			if (s == ARC_NONE || pos_of[s * 2 + (xm < x)] != p || arc[p].bits != 0) return -6;
+			if (s2 == ARC_NONE || tpos[s2 * 2 + (xm < x)] != p) return -7;
+		}
 		if (r == 0) {
 			memcpy(in->arc, arc.data(), (size_t)dc->n_arc * sizeof(ArcDev)); memcpy(in->idx, idx.data(), (size_t)NV * 8); memcpy(in->nl_off, nl_off.data(), (size_t)(NV + 1) * 4);
 			memcpy(in->seg_ng, occ.data(), (size_t)in->n_seg0 * 4); memcpy(in->seg_tot, occ.data() + in->n_seg0, (size_t)in->n_seg0 * 4);
@@ -231,20 +243,26 @@ extern "C" int round_emu_compact(const uint32_t *bits, const uint32_t *perm, int
 	return (dc.n_part | dc.n_ovf | dc.n_l2 | dc.n_gpart) == 0? 0 : -1;
 }
 
-extern "C" int round_emu_seg_filter(pgx::SegDev *seg, int32_t *n_seg, const unsigned long long *idx, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, int32_t *g2s, int32_t n_gene)
+extern "C" int round_emu_seg_filter(const pgx::SegDev *seg, pgx::SegDev *out, int32_t *n_seg, int32_t cap, const unsigned long long *idx, int32_t max_occ_total, int32_t max_degree, int32_t max_dist_loci, int32_t *g2s, int32_t n_gene)
 {
 	using namespace pgx;
 	DevCounts dc; memset(&dc, 0, sizeof(dc)); dc.n_seg = *n_seg;
-	std::vector<SegDev> tmp(*n_seg + 1);
-	emu::launch(1, SEGF_B, [&] { k_seg_filter(seg, tmp.data(), &dc, idx, max_occ_total, max_degree, max_dist_loci, g2s, n_gene); });
-	*n_seg = dc.n_seg;
+	const int tiles = (cap + 1 + SCAN_TILE - 1) / SCAN_TILE;
+	std::vector<unsigned long long> status(tiles + 1, 0ull); uint32_t ticket = 0, n_keep = 0xffffffffu;
+	std::vector<uint32_t> pos(cap + 8, 0x55555555u);
+	for (int g = 0; g < n_gene; ++g) g2s[g] = -1;
+	emu::launch(tiles, SCAN_B, [&] { k_seg_keep_scan(seg, &dc, idx, max_occ_total, max_degree, max_dist_loci, pos.data(), &n_keep, status.data(), &ticket); });
+	emu::launch(3, 256, [&] { k_seg_compact_fast(seg, out, &dc, pos.data(), &n_keep, g2s); });
+	*n_seg = (int32_t)n_keep;
 	return 0;
 }
 
 extern "C" int round_emu_dirty(const int32_t *ctg, const int32_t *cs, const int32_t *ce, const int32_t *pmax, int32_t n, int32_t tile, const int32_t *changed, int32_t n_changed, uint32_t *tiles)
 {
 	using namespace pgx;
-	DirtyCols D; D.ctg = ctg; D.cs = cs; D.ce = ce; D.pmax = pmax; D.n = n; D.tiles = tiles; D.tile = tile;
+	std::vector<int2> reach(n + 1);
+	emu::launch(3, 256, [&] { k_reach(ctg, cs, ce, pmax, n, tile, reach.data()); });
+	DirtyCols D; D.reach = reach.data(); D.tiles = tiles;
 	for (int i = 0; i < n_changed; ++i) mark_dirty(D, changed[i]);
 	return 0;
 }

@@ -2,7 +2,7 @@
 this test runs the launch sequence of Session::gen_arc_fast -- table insert, (key, genome) marks, singleton fold, overflow groups, the
 rank-to-rank merge, vertex scan, counting sort -- on random survivor lists against a plain-Python restatement of graph.c:97-176 (per-genome
 collapse with the rounded mean, global collapse, arcs sorted by key, idx of graph.c:202-211).  Also: the one-pass survivor compaction, the
-one-CTA segment filter (graph.c:237-263) and the dirty-tile marks of the incremental sweep against brute force."""
+two-launch segment filter (graph.c:237-263) and the dirty-tile marks of the incremental sweep against brute force."""
 import ctypes as C
 import os
 import sys
@@ -27,7 +27,7 @@ def emu():
     L = C.CDLL(emu_build.build_round())
     L.round_emu_arc_build.argtypes = [C.POINTER(EmuArcIn)]
     L.round_emu_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.round_emu_seg_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    L.round_emu_seg_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
     L.round_emu_dirty.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     return L
 
@@ -190,8 +190,8 @@ def test_segment_filter(emu, n_seg):
     keep = ~((seg["tot_cnt"] > 40) | (deg[0::2] > 8) | (deg[1::2] > 8) | (np.maximum(seg["l0"], seg["l1"]) > 3))
     want = seg[keep].copy()
     g2s = np.full(n_gene, 12345, np.int32); n = np.array([n_seg], np.int32)
-    work = seg.copy()
-    assert emu.round_emu_seg_filter(work.ctypes.data, n.ctypes.data, idx.ctypes.data, 40, 8, 3, g2s.ctypes.data, n_gene) == 0
+    work = np.zeros(n_seg + 300, dtype=SEG)
+    assert emu.round_emu_seg_filter(seg.ctypes.data, work.ctypes.data, n.ctypes.data, n_seg + 300, idx.ctypes.data, 40, 8, 3, g2s.ctypes.data, n_gene) == 0   # capacity > count: segments were deleted in earlier rounds
     assert n[0] == keep.sum() and np.array_equal(work[:n[0]], want)
     want_g2s = np.full(n_gene, -1, np.int32); want_g2s[want["gid"]] = np.arange(len(want))
     assert np.array_equal(g2s, want_g2s)
