@@ -399,8 +399,11 @@ struct Session {
 			launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits_alt, A.pdom, nullptr);
 			a_bits.swap(a_bits_alt); set_active();
 		}
+		const double tp0 = wall_s();
 		PGX_CHECK(cudaStreamSynchronize(st));
+		const double tp1 = wall_s();
 		choose_representatives(hz.data(), h_prot_gid.data(), n_prot, n_gene, rep);      // host: exact tie order
+		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] stage_post: drained the stream in %.2f ms, representatives on the host %.2f ms\n", (tp1 - tp0) * 1e3, (wall_s() - tp1) * 1e3);
 		PGX_CHECK(cudaMemcpyAsync(prot_rep.p, rep.prot_rep.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
 		done_post = true;
 		g_stats.n_active = Nw;
@@ -523,43 +526,48 @@ struct Session {
 	{
 		size_t mk = scratch.mark();
 		size_t tab = (size_t)G * n_gene;
-		int Gmax = 0;
-		for (int g : rank_G) Gmax = g > Gmax? g : Gmax;
-		size_t tab_max = (size_t)Gmax * n_gene;
 		uint8_t *t_dom = scratch.get<uint8_t>(tab + 1);
 		int32_t *t_first = scratch.get<int32_t>(tab + 1);
-		int32_t *aux_all = scratch.get<int32_t>(tab_max * g_comm.nranks + 1);
-		int32_t *aux = aux_all + tab_max * g_comm.rank;
+		int32_t *aux = scratch.get<int32_t>(tab + 1);
 		PGX_CHECK(cudaMemsetAsync(t_dom, 0, tab + 1, st));
 		PGX_LAUNCH(k_fill_i32, grid_for((int64_t)tab + 1, TB), TB, 0, st, t_first, (int64_t)tab + 1, INT32_MAX);
 		if (Nw) PGX_LAUNCH(k_vtx_mark, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, A.rank, A.bits, Nw, G, t_dom, t_first);
 		if (tab) PGX_LAUNCH(k_vtx_resolve, grid_for((int64_t)tab, TB), TB, 0, st, t_dom, t_first, A.pdom, prot_gid.p, tab, aux, counters.p + C_ERR);
-		g_comm.allgather(aux, aux_all, tab_max * 4, st);
 		double tv0 = wall_s();
-		// the table comes back through a pinned staging buffer when it fits (8 MB at 100 genomes x 20k genes)
-		const size_t all_bytes = tab_max * g_comm.nranks * 4;
-		std::vector<int32_t> h_all_v, h_aux_v;
-		const int32_t *h_all;
-		if (all_bytes <= PinnedRing::CAP) { h_all = (const int32_t*)PinnedRing::get().buf[0]; PGX_CHECK(cudaMemcpyAsync(PinnedRing::get().buf[0], aux_all, all_bytes, cudaMemcpyDeviceToHost, st)); }
-		else { h_all_v.resize(tab_max * g_comm.nranks + 1); h_all = h_all_v.data(); PGX_CHECK(cudaMemcpyAsync(h_all_v.data(), aux_all, all_bytes, cudaMemcpyDeviceToHost, st)); }
+		// the election's input in compact form: per-gene counts + the shadowed cells (k_vtx_cells); a few hundred KB instead of the whole table
+		int32_t *cnt2 = scratch.get<int32_t>(2 * (size_t)n_gene + 2);
+		uint32_t *n_cells_d = scratch.get<uint32_t>(g_comm.nranks + 1);
+		if (tab >= 0xfffffff0u) PGX_FATAL("vertex selection: the (gene, genome) table has %zu cells; 32-bit cell indices", tab);
+		const uint32_t cap0 = (uint32_t)tab + 16;                                              // every cell could be a shadowed one
+		VtxCell *cells_d = scratch.get<VtxCell>((size_t)cap0);
+		PGX_CHECK(cudaMemsetAsync(cnt2, 0, (2 * (size_t)n_gene + 2) * 4, st));
+		PGX_CHECK(cudaMemsetAsync(n_cells_d, 0, ((size_t)g_comm.nranks + 1) * 4, st));
+		if (tab) PGX_LAUNCH(k_vtx_cells, grid_for((int64_t)tab, TB), TB, 0, st, aux, tab, G, g_comm.genome_begin, cnt2, cells_d, cap0, n_cells_d + g_comm.rank);
+		g_comm.allreduce(cnt2, 2 * (size_t)n_gene, Comm::T_INT32, Comm::OP_SUM, st);
+		g_comm.allgather(n_cells_d + g_comm.rank, n_cells_d, 4, st);
+		std::vector<int32_t> h_cnt2(2 * (size_t)n_gene + 2);
+		std::vector<uint32_t> h_nc(g_comm.nranks);
+		PGX_CHECK(cudaMemcpyAsync(h_cnt2.data(), cnt2, 2 * (size_t)n_gene * 4, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaMemcpyAsync(h_nc.data(), n_cells_d, (size_t)g_comm.nranks * 4, cudaMemcpyDeviceToHost, st));
 		check_err("vertex selection");
-		double tv1 = wall_s();
-		const int32_t *h_aux = h_all;
-		if (g_comm.nranks > 1) {   // stitch the per-rank [gene][local genome] blocks into [gene][genome] (ranks hold consecutive genome ranges)
-			h_aux_v.resize((size_t)Gtot * n_gene + 1);
-			int32_t jb = 0;
-			for (int r = 0; r < g_comm.nranks; ++r) {
-				const int32_t Gr = rank_G[r];
-				const int32_t *blk = h_all + tab_max * r;
-				for (int32_t g = 0; g < n_gene; ++g) memcpy(h_aux_v.data() + (size_t)g * Gtot + jb, blk + (size_t)g * Gr, (size_t)Gr * 4);
-				jb += Gr;
+		uint32_t nc_max = 0; size_t nc_tot = 0;
+		for (uint32_t c : h_nc) { nc_max = c > nc_max? c : nc_max; nc_tot += c; }
+		std::vector<VtxCellHost> h_cells(nc_tot + 1);
+		static_assert(sizeof(VtxCell) == sizeof(VtxCellHost), "cell record");
+		if (g_comm.nranks > 1) {
+			VtxCell *all = scratch.get<VtxCell>((size_t)nc_max * g_comm.nranks + 1);
+			if (nc_max) {
+				if (h_nc[g_comm.rank]) PGX_CHECK(cudaMemcpyAsync(all + (size_t)nc_max * g_comm.rank, cells_d, (size_t)h_nc[g_comm.rank] * sizeof(VtxCell), cudaMemcpyDeviceToDevice, st));
+				g_comm.allgather(all + (size_t)nc_max * g_comm.rank, all, (size_t)nc_max * sizeof(VtxCell), st);
+				size_t o = 0;
+				for (int r = 0; r < g_comm.nranks; ++r) { if (h_nc[r]) PGX_CHECK(cudaMemcpyAsync(h_cells.data() + o, all + (size_t)nc_max * r, (size_t)h_nc[r] * sizeof(VtxCell), cudaMemcpyDeviceToHost, st)); o += h_nc[r]; }
 			}
-			if (jb != Gtot) PGX_FATAL("genome partition inconsistent: %d genomes gathered, %d expected", jb, Gtot);
-			h_aux = h_aux_v.data();
-		}
-		elect_vertices(h_aux, Gtot, n_gene, rep.gene_rep_pid.data(), rep.prot_avg.data(), h_gene_pref.data(), h_gene_incl.data(), opt->min_vertex_ratio,
+		} else if (nc_tot) PGX_CHECK(cudaMemcpyAsync(h_cells.data(), cells_d, nc_tot * sizeof(VtxCell), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		double tv1 = wall_s();
+		elect_vertices_cells(h_cnt2.data(), h_cells.data(), nc_tot, Gtot, n_gene, rep.gene_rep_pid.data(), rep.prot_avg.data(), h_gene_pref.data(), h_gene_incl.data(), opt->min_vertex_ratio,
 			!!(opt->flag & PG_F_WRITE_VTX_SEL), h_gene_names, h_seg0);
-		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] gen_vtx: table D2H %.2f ms, host election %.2f ms\n", (tv1 - tv0) * 1e3, (wall_s() - tv1) * 1e3);
+		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] gen_vtx: counts + %zu cells D2H %.2f ms, host election %.2f ms\n", nc_tot, (tv1 - tv0) * 1e3, (wall_s() - tv1) * 1e3);
 		n_seg = n_seg0 = (int32_t)h_seg0.size();
 		std::vector<SegDev> hs(n_seg > 0? n_seg : 1);
 		for (int32_t i = 0; i < n_seg; ++i) { memset(&hs[i], 0, sizeof(SegDev)); hs[i].gid = h_seg0[i].gid; hs[i].n_dom = h_seg0[i].n_dom; hs[i].n_sub = h_seg0[i].n_sub; }

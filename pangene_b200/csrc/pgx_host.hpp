@@ -45,6 +45,11 @@ public:
 			const int sh = r.shift;
 			std::fill(end, end + 256, 0);
 			for (int64_t i = 0; i < r.n; ++i) ++end[p[i].x >> sh & 255];
+			{   // every record in one bucket (a byte all keys share: the high bytes of small keys): the permutation below is the identity
+				bool one = false;
+				for (int k = 0; k < 256 && !one; ++k) one = end[k] == r.n;
+				if (one) { if (sh > 0) todo.push_back(Range{r.beg, r.n, sh > 8? sh - 8 : 0}); continue; }
+			}
 			int64_t acc = 0;
 			for (int k = 0; k < 256; ++k) { beg[k] = nxt[k] = acc; acc += end[k]; end[k] = acc; }
 			// permute in place: walk the buckets in order; whatever sits at the write cursor of bucket k and does not
@@ -87,62 +92,49 @@ static inline void choose_representatives(const unsigned long long *z, const int
 	}
 }
 
-// vertex.c:52-98.  aux[g*n_genome+j] (gene-major): -2 = g has an unshadowed rank-0 hit in genome j, >=0 = the gene shadowing
-// its only rank-0 hit there, -1 = absent.  Returns the accepted genes as segments sorted by gene id.
-// The reference recounts, for every gene, in how many of its dominant genomes it has already been claimed by an accepted
-// gene (vertex.c:63-65: O(n_gene * n_genome) with a stride of n_gene words).  Here that count is kept incrementally -- it only
-// changes when an accepted gene claims a (genome, gene) cell for the first time -- so the pass touches only the rows of
-// accepted genes.  Same decisions, same order.
 struct SegHost { int32_t gid, n_dom, n_sub; };
-static inline void elect_vertices(const int32_t *aux, int32_t n_genome, int32_t n_gene, const int32_t *gene_rep_pid, const int32_t *prot_avg,
+
+// vertex.c:52-98, the greedy election, from the compact form the device hands over (k_vtx_cells): per-gene counts and the shadowed cells only.  The reference
+// walks a whole row of the [gene][genome] table for every accepted gene (vertex.c:74-77); the only cells that matter there are the
+// shadowed ones, and the only thing read of the claimed gene is whether it is dominant in that genome -- both are in the cell record.
+// Same decisions in the same order (the order is the exact replay of the reference's radix sort).
+struct VtxCellHost { int32_t g, j, t, t_dom; };
+static inline void elect_vertices_cells(const int32_t *cnt2, const VtxCellHost *cells, size_t n_cells, int32_t n_genome, int32_t n_gene, const int32_t *gene_rep_pid, const int32_t *prot_avg,
 	const uint8_t *gene_pref, const uint8_t *gene_incl, double min_vertex_ratio, bool dump, const pg_gene_t *names, std::vector<SegHost> &out)
 {
-	struct timespec ts0, ts1, ts2, ts3;
-	clock_gettime(CLOCK_MONOTONIC, &ts0);
 	std::vector<pg128_t> cnt(n_gene);
-	std::vector<uint8_t> claimed((size_t)n_genome * n_gene, 0);
-	std::vector<int32_t> n_dom_of(n_gene, 0), n_claimed(n_gene, 0);
-	const int64_t GB = 512;
-	ThreadPool::get().parallel_for((n_gene + GB - 1) / GB, [&](int64_t blk) {                 // per-gene counts: independent rows
-		for (int32_t g = (int32_t)(blk * GB); g < n_gene && g < (int32_t)((blk + 1) * GB); ++g) {
-			const int32_t *row = aux + (size_t)g * n_genome;
-			uint64_t x = (uint64_t)(int64_t)prot_avg[gene_rep_pid[g]], y = (uint64_t)g;      // vertex.c:19-20
-			int32_t nd = 0;
-			for (int32_t j = 0; j < n_genome; ++j) {
-				if (row[j] == -2) x += 1ull << 32, ++nd;                                      // vertex.c:49
-				else if (row[j] >= 0) y += 1ull << 32;                                        // vertex.c:50
-			}
-			if (gene_pref[g]) x |= 1ull << 63;                                                // vertex.c:55-57
-			cnt[g].x = x; cnt[g].y = y; n_dom_of[g] = nd;
-		}
-	});
-	clock_gettime(CLOCK_MONOTONIC, &ts1);
+	for (int32_t g = 0; g < n_gene; ++g) {
+		uint64_t x = (uint64_t)(int64_t)prot_avg[gene_rep_pid[g]] + ((uint64_t)(uint32_t)cnt2[2 * g] << 32), y = (uint64_t)g + ((uint64_t)(uint32_t)cnt2[2 * g + 1] << 32);   // vertex.c:19-20,49-50
+		if (gene_pref[g]) x |= 1ull << 63;                                                // vertex.c:55-57
+		cnt[g].x = x; cnt[g].y = y;
+	}
+	// cells grouped by their gene (counting sort; the order inside a group is irrelevant: every cell of a row names a different genome)
+	std::vector<uint32_t> start(n_gene + 1, 0);
+	for (size_t i = 0; i < n_cells; ++i) ++start[cells[i].g + 1];
+	for (int32_t g = 0; g < n_gene; ++g) start[g + 1] += start[g];
+	std::vector<uint32_t> fill(start.begin(), start.end() - 1), by_gene(n_cells);
+	for (size_t i = 0; i < n_cells; ++i) by_gene[fill[cells[i].g]++] = (uint32_t)i;
 	FlagSortReplay::run(cnt.data(), n_gene);                                                  // vertex.c:60
-	clock_gettime(CLOCK_MONOTONIC, &ts2);
-	out.clear();
+	std::vector<uint64_t> claimed(((size_t)n_genome * n_gene + 63) / 64, 0);
+	std::vector<int32_t> n_claimed(n_gene, 0);
+	std::vector<uint8_t> accepted(n_gene, 0);
+	std::vector<int32_t> n_dom_out(n_gene, 0);                                                // as the reference reads it back from the sort key (a negative mean score leaks into the field)
 	for (int32_t i = n_gene - 1; i >= 0; --i) {
-		int32_t n_dom = (int32_t)(cnt[i].x << 1 >> 33), n_sub = (int32_t)(cnt[i].y >> 32), gid = (int32_t)cnt[i].y;
-		int32_t x = n_dom_of[gid], y = n_claimed[gid];                                       // vertex.c:63-65
+		const int32_t n_dom = (int32_t)(cnt[i].x << 1 >> 33), n_sub = (int32_t)(cnt[i].y >> 32), gid = (int32_t)cnt[i].y;
+		const int32_t x = cnt2[2 * gid], y = n_claimed[gid];                                  // vertex.c:63-65
 		if (dump && names) printf("g\t%s\t%d\t%d\t%d\t%d\t%c\t%c\n", names[gid].name, (int32_t)cnt[i].x, x, y, n_sub, "NY"[gene_incl[gid]], "NY"[gene_pref[gid]]);   // vertex.c:66-67
 		if (gene_incl[gid] || (n_dom >= n_genome * min_vertex_ratio && y < x)) {             // vertex.c:69
-			out.push_back(SegHost{gid, n_dom, n_sub});
-			if (x > 0 && n_sub > 0) {                                                         // vertex.c:74-77 (n_sub == 0: no cell of this row names a shadowing gene)
-				const int32_t *row = aux + (size_t)gid * n_genome;
-				for (int32_t j = 0; j < n_genome; ++j) {
-					int32_t t = row[j];
-					if (t < 0) continue;
-					uint8_t &c = claimed[(size_t)t * n_genome + j];
-					if (!c) { c = 1; if (aux[(size_t)t * n_genome + j] == -2) ++n_claimed[t]; }
+			accepted[gid] = 1; n_dom_out[gid] = n_dom;
+			if (x > 0 && n_sub > 0)                                                           // vertex.c:74-77
+				for (uint32_t q = start[gid]; q < start[gid + 1]; ++q) {
+					const VtxCellHost &c = cells[by_gene[q]];
+					const size_t bit = (size_t)c.t * n_genome + c.j;
+					if (!(claimed[bit >> 6] >> (bit & 63) & 1ull)) { claimed[bit >> 6] |= 1ull << (bit & 63); if (c.t_dom) ++n_claimed[c.t]; }
 				}
-			}
 		}
 	}
-	std::sort(out.begin(), out.end(), [](const SegHost &a, const SegHost &b) { return a.gid < b.gid; });   // vertex.c:85-94
-	clock_gettime(CLOCK_MONOTONIC, &ts3);
-	if (getenv("PGX_TIMING")) {
-		auto ms = [](const timespec &a, const timespec &b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
-		fprintf(stderr, "[pgx timing] election: counts %.2f ms, order replay %.2f ms, greedy+sort %.2f ms\n", ms(ts0, ts1), ms(ts1, ts2), ms(ts2, ts3));
-	}
+	out.clear();
+	for (int32_t g = 0; g < n_gene; ++g) if (accepted[g]) out.push_back(SegHost{g, n_dom_out[g], cnt2[2 * g + 1]});   // vertex.c:85-94: sorted by gene id
 }
 
 } // namespace pgx

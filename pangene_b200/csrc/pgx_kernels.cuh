@@ -1036,6 +1036,23 @@ __global__ void k_vtx_resolve(const uint8_t *__restrict__ t_dom, const int32_t *
 	aux[k] = v;
 }
 
+// What the greedy election (vertex.c:52-80) needs of the [gene][genome] table, compact: per gene the number of genomes where it is dominant /
+// only shadowed (vertex.c:49-50), and one record per "shadowed" cell -- gene g, genome j, the gene t that shadows it there, and whether t is
+// dominant in j (the only cells the election ever reads: an accepted gene claims the genes that shadow it, vertex.c:74-77).
+struct VtxCell { int32_t g, j, t, t_dom; };
+__global__ void k_vtx_cells(const int32_t *__restrict__ aux, size_t n_tab, int32_t G, int32_t genome_begin, int32_t *cnt, VtxCell *cells, uint32_t cap, uint32_t *n_cells)
+{
+	size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n_tab) return;
+	const int32_t v = aux[k];
+	if (v == -1) return;
+	const int32_t g = (int32_t)(k / G), j = (int32_t)(k % G);
+	if (v == -2) { atomicAdd(&cnt[2 * g], 1); return; }
+	atomicAdd(&cnt[2 * g + 1], 1);
+	const uint32_t id = atomicAdd(n_cells, 1u);
+	if (id < cap) { VtxCell c; c.g = g; c.j = genome_begin + j; c.t = v; c.t_dom = aux[(size_t)v * G + j] == -2? 1 : 0; cells[id] = c; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // arc generation (graph.c:87-177)
 // ------------------------------------------------------------------------------------------------
