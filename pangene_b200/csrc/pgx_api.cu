@@ -82,6 +82,7 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	if (timing_on()) fprintf(stderr, "[pgx timing] device check %.1f ms, session+upload %.1f ms, stage 1 %.1f ms\n", (t0 - t_enter) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
 	if (!g_lazy) s->download(d, nullptr);
 	else {   // the protein/gene tables are cheap and always current
+		s->ensure_rep();
 		for (int32_t i = 0; i < d->n_prot; ++i) { d->prot[i].n = s->rep.prot_n[i]; d->prot[i].avg_score_adj = s->rep.prot_avg[i]; d->prot[i].rep = s->rep.prot_rep[i]; d->prot[i].max_score_ori = s->h_prot_max[i]; }
 		for (int32_t i = 0; i < d->n_gene; ++i) d->gene[i].rep_pid = s->rep.gene_rep_pid[i];
 	}

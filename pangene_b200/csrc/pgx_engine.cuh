@@ -23,6 +23,7 @@
 #include "pgx_hostpipe.hpp"
 #include <atomic>
 #include <algorithm>
+#include <thread>
 
 namespace pgx {
 
@@ -103,10 +104,21 @@ struct Session {
 	std::map<int32_t, TieChain> tie_chains;
 	Arena scratch;
 	uint32_t *h_pin = nullptr;           // pinned word(s) for small read-backs
+	unsigned long long *h_z_pin = nullptr;   // pinned copy of the per-protein sums for the host thread below
+	cudaEvent_t ev_z = nullptr;
+	std::thread rep_thread; bool rep_pending = false;
 	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_TIE_ROUND = 8, C_LONG_RUN = 9, C_ORD_SENS = 10, C_N = 12 };
 
-	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
-	~Session() { if (st) cudaStreamDestroy(st); for (auto &e : ev) if (e) cudaEventDestroy(e); if (h_pin) cudaFreeHost(h_pin); }
+	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaEventCreateWithFlags(&ev_z, cudaEventDisableTiming)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
+	~Session()
+	{
+		if (rep_pending) { rep_thread.join(); rep_pending = false; }
+		if (st) cudaStreamDestroy(st);
+		for (auto &e : ev) if (e) cudaEventDestroy(e);
+		if (ev_z) cudaEventDestroy(ev_z);
+		if (h_pin) cudaFreeHost(h_pin);
+		if (h_z_pin) cudaFreeHost(h_z_pin);
+	}
 
 	uint32_t read_u32(const uint32_t *dptr)
 	{
@@ -128,6 +140,7 @@ struct Session {
 	// ------------------------------------------------------------------------------------------------
 	void upload(const pg_data_t *d)
 	{
+		if (rep_pending) { rep_thread.join(); rep_pending = false; }
 		G = d->n_genome; n_prot = d->n_prot; n_gene = d->n_gene;
 		Gtot = g_comm.active()? g_comm.n_genome_total : G;
 		h_hoff.assign(G + 1, 0); h_coff.assign(G + 1, 0); h_eoffg.assign(G + 1, 0);
@@ -166,6 +179,8 @@ struct Session {
 		f_sdom.alloc(n1); f_pdom0.alloc(n1); f_pdom.alloc(n1); f_cds.alloc(n1); f_pmax.alloc(n1); f_bits.alloc(n1); f_bits_alt.alloc(n1); f_nex.alloc(n1); f_eoff.alloc(n1 + 16); f_esrc.alloc(n1);
 		src.alloc(n1); ex.alloc((size_t)E + 16);
 		set_full();
+		if (h_z_pin) { cudaFreeHost(h_z_pin); h_z_pin = nullptr; }
+		PGX_CHECK(cudaMallocHost((void**)&h_z_pin, ((size_t)(n_prot > 0? n_prot : 1)) * 8));
 		prot_max.alloc(n_prot); prot_rep.alloc(n_prot); z.alloc(n_prot); cs4.alloc((size_t)n_prot * 4); g2s.alloc(n_gene);
 		prot_rep.zero(st);
 		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
@@ -385,28 +400,46 @@ struct Session {
 		if (N) PGX_LAUNCH(k_cap_apply, grid_for(N, TB), TB, 0, st, F.pid, F.sdom, N, prot_max.p);
 		h_prot_max.resize(n_prot);
 		PGX_CHECK(cudaMemcpyAsync(h_prot_max.data(), prot_max.p, (size_t)n_prot * 4, cudaMemcpyDeviceToHost, st));
-		build_active();
-		// per-protein sums (hit.c:196-204, 158-169), one pass, then one reduction across ranks
+		// per-protein sums (hit.c:196-204, 158-169) over the rank-0 unfiltered hits, one pass over the full columns, one reduction across
+		// ranks.  The sums go to the host at once: the representative of every gene needs the exact permutation of the reference's unstable
+		// radix sort (hit.c:209), ~2.5 ms on one host thread -- it runs beside the device work below and is joined where its
+		// result is first needed (vertex election, materialisation).
+		ensure_rep();
 		z.zero(st); cs4.zero(st);
-		if (Nw) PGX_LAUNCH(k_prot_stats, grid_for(Nw, TB), TB, 0, st, A.pid, A.sadj, A.sori, A.rank, A.bits, A.eoff, Nw, z.p, cs4.p);
+		if (N) PGX_LAUNCH(k_prot_stats, grid_for(N, TB), TB, 0, st, F.pid, F.sadj, F.sori, F.rank, F.bits, F.eoff, N, z.p, cs4.p);
 		g_comm.allreduce(z.p, n_prot, Comm::T_UINT64, Comm::OP_SUM, st);
 		g_comm.allreduce(cs4.p, (size_t)n_prot * 4, Comm::T_UINT64, Comm::OP_SUM, st);
-		std::vector<unsigned long long> hz(n_prot);
-		PGX_CHECK(cudaMemcpyAsync(hz.data(), z.p, (size_t)n_prot * 8, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaMemcpyAsync(h_z_pin, z.p, (size_t)n_prot * 8, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaEventRecord(ev_z, st));
+		{
+			int dev = 0; PGX_CHECK(cudaGetDevice(&dev));
+			rep_thread = std::thread([this, dev]() {
+				cudaSetDevice(dev);
+				cudaEventSynchronize(ev_z);
+				choose_representatives(h_z_pin, h_prot_gid.data(), n_prot, n_gene, rep);  // host: exact tie order
+			});
+			rep_pending = true;
+		}
+		build_active();
 		if (!(opt->flag & PG_F_NO_JOINT_PSEUDO) && Nw)
 			PGX_LAUNCH(k_pseudo_joint, grid_for(Nw, TB), TB, 0, st, A.pid, A.bits, A.eoff, Nw, cs4.p, Gtot, opt->min_vertex_ratio, !!(opt->flag & PG_F_DROP_SGL_EXON));
 		if (Nw) {
 			launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits_alt, A.pdom, nullptr);
 			a_bits.swap(a_bits_alt); set_active();
 		}
-		const double tp0 = wall_s();
-		PGX_CHECK(cudaStreamSynchronize(st));
-		const double tp1 = wall_s();
-		choose_representatives(hz.data(), h_prot_gid.data(), n_prot, n_gene, rep);      // host: exact tie order
-		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] stage_post: drained the stream in %.2f ms, representatives on the host %.2f ms\n", (tp1 - tp0) * 1e3, (wall_s() - tp1) * 1e3);
-		PGX_CHECK(cudaMemcpyAsync(prot_rep.p, rep.prot_rep.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
 		done_post = true;
 		g_stats.n_active = Nw;
+	}
+
+	// joins the host thread that picks the representatives; uploads the per-protein flag the materialisation needs
+	void ensure_rep()
+	{
+		if (!rep_pending) return;
+		const double t0 = wall_s();
+		rep_thread.join();
+		rep_pending = false;
+		PGX_CHECK(cudaMemcpyAsync(prot_rep.p, rep.prot_rep.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
+		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] waited %.2f ms for the representatives (host thread)\n", (wall_s() - t0) * 1e3);
 	}
 
 	void build_active()
@@ -565,6 +598,7 @@ struct Session {
 		} else if (nc_tot) PGX_CHECK(cudaMemcpyAsync(h_cells.data(), cells_d, nc_tot * sizeof(VtxCell), cudaMemcpyDeviceToHost, st));
 		PGX_CHECK(cudaStreamSynchronize(st));
 		double tv1 = wall_s();
+		ensure_rep();
 		elect_vertices_cells(h_cnt2.data(), h_cells.data(), nc_tot, Gtot, n_gene, rep.gene_rep_pid.data(), rep.prot_avg.data(), h_gene_pref.data(), h_gene_incl.data(), opt->min_vertex_ratio,
 			!!(opt->flag & PG_F_WRITE_VTX_SEL), h_gene_names, h_seg0);
 		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] gen_vtx: counts + %zu cells D2H %.2f ms, host election %.2f ms\n", nc_tot, (tv1 - tv0) * 1e3, (wall_s() - tv1) * 1e3);
@@ -1192,6 +1226,7 @@ struct Session {
 	void download(pg_data_t *d, pg_graph_t *q)
 	{
 		if (d->n_genome != G) PGX_FATAL("download: pg_data_t does not match the uploaded one");
+		ensure_rep();
 		if (Nw) PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
 		if (N) {
 			DBuf<OutHit> out;
