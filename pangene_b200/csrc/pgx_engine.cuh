@@ -52,7 +52,39 @@ static inline pg_hit_t *alloc_hit_array(size_t n)
 
 static inline double wall_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 
+// device-clock breakdown of a run by phase (PGX_TIMING): events at phase boundaries, summed per label at the end; works at any rank count
+struct PhaseTimer {
+	bool on = false;
+	std::vector<cudaEvent_t> ev; std::vector<const char*> label; size_t used = 0;
+	void begin(cudaStream_t st) { on = getenv("PGX_TIMING") != nullptr; used = 0; label.clear(); if (on) mark("(start)", st); }
+	void mark(const char *what, cudaStream_t st)
+	{
+		if (!on) return;
+		if (used == ev.size()) { cudaEvent_t e; PGX_CHECK(cudaEventCreate(&e)); ev.push_back(e); }
+		PGX_CHECK(cudaEventRecord(ev[used++], st)); label.push_back(what);
+	}
+	void report(const char *title, int rank, cudaStream_t st)
+	{
+		if (!on || used < 2) return;
+		PGX_CHECK(cudaStreamSynchronize(st));
+		std::vector<std::pair<const char*, double>> acc;
+		double tot = 0;
+		for (size_t i = 1; i < used; ++i) {
+			float ms = 0; PGX_CHECK(cudaEventElapsedTime(&ms, ev[i - 1], ev[i]));
+			tot += ms;
+			size_t k = 0; for (; k < acc.size(); ++k) if (strcmp(acc[k].first, label[i]) == 0) break;
+			if (k == acc.size()) acc.push_back({label[i], 0.0});
+			acc[k].second += ms;
+		}
+		fprintf(stderr, "[pgx timing] rank %d %s by phase (device clock, %.2f ms):", rank, title, tot);
+		for (auto &a : acc) fprintf(stderr, " %s %.2f |", a.first, a.second);
+		fprintf(stderr, "\n");
+	}
+	~PhaseTimer() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
 struct Session {
+	PhaseTimer pt;
 	cudaStream_t st = nullptr;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	// ---- shapes
@@ -107,12 +139,21 @@ struct Session {
 	unsigned long long *h_z_pin = nullptr;   // pinned copy of the per-protein sums for the host thread below
 	cudaEvent_t ev_z = nullptr;
 	std::thread rep_thread; bool rep_pending = false;
+	// second stream: the gene-position tables of the next branch round are built beside the arc table of the current pg_gen_arc
+	// (both only read the flag words the sweep has just finished with)
+	cudaStream_t st2 = nullptr;
+	cudaEvent_t ev_swept = nullptr, ev_pos = nullptr;
+	bool pos_ready = false;
 	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_TIE_ROUND = 8, C_LONG_RUN = 9, C_ORD_SENS = 10, C_N = 12 };
 
-	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaEventCreateWithFlags(&ev_z, cudaEventDisableTiming)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64)); }
+	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaEventCreateWithFlags(&ev_z, cudaEventDisableTiming)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64));
+		PGX_CHECK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking)); PGX_CHECK(cudaEventCreateWithFlags(&ev_swept, cudaEventDisableTiming)); PGX_CHECK(cudaEventCreateWithFlags(&ev_pos, cudaEventDisableTiming)); }
 	~Session()
 	{
 		if (rep_pending) { rep_thread.join(); rep_pending = false; }
+		if (st2) { cudaStreamSynchronize(st2); cudaStreamDestroy(st2); }
+		if (ev_swept) cudaEventDestroy(ev_swept);
+		if (ev_pos) cudaEventDestroy(ev_pos);
 		if (st) cudaStreamDestroy(st);
 		for (auto &e : ev) if (e) cudaEventDestroy(e);
 		if (ev_z) cudaEventDestroy(ev_z);
@@ -970,24 +1011,22 @@ struct Session {
 		return e;
 	}
 
-	// Sizes the tables of the fast rounds from the round-2 graph (one read-back per run) and builds, for the first branch round, what the
-	// later rounds get from their own arc build: survivor records, the key table over the round-2 arcs, degrees and pair offsets.
+	// Allocates the tables of the fast rounds before the first pg_gen_arc, sized from the vertex count (the arc count is not known yet;
+	// a graph with more than ~14 arcs per vertex side overflows the table, raises the fallback and is redone on the careful path).
 	// Every decision here depends on replicated values only, so all ranks decide alike.
-	bool setup_fast(const pg_opt_t *opt)
+	bool setup_fast_tables(const pg_opt_t *opt)
 	{
 		fast.on = false;
 		static const bool env_careful = []() { const char *e = getenv("PGX_ROUNDS"); return e && strcmp(e, "careful") == 0; }();
-		if (env_careful || force_careful || opt->n_branch_flt <= 0 || n_seg0 == 0) return false;
+		if (env_careful || force_careful || n_seg0 == 0) return false;
 		// the packed sums of ArcAcc: counts below 2^26, score sums below 2^38
 		int64_t n_hits_all = 0, s_max = 0;
 		for (int64_t x : rank_N) n_hits_all += x;
 		for (int32_t x : h_prot_max) s_max = x > s_max? x : s_max;
 		if (n_hits_all >= (1ll << 26) || Gtot >= (1 << 26) || (double)s_max * (double)Gtot >= (double)(1ll << ACC_SHIFT)) return false;
-		arc_index();                                                                     // graph.c:306 of the first round
-		const uint32_t n_arc2 = read_counts().n_arc;
 		Fast &f = fast;
 		f.NV = 2 * n_seg0;
-		uint64_t want = 2ull * n_arc2; if (want < (1u << 16)) want = 1u << 16;           // canonical keys: half the arcs; load factor <= 1/4 at the start
+		uint64_t want = 28ull * n_seg0; if (want < (1u << 16)) want = 1u << 16;          // canonical keys at load factor <= 1/2: room for 14 arcs per oriented vertex
 		uint32_t H = 1u << 16; while (H < want && H < (1u << 29)) H <<= 1;
 		int Gmax = 0; for (int g : rank_G) Gmax = g > Gmax? g : Gmax;
 		if ((uint64_t)H * (uint64_t)(Gmax > 0? Gmax : 1) / 8 > ((uint64_t)1 << 30)) return false;   // (key, genome) marks beyond 1 GB: stay on the sort path
@@ -1001,7 +1040,7 @@ struct Session {
 		if (multi) {
 			f.gkey.ensure(H); f.gacc.ensure(H); f.glist.ensure(H);
 			f.glob.key = f.gkey.p; f.glob.acc = f.gacc.p; f.glob.list = f.glist.p; f.glob.bm1 = f.glob.bm2 = nullptr;
-			f.part_cap = n_arc2 / 2 + n_arc2 / 4 + 4096; if (f.part_cap > H / 2) f.part_cap = H / 2;
+			f.part_cap = H / 2;                                                            // rounds 1-2: whatever the table can hold; shrunk to the measured size afterwards
 			f.all.ensure((size_t)g_comm.nranks * (f.part_cap + 1));
 		}
 		f.l2key.ensure(f.H2); f.l2dsum.ensure(f.H2); f.l2n.ensure(f.H2); f.l2list.ensure(f.H2); f.l2m.ensure(2 * (size_t)f.H2);
@@ -1018,48 +1057,47 @@ struct Session {
 		f.dirty.ensure(f.dirty_words);
 		f.tiles_hit = (int32_t)(((size_t)Nw + 1 + SCAN_TILE - 1) / SCAN_TILE); f.tiles_vtx = (int32_t)(((size_t)f.NV + 1 + SCAN_TILE - 1) / SCAN_TILE);
 		f.tiles_seg = (int32_t)(((size_t)n_seg0 + 1 + SCAN_TILE - 1) / SCAN_TILE);
-		const size_t lb_words = 2 * (size_t)f.tiles_hit + 2 * (size_t)f.tiles_vtx + (size_t)f.tiles_seg + 4;
+		const size_t lb_words = 2 * (size_t)f.tiles_hit + 2 * (size_t)f.tiles_vtx + (size_t)f.tiles_seg + 4;   // (sized for the active set as it is now: it only shrinks)
 		f.lb.ensure(lb_words + 2); f.lb_bytes = ((lb_words * 8) + 15) & ~(size_t)15;
 		f.st_cm = f.lb.p; f.st_cs = f.st_cm + f.tiles_hit; f.st_vs = f.st_cs + f.tiles_hit; f.st_sg = f.st_vs + 2 * (size_t)f.tiles_vtx;
 		f.tk_cm = (uint32_t*)(f.st_sg + f.tiles_seg); f.tk_vs = f.tk_cm + 1; f.tk_cs = f.tk_cm + 2; f.tk_sg = f.tk_cm + 3; f.n_keep = f.tk_cm + 4;
-		uint32_t need_arc = H > n_arc2 + 16? H : n_arc2 + 16;                             // up to H / 2 canonical keys -> H arcs
-		if (arc.n < (size_t)need_arc + 1) {   // the merged graph of a sharded run can exceed this rank's own bound; keep the round-2 arcs
-			DBuf<ArcDev> bigger; bigger.alloc((size_t)need_arc + 1);
-			if (n_arc2) PGX_CHECK(cudaMemcpyAsync(bigger.p, arc.p, (size_t)n_arc2 * sizeof(ArcDev), cudaMemcpyDeviceToDevice, st));
-			PGX_CHECK(cudaStreamSynchronize(st));
-			arc.swap(bigger); arc_alt.alloc((size_t)need_arc + 1); arc_cap = arc.n - 1;
-		}
+		if (arc.n < (size_t)H + 1) { arc.alloc((size_t)H + 1); arc_alt.alloc((size_t)H + 1); arc_cap = arc.n - 1; }   // up to H / 2 canonical keys -> H arcs
 		f.arc_cap = (uint32_t)(arc.n - 1);
 		f.arc_tmp.ensure((size_t)f.arc_cap + 1); f.grp.ensure((size_t)f.arc_cap + 1);
-		f.use_dirty = n_first == 0 && !(getenv("PGX_SWEEP") && strcmp(getenv("PGX_SWEEP"), "global") == 0) && !getenv("PGX_NO_DIRTY");
-		PGX_CHECK(cudaMemsetAsync(f.dirty.p, 0, f.dirty_words * 4, st));
+		f.use_dirty = false;                                                              // the first sweeps are complete ones; setup_fast_pairs() turns the incremental mode on
+		f.nl_cap = 0;
 		PGX_CHECK(cudaMemsetAsync(f.lb.p, 0, f.lb_bytes, st));
-		PGX_CHECK(cudaMemsetAsync(f.nl_total.p, 0, 16, st));
-		PGX_CHECK(cudaMemsetAsync(f.glob.key, 0xff, (size_t)H * 8, st));
-		PGX_CHECK(cudaMemsetAsync(f.segocc.p, 0, 2 * (size_t)n_seg0 * 4, st)); PGX_CHECK(cudaMemsetAsync(f.seg_seen.p, 0, f.seen_words * 4, st));
 		PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, fallback)), 0u);
-		PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_gpart)), 0u);
-		if (f.use_dirty && Nw) PGX_LAUNCH(k_reach, GS_GRID, TB, 0, st, A.ctg, A.cs, A.ce, A.pmax, Nw, (int32_t)SWQ_TILE, f.reach.p);
-		// the round-2 graph as the first branch round needs it: survivor records, key table + arc positions, degrees, pair offsets
-		PGX_LAUNCH(k_survivor_info, GS_GRID, TB, 0, st, arc_src(opt), dc.p, f.info.p, f.seg_seen.p, f.segocc.p, f.segocc.p + n_seg0, counters.p + C_ERR);
-		PGX_LAUNCH(k_table_from_arcs, GS_GRID, TB, 0, st, arc.p, dc.p, f.glob, f.pos_of.p);
-		uint32_t *deg = f.degcur.p;
-		PGX_LAUNCH(k_deg_from_idx, GS_GRID, TB, 0, st, idx.p, f.NV, dc.p, deg);
-		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, 0xffffffffu, f.nl_total.p, f.st_vs, f.tk_vs);
-		unsigned long long h_tot = 0;
-		PGX_CHECK(cudaMemcpyAsync(&h_tot, f.nl_total.p, 8, cudaMemcpyDeviceToHost, st));
+		fast.on = true;
+		return true;
+	}
+	// After the round-2 graph: the size of the locality table of the branch rounds (one read-back per run), the exchange buffer of a
+	// sharded run cut down to the measured graph, the reach of every active hit for the incremental sweeps.
+	bool setup_fast_pairs(const pg_opt_t *opt)
+	{
+		Fast &f = fast;
+		if (opt->n_branch_flt <= 0) return true;
+		struct { unsigned long long nl; DevCounts c; } h;
+		PGX_CHECK(cudaMemcpyAsync(&h.nl, f.nl_total.p, 8, cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaMemcpyAsync(&h.c, dc.p, sizeof(DevCounts), cudaMemcpyDeviceToHost, st));
 		PGX_CHECK(cudaStreamSynchronize(st));
-		if (h_tot > (1ull << 29)) return false;                                           // half a billion arc pairs: not the regime this path is for
-		f.nl_cap = (uint32_t)(2 * h_tot + (1u << 20));
+		if (g_comm.active()) {   // (the fallback word may differ between ranks at this point; the arc counts are replicated)
+			g_comm.allreduce(dcp(offsetof(DevCounts, fallback)), 1, Comm::T_UINT32, Comm::OP_MAX, st);
+			h.c.fallback = read_counts().fallback;
+		}
+		if (h.c.fallback || h.nl > (1ull << 29)) return false;                           // overflow already, or half a billion arc pairs: not the regime this path is for
+		f.nl_cap = (uint32_t)(2 * h.nl + (1u << 20));
 		f.nl.ensure((size_t)f.nl_cap + 16);
 		PGX_CHECK(cudaMemsetAsync(f.nl.p, 0, f.nl.n, st));
-		PGX_CHECK(cudaMemsetAsync(f.lb.p, 0, f.lb_bytes, st));
-		fast.on = true;
+		if (g_comm.active()) { uint32_t c = h.c.n_arc / 2 + h.c.n_arc / 4 + 4096; if (c < f.part_cap) f.part_cap = c; }
+		f.use_dirty = n_first == 0 && !(getenv("PGX_SWEEP") && strcmp(getenv("PGX_SWEEP"), "global") == 0) && !getenv("PGX_NO_DIRTY");
+		PGX_CHECK(cudaMemsetAsync(f.dirty.p, 0, f.dirty_words * 4, st));
+		if (f.use_dirty && Nw) PGX_LAUNCH(k_reach, GS_GRID, TB, 0, st, A.ctg, A.cs, A.ce, A.pmax, Nw, (int32_t)SWQ_TILE, f.reach.p);
 		return true;
 	}
 
 	// graph.c:87-177 without sorting the records and without a host round trip (pgx_round.cuh)
-	void gen_arc_fast(const pg_opt_t *opt)
+	void gen_arc_fast(const pg_opt_t *opt, bool branch_round_follows = false)
 	{
 		Fast &f = fast;
 		set_first_for_this_call();
@@ -1077,9 +1115,19 @@ struct Session {
 		clear_add(cl, f.nl_total.p, 16, 0u);
 		if (multi) { clear_add(cl, f.gkey.p, (size_t)f.H * 8, 0xffffffffu); clear_add(cl, f.gacc.p, (size_t)f.H * sizeof(ArcAcc), 0u); }
 		clear_launch(cl);
+		pt.mark("arc:clear", st);
 		SweepOpt so; so.min_ov_ratio = opt->min_ov_ratio; so.check_strand = !!(opt->flag & PG_F_CHECK_STRAND);
 		launch_sweep<SW_SHADOW>(sweep_active(), so, A.bits, A.pdom, nullptr, f.use_dirty? f.dirty.p : nullptr);   // in place: a sweep reads flt / weak_br / rev of its partners, writes its own shadow bit
-		PGX_LAUNCH(k_compact_survivors, f.tiles_hit, SCAN_B, 0, st, A.bits, by_cm.p, Nw, (uint32_t*)nullptr, sv.p, dcp(offsetof(DevCounts, m_sv)), f.st_cm, f.tk_cm, dc.p);
+		pt.mark("arc:sweep", st);
+		if (branch_round_follows) {   // fork: the position tables of that round, on the second stream
+			PGX_CHECK(cudaEventRecord(ev_swept, st));
+			PGX_CHECK(cudaStreamWaitEvent(st2, ev_swept, 0));
+			branch_positions(st2);
+			PGX_CHECK(cudaEventRecord(ev_pos, st2));
+			pos_ready = true;
+		}
+		const int32_t tiles_now = (int32_t)(((size_t)Nw + 1 + SCAN_TILE - 1) / SCAN_TILE);   // <= f.tiles_hit: the active set only shrinks
+		PGX_LAUNCH(k_compact_survivors, tiles_now, SCAN_B, 0, st, A.bits, by_cm.p, Nw, (uint32_t*)nullptr, sv.p, dcp(offsetof(DevCounts, m_sv)), f.st_cm, f.tk_cm, dc.p);
 		const ArcSrc e = arc_src(opt);
 		int32_t *seg_ng_f = f.segocc.p, *seg_tot_f = f.segocc.p + n_seg0;
 		PGX_LAUNCH(k_survivor_info, GS_GRID, TB, 0, st, e, dc.p, f.info.p, f.seg_seen.p, seg_ng_f, seg_tot_f, counters.p + C_ERR);
@@ -1087,6 +1135,7 @@ struct Session {
 		PGX_LAUNCH(k_arc_fold, GS_GRID, TB, 0, st, f.info.p, f.rec.p, ctg2g.p, f.loc, dc.p, e.Gl, f.ovf.p, f.ovf_cap);
 		PGX_LAUNCH(k_arc_ovf_insert, 148, TB, 0, st, f.ovf.p, f.ovf_cap, f.l2, dc.p);
 		PGX_LAUNCH(k_arc_ovf_fold, 148, TB, 0, st, f.l2, f.loc, dc.p);
+		pt.mark("arc:survivors+table", st);
 		if (multi) {
 			ArcWire *mine = f.all.p + (size_t)g_comm.rank * (f.part_cap + 1);
 			PGX_LAUNCH(k_arc_pack, GS_GRID, TB, 0, st, f.loc, dc.p, mine, f.part_cap);
@@ -1095,16 +1144,20 @@ struct Session {
 			g_comm.allreduce(f.segocc.p, 2 * (size_t)n_seg0, Comm::T_INT32, Comm::OP_SUM, st);
 			g_comm.group_end();
 			PGX_LAUNCH(k_arc_merge, GS_GRID, TB, 0, st, f.all.p, g_comm.nranks, f.part_cap, f.glob, dc.p, deg);
+			pt.mark("arc:exchange+merge", st);
 		}
 		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, f.arc_cap, f.nl_total.p, f.st_vs, f.tk_vs);
 		PGX_LAUNCH(k_arc_place, GS_GRID, TB, 0, st, f.glob, dcp(multi? offsetof(DevCounts, n_gpart) : offsetof(DevCounts, n_part)), f.off.p, cur, dc.p, f.arc_tmp.p);
 		PGX_LAUNCH(k_arc_rank, GS_GRID, TB, 0, st, f.arc_tmp.p, f.off.p, dc.p, arc.p, idx.p, f.pos_of.p);
 		PGX_LAUNCH(k_seg_store_occ_fast, 148, TB, 0, st, seg.p, dc.p, seg_ng_f, seg_tot_f);
+		pt.mark("arc:scan+place+rank", st);
 		++g_stats.fast_rounds;
 	}
 
-	// branch.c:48-145 + graph.c:309-313, same rules as branch_round() below; idx / nl_off / the key table come from the preceding arc build
-	void branch_round_fast(const pg_opt_t *opt, int32_t round, int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)
+	// branch.c:6-29: the representative position of every gene in every local genome, from the flag words as the last sweep left them;
+	// plus the detector for survivors that share one (contig, cs) (DESIGN.md "tie order").  Clears the dirty-tile marks: the sweep that
+	// consumed them is done, the next ones come from k_branch_hits_fast.
+	void branch_positions(cudaStream_t s)
 	{
 		Fast &f = fast;
 		const size_t tab = (size_t)n_gene * G;
@@ -1112,25 +1165,43 @@ struct Session {
 		clear_add(cl, f.t_last.p, (tab + 1) * 4, 0xffffffffu);
 		clear_add(cl, counters.p + C_TIE_ROUND, 16, 0u);
 		clear_add(cl, f.dirty.p, f.dirty_words * 4, 0u);
-		clear_launch(cl);
-		PGX_LAUNCH(k_compact_survivors, f.tiles_hit, SCAN_B, 0, st, A.bits, (const uint32_t*)nullptr, Nw, f.spos.p, f.svcs.p, dcp(offsetof(DevCounts, m_cs)), f.st_cs, f.tk_cs, (DevCounts*)nullptr);
-		if (Nw) PGX_LAUNCH(k_pos_last, grid_for(Nw, TB), TB, 0, st, A.ctg, ctg2g.p, A.gidp, f.spos.p, Nw, G, f.t_last.p);
-		if (tab) PGX_LAUNCH(k_pos_fill, grid_for((int64_t)tab, TB), TB, 0, st, f.t_last.p, tab, G, A.ctg, A.cm, f.spos.p, goff_act.p, f.gpos.p);
-		PGX_LAUNCH(k_cs_tie_mark, GS_GRID, TB, 0, st, A.ctg, A.cs, A.gidp, ctg2g.p, G, f.svcs.p, dc.p, f.t_last.p, f.gpos.p, counters.p + C_TIE_CS, counters.p + C_TIE_ROUND, f.tie_list.p, counters.p + C_LONG_RUN);
+		PGX_LAUNCH(k_round_clear, 148 * 4, 256, 0, s, cl);
+		const int32_t tiles_now = (int32_t)(((size_t)Nw + 1 + SCAN_TILE - 1) / SCAN_TILE);
+		PGX_LAUNCH(k_compact_survivors, tiles_now, SCAN_B, 0, s, A.bits, (const uint32_t*)nullptr, Nw, f.spos.p, f.svcs.p, dcp(offsetof(DevCounts, m_cs)), f.st_cs, f.tk_cs, (DevCounts*)nullptr);
+		if (Nw) PGX_LAUNCH(k_pos_last, grid_for(Nw, TB), TB, 0, s, A.ctg, ctg2g.p, A.gidp, f.spos.p, Nw, G, f.t_last.p);
+		if (tab) PGX_LAUNCH(k_pos_fill, grid_for((int64_t)tab, TB), TB, 0, s, f.t_last.p, tab, G, A.ctg, A.cm, f.spos.p, goff_act.p, f.gpos.p);
+		PGX_LAUNCH(k_cs_tie_mark, GS_GRID, TB, 0, s, A.ctg, A.cs, A.gidp, ctg2g.p, G, f.svcs.p, dc.p, f.t_last.p, f.gpos.p, counters.p + C_TIE_CS, counters.p + C_TIE_ROUND, f.tie_list.p, counters.p + C_LONG_RUN);
+	}
+
+	// branch.c:48-145 + graph.c:309-313, same rules as branch_round() below; idx / nl_off / the key table come from the preceding arc build
+	void branch_round_fast(const pg_opt_t *opt, int32_t round, int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)
+	{
+		Fast &f = fast;
+		if (pos_ready) { PGX_CHECK(cudaStreamWaitEvent(st, ev_pos, 0)); pos_ready = false; }   // join: built beside the preceding pg_gen_arc
+		else branch_positions(st);
+		pt.mark("br:positions", st);
 		BranchOpt bo; bo.local_dist = opt->local_dist; bo.local_count = opt->local_count; bo.frag_mode = !!(opt->flag & PG_F_FRAG_MODE);
 		bo.branch_diff = opt->branch_diff; bo.branch_diff_dist = opt->branch_diff_dist; bo.branch_diff_cut = opt->branch_diff_cut;
 		PGX_LAUNCH(k_branch_local, GS_GRID, TB, 0, st, idx.p, dc.p, arc.p, seg.p, f.gpos.p, G, f.nl_off.p, f.NV, f.nl_cap, f.nl_total.p, bo, f.nl.p, counters.p + C_ORD_SENS);
+		pt.mark("br:locality", st);
 		g_comm.allreduce(f.nl.p, f.nl_cap, Comm::T_UINT8, Comm::OP_SUM, st);
+		if (g_comm.active()) pt.mark("br:allreduce", st);
 		PGX_LAUNCH(k_branch_decide_fast, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, f.nl_off.p, f.nl.p, f.nl_cap, f.nl_total.p, bo, f.grp.p, counters.p + C_TIE_ROUND);
 		PGX_LAUNCH(k_branch_hits_fast, GS_GRID, TB, 0, st, sv.p, f.info.p, dc.p, A.bits, arc.p, f.glob, f.pos_of.p, dirty_cols(), counters.p + C_BR_CHANGED);
-		if (round > 0) {                                                                  // graph.c:310-313
-			PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
-			PGX_LAUNCH(k_seg_keep_scan, f.tiles_seg, SCAN_B, 0, st, seg.p, dc.p, idx.p, max_avg_occ * Gtot, max_degree, max_dist_loci, f.seg_pos.p, f.n_keep, f.st_sg, f.tk_sg);
-			PGX_LAUNCH(k_seg_compact_fast, 148, TB, 0, st, seg.p, seg_alt.p, dc.p, f.seg_pos.p, f.n_keep, g2s.p);
-			PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_seg)), f.n_keep);
-			seg.swap(seg_alt);
-			if (Nw) PGX_LAUNCH(k_flag_vtx_fast, grid_for(Nw, TB), TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols());
-		}
+		pt.mark("br:decide+hits", st);
+		if (round > 0) flt_high_occ_fast(max_avg_occ, max_degree, max_dist_loci);          // graph.c:310-313
+	}
+	// graph.c:237-263 + PG_SET_FILTER(vtx == 0); needs idx[] of the current arcs and a zeroed look-back block (every gen_arc_fast leaves both)
+	void flt_high_occ_fast(int32_t max_avg_occ, int32_t max_degree, int32_t max_dist_loci)
+	{
+		Fast &f = fast;
+		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
+		PGX_LAUNCH(k_seg_keep_scan, f.tiles_seg, SCAN_B, 0, st, seg.p, dc.p, idx.p, max_avg_occ * Gtot, max_degree, max_dist_loci, f.seg_pos.p, f.n_keep, f.st_sg, f.tk_sg);
+		PGX_LAUNCH(k_seg_compact_fast, 148, TB, 0, st, seg.p, seg_alt.p, dc.p, f.seg_pos.p, f.n_keep, g2s.p);
+		PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_seg)), f.n_keep);
+		seg.swap(seg_alt);
+		if (Nw) PGX_LAUNCH(k_flag_vtx_fast, grid_for(Nw, TB), TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols());
+		pt.mark("br:segfilter+vtx", st);
 	}
 
 	void stage_graph(const pg_opt_t *opt)
@@ -1148,18 +1219,36 @@ struct Session {
 	}
 	bool stage_graph_impl(const pg_opt_t *opt, bool allow_fast)
 	{
+		pt.begin(st);
+		PGX_CHECK(cudaStreamSynchronize(st2)); pos_ready = false;
 		set_filter(SF_PSEUDO);                                                           // graph.c:285
 		gen_vtx(opt);                                                                    // graph.c:286
+		pt.mark("vertex election", st);
 		prepare_first_replay(opt);
 		tie_chains.clear();
 		flag_vtx();                                                                      // graph.c:287-288
 		recompact_active();
-		gen_arc(opt);                                                                    // graph.c:289
-		flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);     // graph.c:294-295
-		recompact_active();
-		gen_arc(opt);                                                                    // graph.c:296
+		pt.mark("recompact", st);
 		force_careful = !allow_fast;
-		const bool use_fast = setup_fast(opt);
+		bool use_fast = setup_fast_tables(opt);
+		pt.mark("fast-round setup", st);
+		if (use_fast) {
+			gen_arc_fast(opt);                                                             // graph.c:289
+			flt_high_occ_fast(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);   // graph.c:294-295
+			recompact_active();
+			pt.mark("recompact", st);
+			gen_arc_fast(opt, opt->n_branch_flt > 0);                                      // graph.c:296
+			if (!setup_fast_pairs(opt)) { fast.on = false; PGX_CHECK(cudaStreamSynchronize(st2)); pos_ready = false; return false; }
+			pt.mark("fast-round setup", st);
+		} else {
+			gen_arc(opt);                                                                  // graph.c:289
+			pt.mark("arcs round 1-2 (sort path)", st);
+			flt_high_occ(opt->max_avg_occ * 2, opt->max_degree * 2, opt->max_dist_loci);   // graph.c:294-295
+			recompact_active();
+			pt.mark("recompact", st);
+			gen_arc(opt);                                                                  // graph.c:296
+			pt.mark("arcs round 1-2 (sort path)", st);
+		}
 		for (int32_t i = 0; i < opt->n_branch_flt; ++i) {                                // graph.c:301-315
 			double r = 1.0 + (double)(opt->n_branch_flt - 1 - i) / opt->n_branch_flt;
 			int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
@@ -1179,11 +1268,11 @@ struct Session {
 				DevCounts hc = read_counts();
 				fprintf(stderr, "[pgx timing] branch round %d: %u hit words changed, segments %u -> %u, arcs %u, survivors %u, arc pairs %u, overflow records %u, fallback %u\n", i, chg, seg_before, hc.n_seg, hc.n_arc, hc.m_sv, hc.n_nl, hc.n_ovf, hc.fallback);
 			}
-			if (use_fast) gen_arc_fast(opt); else gen_arc(opt);
+			if (use_fast) gen_arc_fast(opt, i + 1 < opt->n_branch_flt); else { gen_arc(opt); pt.mark("careful rounds", st); }
 		}
 		if (use_fast) {
 			if (g_comm.active()) g_comm.allreduce(dcp(offsetof(DevCounts, fallback)), 1, Comm::T_UINT32, Comm::OP_MAX, st);
-			if (read_counts().fallback) { fast.on = false; return false; }
+			if (read_counts().fallback) { fast.on = false; PGX_CHECK(cudaStreamSynchronize(st2)); pos_ready = false; return false; }
 		}
 		set_filter(SF_SHADOW);                                                           // graph.c:316
 		DevCounts hc = read_counts();
@@ -1204,6 +1293,8 @@ struct Session {
 		if (pg_verbose >= 3) fprintf(stderr, "[M::pgx::graph_gen] final graph: %d genes and %d arcs\n", n_seg, n_arc);
 		done_graph = true;
 		g_stats.n_seg = n_seg; g_stats.n_arc = n_arc;
+		pt.mark("tail", st);
+		pt.report("stage 2", g_comm.rank, st);
 		if (getenv("PGX_TIMING")) fprintf(stderr, "[pgx timing] rank %d stage 2 host wall: arc rounds %.2f ms (of which cross-rank merge %.2f), branch rounds %.2f ms\n", g_comm.rank, t_arc * 1e3, t_merge * 1e3, t_branch * 1e3);
 		t_arc = t_merge = t_branch = 0;
 		return true;

@@ -444,21 +444,6 @@ __global__ void k_arc_rank(const ArcDev *__restrict__ tmp, const uint32_t *__res
 		if (rank == 0) idx[v] = (unsigned long long)b << 32 | (e - b);                  // graph.c:202-211
 	}
 }
-// first branch round of a run: the arcs come from the round-1 path, which leaves idx[] but no table: build one over the arc keys
-__global__ void k_deg_from_idx(const unsigned long long *__restrict__ idx, int32_t NV, const DevCounts *__restrict__ dc, uint32_t *deg)
-{
-	const int32_t n_vtx = 2 * (int32_t)dc->n_seg;
-	PGX_GS(v, NV) deg[v] = v < n_vtx? (uint32_t)idx[v] : 0u;
-}
-__global__ void k_table_from_arcs(const ArcDev *__restrict__ arc, DevCounts *dc, ArcTable T, uint32_t *pos_of)
-{
-	PGX_GS(p, dc->n_arc) {
-		const unsigned long long x = arc[p].x, xm = arc_mirror(x);
-		const uint32_t slot = arc_slot(T, x < xm? x : xm, &dc->n_gpart, (uint32_t*)nullptr, &dc->fallback);
-		pos_of[slot * 2 + (xm < x? 1u : 0u)] = (uint32_t)p;
-	}
-}
-
 // ---- which tiles of the next overlap sweep can a changed hit influence? ---------------------------------------------------------------
 // A hit's sweep result (shadow bit, pid_dom; overlap.c:101-178) depends on its own flag word and on the flag words of its window partners,
 // nothing else that changes after the load-time block.  When hit h changes its flt / weak_br bits, the hits that have h in their window

@@ -211,16 +211,11 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 		emu::launch(grid, TBk, [&] { k_arc_place(glob[r], R > 1? &dc->n_gpart : &dc->n_part, off.data(), cur, dc, tmp.data()); });
 		emu::launch(grid, TBk, [&] { k_arc_rank(tmp.data(), off.data(), dc, arc.data(), idx.data(), pos_of.data()); });
 		if (nl_total != dc->n_nl) return -4;
-		// every arc is found again through the key table (what k_branch_hits_fast does), and a table rebuilt from the arcs (first round of a run) agrees
-		std::vector<unsigned long long> tkey(in->H, KEY_EMPTY); std::vector<uint32_t> tlist(in->H, 0), tpos(2 * (size_t)in->H, 0xffffffffu);
-		ArcTable T2 = glob[r]; T2.key = tkey.data(); T2.list = tlist.data();
-		DevCounts dc2 = *dc; dc2.n_gpart = 0;
-		emu::launch(grid, TBk, [&] { k_table_from_arcs(arc.data(), &dc2, T2, tpos.data()); });
+		// every arc is found again through the key table (what k_branch_hits_fast does)
 		for (uint32_t p = 0; p < dc->n_arc && !dc->fallback; ++p) {
 			const unsigned long long x = arc[p].x, xm = arc_mirror(x);
-			const uint32_t s = arc_find(glob[r], x < xm? x : xm), s2 = arc_find(T2, x < xm? x : xm);
+			const uint32_t s = arc_find(glob[r], x < xm? x : xm);
 			if (s == ARC_NONE || pos_of[s * 2 + (xm < x)] != p || arc[p].bits != 0) return -6;
-			if (s2 == ARC_NONE || tpos[s2 * 2 + (xm < x)] != p) return -7;
 		}
 		if (r == 0) {
 			memcpy(in->arc, arc.data(), (size_t)dc->n_arc * sizeof(ArcDev)); memcpy(in->idx, idx.data(), (size_t)NV * 8); memcpy(in->nl_off, nl_off.data(), (size_t)(NV + 1) * 4);
