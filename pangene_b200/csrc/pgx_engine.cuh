@@ -1089,7 +1089,13 @@ struct Session {
 		f.nl_cap = (uint32_t)(2 * h.nl + (1u << 20));
 		f.nl.ensure((size_t)f.nl_cap + 16);
 		PGX_CHECK(cudaMemsetAsync(f.nl.p, 0, f.nl.n, st));
-		if (g_comm.active()) { uint32_t c = h.c.n_arc / 2 + h.c.n_arc / 4 + 4096; if (c < f.part_cap) f.part_cap = c; }
+		if (g_comm.active()) {   // the exchange buffer: the largest per-rank table of round 2 plus a quarter (the graph only loses arcs from here on)
+			uint32_t *w = (uint32_t*)(f.nl_total.p + 1);
+			PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, w, dcp(offsetof(DevCounts, n_part)));
+			g_comm.allreduce(w, 1, Comm::T_UINT32, Comm::OP_MAX, st);
+			const uint32_t mx = read_u32(w), c = mx + mx / 4 + 1024;
+			if (c < f.part_cap) f.part_cap = c;
+		}
 		f.use_dirty = n_first == 0 && !(getenv("PGX_SWEEP") && strcmp(getenv("PGX_SWEEP"), "global") == 0) && !getenv("PGX_NO_DIRTY");
 		PGX_CHECK(cudaMemsetAsync(f.dirty.p, 0, f.dirty_words * 4, st));
 		if (f.use_dirty && Nw) PGX_LAUNCH(k_reach, GS_GRID, TB, 0, st, A.ctg, A.cs, A.ce, A.pmax, Nw, (int32_t)SWQ_TILE, f.reach.p);
@@ -1254,7 +1260,7 @@ struct Session {
 			int32_t max_avg_occ = (int32_t)(opt->max_avg_occ * r + .499);
 			int32_t max_degree = (int32_t)(opt->max_degree * r + .499);
 			int32_t max_dist_loci = (int32_t)(opt->max_dist_loci * r + .499);
-			static const bool trace = getenv("PGX_TIMING") != nullptr;
+			static const bool trace = getenv("PGX_TRACE") != nullptr;   // (per-round read-backs: they stall the pipeline, keep them out of timing runs)
 			uint32_t seg_before = 0;
 			if (trace) { seg_before = read_counts().n_seg; PGX_CHECK(cudaMemsetAsync(counters.p + C_BR_CHANGED, 0, 4, st)); }
 			branch_round_no = i;
@@ -1266,7 +1272,7 @@ struct Session {
 			if (trace) {   // how much does a round change?
 				const uint32_t chg = read_u32(counters.p + C_BR_CHANGED);
 				DevCounts hc = read_counts();
-				fprintf(stderr, "[pgx timing] branch round %d: %u hit words changed, segments %u -> %u, arcs %u, survivors %u, arc pairs %u, overflow records %u, fallback %u\n", i, chg, seg_before, hc.n_seg, hc.n_arc, hc.m_sv, hc.n_nl, hc.n_ovf, hc.fallback);
+				fprintf(stderr, "[pgx trace] branch round %d: %u hit words changed, segments %u -> %u, arcs %u, survivors %u, arc pairs %u, overflow records %u, fallback %u\n", i, chg, seg_before, hc.n_seg, hc.n_arc, hc.m_sv, hc.n_nl, hc.n_ovf, hc.fallback);
 			}
 			if (use_fast) gen_arc_fast(opt, i + 1 < opt->n_branch_flt); else { gen_arc(opt); pt.mark("careful rounds", st); }
 		}

@@ -32,45 +32,59 @@ class FlagSortReplay {
 		}
 	}
 	struct Range { int64_t beg, n; int shift; };
+	// one digit pass over a range (ksort.h:56-78); the sub-ranges that need another pass are appended to `todo`, small buckets are finished here
+	static void pass(pg128_t *a, const Range &r, std::vector<Range> &todo)
+	{
+		int64_t nxt[256], end[256], beg[256];
+		pg128_t *p = a + r.beg;
+		const int sh = r.shift;
+		std::fill(end, end + 256, 0);
+		for (int64_t i = 0; i < r.n; ++i) ++end[p[i].x >> sh & 255];
+		{   // every record in one bucket (a byte all keys share: the high bytes of small keys): the permutation below is the identity
+			bool one = false;
+			for (int k = 0; k < 256 && !one; ++k) one = end[k] == r.n;
+			if (one) { if (sh > 0) todo.push_back(Range{r.beg, r.n, sh > 8? sh - 8 : 0}); return; }
+		}
+		int64_t acc = 0;
+		for (int k = 0; k < 256; ++k) { beg[k] = nxt[k] = acc; acc += end[k]; end[k] = acc; }
+		// permute in place: walk the buckets in order; whatever sits at the write cursor of bucket k and does not
+		// belong there is carried from bucket to bucket, each time swapped against that bucket's cursor, until a
+		// record of bucket k turns up.  Records already at home are stepped over one by one.
+		for (int k = 0; k < 256;) {
+			if (nxt[k] == end[k]) { ++k; continue; }
+			int d = (int)(p[nxt[k]].x >> sh & 255);
+			if (d == k) { ++nxt[k]; continue; }
+			pg128_t hold = p[nxt[k]];
+			while (d != k) { std::swap(hold, p[nxt[d]]); ++nxt[d]; d = (int)(hold.x >> sh & 255); }
+			p[nxt[k]++] = hold;
+		}
+		if (sh == 0) return;
+		const int sub = sh > 8? sh - 8 : 0;
+		for (int k = 0; k < 256; ++k) {
+			int64_t m = end[k] - beg[k];
+			if (m > 64) todo.push_back(Range{r.beg + beg[k], m, sub});
+			else if (m > 1) insertion(p + beg[k], m);
+		}
+	}
+	static void finish(pg128_t *a, Range r0)
+	{
+		std::vector<Range> todo;
+		todo.push_back(r0);
+		while (!todo.empty()) { Range r = todo.back(); todo.pop_back(); pass(a, r, todo); }
+	}
 public:
+	// Reproduce the permutation of an American-flag sort (8-bit digits from the top byte down; buckets of <= 64 records finished by a
+	// stable insertion sort; ranges of <= 64 records never enter the digit pass at all).  Ranges are disjoint and their order of
+	// processing does not matter, so once the first real split has produced many of them they are finished on the host thread pool.
 	static void run(pg128_t *a, int64_t n)
 	{
 		if (n <= 64) { insertion(a, n); return; }
 		std::vector<Range> todo;
 		todo.push_back(Range{0, n, 56});
-		int64_t nxt[256], end[256], beg[256];
-		while (!todo.empty()) {
-			Range r = todo.back(); todo.pop_back();
-			pg128_t *p = a + r.beg;
-			const int sh = r.shift;
-			std::fill(end, end + 256, 0);
-			for (int64_t i = 0; i < r.n; ++i) ++end[p[i].x >> sh & 255];
-			{   // every record in one bucket (a byte all keys share: the high bytes of small keys): the permutation below is the identity
-				bool one = false;
-				for (int k = 0; k < 256 && !one; ++k) one = end[k] == r.n;
-				if (one) { if (sh > 0) todo.push_back(Range{r.beg, r.n, sh > 8? sh - 8 : 0}); continue; }
-			}
-			int64_t acc = 0;
-			for (int k = 0; k < 256; ++k) { beg[k] = nxt[k] = acc; acc += end[k]; end[k] = acc; }
-			// permute in place: walk the buckets in order; whatever sits at the write cursor of bucket k and does not
-			// belong there is carried from bucket to bucket, each time swapped against that bucket's cursor, until a
-			// record of bucket k turns up.  Records already at home are stepped over one by one.
-			for (int k = 0; k < 256;) {
-				if (nxt[k] == end[k]) { ++k; continue; }
-				int d = (int)(p[nxt[k]].x >> sh & 255);
-				if (d == k) { ++nxt[k]; continue; }
-				pg128_t hold = p[nxt[k]];
-				while (d != k) { std::swap(hold, p[nxt[d]]); ++nxt[d]; d = (int)(hold.x >> sh & 255); }
-				p[nxt[k]++] = hold;
-			}
-			if (sh == 0) continue;
-			const int sub = sh > 8? sh - 8 : 0;
-			for (int k = 0; k < 256; ++k) {
-				int64_t m = end[k] - beg[k];
-				if (m > 64) todo.push_back(Range{r.beg + beg[k], m, sub});
-				else if (m > 1) insertion(p + beg[k], m);
-			}
-		}
+		while (todo.size() == 1) { Range r = todo.back(); todo.pop_back(); pass(a, r, todo); }   // identity levels, then the first split
+		if (todo.empty()) return;
+		if (n < (1 << 14)) { for (const Range &r : todo) finish(a, r); return; }
+		ThreadPool::get().parallel_for((int64_t)todo.size(), [&](int64_t i) { finish(a, todo[i]); });
 	}
 };
 

@@ -471,49 +471,61 @@ __device__ __forceinline__ void mark_dirty(const DirtyCols &D, int32_t h)
 }
 
 // ---- branch round -----------------------------------------------------------------------------------------------------------
-// one WARP per table entry = one (vertex, arc pair): is there a LOCAL genome in which the two target genes are local to each other
-// (branch.c:31-46)?  Every use of pg_n_local() in branch.c:60-98 only asks "== 0 ?" / "> 0 ?", so the warp stops at the first genome that says
-// yes.  ord_sensitive: an ordinal of a cs-tied survivor (GenePos.pad, k_cs_tie_mark) sits within 8 of the local_count threshold in a comparison
-// that the distance clause does not settle, and no other genome settles the entry: the reference's numbering of those hits may differ.
+// The locality table of a branch round: one entry per (vertex, pair of its out-arcs): is there a LOCAL genome in which the two target genes
+// are local to each other (branch.c:31-46)?  Every use of pg_n_local() in branch.c:60-98 only asks "== 0 ?" / "> 0 ?", so an entry is settled
+// by the first genome that says yes.  A warp takes 32 consecutive entries: every lane decodes ONE entry (owner vertex by binary search in the
+// offsets, position in the upper triangle, the two gene ids -- a chain of ~25 dependent loads, paid once per 32 entries instead of once per
+// entry), then the warp goes through its entries with the lanes spread over the genomes.  ord_sensitive: an ordinal of a cs-tied survivor
+// (GenePos.pad, k_cs_tie_mark) sits within 8 of the local_count threshold in a comparison that the distance clause does not settle, and no
+// other genome settles the entry: the reference's numbering of those hits may differ (DESIGN.md "tie order").
 __global__ void k_branch_local(const unsigned long long *__restrict__ idx, const DevCounts *__restrict__ dc, const ArcDev *__restrict__ arc, const SegDev *__restrict__ seg, const GenePos *__restrict__ pos, int32_t G,
 	const uint32_t *__restrict__ nl_off, int32_t NV, uint32_t nl_cap, const unsigned long long *__restrict__ nl_total, BranchOpt o, uint8_t *nl, uint32_t *ord_sensitive)
 {
 	const int32_t n_vtx = 2 * (int32_t)dc->n_seg < NV? 2 * (int32_t)dc->n_seg : NV, lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
 	const int32_t n_nl = *nl_total <= (unsigned long long)nl_cap? (int32_t)dc->n_nl : 0;   // too many pairs for the table: k_branch_decide_fast raises the fallback
-	for (int32_t ent = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ent < n_nl; ent += n_warps) {
-		int32_t lo = 0, hi = n_vtx;                             // vertex owning this entry: last v with nl_off[v] <= ent
-		while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (nl_off[m] <= (uint32_t)ent) lo = m + 1; else hi = m; }
-		const int32_t v = lo - 1;
-		const unsigned long long e = idx[v];
-		const uint32_t n = (uint32_t)e;
-		uint32_t r = (uint32_t)ent - nl_off[v], i = 0;
-		while (r >= n - i) { r -= n - i; ++i; }                 // row i of the upper triangle holds n - i entries (k = i .. n-1)
-		const uint32_t k = i + r;
-		const ArcDev *a = arc + (e >> 32);
-		const GenePos *p1 = pos + (size_t)seg[(uint32_t)a[i].x >> 1].gid * G, *p2 = pos + (size_t)seg[(uint32_t)a[k].x >> 1].gid * G;
-		bool any = false, sens = false, settled = false;
-		for (int32_t j0 = 0; j0 < G && !settled; j0 += 32) {
-			const int32_t j = j0 + lane;
-			bool robust = false;
-			if (j < G) {
-				const GenePos x = p1[j], y = p2[j];
-				if (x.cid >= 0 && y.cid >= 0 && (o.frag_mode || x.cid == y.cid)) {
-					const long long dd = (long long)x.cm - y.cm; const int32_t dcnt = x.ord - y.ord;
-					const bool by_dist = dd >= -o.local_dist && dd <= o.local_dist, by_cnt = dcnt >= -o.local_count && dcnt <= o.local_count;
-					bool shaky = false;
-					if ((x.pad | y.pad) && !by_dist) {
-						const long long ac = dcnt < 0? -(long long)dcnt : dcnt;
-						shaky = ac > (long long)o.local_count - 8 && ac <= (long long)o.local_count + 8;
-					}
-					any = any || by_dist || by_cnt;
-					sens = sens || shaky;
-					robust = (by_dist || by_cnt) && !shaky;
-				}
-			}
-			settled = __any_sync(0xffffffffu, robust);
+	for (int32_t base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_nl; base += n_warps * 32) {
+		const int32_t ent = base + lane;
+		int32_t g1 = 0, g2 = 0;
+		if (ent < n_nl) {
+			int32_t lo = 0, hi = n_vtx;                         // vertex owning this entry: last v with nl_off[v] <= ent
+			while (lo < hi) { const int32_t m = (lo + hi) >> 1; if (nl_off[m] <= (uint32_t)ent) lo = m + 1; else hi = m; }
+			const int32_t v = lo - 1;
+			const unsigned long long e = idx[v];
+			const uint32_t n = (uint32_t)e;
+			uint32_t r = (uint32_t)ent - nl_off[v], i = 0;
+			while (r >= n - i) { r -= n - i; ++i; }             // row i of the upper triangle holds n - i entries (k = i .. n-1)
+			const ArcDev *a = arc + (e >> 32);
+			g1 = seg[(uint32_t)a[i].x >> 1].gid; g2 = seg[(uint32_t)a[i + r].x >> 1].gid;
 		}
-		any = __any_sync(0xffffffffu, any); sens = __any_sync(0xffffffffu, sens);
-		if (lane == 0) { nl[ent] = any? 1 : 0; if (sens && !settled) *ord_sensitive = 1u; }
+		const int32_t n_here = n_nl - base < 32? n_nl - base : 32;
+		bool my_any = false, my_shaky = false;
+		for (int32_t q = 0; q < n_here; ++q) {
+			const GenePos *p1 = pos + (size_t)__shfl_sync(0xffffffffu, g1, q) * G, *p2 = pos + (size_t)__shfl_sync(0xffffffffu, g2, q) * G;
+			bool any = false, sens = false, settled = false;
+			for (int32_t j0 = 0; j0 < G && !settled; j0 += 32) {
+				const int32_t j = j0 + lane;
+				bool robust = false;
+				if (j < G) {
+					const GenePos x = p1[j], y = p2[j];
+					if (x.cid >= 0 && y.cid >= 0 && (o.frag_mode || x.cid == y.cid)) {
+						const long long dd = (long long)x.cm - y.cm; const int32_t dcnt = x.ord - y.ord;
+						const bool by_dist = dd >= -o.local_dist && dd <= o.local_dist, by_cnt = dcnt >= -o.local_count && dcnt <= o.local_count;
+						bool shaky = false;
+						if ((x.pad | y.pad) && !by_dist) {
+							const long long ac = dcnt < 0? -(long long)dcnt : dcnt;
+							shaky = ac > (long long)o.local_count - 8 && ac <= (long long)o.local_count + 8;
+						}
+						any = any || by_dist || by_cnt;
+						sens = sens || shaky;
+						robust = (by_dist || by_cnt) && !shaky;
+					}
+				}
+				settled = __any_sync(0xffffffffu, robust);
+			}
+			any = __any_sync(0xffffffffu, any); sens = __any_sync(0xffffffffu, sens);
+			if (lane == q) { my_any = any; my_shaky = sens && !settled; }
+		}
+		if (ent < n_nl) { nl[ent] = my_any? 1 : 0; if (my_shaky) *ord_sensitive = 1u; }
 	}
 }
 
