@@ -1193,7 +1193,7 @@ struct Session {
 		g_comm.allreduce(f.nl.p, f.nl_cap, Comm::T_UINT8, Comm::OP_SUM, st);
 		if (g_comm.active()) pt.mark("br:allreduce", st);
 		PGX_LAUNCH(k_branch_decide_fast, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, f.nl_off.p, f.nl.p, f.nl_cap, f.nl_total.p, bo, f.grp.p, counters.p + C_TIE_ROUND);
-		PGX_LAUNCH(k_branch_hits_fast, GS_GRID, TB, 0, st, sv.p, f.info.p, dc.p, A.bits, arc.p, f.glob, f.pos_of.p, dirty_cols(), counters.p + C_BR_CHANGED);
+		PGX_LAUNCH(k_branch_hits_fast, GS_GRID, TB, 0, st, sv.p, f.info.p, dc.p, A.bits, arc.p, f.glob, f.pos_of.p, g_comm.active()? (const uint32_t*)nullptr : (const uint32_t*)f.rec.p, dirty_cols(), counters.p + C_BR_CHANGED);
 		pt.mark("br:decide+hits", st);
 		if (round > 0) flt_high_occ_fast(max_avg_occ, max_degree, max_dist_loci);          // graph.c:310-313
 	}

@@ -116,6 +116,8 @@ struct VtxCellHost { int32_t g, j, t, t_dom; };
 static inline void elect_vertices_cells(const int32_t *cnt2, const VtxCellHost *cells, size_t n_cells, int32_t n_genome, int32_t n_gene, const int32_t *gene_rep_pid, const int32_t *prot_avg,
 	const uint8_t *gene_pref, const uint8_t *gene_incl, double min_vertex_ratio, bool dump, const pg_gene_t *names, std::vector<SegHost> &out)
 {
+	struct timespec ts0, ts1, ts2, ts3;
+	clock_gettime(CLOCK_MONOTONIC, &ts0);
 	std::vector<pg128_t> cnt(n_gene);
 	for (int32_t g = 0; g < n_gene; ++g) {
 		uint64_t x = (uint64_t)(int64_t)prot_avg[gene_rep_pid[g]] + ((uint64_t)(uint32_t)cnt2[2 * g] << 32), y = (uint64_t)g + ((uint64_t)(uint32_t)cnt2[2 * g + 1] << 32);   // vertex.c:19-20,49-50
@@ -128,7 +130,9 @@ static inline void elect_vertices_cells(const int32_t *cnt2, const VtxCellHost *
 	for (int32_t g = 0; g < n_gene; ++g) start[g + 1] += start[g];
 	std::vector<uint32_t> fill(start.begin(), start.end() - 1), by_gene(n_cells);
 	for (size_t i = 0; i < n_cells; ++i) by_gene[fill[cells[i].g]++] = (uint32_t)i;
+	clock_gettime(CLOCK_MONOTONIC, &ts1);
 	FlagSortReplay::run(cnt.data(), n_gene);                                                  // vertex.c:60
+	clock_gettime(CLOCK_MONOTONIC, &ts2);
 	std::vector<uint64_t> claimed(((size_t)n_genome * n_gene + 63) / 64, 0);
 	std::vector<int32_t> n_claimed(n_gene, 0);
 	std::vector<uint8_t> accepted(n_gene, 0);
@@ -149,6 +153,11 @@ static inline void elect_vertices_cells(const int32_t *cnt2, const VtxCellHost *
 	}
 	out.clear();
 	for (int32_t g = 0; g < n_gene; ++g) if (accepted[g]) out.push_back(SegHost{g, n_dom_out[g], cnt2[2 * g + 1]});   // vertex.c:85-94: sorted by gene id
+	clock_gettime(CLOCK_MONOTONIC, &ts3);
+	if (getenv("PGX_TIMING")) {
+		auto ms = [](const timespec &a, const timespec &b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) * 1e-6; };
+		fprintf(stderr, "[pgx timing] election: keys + cell index %.2f ms, order replay %.2f ms, greedy + segments %.2f ms\n", ms(ts0, ts1), ms(ts1, ts2), ms(ts2, ts3));
+	}
 }
 
 } // namespace pgx

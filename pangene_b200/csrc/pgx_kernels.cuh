@@ -440,7 +440,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 // History of the design with the ncu numbers of every step: profiles/README.md.  tests/test_sweep_emu.py runs this kernel on the
 // CPU (SIMT shim) against the thread-per-hit kernel.
 constexpr int SWQ_TILE = 256, SWQ_HALO = 64, SWQ_STG = SWQ_TILE + 2 * SWQ_HALO + 8, SWQ_EXCAP = 2560;
-constexpr int SWQ_LEVELS = 5, SWQ_WIN = 1 << SWQ_LEVELS;   // depth of the range-maximum table / the longest window it answers
 constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (size_t)(SWQ_STG + 4) * 4 + (size_t)SWQ_EXCAP * 8 + 64;
 
 // One walk of two exon lists that live in ONE address space (both staged in shared memory, or both in global memory).
@@ -490,7 +489,10 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	int2 *s_ex = (int2*)sp; sp += (size_t)SWQ_EXCAP * 8;
 	uint64_t *bar = (uint64_t*)sp; sp += 8;
 	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range
-	__shared__ uint16_t s_st[SWQ_LEVELS][SWQ_STG]; // s_st[j][q]: position of the maximum of [q, q + 2^(j+1)) (clipped); windows up to SWQ_WIN hits
+	__shared__ uint16_t s_cst[SWQ_STG + 8];      // s_cst[q]: first staged slot of the overlap cluster that slot q belongs to
+	__shared__ uint16_t s_top[SWQ_STG + 8];      // at a cluster's first slot: slot of its strongest hit (leftmost maximum of the key) | 0x8000 if that key occurs twice
+	__shared__ uint16_t s_cend[SWQ_STG + 8];     // at a cluster's first slot: one past its last slot
+	__shared__ int32_t s_wmax[SWQ_TILE / 32];
 	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
 	__shared__ uint32_t s_hist[64], s_job[SWQ_TILE], s_njob, s_flags;
 
@@ -519,15 +521,16 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	__syncthreads();
 	while (!mbar_try_wait(bar, 0)) { }
 
-	// ---- phase 0 (not for SW_ISO / -S): a sparse table over the staged score keys answers "which hit of an index range has the
-	// largest key (leftmost on ties)?" in two look-ups.  Filtered hits count as key 0 (and get key 0 in the staged copy: nothing
-	// below reads the key of a filtered hit for any other purpose).  The table is only usable where the loser of a pair is
-	// decided by the keys alone, i.e. where no unfiltered hit of the tile carries a weak_br mark (overlap.c:139-147): flag 1.
-	// Flag 2: the staged range spans a contig boundary (then the window bounds are found by the linear scans).
+	// ---- phase 0 (first sweep only, not with -S): overlap clusters.  A cluster is a maximal run of staged hits in which every hit starts
+	// before the running maximum of the ends before it (same contig): a hit's window (overlap.c:67-71,114-120) never leaves its cluster, so the
+	// strongest hit of the cluster -- the leftmost maximum of the score key; filtered hits count as key 0 and get key 0 in the staged copy, nothing
+	// below reads the key of a filtered hit for any other purpose -- is the strongest hit of every window that contains it.  One pass finds
+	// the cluster of every slot (a block-wide running maximum over "I start a cluster"), one loop per cluster finds its strongest hit.
+	// Only usable where the loser of a pair is decided by the keys alone, i.e. where no unfiltered hit of the tile carries a weak_br mark
+	// (overlap.c:139-147): flag 1.
 	const int32_t S = hi - lo;
-	const bool rmq_mode = MODE == SW_LOAD && !o.check_strand;   // (the later sweeps run on the small active set: windows of 1-2 partners, the table would cost more than it saves)
-	// filtered hits (25 % in the first sweep) do no work: the live ones are compacted so that they fill whole warps.  The two
-	// barriers of the compaction are the first two barriers of the table build.
+	const bool rmq_mode = MODE == SW_LOAD && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
+	// filtered hits (25 % in the first sweep) do no work: the live ones are compacted so that they fill whole warps.
 	const int32_t i0 = t0 + tid;
 	const bool r0 = i0 < c.n;
 	const uint32_t bits0 = s_bits[r0? i0 - lo : 0];
@@ -535,17 +538,27 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	const bool live0 = r0 && !(bits0 & PG_HB_FLT);
 	const uint32_t bal = __ballot_sync(0xffffffffu, live0);
 	if ((tid & 31) == 0) s_wcnt[tid >> 5] = (uint16_t)__popc(bal);
+	int32_t cst0 = -1, cst1 = -1;                                                         // cluster starts of slots 2 tid and 2 tid + 1, before the carry from the threads to the left
 	if (rmq_mode) {
 		uint32_t flags = 0;
-		for (int32_t q = tid; q < S; q += SWQ_TILE) {
-			const int32_t b = q + 1 < S? q + 1 : q;
-			const uint32_t bq = s_bits[q], bb = s_bits[b];
-			const uint64_t kq = (bq & PG_HB_FLT)? 0ull : s_key[q], kb = (bb & PG_HB_FLT)? 0ull : s_key[b];
-			s_st[0][q] = (uint16_t)(kb > kq? b : q);
+		const int32_t q0 = 2 * tid, q1 = q0 + 1;
+		if (q0 < S) {
+			const uint32_t bq = s_bits[q0];
 			if (!(bq & PG_HB_FLT) && (bq & PG_HB_WBR_MASK)) flags |= 1u;
-			if (s_ctg[b] != s_ctg[q]) flags |= 2u;
+			if (q0 == 0 || s_ctg[q0] != s_ctg[q0 - 1] || s_pmax[q0 - 1] <= s_cs[q0]) cst0 = q0;
 		}
+		if (q1 < S) {
+			const uint32_t bq = s_bits[q1];
+			if (!(bq & PG_HB_FLT) && (bq & PG_HB_WBR_MASK)) flags |= 1u;
+			cst1 = (s_ctg[q1] != s_ctg[q0] || s_pmax[q0] <= s_cs[q1])? q1 : cst0;
+		} else cst1 = cst0;
 		if (flags) atomicOr(&s_flags, flags);
+		int32_t m = cst1;                                                                 // inclusive running maximum over the threads of the warp
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, m, d); if ((tid & 31) >= d && t > m) m = t; }
+		if ((tid & 31) == 31) s_wmax[tid >> 5] = m;
+		const int32_t left = __shfl_up_sync(0xffffffffu, m, 1);
+		cst1 = m; if ((tid & 31) > 0 && left > cst0) cst0 = left;                         // (lane 0 gets the carry of the warps to its left below)
 	}
 	__syncthreads();
 	int32_t n_live = 0;
@@ -555,18 +568,30 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 		for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
 		if (live0) s_live[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
 	}
-	if (rmq_mode) for (int32_t q = tid; q < S; q += SWQ_TILE) if (s_bits[q] & PG_HB_FLT) s_key[q] = 0ull;
-	__syncthreads();
 	if (rmq_mode) {
-#pragma unroll 1
-		for (int j = 1; j < SWQ_LEVELS; ++j) {
-			for (int32_t q = tid; q < S; q += SWQ_TILE) {
-				const int32_t a = s_st[j - 1][q], q2 = q + (1 << j);
-				const int32_t b = q2 < S? (int32_t)s_st[j - 1][q2] : a;
-				s_st[j][q] = (uint16_t)(s_key[b] > s_key[a]? b : a);
+		int32_t carry = -1;
+#pragma unroll
+		for (int w = 0; w < SWQ_TILE / 32; ++w) if (w < (tid >> 5) && s_wmax[w] > carry) carry = s_wmax[w];
+		if (carry > cst0) cst0 = carry;
+		if (carry > cst1) cst1 = carry;
+		const int32_t q0 = 2 * tid, q1 = q0 + 1;
+		if (q0 < S) { s_cst[q0] = (uint16_t)cst0; if (s_bits[q0] & PG_HB_FLT) s_key[q0] = 0ull; }
+		if (q1 < S) { s_cst[q1] = (uint16_t)cst1; if (s_bits[q1] & PG_HB_FLT) s_key[q1] = 0ull; }
+	}
+	__syncthreads();
+	if (rmq_mode) {   // the first slot of every cluster walks it once: strongest hit, whether its key occurs again, where the cluster ends
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const int32_t q = 2 * tid + r;
+			if (q < S && s_cst[q] == q) {
+				int32_t best = q, dup = 0, p = q + 1;
+				uint64_t bk = s_key[q];
+				for (; p < S && s_cst[p] == q; ++p) { const uint64_t k = s_key[p]; if (k > bk) { bk = k; best = p; dup = 0; } else if (k == bk) dup = 1; }
+				s_top[q] = (uint16_t)(best | (dup? 0x8000 : 0));
+				s_cend[q] = (uint16_t)p;
 			}
-			__syncthreads();
 		}
+		__syncthreads();
 	}
 	const bool in_range = tid < n_live;
 	const int32_t i = in_range? t0 + (int32_t)s_live[tid] : t0;
@@ -600,57 +625,21 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	};
 
 	if (in_range) {
-	// ---- phase 1a: the would-be dominator from the sparse table: window bounds, then two range-maximum queries.  Whatever the
-	// table cannot settle (a strongest hit that ended before my start, equal keys, windows longer than SWQ_WIN or leaving the
-	// staged range) falls through to the partner-by-partner scan below.
+	// ---- phase 1a: the would-be dominator from the cluster: if the strongest hit of my cluster is in my window, no partner can have a larger
+	// key.  Whatever this cannot settle (the strongest hit does not reach me, its key occurs twice in the cluster -- same protein, same score:
+	// ranks and the tie detector need the partner-by-partner view --, or I am the strongest hit of a cluster with such a twin) falls through to
+	// the scan below; clusters that touch the ends of the staged range are finished by the parked path (phase 3).
 	bool scan = true;
 	if (rmq_mode && !(s_flags & 1u)) {
-		auto rmq = [&](int32_t a, int32_t b) -> int32_t {   // leftmost maximum of the key over [a, b), 1 <= b - a <= SWQ_WIN
-			const int32_t len = b - a;
-			if (len == 1) return a;
-			const int k = 31 - __clz(len);                  // 2^k <= len, k >= 1
-			const int32_t x = s_st[k - 1][a], y = s_st[k - 1][b - (1 << k)];
-			const uint64_t kx = s_key[x], ky = s_key[y];
-			return (ky > kx || (ky == kx && y < x))? y : x;
-		};
-		int32_t wb, wf;
-		if (!(s_flags & 2u)) {   // one contig: pmax (running maximum of ce) and cs are non-decreasing over the staged range
-			int32_t l = mq > SWQ_WIN + 1? mq - (SWQ_WIN + 1) : 0, r = mq;
-			while (l < r) { const int32_t m = (l + r) >> 1; if (s_pmax[m] > mcs) r = m; else l = m + 1; }   // overlap.c:67-71,114-120
-			wb = l;
-			l = mq + 1; r = S < mq + SWQ_WIN + 2? S : mq + SWQ_WIN + 2;
-			while (l < r) { const int32_t m = (l + r) >> 1; if (s_cs[m] < mce) l = m + 1; else r = m; }
-			wf = l;
-		} else {
-			wb = mq; wf = mq + 1;
-			while (wb > 0 && s_ctg[wb - 1] == mctg && s_pmax[wb - 1] > mcs) --wb;
-			while (wf < S && s_ctg[wf] == mctg && s_cs[wf] < mce) ++wf;
-		}
-		const bool open_back = wb == 0 && lo > 0, open_fwd = wf == S && hi < c.n;   // the window may continue outside the staged range
+		const int32_t head = s_cst[mq], ce_ = s_cend[head], tq = s_top[head] & 0x7fff;
+		const bool dup = (s_top[head] & 0x8000) != 0;
 		scan = false;
-		if (open_back || open_fwd) slow = true;
-		else if (mq - wb > SWQ_WIN || wf - mq - 1 > SWQ_WIN) scan = true;
-		else {
-			int32_t tb = -1, tf = -1;
-			if (wb < mq) { tb = rmq(wb, mq); if (s_key[tb] == 0) tb = -1; else if (s_ce[tb] <= mcs) scan = true; }   // strongest in range is not a partner: a weaker one may be
-			if (mq + 1 < wf) { tf = rmq(mq + 1, wf); if (s_key[tf] == 0) tf = -1; }
-			if (!scan) {
-				const uint64_t kb = tb >= 0? s_key[tb] : 0ull, kf = tf >= 0? s_key[tf] : 0ull;
-				if ((tb >= 0 && kb == mkey) || (tf >= 0 && kf == mkey)) scan = true;       // same protein, same score: ranks decide (rare)
-				else {
-					if (tb >= 0 && kb > mkey) { top_key = kb; top_p = lo + tb; }
-					if (tf >= 0 && kf > mkey && kf > top_key) { top_key = kf; top_p = lo + tf; }   // equal keys: the backward one has the smaller index
-					if (MODE == SW_LOAD && top_p != INT32_MAX) {   // tie detector: a second partner with the winning key and the same start
-						const int32_t tq = top_p - lo;
-						int32_t r1 = -1, r2 = -1;
-						if (tq < mq) { if (wb < tq) r1 = rmq(wb, tq); if (tq + 1 < mq) r2 = rmq(tq + 1, mq); if (tf >= 0 && kf == top_key && s_cs[tf] == s_cs[tq]) atomicAdd(tie_cnt, 1u); }
-						else { if (mq + 1 < tq) r1 = rmq(mq + 1, tq); if (tq + 1 < wf) r2 = rmq(tq + 1, wf); }
-						if (r1 >= 0 && s_key[r1] == top_key && s_cs[r1] == s_cs[tq]) atomicAdd(tie_cnt, 1u);
-						if (r2 >= 0 && s_key[r2] == top_key && s_cs[r2] == s_cs[tq]) atomicAdd(tie_cnt, 1u);
-					}
-				}
-			}
-		}
+		if ((head == 0 && lo > 0) || (ce_ == S && hi < c.n)) slow = true;                // the cluster (and with it possibly my window) may continue outside the staged range
+		else if (dup) scan = true;
+		else if (tq == mq) { }                                                            // nobody in my cluster beats me: top_p stays unset
+		else if (s_key[tq] == 0) { }                                                      // (all other hits of the cluster are filtered)
+		else if (tq < mq? s_ce[tq] > mcs : s_cs[tq] < mce) { top_key = s_key[tq]; top_p = lo + tq; }   // overlap.c:70,118: it is one of my partners
+		else scan = true;
 	}
 	// ---- phase 1b: the would-be dominator by scanning the window.  One loop walks back, then forward: a lane whose backward
 	// window is short starts its forward window while its neighbours are still going back.

@@ -570,15 +570,17 @@ __global__ void k_branch_decide_fast(const unsigned long long *__restrict__ idx,
 
 // branch.c:108-145 + PG_SET_FILTER(weak_br == 2) (graph.c:309).  The two arcs an adjacency sits on (pg_get_arc, pgpriv.h:99-107) are found
 // through the table of canonical keys and pos_of[]; a hit whose flt / weak_br bits change marks the sweep tiles it can influence.
-__device__ __forceinline__ uint32_t arc_weak_of(const ArcTable &T, const uint32_t *__restrict__ pos_of, const ArcDev *__restrict__ arc, unsigned long long x)
+// rec (optional): the pair record of the adjacency, written by k_arc_insert against THIS table (single rank: no look-up needed)
+__device__ __forceinline__ uint32_t arc_weak_of(const ArcTable &T, const uint32_t *__restrict__ pos_of, const ArcDev *__restrict__ arc, unsigned long long x, const uint32_t *__restrict__ rec, int32_t t)
 {
 	const unsigned long long xm = arc_mirror(x);
-	const uint32_t s = arc_find(T, x < xm? x : xm);
+	uint32_t s;
+	if (rec) { const uint32_t r = rec[t]; s = r == ARC_NONE? ARC_NONE : r & REC_SLOT; } else s = arc_find(T, x < xm? x : xm);
 	if (s == ARC_NONE) return 0u;
 	return arc[pos_of[s * 2 + (xm < x? 1u : 0u)]].bits >> 1 & 3u;
 }
 __global__ void k_branch_hits_fast(const uint32_t *__restrict__ sv, const SvInfo *__restrict__ info, const DevCounts *__restrict__ dc, uint32_t *bits,
-	const ArcDev *__restrict__ arc, ArcTable T, const uint32_t *__restrict__ pos_of, DirtyCols D, uint32_t *n_changed)
+	const ArcDev *__restrict__ arc, ArcTable T, const uint32_t *__restrict__ pos_of, const uint32_t *__restrict__ rec, DirtyCols D, uint32_t *n_changed)
 {
 	const int32_t m = (int32_t)dc->m_sv;
 	PGX_GS(t, m) {
@@ -588,14 +590,14 @@ __global__ void k_branch_hits_fast(const uint32_t *__restrict__ sv, const SvInfo
 		if (t > 0) {
 			const SvInfo p = info[t - 1];
 			if (p.ctg == me.ctg) {                              // I am the later hit of (prev, me): arc (w^1 -> v^1), branch.c:130-132
-				const uint32_t x = arc_weak_of(T, pos_of, arc, (unsigned long long)(me.w ^ 1u) << 32 | (p.w ^ 1u));
+				const uint32_t x = arc_weak_of(T, pos_of, arc, (unsigned long long)(me.w ^ 1u) << 32 | (p.w ^ 1u), rec, t);
 				wb = wb > x? wb : x;
 			}
 		}
 		if (t + 1 < m) {
 			const SvInfo nx = info[t + 1];
 			if (nx.ctg == me.ctg) {                             // I am the earlier hit of (me, next): arc (v -> w), branch.c:127-129
-				const uint32_t x = arc_weak_of(T, pos_of, arc, (unsigned long long)me.w << 32 | nx.w);
+				const uint32_t x = arc_weak_of(T, pos_of, arc, (unsigned long long)me.w << 32 | nx.w, rec, t + 1);
 				wb = wb > x? wb : x;
 			}
 		}
