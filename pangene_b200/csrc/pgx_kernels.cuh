@@ -448,15 +448,19 @@ constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (siz
 // from non-negative CIGAR lengths), and the list to advance is the reference's.
 template<bool EARLY> __device__ __forceinline__ int32_t walk_exons(const int2 *p0, const int2 *e0, int32_t cs0, const int2 *p1, const int2 *e1, int32_t cs1, int32_t need)
 {
-	int2 x0 = *p0, x1 = *p1;
+	const int2 x0 = *p0, x1 = *p1;
 	int32_t s0 = cs0 + x0.x, t0 = cs0 + x0.y, s1 = cs1 + x1.x, t1 = cs1 + x1.y, inter = 0;
 	while (true) {
 		const bool adv0 = s0 < s1? t0 < t1 : !(t1 < t0);
 		const int32_t o = (t0 < t1? t0 : t1) - (s0 > s1? s0 : s1);
 		inter += o > 0? o : 0;
 		if (EARLY && inter >= need) break;
-		if (adv0) { if (++p0 == e0) break; x0 = *p0; s0 = cs0 + x0.x; t0 = cs0 + x0.y; }
-		else { if (++p1 == e1) break; x1 = *p1; s1 = cs1 + x1.x; t1 = cs1 + x1.y; }
+		// advance ONE list, without a branch per list: the lanes of a warp take the two sides in any mix
+		p0 += adv0? 1 : 0; p1 += adv0? 0 : 1;
+		if ((adv0? p0 : p1) == (adv0? e0 : e1)) break;
+		const int2 x = *(adv0? p0 : p1);
+		const int32_t base = adv0? cs0 : cs1, ns = base + x.x, nt = base + x.y;
+		s0 = adv0? ns : s0; t0 = adv0? nt : t0; s1 = adv0? s1 : ns; t1 = adv0? t1 : nt;
 	}
 	return inter;
 }
@@ -490,8 +494,9 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	uint64_t *bar = (uint64_t*)sp; sp += 8;
 	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range
 	__shared__ uint16_t s_cst[SWQ_STG + 8];      // s_cst[q]: first staged slot of the overlap cluster that slot q belongs to
-	__shared__ uint16_t s_top[SWQ_STG + 8];      // at a cluster's first slot: slot of its strongest hit (leftmost maximum of the key) | 0x8000 if that key occurs twice
-	__shared__ uint16_t s_cend[SWQ_STG + 8];     // at a cluster's first slot: one past its last slot
+	__shared__ unsigned long long s_cmax[SWQ_STG + 8];   // at a cluster's first slot: the largest key in the cluster ...
+	__shared__ uint32_t s_ctop[SWQ_STG + 8];     // ... the leftmost slot that holds it ...
+	__shared__ uint32_t s_ccnt[SWQ_STG + 8];     // ... and how many slots hold it
 	__shared__ int32_t s_wmax[SWQ_TILE / 32];
 	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
 	__shared__ uint32_t s_hist[64], s_job[SWQ_TILE], s_njob, s_flags;
@@ -575,22 +580,18 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 		if (carry > cst0) cst0 = carry;
 		if (carry > cst1) cst1 = carry;
 		const int32_t q0 = 2 * tid, q1 = q0 + 1;
-		if (q0 < S) { s_cst[q0] = (uint16_t)cst0; if (s_bits[q0] & PG_HB_FLT) s_key[q0] = 0ull; }
-		if (q1 < S) { s_cst[q1] = (uint16_t)cst1; if (s_bits[q1] & PG_HB_FLT) s_key[q1] = 0ull; }
+		if (q0 < S) { s_cst[q0] = (uint16_t)cst0; if (s_bits[q0] & PG_HB_FLT) s_key[q0] = 0ull; if (cst0 == q0) { s_cmax[q0] = 0ull; s_ctop[q0] = 0xffffffffu; s_ccnt[q0] = 0u; } }
+		if (q1 < S) { s_cst[q1] = (uint16_t)cst1; if (s_bits[q1] & PG_HB_FLT) s_key[q1] = 0ull; if (cst1 == q1) { s_cmax[q1] = 0ull; s_ctop[q1] = 0xffffffffu; s_ccnt[q1] = 0u; } }
 	}
 	__syncthreads();
-	if (rmq_mode) {   // the first slot of every cluster walks it once: strongest hit, whether its key occurs again, where the cluster ends
-#pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const int32_t q = 2 * tid + r;
-			if (q < S && s_cst[q] == q) {
-				int32_t best = q, dup = 0, p = q + 1;
-				uint64_t bk = s_key[q];
-				for (; p < S && s_cst[p] == q; ++p) { const uint64_t k = s_key[p]; if (k > bk) { bk = k; best = p; dup = 0; } else if (k == bk) dup = 1; }
-				s_top[q] = (uint16_t)(best | (dup? 0x8000 : 0));
-				s_cend[q] = (uint16_t)p;
-			}
-		}
+	if (rmq_mode) {   // strongest hit of every cluster: maximum of the key, then the leftmost slot that holds it and how many do (shared-memory atomics)
+		const int32_t q0 = 2 * tid, q1 = q0 + 1;
+		const unsigned long long k0 = q0 < S? s_key[q0] : 0ull, k1 = q1 < S? s_key[q1] : 0ull;
+		if (k0) atomicMax(&s_cmax[cst0], k0);
+		if (k1) atomicMax(&s_cmax[cst1], k1);
+		__syncthreads();
+		if (k0 && k0 == s_cmax[cst0]) { atomicMin(&s_ctop[cst0], (uint32_t)q0); atomicAdd(&s_ccnt[cst0], 1u); }
+		if (k1 && k1 == s_cmax[cst1]) { atomicMin(&s_ctop[cst1], (uint32_t)q1); atomicAdd(&s_ccnt[cst1], 1u); }
 		__syncthreads();
 	}
 	const bool in_range = tid < n_live;
@@ -631,14 +632,13 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	// the scan below; clusters that touch the ends of the staged range are finished by the parked path (phase 3).
 	bool scan = true;
 	if (rmq_mode && !(s_flags & 1u)) {
-		const int32_t head = s_cst[mq], ce_ = s_cend[head], tq = s_top[head] & 0x7fff;
-		const bool dup = (s_top[head] & 0x8000) != 0;
+		const int32_t head = s_cst[mq];
+		const uint32_t tq = s_ctop[head];
 		scan = false;
-		if ((head == 0 && lo > 0) || (ce_ == S && hi < c.n)) slow = true;                // the cluster (and with it possibly my window) may continue outside the staged range
-		else if (dup) scan = true;
-		else if (tq == mq) { }                                                            // nobody in my cluster beats me: top_p stays unset
-		else if (s_key[tq] == 0) { }                                                      // (all other hits of the cluster are filtered)
-		else if (tq < mq? s_ce[tq] > mcs : s_cs[tq] < mce) { top_key = s_key[tq]; top_p = lo + tq; }   // overlap.c:70,118: it is one of my partners
+		if ((head == 0 && lo > 0) || (head == (int32_t)s_cst[S - 1] && hi < c.n)) slow = true;   // the cluster (and with it possibly my window) may continue outside the staged range
+		else if (s_ccnt[head] > 1u) scan = true;                                          // the strongest key occurs twice
+		else if (tq == (uint32_t)mq || tq == 0xffffffffu) { }                             // nobody in my cluster beats me: top_p stays unset
+		else if ((int32_t)tq < mq? s_ce[tq] > mcs : s_cs[tq] < mce) { top_key = s_cmax[head]; top_p = lo + (int32_t)tq; }   // overlap.c:70,118: it is one of my partners
 		else scan = true;
 	}
 	// ---- phase 1b: the would-be dominator by scanning the window.  One loop walks back, then forward: a lane whose backward
