@@ -287,7 +287,15 @@ __device__ __forceinline__ int32_t related_threshold(bool same_gene, int32_t cds
 	if (same_gene) return 1;
 	const int32_t shorter = cds_a < cds_b? cds_a : cds_b;
 	if (shorter <= 0) return 1;
-	double t = ceil(ratio * (double)shorter);
+	const double x = ratio * (double)shorter;
+	double t = ceil(x);
+	// Away from the rounding boundary the candidate needs no division at all: with shorter < 2^22 and both t - x and x - (t - 1) above
+	// 2^-20, the two quotients below differ from `ratio` by more than 2^-42, far beyond the 2^-53 relative error of a double division;
+	// and when x is an integer AND the product was exact (fma residue 0), t / shorter IS ratio (not less), (t - 1) / shorter is less.
+	if (shorter < (1 << 22) && t >= 1.0 && t < 2147483000.0) {
+		const double frac = t - x;
+		if ((frac > 9.5367431640625e-07 && frac < 1.0 - 9.5367431640625e-07) || (frac == 0.0 && fma(ratio, (double)shorter, -x) == 0.0)) return (int32_t)t;
+	}
 	int32_t need = t < 1.0? 1 : (t > 2147483000.0? 2147483000 : (int32_t)t);
 	while (need > 1 && !((double)(uint64_t)(need - 1) / shorter < ratio)) --need;
 	while (need < 2147483000 && (double)(uint64_t)need / shorter < ratio) ++need;
@@ -446,19 +454,20 @@ constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (siz
 // Adds up exactly what cds_overlap()/cds_related() add (overlap.c:6-42): in every one of the reference's four cases the
 // amount is min(t0,t1) - max(s0,s1), clipped at 0 where the reference clips (exon records have y >= x: read.c builds them
 // from non-negative CIGAR lengths), and the list to advance is the reference's.
-template<bool EARLY> __device__ __forceinline__ int32_t walk_exons(const int2 *p0, const int2 *e0, int32_t cs0, const int2 *p1, const int2 *e1, int32_t cs1, int32_t need)
+template<bool EARLY> __device__ __forceinline__ int32_t walk_exons(const int2 *ex, uint32_t i0, uint32_t e0, int32_t cs0, uint32_t i1, uint32_t e1, int32_t cs1, int32_t need)
 {
-	const int2 x0 = *p0, x1 = *p1;
+	const int2 x0 = ex[i0], x1 = ex[i1];
 	int32_t s0 = cs0 + x0.x, t0 = cs0 + x0.y, s1 = cs1 + x1.x, t1 = cs1 + x1.y, inter = 0;
 	while (true) {
 		const bool adv0 = s0 < s1? t0 < t1 : !(t1 < t0);
 		const int32_t o = (t0 < t1? t0 : t1) - (s0 > s1? s0 : s1);
 		inter += o > 0? o : 0;
 		if (EARLY && inter >= need) break;
-		// advance ONE list, without a branch per list: the lanes of a warp take the two sides in any mix
-		p0 += adv0? 1 : 0; p1 += adv0? 0 : 1;
-		if ((adv0? p0 : p1) == (adv0? e0 : e1)) break;
-		const int2 x = *(adv0? p0 : p1);
+		// advance ONE list, without a branch per list (the lanes of a warp take the two sides in any mix) and on 32-bit list positions
+		i0 += adv0? 1u : 0u; i1 += adv0? 0u : 1u;
+		const uint32_t in = adv0? i0 : i1;
+		if (in == (adv0? e0 : e1)) break;
+		const int2 x = ex[in];
 		const int32_t base = adv0? cs0 : cs1, ns = base + x.x, nt = base + x.y;
 		s0 = adv0? ns : s0; t0 = adv0? nt : t0; s1 = adv0? s1 : ns; t1 = adv0? t1 : nt;
 	}
@@ -470,8 +479,8 @@ template<bool EARLY> __device__ __forceinline__ int32_t pair_overlap(const int2 
                                                                      uint32_t b1, uint32_t e1, int32_t cs1, int32_t ce1, int32_t need)
 {
 	if (!(cs0 < ce1 && ce0 > cs1)) return 0;                                         // overlap.c:13
-	if (b0 >= elo && e0 <= ehi && b1 >= elo && e1 <= ehi) return walk_exons<EARLY>(s_ex + (b0 - elo), s_ex + (e0 - elo), cs0, s_ex + (b1 - elo), s_ex + (e1 - elo), cs1, need);
-	return walk_exons<EARLY>(g_ex + b0, g_ex + e0, cs0, g_ex + b1, g_ex + e1, cs1, need);
+	if (b0 >= elo && e0 <= ehi && b1 >= elo && e1 <= ehi) return walk_exons<EARLY>(s_ex, b0 - elo, e0 - elo, cs0, b1 - elo, e1 - elo, cs1, need);
+	return walk_exons<EARLY>(g_ex, b0, e0, cs0, b1, e1, cs1, need);
 }
 
 // dirty (optional, SW_SHADOW with bits_out == c.bits): one bit per tile; a tile whose bit is clear holds no hit whose inputs changed since the

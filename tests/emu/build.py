@@ -25,6 +25,11 @@ extern "C" int sweep_emu(int variant, int mode, const EmuCols *e, double min_ov_
 	else return -1;
 	return 0;
 }
+// related_threshold() as compiled from the product header, for a batch of (shorter CDS, ratio) pairs
+extern "C" void sweep_emu_thresholds(const int32_t *shorter, const double *ratio, int64_t n, int32_t *out)
+{
+	for (int64_t i = 0; i < n; ++i) out[i] = pgx::related_threshold(false, shorter[i], shorter[i] + 7, ratio[i]);
+}
 '''
 
 

@@ -138,3 +138,23 @@ def test_tiled_sweeps_equal_plain_sweep(emu, case):
                 bad = np.nonzero(ref[k] != got[k])[0]
                 assert len(bad) == 0, "%s: variant %d mode %d: %s differs at %s (plain %s, tiled %s)" % (name, variant, mode, what, bad[:5], ref[k][bad[:5]], got[k][bad[:5]])
     hostio.destroy(d)
+
+
+def test_related_threshold_shortcut_is_exact(emu):
+    """related_threshold() answers most pairs without a division (a margin argument on ceil(ratio * shorter)); the result must be the smallest
+    integer overlap ov with NOT ((double)ov / shorter < ratio) -- the reference's own predicate (overlap.c:134-136) -- for every input"""
+    rng = np.random.default_rng(9)
+    shorter = np.concatenate([np.arange(1, 200001, dtype=np.int32), rng.integers(1, 5_000_000, 400000).astype(np.int32)])
+    out = np.zeros(len(shorter), np.int32)
+    emu.sweep_emu_thresholds.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    for r in [0.5, 0.2, 1.0 / 3, 0.9, 0.05, 0.999999, 0.6180339887, 1.0]:
+        ratio = np.full(len(shorter), r, np.float64)
+        emu.sweep_emu_thresholds(shorter.ctypes.data, ratio.ctypes.data, len(shorter), out.ctypes.data)
+        need = out.astype(np.int64)
+        s = shorter.astype(np.float64)
+        assert np.all(~(need.astype(np.float64) / s < r))                                       # need itself puts the pair in relation
+        assert np.all((need == 1) | ((need - 1).astype(np.float64) / s < r))                    # need - 1 does not
+    ratio = rng.random(len(shorter))
+    emu.sweep_emu_thresholds(shorter.ctypes.data, ratio.ctypes.data, len(shorter), out.ctypes.data)
+    need = out.astype(np.int64); s = shorter.astype(np.float64)
+    assert np.all(~(need.astype(np.float64) / s < ratio)) and np.all((need == 1) | ((need - 1).astype(np.float64) / s < ratio))
