@@ -242,6 +242,7 @@ def main():
     stage1_ms, stage2_ms = max_over_ranks(sum(st_ms[0]) / len(st_ms[0])), max_over_ranks(sum(st_ms[1]) / len(st_ms[1]))
     wall_step = max_over_ranks(wall / a.steps * 1e3)
     launches = (st1.launches - st0.launches) // a.steps
+    fast_rounds, redos = (st1.fast_rounds - st0.fast_rounds) // a.steps, st1.redo - st0.redo
     sweep_bytes, sweep_t = st1.sweep_bytes, sum(sweep_ms) / len(sweep_ms)
     n_active = st1.n_active
     L.pgx_session_free(sess)
@@ -304,7 +305,8 @@ def main():
         "metric": METRIC, "value": n_total / (ms_step * 1e-3), "unit": "hits/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
         "config": workload_config(n_total, G_total, world),
-        "detail": {"active_hits_after_load_filters_rank0": int(n_active), "wall_ms_per_step_incl_host": wall_step, "stage_ms": [stage1_ms, stage2_ms]},
+        "detail": {"active_hits_after_load_filters_rank0": int(n_active), "wall_ms_per_step_incl_host": wall_step, "stage_ms": [stage1_ms, stage2_ms],
+                   "ms_per_step_rank0": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms)}, "fast_rounds_per_step": int(fast_rounds), "careful_redos": int(redos)},
         "parity": parity,
         "e2e": {"value": n_total / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "api": "pg_post_process + pg_graph_init + pg_graph_gen on malloc'd pg_data_t (lazy materialisation, as the CLI does); bytes are rank 0's, counted by the library: 48 B/hit + exons up, 24 B/hit + graph down"},

@@ -382,7 +382,7 @@ struct Session {
 			scratch.reset(m2);
 		}
 		PGX_LAUNCH(k_gather, grid_for(N, TB), TB, 0, st, raw.p, src.p, N, hoff.p, coff.p, eoffg.p, r_rank, r_pseudo, r_gl, prot_gid.p, gene_pref.p, F);
-		first_grp.alloc((size_t)G + 1);
+		first_grp.ensure((size_t)G + 1);
 		PGX_LAUNCH(k_first_group, grid_for(G, TB), TB, 0, st, hoff.p, G, F.ctg, F.cs, first_grp.p, counters.p + C_FIRST_TIE);
 		{
 			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(N));
@@ -492,20 +492,20 @@ struct Session {
 			PGX_LAUNCH(k_flag_unfiltered, grid_for(N, TB), TB, 0, st, F.bits, N, flag);
 			Nw = (int32_t)scan_flags(flag, pos, N);
 			size_t n1 = (size_t)Nw + 16;
-			a_key.alloc(n1); a_ctg.alloc(n1); a_cs.alloc(n1); a_ce.alloc(n1); a_cm.alloc(n1); a_pid.alloc(n1); a_gidp.alloc(n1); a_sadj.alloc(n1); a_rank.alloc(n1); a_sori.alloc(n1);
-			a_sdom.alloc(n1); a_pdom0.alloc(n1); a_pdom.alloc(n1); a_cds.alloc(n1); a_pmax.alloc(n1); a_full.alloc(n1); a_bits.alloc(n1); a_bits_alt.alloc(n1); a_nex.alloc(n1); a_eoff.alloc(n1 + 16);
-			by_cm.alloc(n1); sv.alloc(n1);
+			a_key.ensure(n1); a_ctg.ensure(n1); a_cs.ensure(n1); a_ce.ensure(n1); a_cm.ensure(n1); a_pid.ensure(n1); a_gidp.ensure(n1); a_sadj.ensure(n1); a_rank.ensure(n1); a_sori.ensure(n1);
+			a_sdom.ensure(n1); a_pdom0.ensure(n1); a_pdom.ensure(n1); a_cds.ensure(n1); a_pmax.ensure(n1); a_full.ensure(n1); a_bits.ensure(n1); a_bits_alt.ensure(n1); a_nex.ensure(n1); a_eoff.ensure(n1 + 16);
+			by_cm.ensure(n1); sv.ensure(n1);
 			set_active();
 			PGX_LAUNCH(k_build_active, grid_for(N, TB), TB, 0, st, F, pos, N, A);
 			// where each local genome starts inside the active set
-			goff_act.alloc(G + 1);
+			goff_act.ensure(G + 1);
 			PGX_LAUNCH(k_gather_u32, grid_for(G + 1, TB), TB, 0, st, pos, (const uint32_t*)hoff.p, G + 1, (uint32_t*)goff_act.p);
-		} else { goff_act.alloc(G + 1); goff_act.zero(st); }
+		} else { goff_act.ensure(G + 1); goff_act.zero(st); }
 		if (Nw) {
 			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(Nw));
 			exclusive_sum_u32(A.nex, A.eoff, Nw, agg, st);
 			uint32_t ne = read_u32(A.eoff + Nw);
-			wex.alloc((size_t)ne + 16);
+			wex.ensure((size_t)ne + 16);
 			PGX_LAUNCH(k_copy_exons, grid_for(Nw, 128), 128, 0, st, ex.p, F.eoff, A.full, A.eoff, Nw, wex.p);
 			SegVal *sagg = scratch.get<SegVal>((size_t)(Nw / SCAN_TILE + 2));
 			segmented_running_max(A.ctg, A.ce, A.pmax, Nw, sagg, st);
@@ -646,10 +646,10 @@ struct Session {
 		n_seg = n_seg0 = (int32_t)h_seg0.size();
 		std::vector<SegDev> hs(n_seg > 0? n_seg : 1);
 		for (int32_t i = 0; i < n_seg; ++i) { memset(&hs[i], 0, sizeof(SegDev)); hs[i].gid = h_seg0[i].gid; hs[i].n_dom = h_seg0[i].n_dom; hs[i].n_sub = h_seg0[i].n_sub; }
-		seg.alloc(hs.size()); seg_alt.alloc(hs.size()); seg_ng.alloc(hs.size()); seg_tot.alloc(hs.size()); idx.alloc(hs.size() * 2);
+		seg.ensure(hs.size()); seg_alt.ensure(hs.size()); seg_ng.ensure(hs.size()); seg_tot.ensure(hs.size()); idx.ensure(hs.size() * 2);
 		arc_cap = 2 * (size_t)(Nw > 0? Nw : 1);
-		arc.alloc(arc_cap + 1); arc_alt.alloc(arc_cap + 1);
-		dc.alloc(1);
+		arc.ensure(arc_cap + 1); arc_alt.ensure(arc_cap + 1);
+		dc.ensure(1);
 		DevCounts h0; memset(&h0, 0, sizeof(h0)); h0.n_seg = (uint32_t)n_seg0;
 		PGX_CHECK(cudaMemcpyAsync(dc.p, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
 		PGX_CHECK(cudaMemcpyAsync(seg.p, hs.data(), hs.size() * sizeof(SegDev), cudaMemcpyHostToDevice, st));

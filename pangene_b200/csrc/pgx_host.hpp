@@ -84,7 +84,14 @@ public:
 		while (todo.size() == 1) { Range r = todo.back(); todo.pop_back(); pass(a, r, todo); }   // identity levels, then the first split
 		if (todo.empty()) return;
 		if (n < (1 << 14)) { for (const Range &r : todo) finish(a, r); return; }
-		ThreadPool::get().parallel_for((int64_t)todo.size(), [&](int64_t i) { finish(a, todo[i]); });
+		// a handful of balanced groups, not one task per range: the caller waits for the slowest thread, and a pool that needs every core of
+		// the host at once waits a scheduler time slice (milliseconds) whenever one of them is busy with something else
+		const int n_grp = 6;
+		std::sort(todo.begin(), todo.end(), [](const Range &x, const Range &y) { return x.n > y.n; });
+		std::vector<std::vector<Range>> grp(n_grp);
+		int64_t load[n_grp] = {0};
+		for (const Range &r : todo) { int g = 0; for (int k = 1; k < n_grp; ++k) if (load[k] < load[g]) g = k; grp[g].push_back(r); load[g] += r.n; }
+		ThreadPool::get().parallel_for(n_grp, [&](int64_t g) { for (const Range &r : grp[g]) finish(a, r); });
 	}
 };
 

@@ -67,7 +67,7 @@ public:
 	{
 		const char *e = getenv("PGX_THREADS");
 		int hw = (int)std::thread::hardware_concurrency();
-		n_threads = e? atoi(e) : (hw > 32? 32 : hw);
+		n_threads = e? atoi(e) : (hw > 34? 32 : hw - 2);   // two cores stay free for the caller's other threads (CUDA's own, a sampler, the rep thread)
 		if (n_threads < 1) n_threads = 1;
 		for (int t = 1; t < n_threads; ++t) workers.emplace_back([this] { loop(); });
 	}

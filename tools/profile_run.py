@@ -17,8 +17,13 @@ L = engine.lib()
 engine.set_verbose(1)
 s = L.pgx_upload(d)
 L.pgx_set_sweep_stat(1 if os.environ.get("PGX_SWEEP_STAT") else 0)
+per_pass = []
 for _ in range(passes):
     L.pgx_run(s, C.byref(opt), 3)
+    t = engine.stats()
+    per_pass.append("%.2f+%.2f" % (t.run_ms[0], t.run_ms[1]))
 st = engine.stats()
+if passes > 1:
+    print("per pass (stage 1 + stage 2 ms):", " ".join(per_pass), " redo:", st.redo)
 print("hits %d active %d seg %d arc %d launches %d run_ms %.2f %.2f sweep_ms %.3f sweep_GB %.3f" % (st.n_hit, st.n_active, st.n_seg, st.n_arc, st.launches, st.run_ms[0], st.run_ms[1], st.sweep_ms, st.sweep_bytes / 1e9))
 L.pgx_session_free(s)
