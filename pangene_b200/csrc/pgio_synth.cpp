@@ -277,7 +277,9 @@ static void gen_genome_bact(const Pop &P, int32_t j, std::vector<Rec> &out, std:
 	for (int32_t g = 0; g < G; ++g) {   // file order = protein order; extras are partial hits at random places
 		std::vector<Rec> pr;
 		if (has[g]) pr.push_back(recs[g]);
-		if (r.flip(0.04) && n > 0) {
+		// (the rate of these stray hits shrinks with the population: every one of them makes two adjacencies nobody else has, and at 4 % per
+		// gene and genome a 1000-genome set gives every gene ~80 one-off neighbours -- all vertices go over the degree cap and the graph is empty)
+		if (r.flip(0.04 * (p.n_genome_total > 25? 25.0 / p.n_genome_total : 1.0)) && n > 0) {
 			Rec rec;
 			int32_t plen = P.prot_len[g], naa = (int32_t)(plen * (0.55 + 0.40 * r.uni()));
 			rec.pid = g; rec.qlen = plen; rec.qs = r.range(0, plen - naa); rec.qe = rec.qs + naa;
