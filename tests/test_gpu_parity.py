@@ -231,6 +231,30 @@ def test_cli_binary_prints_the_golden_gfa(tmp_path):
     assert out == open(os.path.join(common.GOLDEN, "C4_w.gfa"), "rb").read()
 
 
+DROPIN = os.path.join(common.ROOT, "oracle", "_ref", "pangene_pgx")
+
+
+@pytest.mark.skipif(not (refharness.available() and os.path.exists(DROPIN)), reason="oracle/_ref/pangene_pgx did not travel")
+def test_reference_host_linked_against_libpgx(tmp_path):
+    """THE drop-in: oracle/_ref/pangene_pgx is the reference's OWN main(), reader, dictionary, option parser and writers (main.c sys.c dict.c
+    option.c format.c read.c hit.c, compiled from the reference tree by oracle/Makefile) linked against libpgx.so instead of graph.o vertex.o
+    branch.o overlap.o, with the two edits of INTEGRATION.md (read.c:243-260 compiled out, option.c:4 dropped).  It must print what the stock
+    binary prints: on the reference's C4 example (goldens) and on synthetic PAF files (stock binary run next to it)."""
+    import subprocess
+    files = common.c4_files(tmp_path)
+    run = lambda exe, args, fs: subprocess.run([exe, "-v1"] + args + fs, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    assert run(DROPIN, [], files) == open(os.path.join(common.GOLDEN, "C4.gfa"), "rb").read()
+    assert run(DROPIN, ["-w"], files) == open(os.path.join(common.GOLDEN, "C4_w.gfa"), "rb").read()
+    for flag, gold in (("--bed=raw", "C4.bed_raw"), ("--bed=flag", "C4.bed_flag"), ("--bed", "C4.bed_walk")):   # BED line order follows the reference's unstable sort chain: compare as sets
+        assert sorted(run(DROPIN, [flag], files).splitlines()) == sorted(open(os.path.join(common.GOLDEN, gold), "rb").read().splitlines()), flag
+    opt = hostio.default_opt()
+    p = hostio.synth_params(2, n_genome=6, n_gene=1500, iso_per_gene=4, hits_per_genome=12000, n_genome_total=6)
+    fs = hostio.synth_write_pafs(opt, p, str(tmp_path / "paf"))
+    for args in ([], ["-S", "-T3"], ["-p0", "-a2"]):
+        a, b = run(refharness.REF_BIN, args, fs), run(DROPIN, args, fs)
+        assert sorted(a.splitlines()) == sorted(b.splitlines()), (args, common.first_diff(a, b))
+
+
 def test_config5_bacterial_with_matrix(tmp_path):
     """BASELINE.json configs[4] shape (bacterial, -p0 -a2) at 300 of the 1000 genomes: bit-exact GFA vs the oracle and the
     same presence/absence matrix (gfa2matrix, pangene.js:1168-1246) from both GFAs"""
