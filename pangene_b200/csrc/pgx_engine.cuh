@@ -144,7 +144,7 @@ struct Session {
 	cudaStream_t st2 = nullptr;
 	cudaEvent_t ev_swept = nullptr, ev_pos = nullptr;
 	bool pos_ready = false;
-	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_TIE_ROUND = 8, C_LONG_RUN = 9, C_ORD_SENS = 10, C_N = 12 };
+	enum { C_ERR = 0, C_TIE_CM = 1, C_TIE_CS = 2, C_TIE_DUP = 3, C_TIE_SUB = 4, C_BR_CHANGED = 5, C_FIRST_TIE = 6, C_CMTIE_ROUND = 7, C_TIE_ROUND = 8, C_LONG_RUN = 9, C_ORD_SENS = 10, C_N = 12 };
 
 	Session() { PGX_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); for (auto &e : ev) PGX_CHECK(cudaEventCreate(&e)); PGX_CHECK(cudaEventCreateWithFlags(&ev_z, cudaEventDisableTiming)); PGX_CHECK(cudaMallocHost((void**)&h_pin, 64));
 		PGX_CHECK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking)); PGX_CHECK(cudaEventCreateWithFlags(&ev_swept, cudaEventDisableTiming)); PGX_CHECK(cudaEventCreateWithFlags(&ev_pos, cudaEventDisableTiming)); }
@@ -694,6 +694,10 @@ struct Session {
 			PGX_LAUNCH(k_compact_idx, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, Nw, sv.p);
 			m_sv = (int32_t)read_u32(pos + Nw);      // one read-back per arc round: it sizes the record sort (survivors are ~half of the active set)
 		}
+		{   // cm-tied survivors in the reference's order; pairs completed before this call's cm sort: 0, 1, then 3 + 2 i in branch round i
+			const int32_t m = arc_call - 1;
+			fix_cm_tied_survivors(m < 2? m : 3 + 2 * (m - 2));
+		}
 		if (m_sv == 0) {
 			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_arc)), 0u);
 			PGX_LAUNCH(k_set_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_part)), 0u);
@@ -789,24 +793,16 @@ struct Session {
 		flag_vtx();
 	}
 
-	// branch.c:18-25 numbers the survivors of a genome in array order; survivors that share one (contig, cs) sit in the order the
-	// reference's unstable sort chain left them in after `pairs` (cm, cs) sort pairs.  Replays the chain of the contigs concerned
-	// (cached and advanced from round to round) and shifts the ordinals of the tied hits accordingly.
-	int32_t branch_round_no = 0;
-	void fix_tied_ordinals(int32_t pairs, const uint32_t *tie_list, uint32_t n_ties, const uint32_t *svcs, const int32_t *t_last, GenePos *gpos)
+	// The reference's order of the hits of some contigs after `pairs` (cm, cs) sort pairs of its unstable radix-sort chain:
+	// rank_of[k][i] = position of the contig's i-th hit (our (contig, cs) order) in the reference's array, either as the last cs sort left it
+	// (by_cm = false: branch.c:18-25 numbers survivors in that order) or after one more sort by cm (by_cm = true: the order pg_gen_arc and
+	// pg_mark_branch_flt_hit walk, graph.c:103, branch.c:116).  Chains are fetched once per contig and advanced from call to call.
+	void replay_chains(const std::vector<int32_t> &ctgs, int32_t pairs, bool by_cm, std::vector<std::vector<int32_t>> &rank_of)
 	{
-		size_t mk = scratch.mark();
-		TieRec *d_rec = scratch.get<TieRec>(n_ties + 1);
-		PGX_LAUNCH(k_tie_gather, grid_for(n_ties, TB), TB, 0, st, tie_list, (int32_t)n_ties, svcs, A.ctg, A.full, d_rec);
-		std::vector<TieRec> rec(n_ties);
-		PGX_CHECK(cudaMemcpyAsync(rec.data(), d_rec, (size_t)n_ties * sizeof(TieRec), cudaMemcpyDeviceToHost, st));
-		PGX_CHECK(cudaStreamSynchronize(st));
-		std::sort(rec.begin(), rec.end(), [](const TieRec &x, const TieRec &y) { return x.t < y.t; });
-		std::vector<int32_t> ctgs, fresh;
-		for (const TieRec &r : rec) ctgs.push_back(r.ctg);
-		std::sort(ctgs.begin(), ctgs.end()); ctgs.erase(std::unique(ctgs.begin(), ctgs.end()), ctgs.end());
+		std::vector<int32_t> fresh;
 		for (int32_t c : ctgs) if (!tie_chains.count(c)) fresh.push_back(c);
 		if (!fresh.empty()) {   // fetch (cs, cm, file position) of the contigs seen for the first time
+			size_t mk = scratch.mark();
 			int32_t *d_ids = scratch.get<int32_t>(fresh.size());
 			int2 *d_rng = scratch.get<int2>(fresh.size());
 			PGX_CHECK(cudaMemcpyAsync(d_ids, fresh.data(), fresh.size() * 4, cudaMemcpyHostToDevice, st));
@@ -833,8 +829,9 @@ struct Session {
 				for (int32_t i = 0; i < c.n; ++i) { c.a[i].y = (uint64_t)ord[i]; c.a[i].x = (uint64_t)c.cs[ord[i]]; }
 				FlagSortReplay::run(c.a.data(), c.n);                                                                   // read.c:247
 			});
+			scratch.reset(mk);
 		}
-		std::vector<std::vector<int32_t>> rank_of(ctgs.size());
+		rank_of.assign(ctgs.size(), std::vector<int32_t>());
 		ThreadPool::get().parallel_for((int64_t)ctgs.size(), [&](int64_t k) {
 			TieChain &c = tie_chains.find(ctgs[k])->second;
 			for (; c.pairs_done < pairs; ++c.pairs_done) {
@@ -844,8 +841,79 @@ struct Session {
 				FlagSortReplay::run(c.a.data(), c.n);                                                                   // graph.c:123, branch.c:140
 			}
 			rank_of[k].resize(c.n);
-			for (int32_t i = 0; i < c.n; ++i) rank_of[k][c.a[i].y] = i;
+			if (!by_cm) { for (int32_t i = 0; i < c.n; ++i) rank_of[k][c.a[i].y] = i; return; }
+			std::vector<pg128_t> b(c.a);                                                                                // one more sort, by cm, on a copy
+			for (int32_t i = 0; i < c.n; ++i) b[i].x = (uint64_t)c.cm[b[i].y];
+			FlagSortReplay::run(b.data(), c.n);
+			for (int32_t i = 0; i < c.n; ++i) rank_of[k][b[i].y] = i;
 		});
+	}
+
+	// Survivors that share one (contig, cm) with their neighbour in the (contig, cm) list: the reference walks them in the order its sort chain
+	// left them in (graph.c:103-122, branch.c:116-136) -- the direction of the arc between two of them and the arcs to their outer neighbours
+	// depend on it (DESIGN.md "tie order", tie[0]).  Careful path only: lists the tied positions of `sv`, replays the chains of their contigs
+	// on the host and re-orders every tied group.  Returns true if `sv` changed.  pairs: (cm, cs) sort pairs completed before this cm sort.
+	bool fix_cm_tied_survivors(int32_t pairs)
+	{
+		if (Nw == 0) return false;
+		size_t mk = scratch.mark();
+		uint32_t *list = scratch.get<uint32_t>((size_t)Nw + 1);
+		PGX_CHECK(cudaMemsetAsync(counters.p + C_CMTIE_ROUND, 0, 4, st));
+		PGX_LAUNCH(k_cm_tie_list, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.cm, list, counters.p + C_CMTIE_ROUND);
+		const uint32_t n_ties = read_u32(counters.p + C_CMTIE_ROUND);
+		if (n_ties == 0) { scratch.reset(mk); return false; }
+		TieRec *d_rec = scratch.get<TieRec>(n_ties + 1);
+		PGX_LAUNCH(k_tie_gather, grid_for(n_ties, TB), TB, 0, st, list, (int32_t)n_ties, sv.p, A.ctg, A.full, d_rec);
+		std::vector<TieRec> rec(n_ties);
+		PGX_CHECK(cudaMemcpyAsync(rec.data(), d_rec, (size_t)n_ties * sizeof(TieRec), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		std::sort(rec.begin(), rec.end(), [](const TieRec &x, const TieRec &y) { return x.t < y.t; });
+		std::vector<int32_t> ctgs;
+		for (const TieRec &r : rec) ctgs.push_back(r.ctg);
+		std::sort(ctgs.begin(), ctgs.end()); ctgs.erase(std::unique(ctgs.begin(), ctgs.end()), ctgs.end());
+		std::vector<std::vector<int32_t>> rank_of;
+		replay_chains(ctgs, pairs, true, rank_of);
+		std::vector<int2> patch;   // (position in sv, active index that belongs there)
+		for (size_t i0 = 0, i1; i0 < rec.size(); i0 = i1) {
+			for (i1 = i0 + 1; i1 < rec.size() && rec[i1].t == rec[i1 - 1].t + 1; ++i1) { }
+			const size_t kc = std::lower_bound(ctgs.begin(), ctgs.end(), rec[i0].ctg) - ctgs.begin();
+			const TieChain &c = tie_chains.find(rec[i0].ctg)->second;
+			struct Mem { int32_t act, rank; };
+			std::vector<Mem> mem;
+			mem.push_back(Mem{rec[i0].a_prev, rank_of[kc][rec[i0].full_prev - c.lo]});
+			for (size_t i = i0; i < i1; ++i) mem.push_back(Mem{rec[i].a, rank_of[kc][rec[i].full - c.lo]});
+			std::vector<Mem> srt(mem);
+			std::stable_sort(srt.begin(), srt.end(), [](const Mem &x, const Mem &y) { return x.rank < y.rank; });
+			for (size_t k = 0; k < mem.size(); ++k) if (srt[k].act != mem[k].act) patch.push_back(make_int2(rec[i0].t - 1 + (int32_t)k, srt[k].act));
+		}
+		if (!patch.empty()) {
+			int2 *d_patch = scratch.get<int2>(patch.size());
+			PGX_CHECK(cudaMemcpyAsync(d_patch, patch.data(), patch.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+			PGX_LAUNCH(k_patch_u32, grid_for((int64_t)patch.size(), TB), TB, 0, st, d_patch, (int32_t)patch.size(), sv.p);
+			PGX_CHECK(cudaStreamSynchronize(st));   // `patch` goes out of scope
+		}
+		scratch.reset(mk);
+		return !patch.empty();
+	}
+
+	// branch.c:18-25 numbers the survivors of a genome in array order; survivors that share one (contig, cs) sit in the order the
+	// reference's unstable sort chain left them in after `pairs` (cm, cs) sort pairs.  Replays the chain of the contigs concerned
+	// (cached and advanced from round to round) and shifts the ordinals of the tied hits accordingly.
+	int32_t branch_round_no = 0;
+	void fix_tied_ordinals(int32_t pairs, const uint32_t *tie_list, uint32_t n_ties, const uint32_t *svcs, const int32_t *t_last, GenePos *gpos)
+	{
+		size_t mk = scratch.mark();
+		TieRec *d_rec = scratch.get<TieRec>(n_ties + 1);
+		PGX_LAUNCH(k_tie_gather, grid_for(n_ties, TB), TB, 0, st, tie_list, (int32_t)n_ties, svcs, A.ctg, A.full, d_rec);
+		std::vector<TieRec> rec(n_ties);
+		PGX_CHECK(cudaMemcpyAsync(rec.data(), d_rec, (size_t)n_ties * sizeof(TieRec), cudaMemcpyDeviceToHost, st));
+		PGX_CHECK(cudaStreamSynchronize(st));
+		std::sort(rec.begin(), rec.end(), [](const TieRec &x, const TieRec &y) { return x.t < y.t; });
+		std::vector<int32_t> ctgs;
+		for (const TieRec &r : rec) ctgs.push_back(r.ctg);
+		std::sort(ctgs.begin(), ctgs.end()); ctgs.erase(std::unique(ctgs.begin(), ctgs.end()), ctgs.end());
+		std::vector<std::vector<int32_t>> rank_of(ctgs.size());
+		replay_chains(ctgs, pairs, false, rank_of);
 		// groups of consecutive tied positions: members t0-1 .. tk hold the ordinals o .. o+m-1 in OUR order; hand them out in the reference's
 		std::vector<int2> patch;
 		for (size_t i0 = 0, i1; i0 < rec.size(); i0 = i1) {
@@ -912,7 +980,8 @@ struct Session {
 			}
 			PGX_LAUNCH(k_branch_decide, GS_GRID, 128, 0, st, idx.p, dc.p, arc.p, seg.p, off, nl, bo, grp);
 			// hits inherit the weakness of the arcs they sit on; weak_br == 2 filters (branch.c:108-145, graph.c:309)
-			PGX_LAUNCH(k_branch_hits, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, (const int32_t*)(g_comm.active()? nullptr : arc_of_rec.p), counters.p + C_BR_CHANGED);
+			const bool resorted = fix_cm_tied_survivors(2 + 2 * branch_round_no);   // branch.c:116: one (cm, cs) pair later than the pg_gen_arc before it
+			PGX_LAUNCH(k_branch_hits, GS_GRID, TB, 0, st, sv.p, dc.p, A.ctg, A.gidp, A.bits, g2s.p, arc.p, (const int32_t*)((g_comm.active() || resorted)? nullptr : arc_of_rec.p), counters.p + C_BR_CHANGED);
 		}
 		scratch.reset(mk);
 	}

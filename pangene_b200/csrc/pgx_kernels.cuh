@@ -1320,6 +1320,21 @@ __global__ void k_tie_gather(const uint32_t *__restrict__ list, int32_t n, const
 	out[k] = r;
 }
 
+// positions t of the (contig, cm) survivor list whose survivor shares contig and cm with the one before it (Session::fix_cm_tied_survivors)
+__global__ void k_cm_tie_list(const uint32_t *__restrict__ sv, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ctg, const int32_t *__restrict__ cm, uint32_t *list, uint32_t *n)
+{
+	PGX_GS(t, dc->m_sv) {
+		if (t < 1) continue;
+		const uint32_t a = sv[t - 1], b = sv[t];
+		if (ctg[a] == ctg[b] && cm[a] == cm[b]) list[atomicAdd(n, 1u)] = (uint32_t)t;
+	}
+}
+__global__ void k_patch_u32(const int2 *__restrict__ patch, int32_t n, uint32_t *a)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) a[patch[k].x] = (uint32_t)patch[k].y;
+}
+
 // [lo, hi) of each listed contig in the (genome, contig, cs)-ordered full columns
 __global__ void k_ctg_ranges(const int32_t *__restrict__ ids, int32_t n_ids, const int32_t *__restrict__ f_ctg, int32_t N, int2 *out)
 {

@@ -244,7 +244,7 @@ __global__ void k_arc_insert(const SvInfo *__restrict__ info, const int32_t *__r
 		if (t > 0) {
 			const SvInfo a = info[t - 1], b = info[t];
 			if (a.ctg == b.ctg) {
-				if (b.cm == a.cm) atomicAdd(tie_cnt, 1u);
+				if (b.cm == a.cm) { atomicAdd(tie_cnt, 1u); dc->fallback = 1u; }             // two survivors with one (contig, cm): the reference's order of the two decides (careful path)
 				const unsigned long long k0 = (unsigned long long)a.w << 32 | b.w, k1 = arc_mirror(k0);
 				const unsigned long long kc = k0 < k1? k0 : k1;
 				const uint32_t slot = arc_slot(T, kc, &dc->n_part, deg, &dc->fallback);

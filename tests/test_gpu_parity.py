@@ -117,6 +117,21 @@ def test_tied_survivor_ordinal_cases(k):
     check_against(fuzz_oracle.data_for(case)[0], lambda: fuzz_oracle.data_for(case)[1], kind, lazy=bool(k & 1))
 
 
+@pytest.mark.parametrize("k", [16, 97, 110, 115])
+def test_cm_tied_survivor_cases(k):
+    """Survivors that share one (contig, cm) (tools/fuzz_oracle.py "cmtie" mode forces them): the reference walks them in the order its
+    unstable sort chain left them in, and the arc between two of them -- with everything the branch rounds derive from it -- depends on that
+    order (graph.c:103-122, branch.c:116-136).  On case 16 a stable-order build differs from the reference.  libpgx: the fast rounds raise the
+    fallback on such a pair, the careful path replays the chain (Session::fix_cm_tied_survivors)."""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import fuzz_oracle
+    case = fuzz_oracle.random_case(k, cmtie=True)
+    kind = "reference" if refharness.available() else "oracle"
+    st, _ = check_against(fuzz_oracle.data_for(case)[0], lambda: fuzz_oracle.data_for(case)[1], kind, lazy=bool(k & 1))
+    assert st.tie[0] > 0 and st.redo > 0
+
+
 @pytest.mark.parametrize("k", [0, 9, 17, 25])
 def test_perturbed_real_alignments(k, tmp_path):
     """Cases of tools/fuzz_c4.py: the reference's test/C4 alignments with genomes subsampled and reordered, lines dropped,

@@ -171,3 +171,23 @@ def test_sort_chain_replay_matches_reference_pg_hit_sort(k):
             assert list(out) == [g.hit[i].lof for i in range(n)], (j, pairs, "cm")
             ref.pg_hit_sort(gp, 0)               # graph.c:123 / branch.c:140
     hostio.destroy(d); hostio.destroy(d2)
+
+
+@needs_ref
+@pytest.mark.parametrize("k", [16, 97, 110])
+def test_oracle_replays_cm_tied_survivors_like_the_reference(k):
+    """tools/fuzz_oracle.py "cmtie" cases: survivors forced to share one (contig, cm); the order the reference walks them in comes out of its
+    unstable sort chain (graph.c:103, branch.c:116) and decides arcs -- the oracle replays the chain (survivors_in_ref_cm_order)"""
+    import sys
+    sys.path.insert(0, os.path.join(common.ROOT, "tools"))
+    import fuzz_oracle
+    case = fuzz_oracle.random_case(k, cmtie=True)
+    opt, d1 = fuzz_oracle.data_for(case)
+    _, d2 = fuzz_oracle.data_for(case)
+    rh = refharness.RefHot()
+    g1, _ = rh.hot_path(opt, d1)
+    g2 = pgoracle.hot_path(opt, d2)
+    assert pgoracle.tie_report()[0] > 0
+    assert common.graph_tuple(g1) == common.graph_tuple(g2)
+    assert sorted(common.gfa_bytes(g1).splitlines()) == sorted(common.gfa_bytes(g2).splitlines())
+    rh.destroy(g1); pgoracle.destroy(g2); hostio.destroy(d1); hostio.destroy(d2)

@@ -67,7 +67,7 @@ def ref_arcs(sv, ctg, cm, sid, rev, score, genome_of_ctg, n_seg0):
     return arcs, seg_ng, seg_tot
 
 
-def make_case(rng, G, n_seg0, n_per_genome, dup_frac):
+def make_case(rng, G, n_seg0, n_per_genome, dup_frac, cm_ties=False):
     """survivors of G genomes: genes in a mostly conserved order (so that arcs repeat across genomes), some tandem repeats of one gene pair
     inside a genome (groups of several records per (key, genome): the overflow path) and some v -> v^1 self-mirror adjacencies"""
     n_gene = n_seg0 + 7
@@ -92,7 +92,7 @@ def make_case(rng, G, n_seg0, n_per_genome, dup_frac):
                 if rng.random() < dup_frac: reps = int(rng.integers(2, 5))
                 for q in range(reps):
                     for gg, rr in ((gid, r), (order[(k + 1) % len(order)], r ^ (q & 1))) if reps > 1 else ((gid, r),):
-                        pos += int(rng.integers(0, 3000)) if rng.random() < 0.9 else 0      # some equal cm: d == 0
+                        pos += int(rng.integers(1, 3000)) if (not cm_ties or rng.random() < 0.9) else 0      # cm_ties: some equal (contig, cm)
                         ctg.append(cid); cm.append(pos); gene.append(gg); rev.append(rr)
                         sori.append(int(rng.integers(0, 900))); sdom.append(int(rng.integers(0, 900))); pdom0.append(int(rng.integers(-1, n_prot)))
                 if rng.random() < 0.05:    # the same gene again on the other strand: v -> v^1
@@ -147,6 +147,23 @@ def test_arc_build_matches_graph_c(emu, seed, G, n_seg0, n_per, dup, ranks, use_
     pairs = np.where(deg >= 2, deg * (deg + 1) // 2, 0)
     assert np.array_equal(nl_off[:2 * n_seg0 + 1], np.concatenate([[0], np.cumsum(pairs)]).astype(np.uint32)) and out[1] == pairs.sum()
     del keepalive
+
+
+def test_arc_build_raises_fallback_on_cm_tied_survivors(emu):
+    """two adjacent survivors with one (contig, cm): which of them the reference walks first depends on its sort chain -- the fast path must
+    hand such a run over to the careful path (Session::fix_cm_tied_survivors), never decide the order itself"""
+    rng = np.random.default_rng(12)
+    cols, sv, n_gene = make_case(rng, 4, 40, 150, 0.0, cm_ties=True)
+    assert np.any((np.diff(cols["cm"][sv].astype(np.int64)) == 0) & (np.diff(cols["ctg"][sv]) == 0))
+    arc_cap = 4 * len(sv) + 16
+    arc = np.zeros(arc_cap, dtype=ARC); idx = np.zeros(82, np.uint64); seg_ng = np.zeros(40, np.int32); seg_tot = np.zeros(40, np.int32); nl_off = np.zeros(88, np.uint32); out = np.zeros(4, np.uint32)
+    e = EmuArcIn(n_hit=len(cols["ctg"]), n_sv=len(sv), n_seg0=40, n_gene=n_gene, G=4, use_ori=0, grid=2, H=4096, H2=256, ovf_cap=4 * len(sv) + 8, arc_cap=arc_cap, ranks=1)
+    for k in ("ctg", "cm", "gidp", "sori", "sdom", "pdom0", "g2s", "prot_gid", "ctg2g", "bits"):
+        setattr(e, k, cols[k].ctypes.data)
+    e.sv = sv.ctypes.data; e.arc = arc.ctypes.data; e.idx = idx.ctypes.data; e.seg_ng = seg_ng.ctypes.data; e.seg_tot = seg_tot.ctypes.data
+    e.nl_off = nl_off.ctypes.data; e.out_counts = out.ctypes.data
+    emu.round_emu_arc_build(C.byref(e))
+    assert out[2] == 1
 
 
 def test_arc_build_raises_fallback_when_the_table_is_too_small(emu):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: randomized campaign of the CUDA path (through the C ABI) against the oracle restatement on a GPU box --
 the same case generator as tools/fuzz_oracle.py (which pins the oracle against the compiled reference in the build container).
-usage: tools/fuzz_gpu.py [first_case | case,case,...] [n_cases] [time_budget_s] [local]      ("local": see tools/fuzz_oracle.py)"""
+usage: tools/fuzz_gpu.py [first_case | case,case,...] [n_cases] [time_budget_s] [local|cmtie]      (modes: see tools/fuzz_oracle.py)"""
 import os
 import sys
 import time
@@ -25,12 +25,13 @@ def main():
         cases = list(range(first, first + n))
     budget = float(sys.argv[3]) if len(sys.argv) > 3 else 1e9
     local = len(sys.argv) > 4 and sys.argv[4] == "local"
+    cmtie = len(sys.argv) > 4 and sys.argv[4] == "cmtie"
     engine.set_verbose(1)
     t0, bad, done = time.time(), 0, 0
     for k in cases:
         if time.time() - t0 > budget:
             break
-        case = random_case(k, local)
+        case = random_case(k, local, cmtie)
         opt, d1 = data_for(case)
         _, d2 = data_for(case)
         g1 = pgoracle.hot_path(opt, d1)
