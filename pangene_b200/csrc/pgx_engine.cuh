@@ -76,7 +76,7 @@ struct PhaseTimer {
 			if (k == acc.size()) acc.push_back({label[i], 0.0});
 			acc[k].second += ms;
 		}
-		fprintf(stderr, "[pgx timing] rank %d %s by phase (device clock, %.2f ms):", rank, title, tot);
+		fprintf(stderr, "[pgx timing] rank %d %s by phase (device clock, %.2f ms; %llu cudaMalloc calls so far):", rank, title, tot, (unsigned long long)DevCache::get_cache().n_malloc);
 		for (auto &a : acc) fprintf(stderr, " %s %.2f |", a.first, a.second);
 		fprintf(stderr, "\n");
 	}

@@ -16,7 +16,7 @@
 namespace pgx {
 
 // [emu-begin sort]  (tests/emu/build.py compiles the two kernels for the host: tests/test_prim_emu.py)
-constexpr int RS_WARPS = 8, RS_BLOCK = RS_WARPS * 32, RS_ITEMS = 16, RS_TILE = RS_BLOCK * RS_ITEMS;   // 4096 keys per tile
+constexpr int RS_WARPS = 8, RS_BLOCK = RS_WARPS * 32, RS_ITEMS = 8, RS_TILE = RS_BLOCK * RS_ITEMS;   // 2048 keys per tile: 34 KB of shared memory, six CTAs per SM (4096 keys: 59 KB, three CTAs, 1.37 TB/s)
 
 __device__ __forceinline__ uint32_t rs_digit(uint64_t k, int shift) { return (uint32_t)(k >> shift) & 0xffu; }
 

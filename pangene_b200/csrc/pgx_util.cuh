@@ -35,6 +35,7 @@ struct DevCache {
 	std::multimap<size_t, void*> free_;
 	std::unordered_map<void*, size_t> size_of;
 	std::mutex mu;
+	uint64_t n_malloc = 0;            // driver allocations so far (a steady-state run makes none)
 	static size_t round(size_t b) { size_t g = b >= ((size_t)1 << 20)? ((size_t)1 << 20) : 512; return (b + g - 1) / g * g; }
 	void *get(size_t bytes)
 	{
@@ -43,6 +44,7 @@ struct DevCache {
 		auto it = free_.lower_bound(bytes);
 		if (it != free_.end() && it->first <= bytes + bytes / 4 + 4096) { void *p = it->second; free_.erase(it); return p; }
 		void *p = nullptr;
+		++n_malloc;
 		cudaError_t e = cudaMalloc(&p, bytes);
 		if (e != cudaSuccess) {   // give cached blocks back and retry once
 			cudaGetLastError();
