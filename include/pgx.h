@@ -60,6 +60,9 @@ int  pgx_warmup(void);
 int  pgx_comm_unique_id(void *out128);
 int  pgx_comm_init(int rank, int nranks, const void *id128, int32_t n_genome_total, int32_t genome_begin);
 void pgx_comm_destroy(void);
+/* The same sharded path over the LOOPBACK transport (pgx_comm.cuh): collectives staged through a POSIX shared-memory segment and reduced on
+ * the host, so that the ranks may be processes sharing ONE device.  For testing the partition / merge logic on a single-GPU box only. */
+int  pgx_comm_init_loopback(int rank, int nranks, const char *segment_name, int32_t n_genome_total, int32_t genome_begin);
 
 /* ---- staged API: the same path with the host<->device boundary made explicit (bench.py, tests) -- */
 typedef struct pgx_session_s pgx_session_t;

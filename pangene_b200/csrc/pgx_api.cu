@@ -166,8 +166,17 @@ int pgx_comm_init(int rank, int nranks, const void *id128, int32_t n_genome_tota
 	return 0;
 }
 
+int pgx_comm_init_loopback(int rank, int nranks, const char *segment_name, int32_t n_genome_total, int32_t genome_begin)
+{
+	need_device();
+	g_comm.rank = rank; g_comm.nranks = nranks; g_comm.n_genome_total = n_genome_total; g_comm.genome_begin = genome_begin;
+	if (nranks > 1) g_comm.shm_open_segment(segment_name, rank, nranks, (size_t)64 << 20);
+	return 0;
+}
+
 void pgx_comm_destroy(void)
 {
+	g_comm.shm_close();
 	if (g_comm.comm) { g_comm.CommDestroy(g_comm.comm); g_comm.comm = nullptr; }
 	g_comm.rank = 0; g_comm.nranks = 1; g_comm.n_genome_total = -1; g_comm.genome_begin = 0;
 }

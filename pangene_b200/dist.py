@@ -37,6 +37,14 @@ def init_comm(lib, rank, world, n_genome_total, genome_begin, group=None):
     lib.pgx_comm_init(rank, world, raw, n_genome_total, genome_begin)
 
 
+def init_comm_loopback(lib, rank, world, n_genome_total, genome_begin, tag="0"):
+    """collective: the loopback transport of libpgx (collectives staged through shared memory, ranks may share one GPU) -- for testing the
+    sharded path on a single-GPU box; the segment name must be the same on every rank and unique per run"""
+    import os
+    name = "/pgx_loop_%s_%s" % (os.environ.get("MASTER_PORT", "0"), tag)
+    lib.pgx_comm_init_loopback(rank, world, name.encode(), n_genome_total, genome_begin)
+
+
 def gather_in_rank_order(obj, world, group=None):
     """list of every rank's object, rank order == genome order for contiguous partitions"""
     import torch.distributed as dist

@@ -40,6 +40,7 @@ def lib():
         L.pgx_set_sweep_stat.argtypes = [C.c_int]
         L.pgx_comm_unique_id.argtypes = [C.c_void_p]
         L.pgx_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int32, C.c_int32]
+        L.pgx_comm_init_loopback.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int32, C.c_int32]
         L.pgx_upload.argtypes = [P(abi.pg_data_t)]
         L.pgx_upload.restype = C.c_void_p
         L.pgx_run.argtypes = [C.c_void_p, P(abi.pg_opt_t), C.c_int]

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU parity check, run under torchrun (one rank per GPU):
    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+With PGX_LOOPBACK=1 the ranks share whatever GPUs are visible (two ranks on one GPU work) and libpgx's collectives go through shared memory.
 Every rank generates ITS genome shard, the sharded GPU path runs with NCCL collectives inside libpgx, and the
 result is compared with the single-process oracle on the whole input: replicated graph identical on every rank
 and equal to the oracle's, per-rank BED/W lines equal to the oracle's lines for those genomes."""
@@ -27,8 +28,14 @@ CASES = [dict(config=2, n_genome=7, n_gene=1800, iso_per_gene=4, hits_per_genome
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    loopback = os.environ.get("PGX_LOOPBACK") == "1"       # ranks share the GPUs there are; collectives through shared memory (pgx_comm.cuh)
+    if loopback:
+        local = local % torch.cuda.device_count()
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if loopback:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = engine.lib()
     L.pgx_set_device(local)
     engine.set_verbose(1)
@@ -36,7 +43,10 @@ def main():
     for ci, case in enumerate(CASES):
         G = case["n_genome"]
         b, e = pgdist.partition(G, world)[rank]
-        pgdist.init_comm(L, rank, world, G, b)
+        if loopback:
+            pgdist.init_comm_loopback(L, rank, world, G, b, tag=str(ci))
+        else:
+            pgdist.init_comm(L, rank, world, G, b)
         opt = common.opt_from_args(case["args"])
         p = hostio.synth_params(case["config"], n_genome=e - b, genome_begin=b, n_gene=case["n_gene"], iso_per_gene=case["iso_per_gene"], hits_per_genome=case["hits_per_genome"], n_genome_total=G)
         d = hostio.synth(opt, p)
