@@ -456,7 +456,15 @@ constexpr size_t SWQ_SMEM = (size_t)SWQ_STG * 8 + (size_t)SWQ_STG * 4 * 7 + (siz
 // from non-negative CIGAR lengths), and the list to advance is the reference's.
 template<bool EARLY> __device__ __forceinline__ int32_t walk_exons(const int2 *ex, uint32_t i0, uint32_t e0, int32_t cs0, uint32_t i1, uint32_t e1, int32_t cs1, int32_t need)
 {
-	const int2 x0 = ex[i0], x1 = ex[i1];
+	int2 x0 = ex[i0], x1 = ex[i1];
+	// Exons of one list that end before the other list begins add nothing and only advance their own list (overlap.c:17-27: "x ends earlier",
+	// o <= 0): step over them without the full merge step.  A long gene against a short hit inside it spends most of its walk here.
+	{
+		const int32_t f1 = cs1 + x1.x;
+		while (cs0 + x0.y <= f1) { if (++i0 == e0) return 0; x0 = ex[i0]; }
+		const int32_t f0 = cs0 + x0.x;
+		while (cs1 + x1.y <= f0) { if (++i1 == e1) return 0; x1 = ex[i1]; }
+	}
 	int32_t s0 = cs0 + x0.x, t0 = cs0 + x0.y, s1 = cs1 + x1.x, t1 = cs1 + x1.y, inter = 0;
 	while (true) {
 		const bool adv0 = s0 < s1? t0 < t1 : !(t1 < t0);

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(RS_BLOCK) k_rs_hist(const uint64_t *__restrict
 // store consecutive elements of a digit run, so every 32-byte sector written is fully used (a direct scatter of 8-byte keys to
 // 256 destinations touches one sector per key: ~4x write amplification, measured 96 us per pass on 3.6 M records).
 constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_TILE * 4 + (size_t)RS_WARPS * 256 * 4 + 256 * 4 * 2;
-__global__ void __launch_bounds__(RS_BLOCK) k_rs_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in, int64_t n, int shift,
+__global__ void __launch_bounds__(RS_BLOCK, 5) k_rs_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals_in, int64_t n, int shift,
 	const uint32_t *__restrict__ hist_scan, int n_tiles, uint64_t *keys_out, uint32_t *vals_out)
 {
 	extern __shared__ __align__(16) unsigned char rs_smem[];
@@ -124,7 +124,11 @@ static void radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int n_bi
 	uint64_t **keys_res, uint32_t **vals_res, cudaStream_t s)
 {
 	static bool attr_set = false;
-	if (!attr_set) { PGX_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM)); attr_set = true; }
+	if (!attr_set) {
+		PGX_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+		PGX_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // five 35 KB CTAs per SM (ncu: the default carve-out left room for three)
+		attr_set = true;
+	}
 	uint64_t *kin = keys, *kout = b.keys_alt;
 	uint32_t *vin = vals, *vout = b.vals_alt;
 	if (n > 0) {
