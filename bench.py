@@ -297,10 +297,11 @@ def main():
         return 0
     peak, peak_src = peaks()
     achieved = sweep_bytes / (sweep_t * 1e-3) / 1e9 if sweep_t > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
-    if os.path.exists(tp) and world == 1 and a.genomes == 100:
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    if os.path.exists(tp) and world == 1 and a.genomes == 100:   # (a constant from the committed ncu capture of this kernel, not measured in this run: the label says which build)
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "%s; %s" % (tj.get("source"), tj.get("build"))
     out = {
         "metric": METRIC, "value": n_total / (ms_step * 1e-3), "unit": "hits/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
@@ -311,8 +312,8 @@ def main():
         "e2e": {"value": n_total / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "api": "pg_post_process + pg_graph_init + pg_graph_gen on malloc'd pg_data_t (lazy materialisation, as the CLI does); bytes are rank 0's, counted by the library: 48 B/hit + exons up, 24 B/hit + graph down"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_tiled<SW_LOAD> (first overlap sweep, pg_shadow cal_dom_sc=1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_t},
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_tiled<SW_LOAD> (first overlap sweep, pg_shadow cal_dom_sc=1; at N > 1: this rank's shard)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_t},
         "clocks": clk.summary(),
     }
     if world == 1 and not a.no_cpu_baseline:
