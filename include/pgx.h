@@ -95,6 +95,7 @@ void pgx_test_radix_sort(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits);
 void pgx_test_exclusive_sum(const uint32_t *in, uint32_t *out, int64_t n);
 void pgx_test_segmented_max(const int32_t *seg, const int32_t *val, int32_t *out, int64_t n);
 void pgx_test_flag_sort_replay(pg128_t *a, int64_t n);
+int  pgx_test_choose_representatives(const unsigned long long *z, const int32_t *prot_gid, int32_t n_prot, int32_t n_gene, int32_t force_replay, int32_t *gene_rep_pid);
 
 #ifdef __cplusplus
 }

@@ -243,4 +243,13 @@ void pgx_test_segmented_max(const int32_t *seg, const int32_t *val, int32_t *out
 
 void pgx_test_flag_sort_replay(pg128_t *a, int64_t n) { FlagSortReplay::run(a, n); }
 
+// hit.c:205-217 on the host (no device needed): gene_rep_pid[n_gene] from the per-protein sums; returns 1 if the exact sort order had to be replayed
+int pgx_test_choose_representatives(const unsigned long long *z, const int32_t *prot_gid, int32_t n_prot, int32_t n_gene, int32_t force_replay, int32_t *gene_rep_pid)
+{
+	RepResult r;
+	choose_representatives(z, prot_gid, n_prot, n_gene, r, force_replay != 0);
+	memcpy(gene_rep_pid, r.gene_rep_pid.data(), (size_t)n_gene * 4);
+	return r.replayed? 1 : 0;
+}
+
 } // extern "C"

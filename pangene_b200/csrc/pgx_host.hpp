@@ -101,21 +101,40 @@ public:
 };
 
 // hit.c:205-217: per-protein count / mean adjusted score, then the representative protein of every gene
-struct RepResult { std::vector<int32_t> prot_n, prot_avg, prot_rep, gene_rep_pid; };
-static inline void choose_representatives(const unsigned long long *z, const int32_t *prot_gid, int32_t n_prot, int32_t n_gene, RepResult &r)
+struct RepResult { std::vector<int32_t> prot_n, prot_avg, prot_rep, gene_rep_pid; bool replayed = false; };
+static inline void choose_representatives(const unsigned long long *z, const int32_t *prot_gid, int32_t n_prot, int32_t n_gene, RepResult &r, bool force_replay = false)
 {
 	r.prot_n.assign(n_prot, 0); r.prot_avg.assign(n_prot, 0); r.prot_rep.assign(n_prot, 0); r.gene_rep_pid.assign(n_gene, -1);
-	std::vector<pg128_t> s(n_prot);
 	for (int32_t i = 0; i < n_prot; ++i) {
-		s[i].x = z[i]; s[i].y = (uint64_t)i;
 		r.prot_n[i] = (int32_t)(uint32_t)z[i];
 		r.prot_avg[i] = r.prot_n[i]? (int32_t)((double)(z[i] >> 32) / r.prot_n[i] + .499) : 0;
 	}
-	FlagSortReplay::run(s.data(), n_prot);
-	for (int32_t i = n_prot - 1; i >= 0; --i) {
-		int32_t pid = (int32_t)s[i].y, gid = prot_gid[pid];
-		if (r.gene_rep_pid[gid] < 0) r.gene_rep_pid[gid] = pid, r.prot_rep[pid] = 1;
+	// The reference sorts the proteins by z (unstable radix sort) and walks the result from the end: the representative of a gene is its
+	// protein with the LARGEST z, and the sort's tie order only matters where two proteins of one gene share that largest value (hit.c:209-217).
+	// One pass finds the maxima and whether any gene has such a twin; only then is the exact permutation replayed (2-3 ms for 80 k proteins,
+	// replicated on every rank: the largest serial piece of a sharded run before this shortcut).
+	bool tie = force_replay;
+	if (!tie) {
+		std::vector<uint8_t> twin(n_gene, 0);
+		for (int32_t i = 0; i < n_prot; ++i) {
+			const int32_t g = prot_gid[i], b = r.gene_rep_pid[g];
+			if (b < 0 || z[i] > z[b]) { r.gene_rep_pid[g] = i; twin[g] = 0; }
+			else if (z[i] == z[b]) twin[g] = 1;
+		}
+		for (int32_t g = 0; g < n_gene && !tie; ++g) tie = twin[g] != 0;
 	}
+	if (tie) {
+		std::fill(r.gene_rep_pid.begin(), r.gene_rep_pid.end(), -1);
+		std::vector<pg128_t> s(n_prot);
+		for (int32_t i = 0; i < n_prot; ++i) { s[i].x = z[i]; s[i].y = (uint64_t)i; }
+		FlagSortReplay::run(s.data(), n_prot);
+		for (int32_t i = n_prot - 1; i >= 0; --i) {
+			int32_t pid = (int32_t)s[i].y, gid = prot_gid[pid];
+			if (r.gene_rep_pid[gid] < 0) r.gene_rep_pid[gid] = pid;
+		}
+	}
+	for (int32_t g = 0; g < n_gene; ++g) if (r.gene_rep_pid[g] >= 0) r.prot_rep[r.gene_rep_pid[g]] = 1;
+	r.replayed = tie;
 }
 
 struct SegHost { int32_t gid, n_dom, n_sub; };

@@ -52,6 +52,8 @@ def lib():
         L.pgx_test_exclusive_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.pgx_test_segmented_max.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.pgx_test_flag_sort_replay.argtypes = [C.c_void_p, C.c_int64]
+        L.pgx_test_choose_representatives.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.pgx_test_choose_representatives.restype = C.c_int
         _LIB = L
     return _LIB
 

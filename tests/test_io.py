@@ -110,6 +110,33 @@ def test_host_side_radix_replay_of_libpgx_matches_oracle():
         assert list(A) == list(B)
 
 
+def test_representatives_shortcut_equals_the_replayed_sort():
+    """hit.c:205-217: the representative of a gene is its protein with the largest z; libpgx replays the reference's unstable sort only when
+    two proteins of one gene share that maximum -- both routes must agree wherever the shortcut applies, and ties must take the replay"""
+    import numpy as np
+    from pangene_b200 import engine
+    L = engine.lib()
+    rng = np.random.default_rng(4)
+    for n_gene, iso, ties in [(500, 4, False), (3000, 3, False), (20000, 4, False), (800, 4, True)]:
+        n_prot = n_gene * iso
+        gid = np.repeat(np.arange(n_gene, dtype=np.int32), iso)
+        perm = rng.permutation(n_prot); gid = gid[perm]
+        score = rng.integers(0, 1 << 22, n_prot).astype(np.uint64); cnt = rng.integers(1, 100, n_prot).astype(np.uint64)
+        z = (score << np.uint64(32)) | cnt
+        z[rng.random(n_prot) < 0.3] = 0                       # proteins without a counted hit (never the unique maximum of a gene with hits)
+        if not ties:                                           # make every gene's maximum unique
+            for g in range(n_gene):
+                idx = np.nonzero(gid == g)[0]
+                z[idx[0]] = (np.uint64(1 << 23) + np.uint64(g)) << np.uint64(32) | np.uint64(1)
+        else:
+            idx = np.nonzero(gid == 7)[0]; z[idx] = z[idx[0]] | np.uint64(1 << 60)     # one gene whose isoforms all share the maximum
+        a = np.zeros(n_gene, np.int32); b = np.zeros(n_gene, np.int32)
+        ra = L.pgx_test_choose_representatives(z.ctypes.data, gid.ctypes.data, n_prot, n_gene, 0, a.ctypes.data)
+        rb = L.pgx_test_choose_representatives(z.ctypes.data, gid.ctypes.data, n_prot, n_gene, 1, b.ctypes.data)
+        assert rb == 1 and ra == (1 if ties else 0)
+        assert np.array_equal(a, b)
+
+
 def _same_data(d, d2):
     assert (d.contents.n_genome, d.contents.n_gene, d.contents.n_prot) == (d2.contents.n_genome, d2.contents.n_gene, d2.contents.n_prot)
     for j in range(d.contents.n_genome):

@@ -3,8 +3,8 @@
 N=${1:-2}; TAG=${2:-r02g}
 mkdir -p gpurun_out
 export PYTHONFAULTHANDLER=1
-run() { if [ "$N" = "1" ]; then python bench.py "$@"; else python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N "$@"; fi; }
-timeout 600 run --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err
+if [ "$N" = "1" ]; then RUN="python bench.py"; else RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N"; fi
+timeout 600 $RUN --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err
 echo "bench rc=$?"
 python - <<PY
 import json
@@ -12,7 +12,7 @@ b=json.loads([l for l in open('gpurun_out/${TAG}_bench_n$N.json') if l.startswit
 print({k:b[k] for k in ('n_gpus','value','ms_per_step','gpu_launches','detail')}); print('parity', b['parity']['status'], 'e2e ms', b['e2e']['ms_per_step'], 'roofline', b['roofline']['frac'])
 PY
 if [ "${3:-}" = "timing" ]; then
-  PGX_TIMING=1 timeout 600 run --steps 3 --warmup 2 --no-parity --no-cpu-baseline > /dev/null 2> gpurun_out/${TAG}_phases_n$N.err
+  PGX_TIMING=1 timeout 600 $RUN --steps 3 --warmup 2 --no-parity --no-cpu-baseline > /dev/null 2> gpurun_out/${TAG}_phases_n$N.err
   grep "rank 0 stage 2 by phase" gpurun_out/${TAG}_phases_n$N.err | tail -n 2 | cut -c1-700
   grep -E "rank 0.*waited|election:" gpurun_out/${TAG}_phases_n$N.err | tail -n 3
 fi
