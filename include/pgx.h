@@ -21,7 +21,11 @@ extern "C" {
 /* reference: `extern int pg_verbose` (pangene.h:126, option.c:4) */
 extern int pg_verbose;
 
-/* reference: pg_post_process(), pangene.h:133 / graph.c:7-32.  ADDITIONALLY runs, first, the per-genome
+/* Limits of this build: hit coordinates (cs, cm, ce) must lie in [0, 2^31) -- the reference keeps them in int64, libpgx packs them into
+ * int32 columns and aborts with a message on upload otherwise (no contig of any sequenced genome reaches 2^31 bp); at most 2^31 / 11 hits and
+ * 2^32 exons per rank.
+ *
+ * reference: pg_post_process(), pangene.h:133 / graph.c:7-32.  ADDITIONALLY runs, first, the per-genome
  * preprocessing block that the reference executes at the tail of pg_read_paf() (read.c:243-260) -- so `d` must
  * hold RAW parsed hits (as left by pgio_read_paf(), or by the reference reader with that block removed). On
  * return every genome's hit[] is a fresh malloc'd array sorted by (cid, cs) with all flags of that stage set
@@ -39,6 +43,10 @@ void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q);
 void pg_graph_destroy(pg_graph_t *g);
 
 /* ---- engine control (no reference counterpart) ------------------------------------------------- */
+
+/* Frees the device state pg_post_process(d) keeps for the pg_graph_gen() that follows; only needed when that call never comes
+ * (e.g. `--bed=raw` stops after pg_post_process, main.c:122-123).  Safe to call at any time; a no-op for unknown pointers. */
+void pgx_data_release(const pg_data_t *d);
 
 int  pgx_device_count(void);
 void pgx_set_device(int dev);                 /* default: current CUDA device */

@@ -1,6 +1,8 @@
 // main.cpp -- the `pangene` command line over libpgio (reader/writers) and libpgx (the CUDA hot path).
 // Same options and output as the reference CLI (main.c:12-152); the call sequence in main() is the
 // reference's own: read every PAF, pg_post_process, pg_graph_init, pg_graph_gen, write.
+// Attribution: the usage text and the option letters / their mapping onto pg_opt_t fields are the command-line CONTRACT of
+// lh3/pangene (main.c:12-113, MIT licence, (c) Heng Li) and are reproduced as such; everything around them is this project's.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,6 +110,7 @@ int main(int argc, char *argv[])
 	pg_post_process(&opt, d);
 	if (opt.flag & PG_F_WRITE_BED_RAW) {
 		pgio_write_bed(d, 0, "-");
+		pgx_data_release(d);                          // no pg_graph_gen() follows: hand the device state back
 	} else {
 		pg_graph_t *g = pg_graph_init(d);
 		pg_graph_gen(&opt, g);

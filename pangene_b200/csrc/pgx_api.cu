@@ -12,6 +12,7 @@ Comm g_comm;
 int g_sweep_stat = 0;
 static int g_device = -1, g_lazy = 0;
 static std::map<const pg_data_t*, Session*> g_sessions;   // pg_post_process() -> pg_graph_gen() hand-over
+static std::mutex g_sessions_mu;
 
 static double wall() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 static bool timing_on() { static const bool on = getenv("PGX_TIMING") != nullptr; return on; }
@@ -71,8 +72,11 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	const double t_enter = wall();
 	need_device();
 	if (pg_verbose >= 3) fprintf(stderr, "[M::%s] %d genes and %d proteins\n", __func__, d->n_gene, d->n_prot);
-	auto it = g_sessions.find(d);
-	if (it != g_sessions.end()) { delete it->second; g_sessions.erase(it); }
+	{
+		std::lock_guard<std::mutex> lk(g_sessions_mu);
+		auto it = g_sessions.find(d);
+		if (it != g_sessions.end()) { delete it->second; g_sessions.erase(it); }
+	}
 	double t0 = wall();
 	Session *s = new Session();
 	s->upload(d);
@@ -86,7 +90,7 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 		for (int32_t i = 0; i < d->n_prot; ++i) { d->prot[i].n = s->rep.prot_n[i]; d->prot[i].avg_score_adj = s->rep.prot_avg[i]; d->prot[i].rep = s->rep.prot_rep[i]; d->prot[i].max_score_ori = s->h_prot_max[i]; }
 		for (int32_t i = 0; i < d->n_gene; ++i) d->gene[i].rep_pid = s->rep.gene_rep_pid[i];
 	}
-	g_sessions[d] = s;
+	{ std::lock_guard<std::mutex> lk(g_sessions_mu); g_sessions[d] = s; }
 	int32_t n_pref = 0;
 	for (int32_t i = 0; i < d->n_gene; ++i) n_pref += d->gene[i].preferred;
 	if (pg_verbose >= 3) {
@@ -106,16 +110,23 @@ pg_graph_t *pg_graph_init(pg_data_t *d)   // graph.c:34-41
 void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q)
 {
 	need_device();
-	auto it = g_sessions.find(q->d);
-	if (it == g_sessions.end()) PGX_FATAL("pg_graph_gen(): no device state for this pg_data_t -- call pg_post_process() of libpgx first");
-	Session *s = it->second;
+	Session *s = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(g_sessions_mu);
+		auto it = g_sessions.find(q->d);
+		if (it == g_sessions.end()) PGX_FATAL("pg_graph_gen(): no device state for this pg_data_t -- call pg_post_process() of libpgx first");
+		s = it->second;
+		g_sessions.erase(it);
+	}
+	// the device state is keyed by the pg_data_t pointer: make sure it still describes THIS data (a freed pg_data_t whose address was reused)
+	if (s->G != q->d->n_genome || s->n_prot != q->d->n_prot || s->n_gene != q->d->n_gene) PGX_FATAL("pg_graph_gen(): the pg_data_t changed since pg_post_process() (%d/%d genomes)", q->d->n_genome, s->G);
+	for (int32_t j = 0; j < s->G; ++j) if (s->h_hoff[j + 1] - s->h_hoff[j] != q->d->genome[j].n_hit) PGX_FATAL("pg_graph_gen(): genome %d changed size since pg_post_process()", j);
 	double t0 = wall();
 	timed_run(s, opt, 2);
 	double t1 = wall();
 	s->download(q->d, q);
 	double t2 = wall();
 	delete s;
-	g_sessions.erase(it);
 	if (timing_on()) fprintf(stderr, "[pgx timing] stage 2 %.1f ms, download %.1f ms, free %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (wall() - t2) * 1e3);
 }
 
@@ -126,8 +137,22 @@ void pg_graph_destroy(pg_graph_t *q)   // graph.c:43-47
 	free(q);
 }
 
+// A pg_post_process() that is not followed by pg_graph_gen() (the CLI's --bed=raw) leaves its device state behind: hand it back.
+void pgx_data_release(const pg_data_t *d)
+{
+	std::lock_guard<std::mutex> lk(g_sessions_mu);
+	auto it = g_sessions.find(d);
+	if (it != g_sessions.end()) { delete it->second; g_sessions.erase(it); }
+}
+
 int pgx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
-void pgx_set_device(int dev) { g_device = dev; PGX_CHECK(cudaSetDevice(dev)); }
+void pgx_set_device(int dev)
+{
+	// the buffer cache and the pinned ring belong to the device they were created on: switching devices inside one process is only allowed
+	// before anything was allocated (one process drives one GPU; the sharded path is one process per GPU)
+	if (g_device >= 0 && g_device != dev && DevCache::get_cache().n_malloc > 0) PGX_FATAL("pgx_set_device(%d): this process already holds device memory on device %d", dev, g_device);
+	g_device = dev; PGX_CHECK(cudaSetDevice(dev));
+}
 void pgx_set_lazy(int lazy) { g_lazy = lazy; }
 
 // Everything the first pg_post_process() would otherwise pay for on the caller's critical path -- CUDA context, the pinned

@@ -313,7 +313,9 @@ struct Session {
 		static const bool plain = []() { const char *e = getenv("PGX_SWEEP"); return e && strcmp(e, "global") == 0; }();
 		if (c.n <= 0) return;
 		if (plain) { PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP); return; }
-		static bool attr_set = false;
+		static int attr_dev = -1;              // (function attributes are per device: set again if the process moved to another one)
+		int cur_dev = 0; PGX_CHECK(cudaGetDevice(&cur_dev));
+		const bool attr_set = attr_dev == cur_dev;
 		if (!attr_set) {
 			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
 			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
@@ -322,7 +324,7 @@ struct Session {
 			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_LOAD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-			attr_set = true;
+			attr_dev = cur_dev;
 		}
 		PGX_LAUNCH(k_sweep_tiled<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
 	}

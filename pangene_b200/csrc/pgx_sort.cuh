@@ -123,11 +123,12 @@ struct RadixSortBuffers {          // caller-provided scratch (no allocation ins
 static void radix_sort_pairs(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits, bool iota_vals, const RadixSortBuffers &b,
 	uint64_t **keys_res, uint32_t **vals_res, cudaStream_t s)
 {
-	static bool attr_set = false;
-	if (!attr_set) {
+	static int attr_dev = -1;                  // per device
+	int cur_dev = 0; PGX_CHECK(cudaGetDevice(&cur_dev));
+	if (attr_dev != cur_dev) {
 		PGX_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
 		PGX_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));   // five 35 KB CTAs per SM (ncu: the default carve-out left room for three)
-		attr_set = true;
+		attr_dev = cur_dev;
 	}
 	uint64_t *kin = keys, *kout = b.keys_alt;
 	uint32_t *vin = vals, *vout = b.vals_alt;

@@ -55,7 +55,14 @@ struct DevCache {
 		size_of[p] = bytes;
 		return p;
 	}
-	void put(void *p) { if (!p) return; std::lock_guard<std::mutex> lk(mu); free_.emplace(size_of[p], p); }
+	void put(void *p)
+	{
+		if (!p) return;
+		std::lock_guard<std::mutex> lk(mu);
+		auto it = size_of.find(p);
+		if (it == size_of.end()) { cudaFree(p); return; }   // not one of ours: never cache a block of unknown size
+		free_.emplace(it->second, p);
+	}
 	void trim() { std::lock_guard<std::mutex> lk(mu); for (auto &kv : free_) { size_of.erase(kv.second); cudaFree(kv.second); } free_.clear(); }
 	static DevCache &get_cache() { static DevCache c; return c; }
 };

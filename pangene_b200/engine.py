@@ -34,6 +34,7 @@ def lib():
         L.pg_graph_gen.argtypes = [P(abi.pg_opt_t), P(abi.pg_graph_t)]
         L.pg_graph_gen.restype = None
         L.pg_graph_destroy.argtypes = [P(abi.pg_graph_t)]
+        L.pgx_data_release.argtypes = [P(abi.pg_data_t)]
         L.pgx_device_count.restype = C.c_int
         L.pgx_set_device.argtypes = [C.c_int]
         L.pgx_set_lazy.argtypes = [C.c_int]
@@ -68,6 +69,7 @@ def hot_path(opt, d, stop_after_post=False, lazy=False):
     L.pgx_set_lazy(1 if lazy else 0)
     L.pg_post_process(C.byref(opt), d)
     if stop_after_post:
+        L.pgx_data_release(d)
         return None
     g = L.pg_graph_init(d)
     L.pg_graph_gen(C.byref(opt), g)
