@@ -8,7 +8,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpgx.so")
+LIB_PATH = os.environ.get("PGX_LIB") or os.path.join(_HERE, "csrc", "libpgx.so")   # (PGX_LIB: an experimental build of the same library, A/B timing only)
 _LIB = None
 
 
