@@ -272,6 +272,28 @@ def main():
         hostio.lib().pgio_data_clone_destroy(d)
     e2e_s = statistics.median(e2e_t)           # median of 5 timed calls after 2 untimed ones (host page-fault/NUMA noise is +-30 %)
 
+    # ---- the GFA-only route of the same C ABI (what the CLI runs for `pangene *.paf > out.gfa`): lazy mode 2 returns the graph, the hits stay
+    # on the device and only the walk tokens of the W lines (12 B per printed hit) come back; checked against the same golden
+    gfa_t, gfa_d2h, digest_tok = [], 0, None
+    n_gfa = 1 + 3
+    for it in range(n_gfa):
+        d = hostio.lib().pgio_data_clone(d0)
+        barrier()
+        s0 = engine.stats()
+        t0 = time.perf_counter()
+        g, tok, off, n_tok = engine.graph_and_tokens(opt, d)
+        dt = time.perf_counter() - t0
+        gfa_d2h = engine.stats().d2h_bytes - s0.d2h_bytes
+        barrier()
+        if it >= 1:
+            gfa_t.append(max_over_ranks(dt))
+        if it == n_gfa - 1 and not a.no_parity:
+            digest_tok = hostio.gfa_digest_tokens(g, tok, off)
+        engine.release_tokens(d, tok)
+        L.pg_graph_destroy(g)
+        hostio.lib().pgio_data_clone_destroy(d)
+    gfa_s = statistics.median(gfa_t)
+
     # ---- parity gate: every rank's replicated S/L lines + the W lines of all ranks in genome order, against the reference's golden
     parity = {"status": "unchecked (--no-parity)"}
     if digest is not None:
@@ -283,6 +305,18 @@ def main():
             parity = parity_verdict([x[0] for x in parts], b"".join(x[1] for x in parts), load_golden() if G_total == 100 else None)
             if G_total != 100:
                 parity["status"] = "unchecked (debug genome count)"
+    parity_tok = {"status": "unchecked (--no-parity)"}
+    if digest_tok is not None:
+        parts = [digest_tok]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, digest_tok)
+        if rank == 0:
+            parity_tok = parity_verdict([x[0] for x in parts], b"".join(x[1] for x in parts), load_golden() if G_total == 100 else None)
+            if G_total != 100:
+                parity_tok["status"] = "unchecked (debug genome count)"
+            if parity_tok["status"] == "FAIL":
+                parity["status"] = "FAIL"          # one gate: either route failing fails the run
 
     # ---- teardown, the same on every rank: flush what we know first, then barrier -> libpgx communicator -> torch process group
     def teardown():
@@ -307,7 +341,9 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
         "config": workload_config(n_total, G_total, world),
         "detail": {"active_hits_after_load_filters_rank0": int(n_active), "wall_ms_per_step_incl_host": wall_step, "stage_ms": [stage1_ms, stage2_ms],
-                   "ms_per_step_rank0": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms)}, "fast_rounds_per_step": int(fast_rounds), "careful_redos": int(redos)},
+                   "ms_per_step_rank0": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms)}, "fast_rounds_per_step": int(fast_rounds), "careful_redos": int(redos),
+                   "e2e_gfa_route": {"value": n_total / gfa_s, "unit": "hits/s", "ms_per_step": gfa_s * 1e3, "d2h_bytes_per_step": int(gfa_d2h), "parity": parity_tok["status"],
+                                     "api": "pgx_set_lazy(2): pg_post_process + pg_graph_init + pg_graph_gen + pgx_walk_tokens -- host pg_data_t in, graph + walk tokens out (everything a GFA needs; no pg_hit_t record is rebuilt)"}},
         "parity": parity,
         "e2e": {"value": n_total / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "api": "pg_post_process + pg_graph_init + pg_graph_gen on malloc'd pg_data_t (lazy materialisation, as the CLI does); bytes are rank 0's, counted by the library: 48 B/hit + exons up, 24 B/hit + graph down"},

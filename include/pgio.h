@@ -13,6 +13,7 @@
 #define PGIO_H
 
 #include "pangene_abi.h"
+#include "pgx_walk.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -45,6 +46,17 @@ void pgio_name_set_destroy(void *set);
  * sorts every genome by cm and back; we sort an index instead). */
 int32_t pgio_write_gfa(const pg_graph_t *g, const char *path, int32_t flags);
 int32_t pgio_write_bed(const pg_data_t *d, int32_t is_walk, const char *path);
+
+/* The same GFA from walk tokens (pgx_walk_tokens(), pgx.h) instead of materialised hits: S/L lines from the graph (bit0), W lines (bit1,
+ * format.c:183-225) from tok[genome_off[j] .. genome_off[j+1]) of genome j -- already in printing order.  d supplies names only
+ * (contigs, genes, genome labels); d->genome[].hit is not read.  Byte-identical to pgio_write_gfa() on the materialised data. */
+int32_t pgio_write_gfa_tokens(const pg_graph_t *g, const pgx_walk_token_t *tok, const int64_t *genome_off, const char *path, int32_t flags);
+
+/* pangene.js:1168-1246 without the GFA in between: the gene x assembly table straight from the graph (rows: segments, in S-line order) and
+ * the walk tokens (columns: sample#hap of the contigs that have a W line, in W-line order; a token counts for the segment of its gene).
+ * Same TSV as pgio_gfa2matrix() prints from the GFA text of the same run.  genome_begin: index of the first local genome (names unlabeled
+ * genomes, format.c:207-208).  Returns #rows or -1. */
+int32_t pgio_matrix_from_tokens(const pg_graph_t *g, const pgx_walk_token_t *tok, const int64_t *genome_off, const char *out_path, int32_t copy_number);
 
 /* pangene.js:1168-1246 (gfa2matrix, without -d): gene x assembly presence/absence (or counts with
  * copy_number != 0) computed from a GFA file; written as TSV to out_path. Returns #rows or -1. */

@@ -13,6 +13,7 @@
 #define PGX_H
 
 #include "pangene_abi.h"
+#include "pgx_walk.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -52,8 +53,19 @@ int  pgx_device_count(void);
 void pgx_set_device(int dev);                 /* default: current CUDA device */
 
 /* 1: pg_post_process() leaves the hits on the device and only updates d->prot/d->gene; pg_graph_gen()
- * materialises everything once.  0 (default): strict reference post-conditions after each call. */
+ * materialises everything once.  0 (default): strict reference post-conditions after each call.
+ * 2: as 1, and pg_graph_gen() returns the graph only -- d->genome[].hit keeps the parsed records and the per-hit results stay on the
+ * device, to be read through pgx_walk_tokens() (what the GFA writer needs) or pgx_fetch_hits() (everything); pgx_data_release(d) ends it. */
 void pgx_set_lazy(int lazy);
+
+/* The walk tokens of the final state, read off the device (lazy mode 2, after pg_graph_gen(); collective under pgx_comm_init: every rank gets
+ * the tokens of its own genomes).  *tokens: malloc'd (the caller frees it), genome-major; inside a genome contig-major, inside a contig by
+ * cm with ties in (cs, file) order -- the order pgio_write_gfa() prints.  genome_off: d->n_genome + 1 offsets into *tokens, caller-provided.
+ * Returns the number of tokens. */
+int64_t pgx_walk_tokens(const pg_data_t *d, pgx_walk_token_t **tokens, int64_t *genome_off);
+
+/* lazy mode 2: materialise the hits after all (what pg_graph_gen() does in modes 0 and 1); the device state stays until pgx_data_release(). */
+void pgx_fetch_hits(pg_data_t *d);
 
 /* Optional: create the CUDA context, the pinned staging ring and the host thread pool now instead of inside the first
  * pg_post_process().  May be called from a side thread while the caller parses its input (join before pg_post_process).

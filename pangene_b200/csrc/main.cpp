@@ -8,6 +8,7 @@
 #include <cstring>
 #include <getopt.h>
 #include <thread>
+#include <vector>
 #include <sys/time.h>
 #include <sys/resource.h>
 #include "pgio.h"
@@ -106,7 +107,10 @@ int main(int argc, char *argv[])
 	pgio_read_pafs(&opt, d, (const char *const*)&argv[optind], argc - optind, 0);   // parallel parse, ids as in sequential order
 	warm.join();
 	double t1 = now();
-	pgx_set_lazy(!(opt.flag & PG_F_WRITE_BED_RAW));   // hits come back once, after pg_graph_gen
+	// --bed=raw: strict post-conditions after pg_post_process; other BED outputs: the hits come back once, after pg_graph_gen; GFA (the
+	// default): no hit record comes back at all -- the W lines are formatted from the walk tokens libpgx reads off its final state
+	const bool want_bed = (opt.flag & (PG_F_WRITE_BED_RAW | PG_F_WRITE_BED_WALK | PG_F_WRITE_BED_FLAG)) != 0;
+	pgx_set_lazy((opt.flag & PG_F_WRITE_BED_RAW)? 0 : want_bed? 1 : 2);
 	pg_post_process(&opt, d);
 	if (opt.flag & PG_F_WRITE_BED_RAW) {
 		pgio_write_bed(d, 0, "-");
@@ -117,7 +121,15 @@ int main(int argc, char *argv[])
 		double t2 = now();
 		if (opt.flag & PG_F_WRITE_BED_WALK) pgio_write_bed(d, 1, "-");
 		else if (opt.flag & PG_F_WRITE_BED_FLAG) pgio_write_bed(d, 0, "-");
-		else pgio_write_gfa(g, "-", 1 | ((opt.flag & PG_F_WRITE_NO_WALK)? 0 : 2));
+		else if (opt.flag & PG_F_WRITE_NO_WALK) { pgio_write_gfa_tokens(g, 0, 0, "-", 1); pgx_data_release(d); }
+		else {
+			pgx_walk_token_t *tok = 0;
+			std::vector<int64_t> off((size_t)d->n_genome + 1);
+			pgx_walk_tokens(d, &tok, off.data());
+			pgx_data_release(d);
+			pgio_write_gfa_tokens(g, tok, off.data(), "-", 3);
+			free(tok);
+		}
 		if (pg_verbose >= 3) fprintf(stderr, "[M::%s] parse %.3f s; hot path (incl. transfers) %.3f s; %ld hits\n", __func__, t1 - t0, t2 - t1, (long)pgio_total_hits(d));
 		pg_graph_destroy(g);
 	}

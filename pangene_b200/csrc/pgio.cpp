@@ -727,6 +727,93 @@ extern "C" int32_t pgio_write_gfa(const pg_graph_t *g, const char *path, int32_t
 	return 0;
 }
 
+// W lines of genome j from walk tokens (already contig-major, cm order inside a contig): format.c:183-225 without the two sorts
+static void walk_lines_from_tokens(const pg_data_t *d, int32_t j, const pgx_walk_token_t *t, int64_t n, std::string &s)
+{
+	const pg_genome_t *g = &d->genome[j];
+	std::string sample;
+	for (int64_t i0 = 0, i = 1; i <= n; ++i) {
+		if (i < n && t[i].cid == t[i0].cid) continue;
+		const int32_t cid = t[i0].cid;
+		const int32_t hap = parse_sample(sample, g->ctg[cid].name);
+		s += "W\t";
+		if (hap >= 0) { s += sample; s.push_back('\t'); put_num(s, hap); }
+		else if (g->label) { s += g->label; s += "\t0"; }
+		else { put_num(s, j); s += "\t0"; }
+		s.push_back('\t'); s += g->ctg[cid].name; s += "\t*\t*\t";
+		for (int64_t k = i0; k < i; ++k) { s.push_back("><"[t[k].gene_strand & 1]); s += d->gene[t[k].gene_strand >> 1].name; }
+		s += "\tlf:B:i";
+		for (int64_t k = i0; k < i; ++k) { s.push_back(','); put_num(s, t[k].lof); }
+		s.push_back('\n');
+		i0 = i;
+	}
+}
+
+extern "C" int32_t pgio_write_gfa_tokens(const pg_graph_t *g, const pgx_walk_token_t *tok, const int64_t *genome_off, const char *path, int32_t flags)
+{
+	Out o(path);
+	if (o.fp == 0) return -1;
+	if (flags & 1) { write_seg_lines(g, o); write_arc_lines(g, o); }
+	if (flags & 2) for_each_genome_text(g->d->n_genome, o, [&](int32_t j, std::string &s) { walk_lines_from_tokens(g->d, j, tok + genome_off[j], genome_off[j + 1] - genome_off[j], s); });
+	return 0;
+}
+
+// gfa2matrix (pangene.js:1168-1246) without the GFA text: rows = segments in S-line order, columns = the "sample#hap" of every W line in
+// order of first appearance, cell = number of walk tokens of that assembly whose gene is the row's segment
+extern "C" int32_t pgio_matrix_from_tokens(const pg_graph_t *g, const pgx_walk_token_t *tok, const int64_t *genome_off, const char *out_path, int32_t copy_number)
+{
+	const pg_data_t *d = g->d;
+	std::unordered_map<std::string, int32_t> asm_id;
+	std::vector<std::string> asm_name;
+	std::vector<int32_t> asm_of_run;                       // one entry per W line (genome, contig run)
+	std::string sample, a;
+	// pass 1: the assemblies, in W-line order
+	for (int32_t j = 0; j < d->n_genome; ++j) {
+		const pgx_walk_token_t *t = tok + genome_off[j];
+		const int64_t n = genome_off[j + 1] - genome_off[j];
+		for (int64_t i0 = 0, i = 1; i <= n; ++i) {
+			if (i < n && t[i].cid == t[i0].cid) continue;
+			const int32_t hap = parse_sample(sample, d->genome[j].ctg[t[i0].cid].name);
+			a.clear();
+			if (hap >= 0) { a = sample; a.push_back('#'); put_num(a, hap); }
+			else if (d->genome[j].label) { a = d->genome[j].label; a += "#0"; }
+			else { put_num(a, j); a += "#0"; }
+			auto it = asm_id.find(a);
+			int32_t ai;
+			if (it == asm_id.end()) { ai = (int32_t)asm_name.size(); asm_id.emplace(a, ai); asm_name.push_back(a); } else ai = it->second;
+			asm_of_run.push_back(ai);
+			i0 = i;
+		}
+	}
+	const size_t n_asm = asm_name.size();
+	std::vector<int32_t> mat((size_t)g->n_seg * (n_asm > 0? n_asm : 1), 0);
+	size_t run = 0;
+	for (int32_t j = 0; j < d->n_genome; ++j) {
+		const pgx_walk_token_t *t = tok + genome_off[j];
+		const int64_t n = genome_off[j + 1] - genome_off[j];
+		for (int64_t i0 = 0, i = 1; i <= n; ++i) {
+			if (i < n && t[i].cid == t[i0].cid) continue;
+			const int32_t ai = asm_of_run[run++];
+			for (int64_t k = i0; k < i; ++k) {
+				const int32_t sid = g->g2s[t[k].gene_strand >> 1];
+				if (sid >= 0) ++mat[(size_t)sid * n_asm + ai];
+			}
+			i0 = i;
+		}
+	}
+	Out o(out_path);
+	if (o.fp == 0) return -1;
+	o.str("Gene");
+	for (auto &x : asm_name) { o.ch('\t'); o.str(x.c_str()); }
+	o.ch('\n');
+	for (int32_t i = 0; i < g->n_seg; ++i) {
+		o.str(d->gene[g->seg[i].gid].name);
+		for (size_t k = 0; k < n_asm; ++k) { const int32_t v = mat[(size_t)i * n_asm + k]; o.ch('\t'); o.num(copy_number? v : (v > 1? 1 : v)); }
+		o.ch('\n'); o.maybe_flush();
+	}
+	return g->n_seg;
+}
+
 static void bed_lines_of_genome(const pg_data_t *d, int32_t j, int32_t is_walk, std::string &s)   // format.c:78-118
 {
 	const pg_genome_t *g = &d->genome[j];

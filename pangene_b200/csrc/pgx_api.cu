@@ -79,11 +79,11 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	}
 	double t0 = wall();
 	Session *s = new Session();
-	s->upload(d);
+	s->upload(d, true);
 	double t1 = wall();
 	timed_run(s, opt, 1);
 	double t2 = wall();
-	if (timing_on()) fprintf(stderr, "[pgx timing] device check %.1f ms, session+upload %.1f ms, stage 1 %.1f ms\n", (t0 - t_enter) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
+	if (timing_on()) fprintf(stderr, "[pgx timing] device check %.1f ms, session + upload of the hits %.1f ms, stage 1 beside the upload of the exons %.1f ms\n", (t0 - t_enter) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3);
 	if (!g_lazy) s->download(d, nullptr);
 	else {   // the protein/gene tables are cheap and always current
 		s->ensure_rep();
@@ -116,7 +116,7 @@ void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q)
 		auto it = g_sessions.find(q->d);
 		if (it == g_sessions.end()) PGX_FATAL("pg_graph_gen(): no device state for this pg_data_t -- call pg_post_process() of libpgx first");
 		s = it->second;
-		g_sessions.erase(it);
+		if (g_lazy != 2) g_sessions.erase(it);
 	}
 	// the device state is keyed by the pg_data_t pointer: make sure it still describes THIS data (a freed pg_data_t whose address was reused)
 	if (s->G != q->d->n_genome || s->n_prot != q->d->n_prot || s->n_gene != q->d->n_gene) PGX_FATAL("pg_graph_gen(): the pg_data_t changed since pg_post_process() (%d/%d genomes)", q->d->n_genome, s->G);
@@ -124,9 +124,9 @@ void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q)
 	double t0 = wall();
 	timed_run(s, opt, 2);
 	double t1 = wall();
-	s->download(q->d, q);
+	s->download(q->d, q, g_lazy != 2);       // lazy 2: the graph only; the hits stay on the device (pgx_walk_tokens / pgx_fetch_hits / pgx_data_release)
 	double t2 = wall();
-	delete s;
+	if (g_lazy != 2) delete s;
 	if (timing_on()) fprintf(stderr, "[pgx timing] stage 2 %.1f ms, download %.1f ms, free %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (wall() - t2) * 1e3);
 }
 
@@ -143,6 +143,27 @@ void pgx_data_release(const pg_data_t *d)
 	std::lock_guard<std::mutex> lk(g_sessions_mu);
 	auto it = g_sessions.find(d);
 	if (it != g_sessions.end()) { delete it->second; g_sessions.erase(it); }
+}
+
+static Session *session_of(const pg_data_t *d, const char *who)
+{
+	std::lock_guard<std::mutex> lk(g_sessions_mu);
+	auto it = g_sessions.find(d);
+	if (it == g_sessions.end()) PGX_FATAL("%s(): no device state for this pg_data_t (lazy mode 2 keeps it after pg_graph_gen; pgx_data_release frees it)", who);
+	return it->second;
+}
+
+int64_t pgx_walk_tokens(const pg_data_t *d, pgx_walk_token_t **tokens, int64_t *genome_off)
+{
+	need_device();
+	static_assert(sizeof(pgx_walk_token_t) == sizeof(WalkToken), "walk token layout");
+	return session_of(d, __func__)->walk_tokens((WalkToken**)tokens, genome_off);
+}
+
+void pgx_fetch_hits(pg_data_t *d)
+{
+	need_device();
+	session_of(d, __func__)->download(d, nullptr);
 }
 
 int pgx_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -224,7 +245,7 @@ void pgx_get_stats(pgx_stats_t *o)
 }
 void pgx_reset_stats(void) { g_launch.launches = 0; g_stats = Stats(); }
 void pgx_set_sweep_stat(int on) { g_sweep_stat = on; }
-void pgx_trim(void) { DevCache::get_cache().trim(); }
+void pgx_trim(void) { DevCache::get_cache().trim(); SpareHitArrays::get().trim(); }
 
 // ---- test hooks -----------------------------------------------------------------------------------
 void pgx_test_radix_sort(uint64_t *keys, uint32_t *vals, int64_t n, int n_bits)

@@ -12,6 +12,8 @@
 #include <cstddef>
 #include <time.h>
 #include <sys/mman.h>
+#include <malloc.h>
+#include <mutex>
 #include "pgx.h"
 #include "pgx_util.cuh"
 #include "pgx_scan.cuh"
@@ -49,6 +51,44 @@ static inline pg_hit_t *alloc_hit_array(size_t n)
 	}
 	return (pg_hit_t*)malloc(bytes);
 }
+
+// Hit arrays that went out of use on the host side of the boundary (the caller's arrays in parsing order, once their permuted copies are
+// installed) are kept here instead of being free()d, and handed out again as the destination of a later genome / a later call: a recycled
+// array is already mapped, so the ~430 k first-touch page faults + the munmap of a 1.8 GB result (a third of the download time) go away after
+// the first few genomes.  Everything in the pool is plain malloc'd memory, as everything the caller gets (hit.c:62-63 free()s it).
+struct SpareHitArrays {
+	struct Item { pg_hit_t *p; size_t cap; };
+	std::vector<Item> items;
+	std::mutex mu;
+	static constexpr size_t MAX_ITEMS = 24, MAX_BYTES = (size_t)1 << 30;
+	size_t bytes = 0;
+	// an array for n records: the smallest pooled one that fits (and is not absurdly larger), else a fresh one; *cap = its capacity in records
+	pg_hit_t *take(size_t n, size_t *cap)
+	{
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			int best = -1;
+			for (int i = 0; i < (int)items.size(); ++i)
+				if (items[i].cap >= n && items[i].cap <= n + n / 2 + 4096 && (best < 0 || items[i].cap < items[best].cap)) best = i;
+			if (best >= 0) { Item it = items[best]; items.erase(items.begin() + best); bytes -= it.cap * sizeof(pg_hit_t); *cap = it.cap; return it.p; }
+		}
+		pg_hit_t *p = alloc_hit_array(n);
+		*cap = malloc_usable_size(p) / sizeof(pg_hit_t);
+		return p;
+	}
+	void give(pg_hit_t *p)   // (capacity from the allocator, not from the caller's m_hit field)
+	{
+		if (!p) return;
+		const size_t cap = malloc_usable_size(p) / sizeof(pg_hit_t);
+		{
+			std::lock_guard<std::mutex> lk(mu);
+			if (cap > 0 && items.size() < MAX_ITEMS && bytes + cap * sizeof(pg_hit_t) <= MAX_BYTES) { items.push_back(Item{p, cap}); bytes += cap * sizeof(pg_hit_t); return; }
+		}
+		free(p);
+	}
+	void trim() { std::lock_guard<std::mutex> lk(mu); for (auto &it : items) free(it.p); items.clear(); bytes = 0; }
+	static SpareHitArrays &get() { static SpareHitArrays s; return s; }
+};
 
 static inline double wall_s() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 
@@ -179,7 +219,10 @@ struct Session {
 	}
 
 	// ------------------------------------------------------------------------------------------------
-	void upload(const pg_data_t *d)
+	// defer_exons: the exon lists (half of the bytes) are not copied here but inside the stage_load() that follows, on the second stream, while
+	// the device already unpacks, flags and sorts the hits -- none of which reads an exon (pg_post_process() does this; `d` must stay valid until then)
+	const pg_data_t *exons_pending = nullptr;
+	void upload(const pg_data_t *d, bool defer_exons = false)
 	{
 		if (rep_pending) { rep_thread.join(); rep_pending = false; }
 		G = d->n_genome; n_prot = d->n_prot; n_gene = d->n_gene;
@@ -209,6 +252,7 @@ struct Session {
 		PGX_CHECK(cudaMemcpyAsync(gene_pref.p, h_gene_pref.data(), (size_t)n_gene, cudaMemcpyHostToDevice, st));
 		raw.alloc((size_t)N + 1); ex_raw.alloc((size_t)E + 16);
 		upload_hits(d);
+		if (defer_exons && E) exons_pending = d; else upload_exons(d, st);
 		g_stats.h2d += (int64_t)N * (int64_t)sizeof(RawHit) + E * 8 + (int64_t)n_prot * 4 + n_gene;
 		g_stats.n_hit = N;
 		counters.alloc(C_N); counters.zero(st);
@@ -262,7 +306,7 @@ struct Session {
 					const pg_hit_t &h = d->genome[g].hit[t - h_hoff[g]];
 					if (h.cs < 0 || h.ce > 0x7fffffffll || h.cm < 0 || h.cm > 0x7fffffffll || h.cs > h.ce) err = 1;
 					o->pid = h.pid; o->cid = h.cid; o->rank = h.rank; o->sori = h.score_ori; o->sadj = h.score_adj; o->nexon = h.n_exon; o->offexon = h.off_exon;
-					o->rev = h.rev; o->cs = (int32_t)h.cs; o->cm = (int32_t)h.cm; o->ce = (int32_t)h.ce; o->pad = 0;
+					o->rev = h.rev; o->cs = (int32_t)h.cs; o->cm = (int32_t)h.cm; o->ce = (int32_t)h.ce; o->lof = h.lof;
 					if (h.cm > mc) mc = h.cm;
 					if (h.cs > mc) mc = h.cs;
 				}
@@ -272,6 +316,10 @@ struct Session {
 		}, st);
 		if (bad.load()) PGX_FATAL("upload: a hit coordinate is outside [0, 2^31) or cs > ce -- this build keeps coordinates in int32");
 		coord_bits = bits_for((uint64_t)max_coord.load());
+	}
+	void upload_exons(const pg_data_t *d, cudaStream_t cs)
+	{
+		ThreadPool &pool = ThreadPool::get();
 		if (E) staged_h2d(ex_raw.p, (size_t)E * 8, 8, [&](size_t off, size_t len, char *dst) {
 			const int64_t e0 = (int64_t)(off / 8), e1 = e0 + (int64_t)(len / 8), EB = 1 << 17;
 			pool.parallel_for((e1 - e0 + EB - 1) / EB, [&](int64_t b) {
@@ -284,7 +332,7 @@ struct Session {
 					a += m;
 				}
 			});
-		}, st);
+		}, cs);
 	}
 	void set_full()
 	{
@@ -389,6 +437,12 @@ struct Session {
 		{
 			uint32_t *agg = scratch.get<uint32_t>(scan_scratch_elems(N));
 			exclusive_sum_u32(F.nex, F.eoff, N, agg, st);
+		}
+		if (exons_pending) {   // the deferred half of the upload: host threads stage the exon lists while the launches above run
+			upload_exons(exons_pending, st2);
+			exons_pending = nullptr;
+			PGX_CHECK(cudaEventRecord(ev_pos, st2));
+			PGX_CHECK(cudaStreamWaitEvent(st, ev_pos, 0));
 		}
 		PGX_LAUNCH(k_gather_exons, grid_for(N, 128), 128, 0, st, ex_raw.p, F.esrc, F.eoff, N, ex.p, F.cds);
 		{
@@ -1391,30 +1445,35 @@ struct Session {
 	// ------------------------------------------------------------------------------------------------
 	// results back into the caller's structs (malloc'd, as the reference's destroy functions expect)
 	// ------------------------------------------------------------------------------------------------
-	void download(pg_data_t *d, pg_graph_t *q)
+	void download(pg_data_t *d, pg_graph_t *q, bool with_hits = true)
 	{
 		if (d->n_genome != G) PGX_FATAL("download: pg_data_t does not match the uploaded one");
 		ensure_rep();
-		if (Nw) PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
-		if (N) {
+		if (Nw && with_hits) PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
+		if (N && with_hits) {
 			DBuf<OutHit> out;
 			out.alloc((size_t)N + 1);
 			PGX_LAUNCH(k_pack_out, grid_for(N, TB), TB, 0, st, src.p, N, F, g2s.p, prot_rep.p, done_graph? 1 : 0, out.p);
 			ThreadPool &pool = ThreadPool::get();
+			SpareHitArrays &spare = SpareHitArrays::get();
 			std::vector<pg_hit_t*> fresh(G, nullptr);
+			std::vector<size_t> fresh_cap(G, 0);
 			// second download of a strict-mode run (after pg_graph_gen): the caller still holds the arrays we returned after
 			// pg_post_process, already permuted -> patch them in place.  Anything else is rebuilt from raw order.
 			bool host_sorted = (int32_t)installed.size() == G && G > 0;
 			for (int32_t j = 0; j < G && host_sorted; ++j) host_sorted = d->genome[j].hit == installed[j];
-			for (int32_t j = 0; j < G; ++j) {
+			for (int32_t j = 0; j < G; ++j)
 				if (h_hoff[j + 1] - h_hoff[j] != d->genome[j].n_hit) PGX_FATAL("download: genome %d changed size since upload", j);
-				if (!host_sorted) fresh[j] = alloc_hit_array((size_t)d->genome[j].n_hit);
-			}
 			const int64_t BLK = 1 << 14;
 			const bool in_place = host_sorted;
-			// only the 24 bytes per hit that changed cross the bus; host threads rebuild the 88-byte records from the caller's own copy
+			int32_t g_next = 0;                       // genomes below g_next have their destination array
+			int32_t g_done = 0;                       // genomes below g_done are complete: new array installed, old one handed to the pool
+			// only the 24 bytes per hit that changed cross the bus; host threads rebuild the 88-byte records from the caller's own copy.
+			// Destination arrays are taken as the chunks reach their genomes, and a genome's old array goes to the pool as soon as its last
+			// chunk is done -- from the second chunk on the destinations are those recycled (mapped) arrays.
 			staged_d2h(out.p, (size_t)N * sizeof(OutHit), sizeof(OutHit), [&](size_t off, size_t len, const char *srcbuf) {
 				const int64_t h0 = (int64_t)(off / sizeof(OutHit)), h1 = h0 + (int64_t)(len / sizeof(OutHit));
+				if (!in_place) for (; g_next < G && h_hoff[g_next] < h1; ++g_next) fresh[g_next] = spare.take((size_t)d->genome[g_next].n_hit, &fresh_cap[g_next]);
 				pool.parallel_for((h1 - h0 + BLK - 1) / BLK, [&](int64_t b) {
 					const int64_t a = h0 + b * BLK, e = std::min(h1, a + BLK);
 					int g = (int)(std::upper_bound(h_hoff.begin(), h_hoff.end(), (int32_t)a) - h_hoff.begin()) - 1;
@@ -1432,9 +1491,19 @@ struct Session {
 						memcpy((char*)dst + PG_HIT_BITS_OFFSET, &o->bits, 4);
 					}
 				});
+				if (!in_place) for (; g_done < G && h_hoff[g_done + 1] <= h1; ++g_done) {   // hit.c:62-63: the array in the old order goes, the new one takes its place
+					pg_genome_t *gn = &d->genome[g_done];
+					spare.give(gn->hit);
+					gn->hit = fresh[g_done]; gn->m_hit = (int32_t)std::min<size_t>(fresh_cap[g_done], 0x7fffffff);
+				}
 			}, st);
 			if (!host_sorted) {
-				pool.parallel_for(G, [&](int64_t j) { free(d->genome[j].hit); d->genome[j].hit = fresh[j]; d->genome[j].m_hit = d->genome[j].n_hit; });   // hit.c:62-63
+				for (; g_done < G; ++g_done) {            // (empty genomes at the end of the list)
+					pg_genome_t *gn = &d->genome[g_done];
+					if (!fresh[g_done]) fresh[g_done] = spare.take((size_t)gn->n_hit, &fresh_cap[g_done]);
+					spare.give(gn->hit);
+					gn->hit = fresh[g_done]; gn->m_hit = (int32_t)std::min<size_t>(fresh_cap[g_done], 0x7fffffff);
+				}
 				installed.assign(fresh.begin(), fresh.end());
 			}
 			g_stats.d2h += (int64_t)N * (int64_t)sizeof(OutHit);
@@ -1458,6 +1527,37 @@ struct Session {
 			PGX_CHECK(cudaStreamSynchronize(st));
 			g_stats.d2h += (int64_t)n_seg * 48 + (int64_t)n_arc * 32 + (int64_t)n_gene * 4;
 		}
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	// what the W lines (format.c:183-225) and the presence/absence matrix (pangene.js:1168-1246) need, read off the device-resident
+	// final state -- 12 bytes per printed hit instead of the 88-byte records of every hit.  tokens: malloc'd, genome-major, inside a genome contig-major,
+	// inside a contig by cm (ties in cs order, as pgio's writer orders them); genome_off[G + 1].  Token contig ids are genome-local (pg_hit_t.cid).
+	// ------------------------------------------------------------------------------------------------
+	int64_t walk_tokens(WalkToken **tokens, int64_t *genome_off)
+	{
+		if (!done_graph) PGX_FATAL("walk tokens are read off the final state: call pg_graph_gen() first");
+		*tokens = nullptr;
+		for (int32_t j = 0; j <= G; ++j) genome_off[j] = 0;
+		if (Nw == 0) { *tokens = (WalkToken*)malloc(sizeof(WalkToken)); return 0; }
+		size_t mk = scratch.mark();
+		uint32_t *flag = scratch.get<uint32_t>((size_t)Nw + 1), *pos = scratch.get<uint32_t>((size_t)Nw + 2);
+		PGX_LAUNCH(k_flag_walk_cm, grid_for(Nw, TB), TB, 0, st, A.bits, by_cm.p, Nw, flag);
+		const int64_t n_tok = (int64_t)scan_flags(flag, pos, Nw);
+		WalkToken *h = (WalkToken*)malloc(sizeof(WalkToken) * (size_t)(n_tok > 0? n_tok : 1));
+		if (n_tok) {
+			WalkToken *dtok = scratch.get<WalkToken>((size_t)n_tok);
+			PGX_LAUNCH(k_walk_tokens, grid_for(Nw, TB), TB, 0, st, pos, by_cm.p, Nw, A, src.p, raw.p, dtok);
+			staged_d2h(dtok, (size_t)n_tok * sizeof(WalkToken), sizeof(WalkToken), [&](size_t off, size_t len, const char *srcbuf) { memcpy((char*)h + off, srcbuf, len); }, st);
+			g_stats.d2h += n_tok * (int64_t)sizeof(WalkToken);
+			// tokens are sorted by contig key: genome boundaries by binary search, then keys -> genome-local contig ids
+			for (int32_t j = 0; j <= G; ++j)
+				genome_off[j] = std::lower_bound(h, h + n_tok, h_coff[j], [](const WalkToken &t, int32_t key) { return t.ctg < key; }) - h;
+			ThreadPool::get().parallel_for(G, [&](int64_t j) { for (int64_t t = genome_off[j]; t < genome_off[j + 1]; ++t) h[t].ctg -= h_coff[j]; });
+		}
+		scratch.reset(mk);
+		*tokens = h;
+		return n_tok;
 	}
 };
 

@@ -38,7 +38,7 @@ __device__ __forceinline__ int upper_bound_i32(const int32_t *a, int n, int32_t 
 // stage A: raw (file) order -- unpack, per-(genome,protein) pseudogene flags (hit.c:66-105)
 // ------------------------------------------------------------------------------------------------
 // what the device needs of a pg_hit_t, packed by the host while it fills the pinned upload chunks (pgx_hostpipe.hpp)
-struct RawHit { int32_t pid, cid, rank, sori, sadj, nexon, offexon, rev, cs, cm, ce, pad; };   // 48 bytes
+struct RawHit { int32_t pid, cid, rank, sori, sadj, nexon, offexon, rev, cs, cm, ce, lof; };   // 48 bytes (lof: never read by the path itself, only handed on to the walk tokens)
 // what changed, packed by the device for the way back
 struct OutHit { uint32_t src; int32_t rank, sdom, pdom, pdom0; uint32_t bits; };               // 24 bytes
 
@@ -551,7 +551,7 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	// Only usable where the loser of a pair is decided by the keys alone, i.e. where no unfiltered hit of the tile carries a weak_br mark
 	// (overlap.c:139-147): flag 1.
 	const int32_t S = hi - lo;
-	const bool rmq_mode = MODE == SW_LOAD && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
+	const bool rmq_mode = (MODE == SW_LOAD || MODE == SW_ISO) && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
 	// filtered hits (25 % in the first sweep) do no work: the live ones are compacted so that they fill whole warps.
 	const int32_t i0 = t0 + tid;
 	const bool r0 = i0 < c.n;
@@ -648,13 +648,14 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	// ranks and the tie detector need the partner-by-partner view --, or I am the strongest hit of a cluster with such a twin) falls through to
 	// the scan below; clusters that touch the ends of the staged range are finished by the parked path (phase 3).
 	bool scan = true;
-	if (rmq_mode && !(s_flags & 1u)) {
+	if (rmq_mode && (MODE == SW_ISO || !(s_flags & 1u))) {   // (the isoform filter compares keys whatever the weak_br marks say, overlap.c:82-84)
 		const int32_t head = s_cst[mq];
 		const uint32_t tq = s_ctop[head];
 		scan = false;
 		if ((head == 0 && lo > 0) || (head == (int32_t)s_cst[S - 1] && hi < c.n)) slow = true;   // the cluster (and with it possibly my window) may continue outside the staged range
 		else if (s_ccnt[head] > 1u) scan = true;                                          // the strongest key occurs twice
 		else if (tq == (uint32_t)mq || tq == 0xffffffffu) { }                             // nobody in my cluster beats me: top_p stays unset
+		else if (MODE == SW_ISO && (s_gidp[tq] >> 1) != mgene) scan = true;               // overlap.c:77: only isoforms of my own gene count; the strongest of THOSE needs the scan
 		else if ((int32_t)tq < mq? s_ce[tq] > mcs : s_cs[tq] < mce) { top_key = s_cmax[head]; top_p = lo + (int32_t)tq; }   // overlap.c:70,118: it is one of my partners
 		else scan = true;
 	}
@@ -1513,6 +1514,28 @@ __global__ void k_pack_out(const uint32_t *__restrict__ src, int32_t n, FullCols
 	if (have_graph && g2s[c.gidp[i] >> 1] >= 0) b |= PG_HB_VTX;                         // graph.c:61-69 (last call)
 	o.bits = b;
 	out[i] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// walk tokens: what format.c:183-225 prints on the W lines, straight from the device-resident state.  The unfiltered hits in
+// (genome, contig, cm) order -- by_cm already is that order of the active set, ties in (contig, cs) order -- each as (contig, gene << 1 | strand, lof).
+// ------------------------------------------------------------------------------------------------
+struct WalkToken { int32_t ctg; uint32_t gene_strand; int32_t lof; };                       // 12 bytes; ctg: the rank-local contig key (coff[genome] + cid)
+__global__ void k_flag_walk_cm(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ by_cm, int32_t n, uint32_t *flag)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) flag[k] = (bits[by_cm[k]] & PG_HB_FLT)? 0u : 1u;                            // format.c:205,213
+}
+__global__ void k_walk_tokens(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ by_cm, int32_t n, ActCols a, const uint32_t *__restrict__ src,
+	const RawHit *__restrict__ raw, WalkToken *out)
+{
+	int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n || pos[k + 1] == pos[k]) return;
+	const uint32_t p = by_cm[k];
+	WalkToken t;
+	t.ctg = a.ctg[p]; t.gene_strand = (uint32_t)(a.gidp[p] >> 1) << 1 | (a.bits[p] & PG_HB_REV);
+	t.lof = raw[src[a.full[p]]].lof;
+	out[pos[k]] = t;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -12,6 +12,11 @@ LIB_PATH = os.environ.get("PGX_LIB") or os.path.join(_HERE, "csrc", "libpgx.so")
 _LIB = None
 
 
+class pgx_walk_token_t(C.Structure):
+    """include/pgx_walk.h: one printed hit of a W line"""
+    _fields_ = [("cid", C.c_int32), ("gene_strand", C.c_uint32), ("lof", C.c_int32)]
+
+
 class pgx_stats_t(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("sweep_ms", C.c_double), ("sweep_bytes", C.c_double),
                 ("run_ms", C.c_double * 3), ("n_hit", C.c_int64), ("n_active", C.c_int64),
@@ -35,6 +40,9 @@ def lib():
         L.pg_graph_gen.restype = None
         L.pg_graph_destroy.argtypes = [P(abi.pg_graph_t)]
         L.pgx_data_release.argtypes = [P(abi.pg_data_t)]
+        L.pgx_walk_tokens.argtypes = [P(abi.pg_data_t), P(P(pgx_walk_token_t)), P(C.c_int64)]
+        L.pgx_walk_tokens.restype = C.c_int64
+        L.pgx_fetch_hits.argtypes = [P(abi.pg_data_t)]
         L.pgx_device_count.restype = C.c_int
         L.pgx_set_device.argtypes = [C.c_int]
         L.pgx_set_lazy.argtypes = [C.c_int]
@@ -74,6 +82,28 @@ def hot_path(opt, d, stop_after_post=False, lazy=False):
     g = L.pg_graph_init(d)
     L.pg_graph_gen(C.byref(opt), g)
     return g
+
+
+def graph_and_tokens(opt, d):
+    """The GFA-only route (lazy mode 2): the graph comes back, the hits stay on the device and only the walk tokens of the W lines
+    (12 bytes per printed hit) are read.  Returns (graph, tokens pointer, genome_off array, n_tokens); free with release_tokens()."""
+    L = lib()
+    L.pgx_set_lazy(2)
+    try:
+        L.pg_post_process(C.byref(opt), d)
+        g = L.pg_graph_init(d)
+        L.pg_graph_gen(C.byref(opt), g)
+        tok = C.POINTER(pgx_walk_token_t)()
+        off = (C.c_int64 * (d.contents.n_genome + 1))()
+        n = L.pgx_walk_tokens(d, C.byref(tok), off)
+    finally:
+        L.pgx_set_lazy(0)
+    return g, tok, off, n
+
+
+def release_tokens(d, tok):
+    C.CDLL(None).free(tok)
+    lib().pgx_data_release(d)
 
 
 def stats():

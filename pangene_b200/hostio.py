@@ -29,6 +29,10 @@ def lib():
         L.pgio_write_gfa.restype = C.c_int32
         L.pgio_write_bed.argtypes = [P(abi.pg_data_t), C.c_int32, C.c_char_p]
         L.pgio_write_bed.restype = C.c_int32
+        L.pgio_write_gfa_tokens.argtypes = [P(abi.pg_graph_t), C.c_void_p, P(C.c_int64), C.c_char_p, C.c_int32]
+        L.pgio_write_gfa_tokens.restype = C.c_int32
+        L.pgio_matrix_from_tokens.argtypes = [P(abi.pg_graph_t), C.c_void_p, P(C.c_int64), C.c_char_p, C.c_int32]
+        L.pgio_matrix_from_tokens.restype = C.c_int32
         L.pgio_gfa2matrix.argtypes = [C.c_char_p, C.c_char_p, C.c_int32]
         L.pgio_gfa2matrix.restype = C.c_int32
         L.pgio_synth_default.argtypes = [P(abi.pgio_synth_t), C.c_int32]
@@ -98,6 +102,14 @@ def write_gfa(graph, path, seg_arc=True, walk=True):
     return lib().pgio_write_gfa(graph, os.fsencode(path), (1 if seg_arc else 0) | (2 if walk else 0))
 
 
+def write_gfa_tokens(graph, tok, off, path, seg_arc=True, walk=True):
+    return lib().pgio_write_gfa_tokens(graph, C.cast(tok, C.c_void_p), off, os.fsencode(path), (1 if seg_arc else 0) | (2 if walk else 0))
+
+
+def matrix_from_tokens(graph, tok, off, path, copy_number=False):
+    return lib().pgio_matrix_from_tokens(graph, C.cast(tok, C.c_void_p), off, os.fsencode(path), 1 if copy_number else 0)
+
+
 def write_bed(d, path, is_walk=False):
     return lib().pgio_write_bed(d, 1 if is_walk else 0, os.fsencode(path))
 
@@ -111,6 +123,18 @@ def gfa_digest(graph):
         write_gfa(graph, t.name, True, False)
         sl = hashlib.md5(open(t.name, "rb").read()).hexdigest()
         write_gfa(graph, t.name, False, True)
+        w = open(t.name, "rb").read()
+    return sl, w
+
+
+def gfa_digest_tokens(graph, tok, off):
+    """gfa_digest() of the same GFA, formatted from walk tokens (pgio_write_gfa_tokens) instead of materialised hits"""
+    import hashlib
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".gfa") as t:
+        write_gfa_tokens(graph, tok, off, t.name, True, False)
+        sl = hashlib.md5(open(t.name, "rb").read()).hexdigest()
+        write_gfa_tokens(graph, tok, off, t.name, False, True)
         w = open(t.name, "rb").read()
     return sl, w
 

@@ -93,3 +93,50 @@ def first_diff(a, b, n=5):
     for x in only_a[:n]: out.append("- " + x.decode(errors="replace"))
     for x in only_b[:n]: out.append("+ " + x.decode(errors="replace"))
     return "\n".join(out) + "\n(%d lines only in expected, %d only in got)" % (len(only_a), len(only_b))
+
+
+def tokens_from_hits(d):
+    """Walk tokens (include/pgx_walk.h) built from MATERIALISED hits the way format.c:183-225 picks them: the unfiltered hits of a genome,
+    contig-major, by cm inside a contig, ties in array order.  Returns (ctypes token array, genome_off array, n)."""
+    import numpy as np
+    from pangene_b200 import engine
+    dd = d.contents
+    HIT = np.dtype([(n, "<i4") for n in ("pid", "qs", "qe", "cid", "mlen", "blen", "lof", "rank", "score_ori", "score_adj", "score_dom", "n_exon", "off_exon", "pid_dom", "pid_dom0")]
+                   + [("bits", "<u4"), ("cs", "<i8"), ("cm", "<i8"), ("ce", "<i8")])
+    gid = np.array([dd.prot[i].gid for i in range(dd.n_prot)], dtype=np.int64)
+    parts, off = [], [0]
+    for j in range(dd.n_genome):
+        g = dd.genome[j]
+        if g.n_hit == 0:
+            off.append(off[-1]); continue
+        h = np.frombuffer((C.c_char * (g.n_hit * 88)).from_address(C.addressof(g.hit.contents)), dtype=HIT)
+        keep = np.nonzero((h["bits"] & abi.PG_HB_FLT) == 0)[0]
+        order = keep[np.lexsort((h["cm"][keep], h["cid"][keep]))]   # lexsort is stable: ties keep array order
+        t = np.zeros(len(order), dtype=[("cid", "<i4"), ("gene_strand", "<u4"), ("lof", "<i4")])
+        t["cid"] = h["cid"][order]; t["gene_strand"] = (gid[h["pid"][order]] << 1) | (h["bits"][order] & 1); t["lof"] = h["lof"][order]
+        parts.append(t); off.append(off[-1] + len(t))
+    n = off[-1]
+    buf = (engine.pgx_walk_token_t * max(n, 1))()
+    if n:
+        allt = np.concatenate(parts)
+        C.memmove(buf, allt.ctypes.data, n * 12)
+    return buf, (C.c_int64 * len(off))(*off), n
+
+
+def gfa_bytes_tokens(graph, tok, off, walk=True):
+    with tempfile.NamedTemporaryFile(suffix=".gfa") as t:
+        hostio.write_gfa_tokens(graph, tok, off, t.name, True, walk)
+        return open(t.name, "rb").read()
+
+
+def matrix_bytes_tokens(graph, tok, off, copy_number=False):
+    with tempfile.NamedTemporaryFile(suffix=".tsv") as t:
+        hostio.matrix_from_tokens(graph, tok, off, t.name, copy_number)
+        return open(t.name, "rb").read()
+
+
+def matrix_bytes_gfa(gfa_data, copy_number=False):
+    with tempfile.NamedTemporaryFile(suffix=".gfa") as a, tempfile.NamedTemporaryFile(suffix=".tsv") as b:
+        a.write(gfa_data); a.flush()
+        hostio.lib().pgio_gfa2matrix(os.fsencode(a.name), os.fsencode(b.name), 1 if copy_number else 0)
+        return open(b.name, "rb").read()

@@ -287,3 +287,45 @@ def test_config5_bacterial_with_matrix(tmp_path):
     n2 = hostio.lib().pgio_gfa2matrix(os.fsencode(f2), os.fsencode(m2), 0)
     assert n1 == n2 > 2000 and open(m1, "rb").read() == open(m2, "rb").read()
     engine.destroy(g2); pgoracle.destroy(g1); hostio.destroy(d1); hostio.destroy(d2)
+
+
+def test_walk_tokens_route(tmp_path):
+    """the GFA and the gfa2matrix table from the DEVICE-RESIDENT final state (lazy mode 2: graph + 12-byte walk tokens,
+    no pg_hit_t record comes back).  C4: the golden GFA byte for byte; synthetic sets incl. the bacterial -p0 -a2 shape: the oracle's GFA,
+    the tokens the oracle's hits give (tests/common.tokens_from_hits) and the table pgio_gfa2matrix computes from the oracle's GFA text.
+    pgx_fetch_hits() afterwards still materialises every per-hit flag."""
+    opt = hostio.default_opt()
+    d = hostio.read_pafs(opt, common.c4_files(tmp_path))
+    g, tok, off, n = engine.graph_and_tokens(opt, d)
+    assert common.gfa_bytes_tokens(g, tok, off) == open(os.path.join(common.GOLDEN, "C4.gfa"), "rb").read()
+    assert common.gfa_bytes_tokens(g, tok, off, walk=False) == open(os.path.join(common.GOLDEN, "C4_w.gfa"), "rb").read()
+    engine.lib().pgx_fetch_hits(d)
+    assert common.bed_bytes(d) == open(os.path.join(common.GOLDEN, "C4.bed_flag"), "rb").read()
+    engine.release_tokens(d, tok); engine.destroy(g); hostio.destroy(d)
+    cases = [([], hostio.synth_params(2, n_genome=7, n_gene=3000, iso_per_gene=4, hits_per_genome=30000)),
+             (["-S", "-T3"], hostio.synth_params(2, n_genome=5, n_gene=2000, iso_per_gene=1, hits_per_genome=9000)),
+             (["-p0", "-a2"], hostio.synth_params(5, n_genome=200, n_genome_total=200))]
+    for args, p in cases:
+        o = common.opt_from_args(args)
+        d1, d2 = hostio.synth(o, p), hostio.synth(o, p)
+        g1 = pgoracle.hot_path(o, d1)
+        g2, tok, off, n = engine.graph_and_tokens(o, d2)
+        t1, off1, n1 = common.tokens_from_hits(d1)
+        assert n == n1 and list(off) == list(off1)
+        want, got = common.gfa_bytes(g1), common.gfa_bytes_tokens(g2, tok, off)
+        assert sorted(got.splitlines()) == sorted(want.splitlines()), common.first_diff(want, got)
+        assert common.gfa_bytes_tokens(g1, t1, off1) == want
+        for cn in (False, True):
+            assert common.matrix_bytes_tokens(g2, tok, off, cn) == common.matrix_bytes_gfa(want, cn)
+        engine.lib().pgx_fetch_hits(d2)
+        assert sorted(common.bed_bytes(d2).splitlines()) == sorted(common.bed_bytes(d1).splitlines())
+        engine.release_tokens(d2, tok); engine.destroy(g2); pgoracle.destroy(g1); hostio.destroy(d1); hostio.destroy(d2)
+
+
+def test_recycled_hit_arrays_keep_results_intact():
+    """the download hands out recycled (already mapped) arrays instead of fresh ones: back-to-back runs over data sets of different
+    shapes -- arrays of one run become destinations of the next -- must each still equal the oracle"""
+    opt = hostio.default_opt()
+    for seed, (ng, hp) in enumerate([(6, 30000), (9, 12000), (4, 50000), (9, 12000)]):
+        p = hostio.synth_params(2, n_genome=ng, n_gene=2500, iso_per_gene=4, hits_per_genome=hp, seed=11 + seed)
+        check_against(opt, lambda: hostio.synth(opt, p), "oracle", lazy=bool(seed & 1))

@@ -79,6 +79,27 @@ def test_gfa2matrix(tmp_path):
             assert (r[1 + k] == "1") == bool(present)
 
 
+def test_token_writers_equal_the_writers_on_materialised_hits(tmp_path):
+    """SURVEY §8f rows 2-3, host half: W lines and the gfa2matrix table formatted from walk tokens are byte-identical to the GFA written from
+    the pg_hit_t records / the table computed from that GFA's text (tokens built here from the oracle's hits; the device builds the same
+    tokens in tests/test_gpu_parity.py)."""
+    from oracle import pgoracle
+    opt = hostio.default_opt()
+    cases = [hostio.read_pafs(opt, common.c4_files(tmp_path)),
+             hostio.synth(opt, hostio.synth_params(2, n_genome=5, n_gene=1500, iso_per_gene=4, hits_per_genome=15000)),
+             hostio.synth(opt, hostio.synth_params(5, n_genome=40, n_gene=600, iso_per_gene=1, hits_per_genome=500))]
+    for k, d in enumerate(cases):
+        o = opt if k < 2 else common.opt_from_args(["-p0", "-a2"])
+        g = pgoracle.hot_path(o, d)
+        tok, off, n = common.tokens_from_hits(d)
+        assert n > 0
+        want = common.gfa_bytes(g)
+        assert common.gfa_bytes_tokens(g, tok, off) == want
+        for cn in (False, True):
+            assert common.matrix_bytes_tokens(g, tok, off, cn) == common.matrix_bytes_gfa(want, cn)
+        pgoracle.destroy(g); hostio.destroy(d)
+
+
 def test_libpgx_exports_every_declared_symbol():
     """the C-ABI library loads without a GPU and exports every function include/pgx.h declares (no compute call)"""
     hdr = open(os.path.join(ROOT, "include", "pgx.h")).read()
