@@ -14,6 +14,7 @@
 
 #include "pangene_abi.h"
 #include "pgx_walk.h"
+#include "pgx_packed.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -36,6 +37,14 @@ int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *fn);
  * argument order -- gene/protein ids, names, ranks and every hit come out exactly as from calling pgio_read_paf() file by file
  * (tests/test_io.py).  n_threads 0 = hardware concurrency.  Returns the number of files opened. */
 int32_t pgio_read_pafs(const pg_opt_t *opt, pg_data_t *d, const char *const *fns, int32_t n_files, int32_t n_threads);
+
+/* The same parse, emitting DEVICE-READY records (pgx_packed.h): every kept alignment becomes a 48-byte pgx_packed_hit_t in pk->hit[genome]
+ * instead of an 88-byte pg_hit_t -- same ids, ranks, scores, exon lists, cm and lof as pgio_read_pafs() computes (tests/test_io.py packs the
+ * one and compares with the other).  d gets everything else (names, contigs, exons, proteins, genes); d->genome[j].hit stays NULL / n_hit 0.
+ * pk: zero-initialised by the caller, released with pgio_packed_destroy().  A coordinate >= 2^31 aborts with a message. */
+int32_t pgio_read_pafs_packed(const pg_opt_t *opt, pg_data_t *d, pgx_packed_t *pk, const char *const *fns, int32_t n_files, int32_t n_threads);
+void pgio_packed_destroy(pgx_packed_t *pk);
+int64_t pgio_packed_total_hits(const pgx_packed_t *pk);
 
 /* read.c:305-318: name set for -X/-I/-P from "a,b,c" or "@file" */
 void *pgio_name_set(const char *spec);

@@ -14,6 +14,7 @@
 
 #include "pangene_abi.h"
 #include "pgx_walk.h"
+#include "pgx_packed.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -63,6 +64,12 @@ void pgx_set_lazy(int lazy);
  * cm with ties in (cs, file) order -- the order pgio_write_gfa() prints.  genome_off: d->n_genome + 1 offsets into *tokens, caller-provided.
  * Returns the number of tokens. */
 int64_t pgx_walk_tokens(const pg_data_t *d, pgx_walk_token_t **tokens, int64_t *genome_off);
+
+/* pg_post_process() on DEVICE-READY input (pgx_packed.h): the hits of genome j are pk->hit[j][0 .. pk->n_hit[j]) -- the
+ * twelve words pg_post_process() would pack out of every pg_hit_t -- in file order; d supplies everything else (n_genome, contigs, exon
+ * lists, proteins, genes) and its genome[].hit arrays are not read.  Needs pgx_set_lazy(2): results come back as graph (pg_graph_gen) and
+ * walk tokens (pgx_walk_tokens) only; d->prot / d->gene are updated as by pg_post_process(). */
+void pgx_post_process_packed(const pg_opt_t *opt, pg_data_t *d, const pgx_packed_t *pk);
 
 /* lazy mode 2: materialise the hits after all (what pg_graph_gen() does in modes 0 and 1); the device state stays until pgx_data_release(). */
 void pgx_fetch_hits(pg_data_t *d);

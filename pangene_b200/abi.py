@@ -77,6 +77,16 @@ class pg_graph_t(C.Structure):
                 ("idx", C.POINTER(C.c_uint64))]
 
 
+class pgx_packed_hit_t(C.Structure):
+    """include/pgx_packed.h: the device-ready 48-byte record"""
+    _fields_ = [(n, C.c_int32) for n in ("pid", "cid", "rank", "score_ori", "score_adj", "n_exon", "off_exon", "rev", "cs", "cm", "ce", "lof")]
+
+
+class pgx_packed_t(C.Structure):
+    _fields_ = [("n_genome", C.c_int32), ("m_genome", C.c_int32), ("n_hit", C.POINTER(C.c_int32)), ("m_hit", C.POINTER(C.c_int32)),
+                ("hit", C.POINTER(C.POINTER(pgx_packed_hit_t)))]
+
+
 class pgio_synth_t(C.Structure):
     _fields_ = [("shape", C.c_int32), ("n_genome", C.c_int32), ("genome_begin", C.c_int32),
                 ("n_genome_total", C.c_int32), ("n_gene", C.c_int32), ("iso_per_gene", C.c_int32),
@@ -86,6 +96,7 @@ class pgio_synth_t(C.Structure):
 
 assert C.sizeof(pg_opt_t) == 128 and C.sizeof(pg_hit_t) == 88 and C.sizeof(pg_prot_t) == 32
 assert C.sizeof(pg_gene_t) == 16 and C.sizeof(pg_seg_t) == 32 and C.sizeof(pg_arc_t) == 32
+assert C.sizeof(pgx_packed_hit_t) == 48 and C.sizeof(pgx_packed_t) == 32
 assert C.sizeof(pg_genome_t) == 56 and C.sizeof(pg_data_t) == 72 and C.sizeof(pg_graph_t) == 56
 
 # option flag bits (pangene.h:8-17)

@@ -104,14 +104,22 @@ int main(int argc, char *argv[])
 
 	pg_data_t *d = pgio_data_init();
 	std::thread warm([]() { pgx_warmup(); });   // CUDA context + pinned staging ring come up while the files are parsed
-	pgio_read_pafs(&opt, d, (const char *const*)&argv[optind], argc - optind, 0);   // parallel parse, ids as in sequential order
+	// GFA output (the default) never needs a pg_hit_t record: the reader emits the device-ready 48-byte records (pgx_packed.h), libpgx uploads them
+	// as they are and hands back the graph and the walk tokens of the W lines.  The BED outputs print every field of every hit: pg_hit_t route.
+	const bool gfa_route = !(opt.flag & (PG_F_WRITE_BED_RAW | PG_F_WRITE_BED_WALK | PG_F_WRITE_BED_FLAG));
+	pgx_packed_t pk;
+	memset(&pk, 0, sizeof(pk));
+	if (gfa_route) pgio_read_pafs_packed(&opt, d, &pk, (const char *const*)&argv[optind], argc - optind, 0);
+	else pgio_read_pafs(&opt, d, (const char *const*)&argv[optind], argc - optind, 0);   // parallel parse, ids as in sequential order
 	warm.join();
 	double t1 = now();
+	const long n_hits_in = gfa_route? (long)pgio_packed_total_hits(&pk) : (long)pgio_total_hits(d);
 	// --bed=raw: strict post-conditions after pg_post_process; other BED outputs: the hits come back once, after pg_graph_gen; GFA (the
 	// default): no hit record comes back at all -- the W lines are formatted from the walk tokens libpgx reads off its final state
 	const bool want_bed = (opt.flag & (PG_F_WRITE_BED_RAW | PG_F_WRITE_BED_WALK | PG_F_WRITE_BED_FLAG)) != 0;
 	pgx_set_lazy((opt.flag & PG_F_WRITE_BED_RAW)? 0 : want_bed? 1 : 2);
-	pg_post_process(&opt, d);
+	if (gfa_route) { pgx_post_process_packed(&opt, d, &pk); pgio_packed_destroy(&pk); }   // (the records are on the device now)
+	else pg_post_process(&opt, d);
 	if (opt.flag & PG_F_WRITE_BED_RAW) {
 		pgio_write_bed(d, 0, "-");
 		pgx_data_release(d);                          // no pg_graph_gen() follows: hand the device state back
@@ -130,7 +138,7 @@ int main(int argc, char *argv[])
 			pgio_write_gfa_tokens(g, tok, off.data(), "-", 3);
 			free(tok);
 		}
-		if (pg_verbose >= 3) fprintf(stderr, "[M::%s] parse %.3f s; hot path (incl. transfers) %.3f s; %ld hits\n", __func__, t1 - t0, t2 - t1, (long)pgio_total_hits(d));
+		if (pg_verbose >= 3) fprintf(stderr, "[M::%s] parse %.3f s; hot path (incl. transfers) %.3f s; %ld hits\n", __func__, t1 - t0, t2 - t1, n_hits_in);
 		pg_graph_destroy(g);
 	}
 	pgio_data_destroy(d);

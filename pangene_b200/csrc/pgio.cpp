@@ -377,6 +377,25 @@ void pgio::push_hit(pg_genome_t *g, pg_hit_t &hit, const std::vector<pg_exon_t> 
 	g->hit[g->n_hit++] = hit;
 }
 
+void pgio::push_hit_packed(pg_genome_t *g, pgx_packed_hit_t *&pk, int32_t &n, int32_t &m, pg_hit_t &hit, const std::vector<pg_exon_t> &ex, int32_t cg_fs, int32_t n_fs, int32_t n_stop)
+{
+	grow0(g->exon, (int64_t)g->n_exon + (int64_t)ex.size() - 1, g->m_exon);
+	memcpy(&g->exon[g->n_exon], ex.data(), ex.size() * sizeof(pg_exon_t));
+	hit.n_exon = (int32_t)ex.size();
+	hit.off_exon = g->n_exon;
+	g->n_exon += (int32_t)ex.size();
+	int32_t lof = (n_fs > 0? n_fs : 0) + (n_stop > 0? n_stop : 0);   // read.c:229-230
+	hit.lof = cg_fs > lof? cg_fs : lof;
+	hit.cm = pgio::cds_mid(&hit, &g->exon[hit.off_exon]);
+	if (hit.cs < 0 || hit.ce > 0x7fffffffll || hit.cm < 0 || hit.cm > 0x7fffffffll || hit.cs > hit.ce) {
+		fprintf(stderr, "[pgio] ERROR: a hit coordinate is outside [0, 2^31) or cs > ce -- device-ready records keep coordinates in int32\n"); abort();
+	}
+	grow0(pk, n, m);
+	pgx_packed_hit_t &o = pk[n++];
+	o.pid = hit.pid; o.cid = hit.cid; o.rank = hit.rank; o.score_ori = hit.score_ori; o.score_adj = hit.score_adj; o.n_exon = hit.n_exon; o.off_exon = hit.off_exon;
+	o.rev = hit.rev; o.cs = (int32_t)hit.cs; o.cm = (int32_t)hit.cm; o.ce = (int32_t)hit.ce; o.lof = hit.lof;
+}
+
 // tab-separated fields of one NUL-terminated line, split in place (the tabs become terminators); like the reference's column
 // loop (read.c:135-137) the line ends at its first NUL byte
 static inline void split_tabs(char *s, size_t len, std::vector<char*> &fld)
@@ -408,6 +427,8 @@ struct LocalFile {
 	std::vector<int32_t> gene_len;                    // per local gene: max protein length seen (read.c:175)
 	std::vector<uint8_t> gene_pref, gene_incl;
 	int64_t n_lines = 0;
+	bool packed = false;                              // emit device-ready records (pgx_packed.h) instead of pg_hit_t
+	pgx_packed_hit_t *ph = nullptr; int32_t n_ph = 0, m_ph = 0;
 	LocalFile() { memset(&g, 0, sizeof(g)); }
 };
 
@@ -429,7 +450,8 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 			const double lines = (double)buf.size() / smp * (double)nl;
 			const int64_t eh = (int64_t)(lines * 1.03) + 64, ee = (int64_t)(lines * 1.05 * (1.0 + (double)nn / nl)) + 64;
 			if (eh < 0x7fffffff && ee < 0x7fffffff) {
-				g->hit = (pg_hit_t*)calloc((size_t)eh, sizeof(pg_hit_t)); g->m_hit = g->hit? (int32_t)eh : 0;
+				if (F.packed) { F.ph = (pgx_packed_hit_t*)calloc((size_t)eh, sizeof(pgx_packed_hit_t)); F.m_ph = F.ph? (int32_t)eh : 0; }
+				else { g->hit = (pg_hit_t*)calloc((size_t)eh, sizeof(pg_hit_t)); g->m_hit = g->hit? (int32_t)eh : 0; }
 				g->exon = (pg_exon_t*)calloc((size_t)ee, sizeof(pg_exon_t)); g->m_exon = g->exon? (int32_t)ee : 0;
 			}
 		}
@@ -522,12 +544,12 @@ void parse_file(const pg_opt_t *opt, const char *fn, LocalFile &F)
 				}
 			}
 		} while (0);
-		if (have_exons) pgio::push_hit(g, hit, ex, cg_fs, n_fs, n_stop);
+		if (have_exons) { if (F.packed) pgio::push_hit_packed(g, F.ph, F.n_ph, F.m_ph, hit, ex, cg_fs, n_fs, n_stop); else pgio::push_hit(g, hit, ex, cg_fs, n_fs, n_stop); }
 	});
 }
 
 // fold one parsed file into the global tables, in command-line order (serial, cheap: names only), then rewrite its hits' ids
-void merge_file(pg_data_t *d, LocalFile &F)
+void merge_file(pg_data_t *d, LocalFile &F, pgx_packed_t *pk = nullptr)
 {
 	pgio::DataPriv *pv = (pgio::DataPriv*)d->d_ctg;
 	std::vector<int32_t> g2g(F.gene.names.size()), p2p(F.prot.names.size());
@@ -551,6 +573,18 @@ void merge_file(pg_data_t *d, LocalFile &F)
 	*g = F.g;
 	for (int32_t c = 0; c < g->n_ctg; ++c) g->ctg[c].name = pv->ctg.intern(g->ctg[c].name, 0, 0);   // global, stable storage
 	for (int32_t i = 0; i < g->n_hit; ++i) g->hit[i].pid = p2p[g->hit[i].pid];
+	if (pk) {   // device-ready records: the genome's hit array stays empty, its records go to pk->hit[genome]
+		for (int32_t i = 0; i < F.n_ph; ++i) F.ph[i].pid = p2p[F.ph[i].pid];
+		const int32_t j = d->n_genome - 1;
+		if (j >= pk->m_genome) {
+			const int32_t m = pk->m_genome? pk->m_genome * 2 : 16;
+			pk->n_hit = (int32_t*)realloc(pk->n_hit, sizeof(int32_t) * m); pk->m_hit = (int32_t*)realloc(pk->m_hit, sizeof(int32_t) * m);
+			pk->hit = (pgx_packed_hit_t**)realloc(pk->hit, sizeof(pgx_packed_hit_t*) * m);
+			pk->m_genome = m;
+		}
+		pk->hit[j] = F.ph; pk->n_hit[j] = F.n_ph; pk->m_hit[j] = F.m_ph; pk->n_genome = j + 1;
+		F.ph = nullptr; F.n_ph = F.m_ph = 0;
+	}
 	memset(&F.g, 0, sizeof(F.g));
 	if (pgio_verbose >= 4)
 		fprintf(stderr, "[M::pgio_read_paf] [%d] %s: %ld lines parsed, %d hits kept\n", d->n_genome - 1, g->label? g->label : "*", (long)F.n_lines, g->n_hit);
@@ -569,14 +603,42 @@ extern "C" int32_t pgio_read_paf(const pg_opt_t *opt, pg_data_t *d, const char *
 
 static double wall_now() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 
+static int32_t read_pafs_impl(const pg_opt_t *opt, pg_data_t *d, pgx_packed_t *pk, const char *const *fns, int32_t n_files, int32_t n_threads);
+
 // All files of a command line: parsed by n_threads workers (0 = hardware concurrency, capped at the file count), merged in
 // order.  Returns the number of files that could be opened (the others are skipped, like main.c:120 ignores the error).
 extern "C" int32_t pgio_read_pafs(const pg_opt_t *opt, pg_data_t *d, const char *const *fns, int32_t n_files, int32_t n_threads)
+{
+	return read_pafs_impl(opt, d, nullptr, fns, n_files, n_threads);
+}
+
+extern "C" int32_t pgio_read_pafs_packed(const pg_opt_t *opt, pg_data_t *d, pgx_packed_t *pk, const char *const *fns, int32_t n_files, int32_t n_threads)
+{
+	if (pk->n_genome != d->n_genome) { fprintf(stderr, "[pgio] ERROR: pgio_read_pafs_packed(): the packed set and the pg_data_t must grow together\n"); abort(); }
+	return read_pafs_impl(opt, d, pk, fns, n_files, n_threads);
+}
+
+extern "C" void pgio_packed_destroy(pgx_packed_t *pk)
+{
+	for (int32_t j = 0; j < pk->n_genome; ++j) free(pk->hit[j]);
+	free(pk->hit); free(pk->n_hit); free(pk->m_hit);
+	memset(pk, 0, sizeof(*pk));
+}
+
+extern "C" int64_t pgio_packed_total_hits(const pgx_packed_t *pk)
+{
+	int64_t n = 0;
+	for (int32_t j = 0; j < pk->n_genome; ++j) n += pk->n_hit[j];
+	return n;
+}
+
+static int32_t read_pafs_impl(const pg_opt_t *opt, pg_data_t *d, pgx_packed_t *pk, const char *const *fns, int32_t n_files, int32_t n_threads)
 {
 	if (n_threads <= 0) n_threads = (int32_t)std::thread::hardware_concurrency();
 	if (n_threads > n_files) n_threads = n_files;
 	if (n_threads < 1) n_threads = 1;
 	std::vector<LocalFile> files(n_files > 0? n_files : 0);
+	for (auto &f : files) f.packed = pk != nullptr;
 	std::atomic<int32_t> next(0);
 	const double t0 = wall_now();
 	auto worker = [&]() { for (int32_t i; (i = next.fetch_add(1)) < n_files;) parse_file(opt, fns[i], files[i]); };
@@ -587,7 +649,8 @@ extern "C" int32_t pgio_read_pafs(const pg_opt_t *opt, pg_data_t *d, const char 
 	std::string().swap(file_buffer());   // the calling thread's read buffer (the workers' went with their threads)
 	const double t1 = wall_now();
 	int32_t n_ok = 0;
-	for (int32_t i = 0; i < n_files; ++i) if (files[i].ok) { merge_file(d, files[i]); ++n_ok; }
+	for (int32_t i = 0; i < n_files; ++i) if (files[i].ok) { merge_file(d, files[i], pk); ++n_ok; }
+	for (auto &f : files) free(f.ph);                     // (files that could not be opened hold nothing)
 	if (getenv("PGIO_TIMING")) fprintf(stderr, "[pgio timing] %d files on %d threads: parse %.3f s, merge %.3f s\n", n_files, n_threads, t1 - t0, wall_now() - t1);
 	return n_ok;
 }

@@ -4,6 +4,7 @@
 #include <string_view>
 #include <vector>
 #include "pangene_abi.h"
+#include "pgx_packed.h"
 
 namespace pgio {
 
@@ -34,5 +35,7 @@ int64_t cds_mid(const pg_hit_t *a, const pg_exon_t *e);
 int64_t cigar_to_exons(const char *cg, bool rev, std::vector<pg_exon_t> &tmp, std::vector<pg_exon_t> &out, int32_t *n_fs);
 int32_t adjusted_score(const pg_opt_t *opt, int32_t ms, int32_t mlen, int32_t blen, int32_t qs, int32_t qe, int32_t plen);
 void push_hit(pg_genome_t *g, pg_hit_t &hit, const std::vector<pg_exon_t> &ex, int32_t cg_fs, int32_t n_fs, int32_t n_stop);
+// the same hit as a device-ready record appended to pk[0..*n) (capacity *m); its exons go to g->exon as usual
+void push_hit_packed(pg_genome_t *g, pgx_packed_hit_t *&pk, int32_t &n, int32_t &m, pg_hit_t &hit, const std::vector<pg_exon_t> &ex, int32_t cg_fs, int32_t n_fs, int32_t n_stop);
 
 }

@@ -67,11 +67,21 @@ extern "C" {
 
 int pg_verbose = 3;
 
-void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
+static void post_process_impl(const pg_opt_t *opt, pg_data_t *d, const pgx_packed_t *pk, const char *who);
+
+void pg_post_process(const pg_opt_t *opt, pg_data_t *d) { post_process_impl(opt, d, nullptr, __func__); }
+
+void pgx_post_process_packed(const pg_opt_t *opt, pg_data_t *d, const pgx_packed_t *pk)
+{
+	if (g_lazy != 2) PGX_FATAL("pgx_post_process_packed() needs pgx_set_lazy(2): packed input has no pg_hit_t records for results to come back in");
+	post_process_impl(opt, d, pk, __func__);
+}
+
+static void post_process_impl(const pg_opt_t *opt, pg_data_t *d, const pgx_packed_t *pk, const char *who)
 {
 	const double t_enter = wall();
 	need_device();
-	if (pg_verbose >= 3) fprintf(stderr, "[M::%s] %d genes and %d proteins\n", __func__, d->n_gene, d->n_prot);
+	if (pg_verbose >= 3) fprintf(stderr, "[M::%s] %d genes and %d proteins\n", who, d->n_gene, d->n_prot);
 	{
 		std::lock_guard<std::mutex> lk(g_sessions_mu);
 		auto it = g_sessions.find(d);
@@ -79,7 +89,7 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	}
 	double t0 = wall();
 	Session *s = new Session();
-	s->upload(d, true);
+	s->upload(d, true, pk);
 	double t1 = wall();
 	timed_run(s, opt, 1);
 	double t2 = wall();
@@ -94,8 +104,8 @@ void pg_post_process(const pg_opt_t *opt, pg_data_t *d)
 	int32_t n_pref = 0;
 	for (int32_t i = 0; i < d->n_gene; ++i) n_pref += d->gene[i].preferred;
 	if (pg_verbose >= 3) {
-		fprintf(stderr, "[M::%s] %ld hits in %d genomes; %ld remain after the per-genome filters (device %.2f ms)\n", __func__, (long)s->N, s->G, (long)s->Nw, g_stats.run_ms[0]);
-		fprintf(stderr, "[M::%s] there are %d preferred genes\n", __func__, n_pref);   // graph.c:31
+		fprintf(stderr, "[M::%s] %ld hits in %d genomes; %ld remain after the per-genome filters (device %.2f ms)\n", who, (long)s->N, s->G, (long)s->Nw, g_stats.run_ms[0]);
+		fprintf(stderr, "[M::%s] there are %d preferred genes\n", who, n_pref);   // graph.c:31
 	}
 }
 
@@ -120,7 +130,7 @@ void pg_graph_gen(const pg_opt_t *opt, pg_graph_t *q)
 	}
 	// the device state is keyed by the pg_data_t pointer: make sure it still describes THIS data (a freed pg_data_t whose address was reused)
 	if (s->G != q->d->n_genome || s->n_prot != q->d->n_prot || s->n_gene != q->d->n_gene) PGX_FATAL("pg_graph_gen(): the pg_data_t changed since pg_post_process() (%d/%d genomes)", q->d->n_genome, s->G);
-	for (int32_t j = 0; j < s->G; ++j) if (s->h_hoff[j + 1] - s->h_hoff[j] != q->d->genome[j].n_hit) PGX_FATAL("pg_graph_gen(): genome %d changed size since pg_post_process()", j);
+	for (int32_t j = 0; j < s->G && !s->packed_input; ++j) if (s->h_hoff[j + 1] - s->h_hoff[j] != q->d->genome[j].n_hit) PGX_FATAL("pg_graph_gen(): genome %d changed size since pg_post_process()", j);
 	double t0 = wall();
 	timed_run(s, opt, 2);
 	double t1 = wall();

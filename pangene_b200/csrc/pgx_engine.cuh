@@ -222,7 +222,8 @@ struct Session {
 	// defer_exons: the exon lists (half of the bytes) are not copied here but inside the stage_load() that follows, on the second stream, while
 	// the device already unpacks, flags and sorts the hits -- none of which reads an exon (pg_post_process() does this; `d` must stay valid until then)
 	const pg_data_t *exons_pending = nullptr;
-	void upload(const pg_data_t *d, bool defer_exons = false)
+	bool packed_input = false;           // the hits came as device-ready records (pgx_packed.h): there is no pg_hit_t array to materialise results into
+	void upload(const pg_data_t *d, bool defer_exons = false, const pgx_packed_t *pk = nullptr)
 	{
 		if (rep_pending) { rep_thread.join(); rep_pending = false; }
 		G = d->n_genome; n_prot = d->n_prot; n_gene = d->n_gene;
@@ -231,7 +232,7 @@ struct Session {
 		int64_t nh = 0, nc = 0, ne = 0;
 		for (int32_t j = 0; j < G; ++j) {
 			h_hoff[j] = (int32_t)nh; h_coff[j] = (int32_t)nc; h_eoffg[j] = (uint32_t)ne;
-			nh += d->genome[j].n_hit; nc += d->genome[j].n_ctg; ne += d->genome[j].n_exon;
+			nh += pk? pk->n_hit[j] : d->genome[j].n_hit; nc += d->genome[j].n_ctg; ne += d->genome[j].n_exon;
 		}
 		if (nh >= 0x7fffffffll / AOS_WORDS * 8 || ne >= 0xffffffffll || nc >= 0x7fffffffll) PGX_FATAL("input too large for 32-bit hit/exon indices (%ld hits, %ld exons)", (long)nh, (long)ne);
 		h_hoff[G] = (int32_t)nh; h_coff[G] = (int32_t)nc; h_eoffg[G] = (uint32_t)ne;
@@ -251,7 +252,8 @@ struct Session {
 		PGX_CHECK(cudaMemcpyAsync(prot_gid.p, h_prot_gid.data(), (size_t)n_prot * 4, cudaMemcpyHostToDevice, st));
 		PGX_CHECK(cudaMemcpyAsync(gene_pref.p, h_gene_pref.data(), (size_t)n_gene, cudaMemcpyHostToDevice, st));
 		raw.alloc((size_t)N + 1); ex_raw.alloc((size_t)E + 16);
-		upload_hits(d);
+		packed_input = pk != nullptr;
+		if (pk) { if (pk->n_genome != G) PGX_FATAL("upload: %d packed genomes for a pg_data_t of %d", pk->n_genome, G); upload_hits_packed(pk); } else upload_hits(d);
 		if (defer_exons && E) exons_pending = d; else upload_exons(d, st);
 		g_stats.h2d += (int64_t)N * (int64_t)sizeof(RawHit) + E * 8 + (int64_t)n_prot * 4 + n_gene;
 		g_stats.n_hit = N;
@@ -315,6 +317,41 @@ struct Session {
 			});
 		}, st);
 		if (bad.load()) PGX_FATAL("upload: a hit coordinate is outside [0, 2^31) or cs > ce -- this build keeps coordinates in int32");
+		coord_bits = bits_for((uint64_t)max_coord.load());
+	}
+	// device-ready records (pgx_packed.h) go into the staging ring as they are; the one thing still computed on the way is the largest coordinate
+	void upload_hits_packed(const pgx_packed_t *pk)
+	{
+		static_assert(sizeof(pgx_packed_hit_t) == sizeof(RawHit), "device-ready record == RawHit");
+		ThreadPool &pool = ThreadPool::get();
+		std::atomic<uint32_t> bad{0};
+		std::atomic<int32_t> max_coord{0};
+		const int64_t BLK = 1 << 14;
+		if (N) staged_h2d(raw.p, (size_t)N * sizeof(RawHit), sizeof(RawHit), [&](size_t off, size_t len, char *dst) {
+			const int64_t h0 = (int64_t)(off / sizeof(RawHit)), h1 = h0 + (int64_t)(len / sizeof(RawHit));
+			pool.parallel_for((h1 - h0 + BLK - 1) / BLK, [&](int64_t b) {
+				int64_t a = h0 + b * BLK;
+				const int64_t e = std::min(h1, a + BLK);
+				int g = (int)(std::upper_bound(h_hoff.begin(), h_hoff.end(), (int32_t)a) - h_hoff.begin()) - 1;
+				int32_t mc = 0; uint32_t err = 0;
+				while (a < e) {
+					while (a >= h_hoff[g + 1]) ++g;
+					const int64_t m = std::min<int64_t>(e, h_hoff[g + 1]) - a;
+					const pgx_packed_hit_t *sp = pk->hit[g] + (a - h_hoff[g]);
+					RawHit *o = (RawHit*)dst + (a - h0);
+					memcpy(o, sp, (size_t)m * sizeof(RawHit));
+					for (int64_t t = 0; t < m; ++t) {
+						if (sp[t].cs < 0 || sp[t].cm < 0 || sp[t].cs > sp[t].ce) err = 1;
+						if (sp[t].cm > mc) mc = sp[t].cm;
+						if (sp[t].cs > mc) mc = sp[t].cs;
+					}
+					a += m;
+				}
+				if (err) bad.store(1);
+				for (int32_t cur = max_coord.load(); mc > cur && !max_coord.compare_exchange_weak(cur, mc);) { }
+			});
+		}, st);
+		if (bad.load()) PGX_FATAL("upload: a packed hit has a negative coordinate or cs > ce");
 		coord_bits = bits_for((uint64_t)max_coord.load());
 	}
 	void upload_exons(const pg_data_t *d, cudaStream_t cs)
@@ -1449,6 +1486,7 @@ struct Session {
 	{
 		if (d->n_genome != G) PGX_FATAL("download: pg_data_t does not match the uploaded one");
 		ensure_rep();
+		if (with_hits && packed_input) PGX_FATAL("the hits of this run came as device-ready records (pgx_post_process_packed): there are no pg_hit_t records to rebuild -- use pgx_walk_tokens()");
 		if (Nw && with_hits) PGX_LAUNCH(k_scatter_back, grid_for(Nw, TB), TB, 0, st, A, Nw, F);
 		if (N && with_hits) {
 			DBuf<OutHit> out;

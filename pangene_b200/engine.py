@@ -43,6 +43,7 @@ def lib():
         L.pgx_walk_tokens.argtypes = [P(abi.pg_data_t), P(P(pgx_walk_token_t)), P(C.c_int64)]
         L.pgx_walk_tokens.restype = C.c_int64
         L.pgx_fetch_hits.argtypes = [P(abi.pg_data_t)]
+        L.pgx_post_process_packed.argtypes = [P(abi.pg_opt_t), P(abi.pg_data_t), P(abi.pgx_packed_t)]
         L.pgx_device_count.restype = C.c_int
         L.pgx_set_device.argtypes = [C.c_int]
         L.pgx_set_lazy.argtypes = [C.c_int]
@@ -84,13 +85,17 @@ def hot_path(opt, d, stop_after_post=False, lazy=False):
     return g
 
 
-def graph_and_tokens(opt, d):
+def graph_and_tokens(opt, d, packed=None):
     """The GFA-only route (lazy mode 2): the graph comes back, the hits stay on the device and only the walk tokens of the W lines
-    (12 bytes per printed hit) are read.  Returns (graph, tokens pointer, genome_off array, n_tokens); free with release_tokens()."""
+    (12 bytes per printed hit) are read.  packed: the hits as device-ready records (abi.pgx_packed_t from hostio.read_pafs_packed)
+    instead of d's pg_hit_t arrays.  Returns (graph, tokens pointer, genome_off array, n_tokens); free with release_tokens()."""
     L = lib()
     L.pgx_set_lazy(2)
     try:
-        L.pg_post_process(C.byref(opt), d)
+        if packed is not None:
+            L.pgx_post_process_packed(C.byref(opt), d, C.byref(packed))
+        else:
+            L.pg_post_process(C.byref(opt), d)
         g = L.pg_graph_init(d)
         L.pg_graph_gen(C.byref(opt), g)
         tok = C.POINTER(pgx_walk_token_t)()

@@ -22,6 +22,11 @@ def lib():
         L.pgio_read_paf.restype = C.c_int32
         L.pgio_read_pafs.argtypes = [P(abi.pg_opt_t), P(abi.pg_data_t), P(C.c_char_p), C.c_int32, C.c_int32]
         L.pgio_read_pafs.restype = C.c_int32
+        L.pgio_read_pafs_packed.argtypes = [P(abi.pg_opt_t), P(abi.pg_data_t), P(abi.pgx_packed_t), P(C.c_char_p), C.c_int32, C.c_int32]
+        L.pgio_read_pafs_packed.restype = C.c_int32
+        L.pgio_packed_destroy.argtypes = [P(abi.pgx_packed_t)]
+        L.pgio_packed_total_hits.argtypes = [P(abi.pgx_packed_t)]
+        L.pgio_packed_total_hits.restype = C.c_int64
         L.pgio_name_set.argtypes = [C.c_char_p]
         L.pgio_name_set.restype = C.c_void_p
         L.pgio_name_set_destroy.argtypes = [C.c_void_p]
@@ -68,6 +73,15 @@ def read_pafs(opt, files, threads=1):
         arr = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
         lib().pgio_read_pafs(C.byref(opt), d, arr, len(files), threads)
     return d
+
+
+def read_pafs_packed(opt, files, threads=0):
+    """the parallel reader emitting device-ready records (include/pgx_packed.h): returns (pg_data_t* without hit arrays, pgx_packed_t)"""
+    d = lib().pgio_data_init()
+    pk = abi.pgx_packed_t()
+    arr = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+    lib().pgio_read_pafs_packed(C.byref(opt), d, C.byref(pk), arr, len(files), threads)
+    return d, pk
 
 
 def synth_params(config=2, **kw):

@@ -329,3 +329,27 @@ def test_recycled_hit_arrays_keep_results_intact():
     for seed, (ng, hp) in enumerate([(6, 30000), (9, 12000), (4, 50000), (9, 12000)]):
         p = hostio.synth_params(2, n_genome=ng, n_gene=2500, iso_per_gene=4, hits_per_genome=hp, seed=11 + seed)
         check_against(opt, lambda: hostio.synth(opt, p), "oracle", lazy=bool(seed & 1))
+
+
+def test_packed_reader_route(tmp_path):
+    """SURVEY §8f row 1 end to end: PAF text -> device-ready records (pgio_read_pafs_packed) -> pgx_post_process_packed -> graph + walk tokens ->
+    GFA, without a single pg_hit_t record.  C4: the golden GFA byte for byte; synthetic PAF files: the oracle's GFA on the pg_hit_t route."""
+    import ctypes as C
+    opt = hostio.default_opt()
+    d, pk = hostio.read_pafs_packed(opt, common.c4_files(tmp_path))
+    g, tok, off, n = engine.graph_and_tokens(opt, d, packed=pk)
+    assert common.gfa_bytes_tokens(g, tok, off) == open(os.path.join(common.GOLDEN, "C4.gfa"), "rb").read()
+    engine.release_tokens(d, tok); engine.destroy(g); hostio.lib().pgio_packed_destroy(C.byref(pk)); hostio.destroy(d)
+    for args, p in [([], hostio.synth_params(2, n_genome=6, n_gene=1500, iso_per_gene=4, hits_per_genome=12000)),
+                    (["-p0", "-a2"], hostio.synth_params(5, n_genome=60, n_gene=800, iso_per_gene=1, hits_per_genome=700))]:
+        o = common.opt_from_args(args)
+        files = hostio.synth_write_pafs(o, p, str(tmp_path / ("paf%d" % p.shape)))
+        d1 = hostio.read_pafs(o, files)
+        g1 = pgoracle.hot_path(o, d1)
+        want = common.gfa_bytes(g1)
+        d2, pk = hostio.read_pafs_packed(o, files)
+        g2, tok, off, n = engine.graph_and_tokens(o, d2, packed=pk)
+        got = common.gfa_bytes_tokens(g2, tok, off)
+        assert sorted(got.splitlines()) == sorted(want.splitlines()), common.first_diff(want, got)
+        engine.release_tokens(d2, tok); engine.destroy(g2); hostio.lib().pgio_packed_destroy(C.byref(pk)); hostio.destroy(d2)
+        pgoracle.destroy(g1); hostio.destroy(d1)

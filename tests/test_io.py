@@ -100,6 +100,40 @@ def test_token_writers_equal_the_writers_on_materialised_hits(tmp_path):
         pgoracle.destroy(g); hostio.destroy(d)
 
 
+def test_packed_reader_emits_what_pg_post_process_would_pack(tmp_path):
+    """pgio_read_pafs_packed() writes the device-ready 48-byte records itself.  Field by field they must be what
+    libpgx packs out of the pg_hit_t records of pgio_read_pafs() (pgx_engine.cuh upload_hits), and every other table must be the same."""
+    import numpy as np
+    opt = hostio.default_opt()
+    sets = [common.c4_files(tmp_path),
+            hostio.synth_write_pafs(opt, hostio.synth_params(2, n_genome=5, n_gene=900, iso_per_gene=4, hits_per_genome=7000), str(tmp_path / "e")),
+            hostio.synth_write_pafs(opt, hostio.synth_params(5, n_genome=9, n_gene=400, iso_per_gene=1, hits_per_genome=300), str(tmp_path / "b"))]
+    HIT = np.dtype([(n, "<i4") for n in ("pid", "qs", "qe", "cid", "mlen", "blen", "lof", "rank", "score_ori", "score_adj", "score_dom", "n_exon", "off_exon", "pid_dom", "pid_dom0")]
+                   + [("bits", "<u4"), ("cs", "<i8"), ("cm", "<i8"), ("ce", "<i8")])
+    PK = np.dtype([(n, "<i4") for n in ("pid", "cid", "rank", "score_ori", "score_adj", "n_exon", "off_exon", "rev", "cs", "cm", "ce", "lof")])
+    for files in sets:
+        for threads in (1, 0):
+            d = hostio.read_pafs(opt, files, threads=0)
+            d2, pk = hostio.read_pafs_packed(opt, files, threads=threads)
+            a, b = d.contents, d2.contents
+            assert (a.n_genome, a.n_gene, a.n_prot) == (b.n_genome, b.n_gene, b.n_prot) and pk.n_genome == a.n_genome
+            assert hostio.lib().pgio_packed_total_hits(C.byref(pk)) == hostio.total_hits(d) > 0
+            assert [(a.prot[i].name, a.prot[i].gid, a.prot[i].len) for i in range(a.n_prot)] == [(b.prot[i].name, b.prot[i].gid, b.prot[i].len) for i in range(b.n_prot)]
+            assert [(a.gene[i].name, a.gene[i].bits) for i in range(a.n_gene)] == [(b.gene[i].name, b.gene[i].bits) for i in range(b.n_gene)]
+            for j in range(a.n_genome):
+                ga, gb = a.genome[j], b.genome[j]
+                assert gb.n_hit == 0 and not gb.hit and pk.n_hit[j] == ga.n_hit and ga.n_exon == gb.n_exon and ga.label == gb.label
+                assert [(ga.ctg[c].name, ga.ctg[c].len) for c in range(ga.n_ctg)] == [(gb.ctg[c].name, gb.ctg[c].len) for c in range(gb.n_ctg)]
+                assert C.string_at(ga.exon, ga.n_exon * 8) == C.string_at(gb.exon, gb.n_exon * 8)
+                h = np.frombuffer(C.string_at(ga.hit, ga.n_hit * 88), dtype=HIT)
+                p = np.frombuffer(C.string_at(pk.hit[j], ga.n_hit * 48), dtype=PK)
+                for f in ("pid", "cid", "rank", "score_ori", "score_adj", "n_exon", "off_exon", "lof", "cs", "cm", "ce"):
+                    assert (h[f] == p[f]).all(), f
+                assert ((h["bits"] & 1) == p["rev"]).all()
+            hostio.lib().pgio_packed_destroy(C.byref(pk))
+            hostio.destroy(d); hostio.destroy(d2)
+
+
 def test_libpgx_exports_every_declared_symbol():
     """the C-ABI library loads without a GPU and exports every function include/pgx.h declares (no compute call)"""
     hdr = open(os.path.join(ROOT, "include", "pgx.h")).read()
