@@ -1151,13 +1151,13 @@ struct Session {
 	struct Fast {
 		bool on = false, use_dirty = false;
 		int32_t NV = 0, tiles_hit = 0, tiles_vtx = 0, tiles_seg = 0;
-		uint32_t H = 0, H2 = 0, ovf_cap = 0, arc_cap = 0, nl_cap = 0, part_cap = 0;
+		uint32_t H = 0, H2 = 0, arc_cap = 0, nl_cap = 0, part_cap = 0;
 		size_t bm_words = 0, lb_bytes = 0, seen_words = 0, dirty_words = 0;
 		DBuf<unsigned long long> lkey, gkey, l2key, l2dsum, lb, nl_total;
 		DBuf<ArcAcc> lacc, gacc;
 		DBuf<uint32_t> llist, glist, bm, l2n, l2list, degcur, off, nl_off, seg_seen, spos, svcs, tie_list, dirty, rec, pos_of, seg_pos;
 		DBuf<int32_t> l2m, segocc, t_last, grp;
-		DBuf<SvInfo> info; DBuf<OvfRec> ovf; DBuf<uint8_t> nl; DBuf<GenePos> gpos; DBuf<ArcDev> arc_tmp; DBuf<ArcWire> all; DBuf<int2> reach;
+		DBuf<SvInfo> info; DBuf<uint8_t> nl; DBuf<GenePos> gpos; DBuf<ArcDev> arc_tmp; DBuf<ArcWire> all; DBuf<int2> reach;
 		ArcTable loc, glob; OvfTable l2;
 		unsigned long long *st_cm = nullptr, *st_vs = nullptr, *st_cs = nullptr, *st_sg = nullptr; uint32_t *tk_cm = nullptr, *tk_vs = nullptr, *tk_cs = nullptr, *tk_sg = nullptr, *n_keep = nullptr;
 	} fast;
@@ -1192,7 +1192,7 @@ struct Session {
 		uint32_t H = 1u << 16; while (H < want && H < (1u << 29)) H <<= 1;
 		int Gmax = 0; for (int g : rank_G) Gmax = g > Gmax? g : Gmax;
 		if ((uint64_t)H * (uint64_t)(Gmax > 0? Gmax : 1) / 8 > ((uint64_t)1 << 30)) return false;   // (key, genome) marks beyond 1 GB: stay on the sort path
-		f.H = H; f.H2 = 1u << 20; f.ovf_cap = 1u << 19;
+		f.H = H; f.H2 = 1u << 20;
 		f.bm_words = ((size_t)H * (size_t)(G > 0? G : 1) + 31) / 32;
 		f.bm_words = (f.bm_words + 3) & ~(size_t)3;
 		const bool multi = g_comm.active();
@@ -1210,7 +1210,7 @@ struct Session {
 		PGX_CHECK(cudaMemsetAsync(f.l2key.p, 0xff, (size_t)f.H2 * 8, st)); PGX_CHECK(cudaMemsetAsync(f.l2dsum.p, 0, (size_t)f.H2 * 8, st));
 		PGX_CHECK(cudaMemsetAsync(f.l2n.p, 0, (size_t)f.H2 * 4, st)); PGX_CHECK(cudaMemsetAsync(f.l2m.p, 0, (size_t)f.H2 * 8, st));
 		const size_t nw1 = (size_t)Nw + 16, tab = (size_t)n_gene * (size_t)(G > 0? G : 1);
-		f.rec.ensure(nw1); f.info.ensure(nw1); f.ovf.ensure((size_t)f.ovf_cap + 2); f.spos.ensure(nw1 + 2); f.svcs.ensure(nw1); f.tie_list.ensure(nw1); f.reach.ensure(nw1);
+		f.rec.ensure(nw1); f.info.ensure(nw1); f.spos.ensure(nw1 + 2); f.svcs.ensure(nw1); f.tie_list.ensure(nw1); f.reach.ensure(nw1);
 		f.degcur.ensure(2 * (size_t)f.NV + 8); f.off.ensure((size_t)f.NV + 8); f.nl_off.ensure((size_t)f.NV + 8); f.nl_total.ensure(2); f.seg_pos.ensure((size_t)n_seg0 + 8);
 		f.seen_words = (((size_t)(G > 0? G : 1) * n_seg0 + 31) / 32 + 4) & ~(size_t)3;
 		f.seg_seen.ensure(f.seen_words); f.segocc.ensure(2 * (size_t)n_seg0 + 4);
@@ -1300,8 +1300,7 @@ struct Session {
 		int32_t *seg_ng_f = f.segocc.p, *seg_tot_f = f.segocc.p + n_seg0;
 		PGX_LAUNCH(k_survivor_info, GS_GRID, TB, 0, st, e, dc.p, f.info.p, f.seg_seen.p, seg_ng_f, seg_tot_f, counters.p + C_ERR);
 		PGX_LAUNCH(k_arc_insert, GS_GRID, TB, 0, st, f.info.p, ctg2g.p, e.Gl, f.loc, dc.p, f.rec.p, multi? (uint32_t*)nullptr : deg, counters.p + C_TIE_CM);
-		PGX_LAUNCH(k_arc_fold, GS_GRID, TB, 0, st, f.info.p, f.rec.p, ctg2g.p, f.loc, dc.p, e.Gl, f.ovf.p, f.ovf_cap);
-		PGX_LAUNCH(k_arc_ovf_insert, 148, TB, 0, st, f.ovf.p, f.ovf_cap, f.l2, dc.p);
+		PGX_LAUNCH(k_arc_fold, GS_GRID, TB, 0, st, f.info.p, f.rec.p, ctg2g.p, f.loc, dc.p, e.Gl, f.l2);
 		PGX_LAUNCH(k_arc_ovf_fold, 148, TB, 0, st, f.l2, f.loc, dc.p);
 		pt.mark("arc:survivors+table", st);
 		if (multi) {
@@ -1316,8 +1315,7 @@ struct Session {
 		}
 		PGX_LAUNCH(k_vertex_scan, f.tiles_vtx, SCAN_B, 0, st, deg, f.NV, f.off.p, f.nl_off.p, dc.p, f.arc_cap, f.nl_total.p, f.st_vs, f.tk_vs);
 		PGX_LAUNCH(k_arc_place, GS_GRID, TB, 0, st, f.glob, dcp(multi? offsetof(DevCounts, n_gpart) : offsetof(DevCounts, n_part)), f.off.p, cur, dc.p, f.arc_tmp.p);
-		PGX_LAUNCH(k_arc_rank, GS_GRID, TB, 0, st, f.arc_tmp.p, f.off.p, dc.p, arc.p, idx.p, f.pos_of.p);
-		PGX_LAUNCH(k_seg_store_occ_fast, 148, TB, 0, st, seg.p, dc.p, seg_ng_f, seg_tot_f);
+		PGX_LAUNCH(k_arc_rank, GS_GRID, TB, 0, st, f.arc_tmp.p, f.off.p, dc.p, arc.p, idx.p, f.pos_of.p, seg.p, seg_ng_f, seg_tot_f);   // (+ graph.c:125-126: the occupancy of this build)
 		pt.mark("arc:scan+place+rank", st);
 		++g_stats.fast_rounds;
 	}
@@ -1366,9 +1364,9 @@ struct Session {
 		PGX_CHECK(cudaMemsetAsync(g2s.p, 0xff, (size_t)n_gene * 4, st));
 		PGX_LAUNCH(k_seg_keep_scan, f.tiles_seg, SCAN_B, 0, st, seg.p, dc.p, idx.p, max_avg_occ * Gtot, max_degree, max_dist_loci, f.seg_pos.p, f.n_keep, f.st_sg, f.tk_sg);
 		PGX_LAUNCH(k_seg_compact_fast, 148, TB, 0, st, seg.p, seg_alt.p, dc.p, f.seg_pos.p, f.n_keep, g2s.p);
-		PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_seg)), f.n_keep);
 		seg.swap(seg_alt);
-		if (Nw) PGX_LAUNCH(k_flag_vtx_fast, grid_for(Nw, TB), TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols());
+		if (Nw) PGX_LAUNCH(k_flag_vtx_fast, grid_for(Nw, TB), TB, 0, st, A.gidp, A.bits, Nw, g2s.p, dirty_cols(), dc.p, f.n_keep);   // (also stores the new segment count)
+		else PGX_LAUNCH(k_copy_u32, 1, 1, 0, st, dcp(offsetof(DevCounts, n_seg)), f.n_keep);
 		pt.mark("br:segfilter+vtx", st);
 	}
 

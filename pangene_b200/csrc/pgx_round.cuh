@@ -9,9 +9,9 @@
 //                                                        the DISTINCT keys (64-bit CAS); per (key, genome) a two-bit "seen once / seen again" mark
 //                                  k_arc_fold            a (key, genome) group with ONE record -- almost all of them -- is its own per-genome
 //                                                        collapse (graph.c:128-145: n = 1, dist = d, max scores = the scores): integer atomics
-//                                                        into the key's sums; records of larger groups go to an overflow list
-//                                  k_arc_ovf_insert/fold the overflow list is grouped by (key, genome) in a second small table (sum, count, max),
-//                                                        each group is collapsed with the reference's rounded mean and added to the key's sums
+//                                                        into the key's sums; records of larger groups are grouped by (key, genome) in a second
+//                                                        small table (sum, count, max)
+//                                  k_arc_ovf_fold        each such group is collapsed with the reference's rounded mean and added to the key's sums
 //                                  [N ranks: k_arc_pack -> one allgather -> k_arc_merge: the per-rank sums are integers, adding them is exact]
 //                                  k_vertex_scan         out-degree -> arc offsets (and the offsets of the n_local pair table), one pass
 //                                  k_arc_place/k_arc_rank counting sort by source vertex, rank by target inside a vertex: arc[] sorted by key
@@ -158,7 +158,6 @@ struct ArcTable {
 };
 struct SvInfo { uint32_t w; int32_t sc, cm, ctg; };             // a survivor as the arc walk sees it: oriented vertex (graph.c:112), score (graph.c:82-85), position, contig
 constexpr uint32_t REC_SWAP = 0x40000000u, REC_SELF = 0x80000000u, REC_SLOT = 0x3fffffffu;   // pair record: slot of the canonical key | canonical is the mirror | arc is its own mirror
-struct OvfRec { uint32_t slot; int32_t gl, d, a1, a2; };
 struct OvfTable { unsigned long long *key; uint32_t *n; unsigned long long *dsum; int32_t *m1, *m2; uint32_t *list; uint32_t H; };   // groups (slot, genome) of the overflow records
 
 __device__ __forceinline__ uint32_t hash_u64(unsigned long long k)
@@ -259,8 +258,35 @@ __global__ void k_arc_insert(const SvInfo *__restrict__ info, const int32_t *__r
 	}
 }
 
-// graph.c:128-145 for the groups of one record, graph.c:153-163 (the additive part) for all of them
-__global__ void k_arc_fold(const SvInfo *__restrict__ info, const uint32_t *__restrict__ rec, const int32_t *__restrict__ ctg2g, ArcTable T, DevCounts *dc, int32_t Gl, OvfRec *ovf, uint32_t ovf_cap)
+// A record of a (key, genome) group with several records (tandem duplicates: ~1 % of the records): the group is found -- or created -- in the
+// second, small table and the record is added to its sum / count / maxima (graph.c:131-135); k_arc_ovf_fold collapses the groups afterwards.
+__device__ __forceinline__ void ovf_group_add(const OvfTable &L, DevCounts *dc, uint32_t slot, int32_t gl, int32_t d, int32_t a1, int32_t a2)
+{
+	const unsigned long long k = (unsigned long long)slot << 32 | (uint32_t)gl;
+	uint32_t j = hash_u64(k) & (L.H - 1), found = ARC_NONE;
+	for (uint32_t probe = 0; probe < L.H; ++probe, j = (j + 1) & (L.H - 1)) {
+		unsigned long long cur = *(volatile unsigned long long*)&L.key[j];
+		if (cur == k) { found = j; break; }
+		if (cur == KEY_EMPTY) {
+			cur = atomicCAS(&L.key[j], KEY_EMPTY, k);
+			if (cur == KEY_EMPTY) {
+				const uint32_t id = atomicAdd(&dc->n_l2, 1u);
+				if (id < L.H) L.list[id] = j;
+				if (2ull * id >= L.H) dc->fallback = 1u;
+				found = j; break;
+			}
+			if (cur == k) { found = j; break; }
+		}
+	}
+	if (found == ARC_NONE) { dc->fallback = 1u; return; }
+	atomicAdd(&L.n[found], 1u);
+	atomicAdd(&L.dsum[found], (unsigned long long)(long long)d);                    // graph.c:133: uint64 sum of sign-extended distances
+	atomicMax(&L.m1[found], a1); atomicMax(&L.m2[found], a2);                       // graph.c:131,134-135: maxima start at 0
+}
+
+// graph.c:128-145 for the groups of one record, graph.c:153-163 (the additive part) for all of them; the records of larger groups go straight
+// into the overflow table (no list of them, no launch of its own)
+__global__ void k_arc_fold(const SvInfo *__restrict__ info, const uint32_t *__restrict__ rec, const int32_t *__restrict__ ctg2g, ArcTable T, DevCounts *dc, int32_t Gl, OvfTable L)
 {
 	const int32_t m = (int32_t)dc->m_sv;
 	PGX_GS(t, m) {
@@ -272,11 +298,9 @@ __global__ void k_arc_fold(const SvInfo *__restrict__ info, const uint32_t *__re
 		const int32_t s1 = (r & REC_SWAP)? b.sc : a.sc, s2 = (r & REC_SWAP)? a.sc : b.sc;   // graph.c:116,118: (s1, s2) of the canonical record
 		const size_t bit = (size_t)slot * Gl + gl;
 		if (T.bm2[bit >> 5] >> (bit & 31) & 1u) {
-			const uint32_t cnt = (r & REC_SELF)? 2u : 1u, id = atomicAdd(&dc->n_ovf, cnt);
-			if (id + cnt <= ovf_cap) {
-				OvfRec o; o.slot = slot; o.gl = gl; o.d = d; o.a1 = s1; o.a2 = s2; ovf[id] = o;
-				if (cnt == 2u) { o.a1 = s2; o.a2 = s1; ovf[id + 1] = o; }
-			} else dc->fallback = 1u;
+			atomicAdd(&dc->n_ovf, (r & REC_SELF)? 2u : 1u);                              // (statistics only)
+			ovf_group_add(L, dc, slot, gl, d, s1, s2);
+			if (r & REC_SELF) ovf_group_add(L, dc, slot, gl, d, s2, s1);                  // an arc that is its own mirror: both records of the pair
 		} else {
 			// one record: n = 1, dist = (int32)((double)d / 1 + .499) = d (d >= 0: survivors are in cm order), max scores start at 0 (graph.c:131)
 			ArcAcc *acc = &T.acc[slot];
@@ -287,33 +311,6 @@ __global__ void k_arc_fold(const SvInfo *__restrict__ info, const uint32_t *__re
 	}
 }
 
-__global__ void k_arc_ovf_insert(const OvfRec *__restrict__ ovf, uint32_t ovf_cap, OvfTable L, DevCounts *dc)
-{
-	const uint32_t n = dc->n_ovf < ovf_cap? dc->n_ovf : ovf_cap;
-	PGX_GS(i, n) {
-		const OvfRec r = ovf[i];
-		const unsigned long long k = (unsigned long long)r.slot << 32 | (uint32_t)r.gl;
-		uint32_t j = hash_u64(k) & (L.H - 1), found = ARC_NONE;
-		for (uint32_t probe = 0; probe < L.H; ++probe, j = (j + 1) & (L.H - 1)) {
-			unsigned long long cur = *(volatile unsigned long long*)&L.key[j];
-			if (cur == k) { found = j; break; }
-			if (cur == KEY_EMPTY) {
-				cur = atomicCAS(&L.key[j], KEY_EMPTY, k);
-				if (cur == KEY_EMPTY) {
-					const uint32_t id = atomicAdd(&dc->n_l2, 1u);
-					if (id < L.H) L.list[id] = j;
-					if (2ull * id >= L.H) dc->fallback = 1u;
-					found = j; break;
-				}
-				if (cur == k) { found = j; break; }
-			}
-		}
-		if (found == ARC_NONE) { dc->fallback = 1u; continue; }
-		atomicAdd(&L.n[found], 1u);
-		atomicAdd(&L.dsum[found], (unsigned long long)(long long)r.d);               // graph.c:133: uint64 sum of sign-extended distances
-		atomicMax(&L.m1[found], r.a1); atomicMax(&L.m2[found], r.a2);                // graph.c:131,134-135: maxima start at 0
-	}
-}
 // one thread per (key, genome) group of the overflow: the reference's per-genome collapse, then into the key's sums; the entry is
 // handed back empty, so the table needs no clearing between rounds
 __global__ void k_arc_ovf_fold(OvfTable L, ArcTable T, DevCounts *dc)
@@ -430,8 +427,10 @@ __global__ void k_arc_place(ArcTable T, const uint32_t *__restrict__ n_created, 
 		}
 	}
 }
-// pos_of[slot * 2 + is_mirror] = where the arc ended up (k_branch_hits_fast finds an adjacency's arcs through it)
-__global__ void k_arc_rank(const ArcDev *__restrict__ tmp, const uint32_t *__restrict__ off, const DevCounts *__restrict__ dc, ArcDev *arc, unsigned long long *idx, uint32_t *pos_of)
+// pos_of[slot * 2 + is_mirror] = where the arc ended up (k_branch_hits_fast finds an adjacency's arcs through it); the same launch stores
+// the segment occupancy of this arc build (graph.c:125-126; summed over ranks by then) -- independent work, one launch less per round
+__global__ void k_arc_rank(const ArcDev *__restrict__ tmp, const uint32_t *__restrict__ off, const DevCounts *__restrict__ dc, ArcDev *arc, unsigned long long *idx, uint32_t *pos_of,
+	SegDev *seg, const int32_t *__restrict__ ng, const int32_t *__restrict__ tot)
 {
 	PGX_GS(p, dc->n_arc) {
 		ArcDev a = tmp[p];
@@ -443,6 +442,7 @@ __global__ void k_arc_rank(const ArcDev *__restrict__ tmp, const uint32_t *__res
 		arc[b + rank] = a;
 		if (rank == 0) idx[v] = (unsigned long long)b << 32 | (e - b);                  // graph.c:202-211
 	}
+	if (seg) { PGX_GS(s, dc->n_seg) { seg[s].n_genome = ng[s]; seg[s].tot_cnt = tot[s]; } }
 }
 // ---- which tiles of the next overlap sweep can a changed hit influence? ---------------------------------------------------------------
 // A hit's sweep result (shadow bit, pid_dom; overlap.c:101-178) depends on its own flag word and on the flag words of its window partners,
@@ -606,10 +606,12 @@ __global__ void k_branch_hits_fast(const uint32_t *__restrict__ sv, const SvInfo
 		if (b != b_in) { bits[h] = b; atomicAdd(n_changed, 1u); if (D.tiles) mark_dirty(D, (int32_t)h); }
 	}
 }
-// graph.c:61-69 + PG_SET_FILTER(vtx == 0) (graph.c:312)
-__global__ void k_flag_vtx_fast(const int32_t *__restrict__ gidp, uint32_t *bits, int32_t n, const int32_t *__restrict__ g2s, DirtyCols D)
+// graph.c:61-69 + PG_SET_FILTER(vtx == 0) (graph.c:312).  n_seg_new (optional): the segment count after the compaction that precedes this
+// launch (k_seg_compact_fast still read the old count; nothing in this kernel reads either) -- stored by one thread instead of a launch of its own
+__global__ void k_flag_vtx_fast(const int32_t *__restrict__ gidp, uint32_t *bits, int32_t n, const int32_t *__restrict__ g2s, DirtyCols D, DevCounts *dc, const uint32_t *__restrict__ n_seg_new)
 {
 	const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0 && n_seg_new) dc->n_seg = *n_seg_new;
 	if (i >= n) return;
 	const uint32_t b_in = bits[i];
 	uint32_t b = b_in;
@@ -660,10 +662,6 @@ __global__ void k_seg_compact_fast(const SegDev *__restrict__ in, SegDev *out, D
 {
 	const int32_t n_seg = (int32_t)dc->n_seg;                  // (the count is replaced by the LAST block to finish reading it: a separate launch does it)
 	PGX_GS(s, n_seg) { const uint32_t p = pos[s]; if (p != ARC_NONE) { const SegDev r = in[s]; out[p] = r; g2s[r.gid] = (int32_t)p; } }
-}
-__global__ void k_seg_store_occ_fast(SegDev *seg, const DevCounts *__restrict__ dc, const int32_t *__restrict__ ng, const int32_t *__restrict__ tot)
-{
-	PGX_GS(s, dc->n_seg) { seg[s].n_genome = ng[s]; seg[s].tot_cnt = tot[s]; }
 }
 // [emu-end round]
 

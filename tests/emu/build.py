@@ -148,7 +148,7 @@ ROUND_DRIVER = r'''
 // host driver in the shape of Session::gen_arc_fast (pgx_engine.cuh): one arc build of `ranks` virtual ranks that own consecutive genome
 // ranges of the same survivor list; the allgather between k_arc_pack and k_arc_merge is a memcpy
 struct EmuArcIn {
-	int32_t n_hit, n_sv, n_seg0, n_gene, G, use_ori, grid, H, H2, ovf_cap, arc_cap, ranks;
+	int32_t n_hit, n_sv, n_seg0, n_gene, G, use_ori, grid, H, H2, arc_cap, ranks;
 	const uint32_t *sv, *bits; const int32_t *ctg, *cm, *gidp, *sori, *sdom, *pdom0, *g2s, *prot_gid, *ctg2g;
 	pgx::ArcDev *arc; unsigned long long *idx; int32_t *seg_ng, *seg_tot; uint32_t *nl_off; uint32_t *out_counts;   // out_counts: n_arc, n_nl, fallback, n_ovf
 };
@@ -183,7 +183,7 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 		if (R > 1) { gkey[r].assign(in->H, KEY_EMPTY); gacc[r].assign(in->H, ArcAcc{0, 0, 0}); glist[r].assign(in->H, 0); glob[r].key = gkey[r].data(); glob[r].acc = gacc[r].data(); glob[r].list = glist[r].data(); glob[r].bm1 = glob[r].bm2 = nullptr; }
 		std::vector<unsigned long long> l2key(in->H2, KEY_EMPTY), l2d(in->H2, 0); std::vector<uint32_t> l2n(in->H2, 0), l2list(in->H2, 0); std::vector<int32_t> l2m(2 * (size_t)in->H2, 0);
 		OvfTable L; L.key = l2key.data(); L.dsum = l2d.data(); L.n = l2n.data(); L.list = l2list.data(); L.m1 = l2m.data(); L.m2 = l2m.data() + in->H2; L.H = in->H2;
-		std::vector<uint32_t> rec(sv.size() + 1); std::vector<SvInfo> info(sv.size() + 1); std::vector<OvfRec> ovf(in->ovf_cap + 2);
+		std::vector<uint32_t> rec(sv.size() + 1); std::vector<SvInfo> info(sv.size() + 1);
 		uint32_t tie = 0, err = 0;
 		ArcSrc e; e.sv = sv.data(); e.ctg = in->ctg; e.cm = in->cm; e.gidp = in->gidp; e.sori = in->sori; e.sdom = in->sdom; e.pdom0 = in->pdom0; e.bits = in->bits;
 		e.g2s = in->g2s; e.prot_gid = in->prot_gid; e.ctg2g = ctg2g_loc.data(); e.use_ori = in->use_ori; e.n_seg0 = in->n_seg0; e.Gl = Gl;
@@ -192,8 +192,7 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 		int32_t *ng = segocc[r].data(), *tot = segocc[r].data() + in->n_seg0;
 		emu::launch(grid, TBk, [&] { k_survivor_info(e, dc, info.data(), seen[r].data(), ng, tot, &err); });
 		emu::launch(grid, TBk, [&] { k_arc_insert(info.data(), ctg2g_loc.data(), Gl, loc[r], dc, rec.data(), R > 1? (uint32_t*)nullptr : deg, &tie); });
-		emu::launch(grid, TBk, [&] { k_arc_fold(info.data(), rec.data(), ctg2g_loc.data(), loc[r], dc, Gl, ovf.data(), (uint32_t)in->ovf_cap); });
-		emu::launch(2, TBk, [&] { k_arc_ovf_insert(ovf.data(), (uint32_t)in->ovf_cap, L, dc); });
+		emu::launch(grid, TBk, [&] { k_arc_fold(info.data(), rec.data(), ctg2g_loc.data(), loc[r], dc, Gl, L); });
 		emu::launch(2, TBk, [&] { k_arc_ovf_fold(L, loc[r], dc); });
 		for (uint32_t j = 0; j < L.H; ++j) if (l2key[j] != KEY_EMPTY || l2n[j] || l2d[j] || l2m[j] || l2m[j + in->H2]) return -2;   // the overflow table hands itself back clean
 		if (err) return -3;
@@ -214,7 +213,10 @@ extern "C" int round_emu_arc_build(const EmuArcIn *in)
 		std::vector<unsigned long long> idx(NV + 2, 0ull);
 		emu::launch(tiles, SCAN_B, [&] { k_vertex_scan(deg, NV, off.data(), nl_off.data(), dc, (uint32_t)in->arc_cap, &nl_total, status.data(), &ticket); });
 		emu::launch(grid, TBk, [&] { k_arc_place(glob[r], R > 1? &dc->n_gpart : &dc->n_part, off.data(), cur, dc, tmp.data()); });
-		emu::launch(grid, TBk, [&] { k_arc_rank(tmp.data(), off.data(), dc, arc.data(), idx.data(), pos_of.data()); });
+		std::vector<SegDev> segs(in->n_seg0 + 1);
+		for (auto &sg : segs) { sg.n_genome = -7; sg.tot_cnt = -7; }
+		emu::launch(grid, TBk, [&] { k_arc_rank(tmp.data(), off.data(), dc, arc.data(), idx.data(), pos_of.data(), segs.data(), occ.data(), occ.data() + in->n_seg0); });
+		for (int sgi = 0; sgi < in->n_seg0; ++sgi) if (segs[sgi].n_genome != occ[sgi] || segs[sgi].tot_cnt != occ[in->n_seg0 + sgi]) return -7;   // the occupancy stored beside the ranking
 		if (nl_total != dc->n_nl) return -4;
 		// every arc is found again through the key table (what k_branch_hits_fast does)
 		for (uint32_t p = 0; p < dc->n_arc && !dc->fallback; ++p) {

@@ -18,7 +18,7 @@ SEG = np.dtype([("gid", "<i4"), ("n_dom", "<i4"), ("n_sub", "<i4"), ("n_genome",
 
 
 class EmuArcIn(C.Structure):
-    _fields_ = [(k, C.c_int32) for k in ("n_hit", "n_sv", "n_seg0", "n_gene", "G", "use_ori", "grid", "H", "H2", "ovf_cap", "arc_cap", "ranks")] + \
+    _fields_ = [(k, C.c_int32) for k in ("n_hit", "n_sv", "n_seg0", "n_gene", "G", "use_ori", "grid", "H", "H2", "arc_cap", "ranks")] + \
                [(k, C.c_void_p) for k in ("sv", "bits", "ctg", "cm", "gidp", "sori", "sdom", "pdom0", "g2s", "prot_gid", "ctg2g", "arc", "idx", "seg_ng", "seg_tot", "nl_off", "out_counts")]
 
 
@@ -124,7 +124,7 @@ def test_arc_build_matches_graph_c(emu, seed, G, n_seg0, n_per, dup, ranks, use_
     nl_off = np.zeros(2 * n_seg0 + 8, np.uint32); out = np.zeros(4, np.uint32)
     H = 1
     while H < 4 * max(len(want), 8): H *= 2
-    e = EmuArcIn(n_hit=n, n_sv=len(sv), n_seg0=n_seg0, n_gene=n_gene, G=G, use_ori=use_ori, grid=3, H=H, H2=8192, ovf_cap=4 * len(sv) + 8, arc_cap=arc_cap, ranks=ranks)
+    e = EmuArcIn(n_hit=n, n_sv=len(sv), n_seg0=n_seg0, n_gene=n_gene, G=G, use_ori=use_ori, grid=3, H=H, H2=8192, arc_cap=arc_cap, ranks=ranks)
     keepalive = [sv, arc, idx, seg_ng, seg_tot, nl_off, out]
     for k in ("ctg", "cm", "gidp", "sori", "sdom", "pdom0", "g2s", "prot_gid", "ctg2g", "bits"):
         setattr(e, k, cols[k].ctypes.data)
@@ -157,7 +157,7 @@ def test_arc_build_raises_fallback_on_cm_tied_survivors(emu):
     assert np.any((np.diff(cols["cm"][sv].astype(np.int64)) == 0) & (np.diff(cols["ctg"][sv]) == 0))
     arc_cap = 4 * len(sv) + 16
     arc = np.zeros(arc_cap, dtype=ARC); idx = np.zeros(82, np.uint64); seg_ng = np.zeros(40, np.int32); seg_tot = np.zeros(40, np.int32); nl_off = np.zeros(88, np.uint32); out = np.zeros(4, np.uint32)
-    e = EmuArcIn(n_hit=len(cols["ctg"]), n_sv=len(sv), n_seg0=40, n_gene=n_gene, G=4, use_ori=0, grid=2, H=4096, H2=256, ovf_cap=4 * len(sv) + 8, arc_cap=arc_cap, ranks=1)
+    e = EmuArcIn(n_hit=len(cols["ctg"]), n_sv=len(sv), n_seg0=40, n_gene=n_gene, G=4, use_ori=0, grid=2, H=4096, H2=256, arc_cap=arc_cap, ranks=1)
     for k in ("ctg", "cm", "gidp", "sori", "sdom", "pdom0", "g2s", "prot_gid", "ctg2g", "bits"):
         setattr(e, k, cols[k].ctypes.data)
     e.sv = sv.ctypes.data; e.arc = arc.ctypes.data; e.idx = idx.ctypes.data; e.seg_ng = seg_ng.ctypes.data; e.seg_tot = seg_tot.ctypes.data
@@ -171,7 +171,7 @@ def test_arc_build_raises_fallback_when_the_table_is_too_small(emu):
     cols, sv, n_gene = make_case(rng, 4, 40, 150, 0.1)
     arc_cap = 4 * len(sv) + 16
     arc = np.zeros(arc_cap, dtype=ARC); idx = np.zeros(82, np.uint64); seg_ng = np.zeros(40, np.int32); seg_tot = np.zeros(40, np.int32); nl_off = np.zeros(88, np.uint32); out = np.zeros(4, np.uint32)
-    e = EmuArcIn(n_hit=len(cols["ctg"]), n_sv=len(sv), n_seg0=40, n_gene=n_gene, G=4, use_ori=0, grid=2, H=64, H2=256, ovf_cap=4 * len(sv) + 8, arc_cap=arc_cap, ranks=1)
+    e = EmuArcIn(n_hit=len(cols["ctg"]), n_sv=len(sv), n_seg0=40, n_gene=n_gene, G=4, use_ori=0, grid=2, H=64, H2=256, arc_cap=arc_cap, ranks=1)
     for k in ("ctg", "cm", "gidp", "sori", "sdom", "pdom0", "g2s", "prot_gid", "ctg2g", "bits"):
         setattr(e, k, cols[k].ctypes.data)
     e.sv = sv.ctypes.data; e.arc = arc.ctypes.data; e.idx = idx.ctypes.data; e.seg_ng = seg_ng.ctypes.data; e.seg_tot = seg_tot.ctypes.data
