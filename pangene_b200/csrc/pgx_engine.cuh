@@ -38,6 +38,7 @@ extern Stats g_stats;
 extern int g_sweep_stat;
 
 constexpr int TB = 256;   // default block size for the streaming kernels
+constexpr int SWEEP_VARIANT_DEFAULT = 1;   // k_sweep_tiled variant (launch_sweep; PGX_SWEEP_VARIANT overrides)
 
 // fresh hit arrays for the caller (it will free() them): 2 MB-aligned and advised huge so that the ~430 k first-touch page
 // faults of a 1.8 GB result become ~900 where transparent huge pages are available (no effect otherwise)
@@ -398,20 +399,26 @@ struct Session {
 		static const bool plain = []() { const char *e = getenv("PGX_SWEEP"); return e && strcmp(e, "global") == 0; }();
 		if (c.n <= 0) return;
 		if (plain) { PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP); return; }
+		// PGX_SWEEP_VARIANT: the A/B switch of k_sweep_tiled (pgx_kernels.cuh): 0 = the kernel as first measured in round 2, 1 (default) = 32-bit cluster
+		// maxima + staged result columns, isoform sweep on the window scan, 2 = as 1 with the isoform sweep on the cluster shortcut
+		static const int variant = []() { const char *e = getenv("PGX_SWEEP_VARIANT"); const int v = e? atoi(e) : SWEEP_VARIANT_DEFAULT; return v < 0 || v > 2? SWEEP_VARIANT_DEFAULT : v; }();
+		constexpr int V2 = MODE == SW_ISO? 2 : 1;   // (variant 2 differs from 1 in the isoform sweep only)
 		static int attr_dev = -1;              // (function attributes are per device: set again if the process moved to another one)
 		int cur_dev = 0; PGX_CHECK(cudaGetDevice(&cur_dev));
-		const bool attr_set = attr_dev == cur_dev;
-		if (!attr_set) {
-			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
-			// five 42 KB CTAs per SM need the large shared-memory carve-out (ncu: the default left room for three)
-			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_LOAD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-			PGX_CHECK(cudaFuncSetAttribute(k_sweep_tiled<SW_ISO>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+		if (attr_dev != cur_dev) {
+			// five 46 KB CTAs per SM need the large shared-memory carve-out (ncu: the default left room for three)
+			auto prep = [](const void *fn) {
+				PGX_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWQ_SMEM));
+				PGX_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+			};
+			prep((const void*)k_sweep_tiled<MODE, 0>);
+			if (MODE != SW_SHADOW) { prep((const void*)k_sweep_tiled<MODE, 1>); prep((const void*)k_sweep_tiled<MODE, V2>); }
 			attr_dev = cur_dev;
 		}
-		PGX_LAUNCH(k_sweep_tiled<MODE>, grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
+		const int v = MODE == SW_SHADOW? 0 : variant;
+		if (v == 0) PGX_LAUNCH((k_sweep_tiled<MODE, 0>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
+		else if (v == 1) PGX_LAUNCH((k_sweep_tiled<MODE, 1>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
+		else PGX_LAUNCH((k_sweep_tiled<MODE, V2>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
 	}
 
 	// stable radix sort of n (key, iota) pairs taken from the scratch arena; returns the permutation (device pointer valid until the arena is reset)

@@ -493,8 +493,15 @@ template<bool EARLY> __device__ __forceinline__ int32_t pair_overlap(const int2 
 
 // dirty (optional, SW_SHADOW with bits_out == c.bits): one bit per tile; a tile whose bit is clear holds no hit whose inputs changed since the
 // previous sweep (pgx_round.cuh: mark_dirty) and keeps its shadow bits and dominators.
-template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt, const uint32_t *dirty)
+// VAR (profiles/README.md has the A/B numbers): 0 = the round-2 kernel as first measured (64-bit cluster maxima by compare-and-swap loops, pid / score
+// columns read from global memory when a result is written, the isoform sweep on the cluster shortcut); 1 = cluster maxima on the upper key
+// word with native 32-bit shared-memory atomics (a tie of that word at the top of a cluster sends its hits to the exact window scan), holder
+// count and slot in ONE atomic, the pid / score_ori columns staged beside the others (no global load on the result path), warp prefixes from
+// one 128-bit load, no flag-word store in SW_LOAD (the isoform sweep that follows writes every flag word), the isoform sweep on the window scan;
+// 2 = as 1 with the isoform sweep on the cluster shortcut.  SW_SHADOW is the same code for every VAR.
+template<int MODE, int VAR> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt, const uint32_t *dirty)
 {
+	constexpr bool NEWP0 = VAR != 0 && MODE != SW_SHADOW;                                // the new cluster pass + staged result columns
 	if (dirty && !(dirty[blockIdx.x >> 5] >> (blockIdx.x & 31) & 1u)) return;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	unsigned char *sp = smem_raw;
@@ -511,11 +518,17 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	uint64_t *bar = (uint64_t*)sp; sp += 8;
 	uint32_t *s_misc = (uint32_t*)sp;                                                    // [0],[1]: staged exon range
 	__shared__ uint16_t s_cst[SWQ_STG + 8];      // s_cst[q]: first staged slot of the overlap cluster that slot q belongs to
-	__shared__ unsigned long long s_cmax[SWQ_STG + 8];   // at a cluster's first slot: the largest key in the cluster ...
-	__shared__ uint32_t s_ctop[SWQ_STG + 8];     // ... the leftmost slot that holds it ...
-	__shared__ uint32_t s_ccnt[SWQ_STG + 8];     // ... and how many slots hold it
-	__shared__ int32_t s_wmax[SWQ_TILE / 32];
-	__shared__ uint16_t s_wcnt[SWQ_TILE / 32], s_live[SWQ_TILE];
+	constexpr int P0N = SWQ_STG + 8;             // 400 entries; every quarter of s_p0 below starts on a 16-byte boundary
+	__shared__ __align__(16) unsigned char s_p0[P0N * 16];
+	// VAR 0: at a cluster's first slot the largest key in the cluster (64 bit), the leftmost slot that holds it, how many slots hold it
+	unsigned long long *s_cmax = (unsigned long long*)s_p0;
+	uint32_t *s_ctop = (uint32_t*)(s_p0 + P0N * 8), *s_ccnt = (uint32_t*)(s_p0 + P0N * 12);
+	// VAR 1, 2: the largest UPPER key word (score_adj << 1 | preferred) of the cluster, holders << 16 | sum of their slots; staged score_ori and pid
+	uint32_t *s_chi = (uint32_t*)s_p0, *s_cinfo = (uint32_t*)(s_p0 + P0N * 4);
+	int32_t *s_sori = (int32_t*)(s_p0 + P0N * 8), *s_pid = (int32_t*)(s_p0 + P0N * 12);
+	__shared__ __align__(16) int32_t s_wmax[SWQ_TILE / 32];
+	__shared__ __align__(16) uint16_t s_wcnt[SWQ_TILE / 32];
+	__shared__ uint16_t s_live[SWQ_TILE];
 	__shared__ uint32_t s_hist[64], s_job[SWQ_TILE], s_njob, s_flags;
 
 	const int32_t t0 = blockIdx.x * SWQ_TILE, tid = threadIdx.x;
@@ -533,7 +546,8 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 		if (ne > SWQ_EXCAP) ne = SWQ_EXCAP;
 		s_misc[0] = e0; s_misc[1] = e0 + ne;
 		fence_proxy_async();
-		mbar_expect_tx(bar, (uint32_t)cnt4 * 4u * 7u + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
+		mbar_expect_tx(bar, (uint32_t)cnt4 * 4u * (7u + (NEWP0 && MODE == SW_LOAD? 2u : 0u)) + (uint32_t)cnt4 * 8u + (uint32_t)cnte * 4u + ne * 8u);
+		if (NEWP0 && MODE == SW_LOAD) { bulk_g2s(s_sori, c.sori + lo, cnt4 * 4, bar); bulk_g2s(s_pid, c.pid + lo, cnt4 * 4, bar); }
 		bulk_g2s(s_ctg, c.ctg + lo, cnt4 * 4, bar); bulk_g2s(s_cs, c.cs + lo, cnt4 * 4, bar); bulk_g2s(s_ce, c.ce + lo, cnt4 * 4, bar);
 		bulk_g2s(s_pmax, c.pmax + lo, cnt4 * 4, bar); bulk_g2s(s_gidp, c.gidp + lo, cnt4 * 4, bar); bulk_g2s(s_cds, c.cds + lo, cnt4 * 4, bar);
 		bulk_g2s(s_bits, c.bits + lo, cnt4 * 4, bar); bulk_g2s(s_key, c.key + lo, cnt4 * 8, bar);
@@ -551,12 +565,12 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	// Only usable where the loser of a pair is decided by the keys alone, i.e. where no unfiltered hit of the tile carries a weak_br mark
 	// (overlap.c:139-147): flag 1.
 	const int32_t S = hi - lo;
-	const bool rmq_mode = (MODE == SW_LOAD || MODE == SW_ISO) && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
+	const bool rmq_mode = (MODE == SW_LOAD || (MODE == SW_ISO && VAR != 1)) && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
 	// filtered hits (25 % in the first sweep) do no work: the live ones are compacted so that they fill whole warps.
 	const int32_t i0 = t0 + tid;
 	const bool r0 = i0 < c.n;
 	const uint32_t bits0 = s_bits[r0? i0 - lo : 0];
-	if (r0 && (bits0 & PG_HB_FLT)) bits_out[i0] = bits0;                                 // overlap.c:63,112
+	if (!(NEWP0 && MODE == SW_LOAD) && r0 && (bits0 & PG_HB_FLT)) bits_out[i0] = bits0;  // overlap.c:63,112
 	const bool live0 = r0 && !(bits0 & PG_HB_FLT);
 	const uint32_t bal = __ballot_sync(0xffffffffu, live0);
 	if ((tid & 31) == 0) s_wcnt[tid >> 5] = (uint16_t)__popc(bal);
@@ -564,6 +578,10 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	if (rmq_mode) {
 		uint32_t flags = 0;
 		const int32_t q0 = 2 * tid, q1 = q0 + 1;
+		if (NEWP0) {   // every slot starts out as an empty cluster head: no barrier between finding the heads and the first atomics below
+			if (q0 < S) { s_chi[q0] = 0u; s_cinfo[q0] = 0u; }
+			if (q1 < S) { s_chi[q1] = 0u; s_cinfo[q1] = 0u; }
+		}
 		if (q0 < S) {
 			const uint32_t bq = s_bits[q0];
 			if (!(bq & PG_HB_FLT) && (bq & PG_HB_WBR_MASK)) flags |= 1u;
@@ -586,22 +604,65 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	int32_t n_live = 0;
 	{
 		int32_t base = 0;
+		if (NEWP0) {   // the eight 16-bit warp counts in one 128-bit load; counts are <= 32, so the packed halves add without carries
+			static_assert(SWQ_TILE / 32 == 8, "eight warps");
+			const uint4 v = *(const uint4*)s_wcnt;
+			const int W = tid >> 5;
+			const uint32_t all = v.x + v.y + v.z + v.w;
+			n_live = (int32_t)((all & 0xffffu) + (all >> 16));
+			uint32_t pre = (W >= 2? v.x : 0u) + (W >= 4? v.y : 0u) + (W >= 6? v.z : 0u);   // whole words before mine
+			const uint32_t mine = W < 2? v.x : W < 4? v.y : W < 6? v.z : v.w;
+			pre += (W & 1)? (mine & 0xffffu) : 0u;                                         // the even warp of my word precedes the odd one
+			base = (int32_t)((pre & 0xffffu) + (pre >> 16));
+		} else {
 #pragma unroll
-		for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
+			for (int w = 0; w < SWQ_TILE / 32; ++w) { if (w < (tid >> 5)) base += s_wcnt[w]; n_live += s_wcnt[w]; }
+		}
 		if (live0) s_live[base + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint16_t)tid;
 	}
 	if (rmq_mode) {
 		int32_t carry = -1;
+		if (NEWP0) {
+			const int4 a = *(const int4*)s_wmax, b = *(const int4*)(s_wmax + 4);
+			const int W = tid >> 5;
+			if (W > 0 && a.x > carry) carry = a.x;
+			if (W > 1 && a.y > carry) carry = a.y;
+			if (W > 2 && a.z > carry) carry = a.z;
+			if (W > 3 && a.w > carry) carry = a.w;
+			if (W > 4 && b.x > carry) carry = b.x;
+			if (W > 5 && b.y > carry) carry = b.y;
+			if (W > 6 && b.z > carry) carry = b.z;
+		} else {
 #pragma unroll
-		for (int w = 0; w < SWQ_TILE / 32; ++w) if (w < (tid >> 5) && s_wmax[w] > carry) carry = s_wmax[w];
+			for (int w = 0; w < SWQ_TILE / 32; ++w) if (w < (tid >> 5) && s_wmax[w] > carry) carry = s_wmax[w];
+		}
 		if (carry > cst0) cst0 = carry;
 		if (carry > cst1) cst1 = carry;
 		const int32_t q0 = 2 * tid, q1 = q0 + 1;
-		if (q0 < S) { s_cst[q0] = (uint16_t)cst0; if (s_bits[q0] & PG_HB_FLT) s_key[q0] = 0ull; if (cst0 == q0) { s_cmax[q0] = 0ull; s_ctop[q0] = 0xffffffffu; s_ccnt[q0] = 0u; } }
-		if (q1 < S) { s_cst[q1] = (uint16_t)cst1; if (s_bits[q1] & PG_HB_FLT) s_key[q1] = 0ull; if (cst1 == q1) { s_cmax[q1] = 0ull; s_ctop[q1] = 0xffffffffu; s_ccnt[q1] = 0u; } }
+		if (NEWP0) {
+			if (q0 < S) { s_cst[q0] = (uint16_t)cst0; if (s_bits[q0] & PG_HB_FLT) s_key[q0] = 0ull; }
+			if (q1 < S) { s_cst[q1] = (uint16_t)cst1; if (s_bits[q1] & PG_HB_FLT) s_key[q1] = 0ull; }
+		} else {
+			if (q0 < S) { s_cst[q0] = (uint16_t)cst0; if (s_bits[q0] & PG_HB_FLT) s_key[q0] = 0ull; if (cst0 == q0) { s_cmax[q0] = 0ull; s_ctop[q0] = 0xffffffffu; s_ccnt[q0] = 0u; } }
+			if (q1 < S) { s_cst[q1] = (uint16_t)cst1; if (s_bits[q1] & PG_HB_FLT) s_key[q1] = 0ull; if (cst1 == q1) { s_cmax[q1] = 0ull; s_ctop[q1] = 0xffffffffu; s_ccnt[q1] = 0u; } }
+		}
 	}
-	__syncthreads();
-	if (rmq_mode) {   // strongest hit of every cluster: maximum of the key, then the leftmost slot that holds it and how many do (shared-memory atomics)
+	if (!(NEWP0 && rmq_mode)) __syncthreads();   // (block-uniform; the new cluster pass goes straight on: its tables were zeroed before the barrier above, and it reads only its own two slots until the next one)
+	if (rmq_mode && NEWP0) {
+		// strongest hit of every cluster, with native 32-bit atomics: the maximum of the UPPER key word (score_adj << 1 | preferred), then one
+		// add per holder of that maximum: holders << 16 | sum of their slots.  One holder: the low half IS its slot, and it holds the largest
+		// 64-bit key of the cluster (a larger key would have a larger or equal upper word).  Several holders (equal adjusted scores at the top
+		// of a cluster: 0.3 % of the clusters of the bench workload) or none: the hits of the cluster take the window scan, which is exact.
+		const int32_t q0 = 2 * tid, q1 = q0 + 1;
+		const unsigned long long k0 = q0 < S? s_key[q0] : 0ull, k1 = q1 < S? s_key[q1] : 0ull;
+		const uint32_t h0 = (uint32_t)(k0 >> 32), h1 = (uint32_t)(k1 >> 32);
+		if (k0) atomicMax(&s_chi[cst0], h0);
+		if (k1) atomicMax(&s_chi[cst1], h1);
+		__syncthreads();
+		if (k0 && h0 == s_chi[cst0]) atomicAdd(&s_cinfo[cst0], 0x10000u + (uint32_t)q0);
+		if (k1 && h1 == s_chi[cst1]) atomicAdd(&s_cinfo[cst1], 0x10000u + (uint32_t)q1);
+		__syncthreads();
+	} else if (rmq_mode) {   // strongest hit of every cluster: maximum of the key, then the leftmost slot that holds it and how many do (shared-memory atomics)
 		const int32_t q0 = 2 * tid, q1 = q0 + 1;
 		const unsigned long long k0 = q0 < S? s_key[q0] : 0ull, k1 = q1 < S? s_key[q1] : 0ull;
 		if (k0) atomicMax(&s_cmax[cst0], k0);
@@ -632,11 +693,13 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 			bits_out[h] = b;
 			pdom_out[h] = (lose && dom)? c.pid[top] : -1;
 		} else {
-			bits_out[h] = hbits;
+			if (!NEWP0) bits_out[h] = hbits;                                              // (unchanged; the isoform sweep that follows writes every flag word)
 			int32_t pd = -1, sd = -1;
 			if (lose && dom) {
-				pd = c.pid[top];
-				sd = (int32_t)(c.sori[h] * (1.0 - (double)ov / s_cds[hq]) + c.sori[top] * ((double)ov / s_cds[top - lo]) + .499);   // overlap.c:170
+				// overlap.c:170; `top` is a staged hit on this path, so with NEWP0 its pid and score come out of shared memory
+				const int32_t so_h = NEWP0? s_sori[hq] : c.sori[h], so_t = NEWP0? s_sori[top - lo] : c.sori[top];
+				pd = NEWP0? s_pid[top - lo] : c.pid[top];
+				sd = (int32_t)(so_h * (1.0 - (double)ov / s_cds[hq]) + so_t * ((double)ov / s_cds[top - lo]) + .499);
 			}
 			pdom_out[h] = pd; sdom_out[h] = sd;
 		}
@@ -650,13 +713,15 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 	bool scan = true;
 	if (rmq_mode && (MODE == SW_ISO || !(s_flags & 1u))) {   // (the isoform filter compares keys whatever the weak_br marks say, overlap.c:82-84)
 		const int32_t head = s_cst[mq];
-		const uint32_t tq = s_ctop[head];
+		const uint32_t info = NEWP0? s_cinfo[head] : 0u;
+		const uint32_t n_top = NEWP0? info >> 16 : s_ccnt[head];
+		const uint32_t tq = NEWP0? (n_top? info & 0xffffu : 0xffffffffu) : s_ctop[head];
 		scan = false;
 		if ((head == 0 && lo > 0) || (head == (int32_t)s_cst[S - 1] && hi < c.n)) slow = true;   // the cluster (and with it possibly my window) may continue outside the staged range
-		else if (s_ccnt[head] > 1u) scan = true;                                          // the strongest key occurs twice
+		else if (n_top > 1u) scan = true;                                                 // the strongest key (NEWP0: its upper word) occurs twice
 		else if (tq == (uint32_t)mq || tq == 0xffffffffu) { }                             // nobody in my cluster beats me: top_p stays unset
 		else if (MODE == SW_ISO && (s_gidp[tq] >> 1) != mgene) scan = true;               // overlap.c:77: only isoforms of my own gene count; the strongest of THOSE needs the scan
-		else if ((int32_t)tq < mq? s_ce[tq] > mcs : s_cs[tq] < mce) { top_key = s_cmax[head]; top_p = lo + (int32_t)tq; }   // overlap.c:70,118: it is one of my partners
+		else if ((int32_t)tq < mq? s_ce[tq] > mcs : s_cs[tq] < mce) { top_key = NEWP0? s_key[tq] : s_cmax[head]; top_p = lo + (int32_t)tq; }   // overlap.c:70,118: it is one of my partners
 		else scan = true;
 	}
 	// ---- phase 1b: the would-be dominator by scanning the window.  One loop walks back, then forward: a lane whose backward
@@ -813,7 +878,7 @@ template<int MODE> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(
 					bits_out[h] = b;
 					pdom_out[h] = (w_lose && w_key > 0)? c.pid[w_p] : -1;
 				} else {
-					bits_out[h] = hbits;
+					if (!NEWP0) bits_out[h] = hbits;
 					int32_t pd = -1, sd = -1;
 					if (w_lose && w_key > 0) {
 						pd = c.pid[w_p];

@@ -18,10 +18,17 @@ extern "C" int sweep_emu(int variant, int mode, const EmuCols *e, double min_ov_
 	SweepOpt o; o.min_ov_ratio = min_ov_ratio; o.check_strand = check_strand;
 	if (c.n <= 0) return 0;
 #define RUN(K, T, ...) emu::launch((c.n + (T) - 1) / (T), (T), [&] { K(c, o, bits_out, pdom_out, sdom_out, tie_cnt __VA_ARGS__); })
-#define BY_MODE(K, T, ...) do { if (mode == 0) RUN(K<SW_LOAD>, T, __VA_ARGS__); else if (mode == 1) RUN(K<SW_SHADOW>, T, __VA_ARGS__); else RUN(K<SW_ISO>, T, __VA_ARGS__); } while (0)
 #define COMMA ,
-	if (variant == 0) BY_MODE(k_sweep, 128);                   // plain thread-per-hit kernel
-	else if (variant == 1) BY_MODE(k_sweep_tiled, SWQ_TILE, COMMA (const uint32_t*)nullptr);   // production kernel (no tile skipping)
+	const uint32_t *no_dirty = nullptr;
+	if (variant == 0) {                                        // plain thread-per-hit kernel
+		if (mode == 0) RUN(k_sweep<SW_LOAD>, 128); else if (mode == 1) RUN(k_sweep<SW_SHADOW>, 128); else RUN(k_sweep<SW_ISO>, 128);
+	} else if (variant == 1) {                                 // production kernel, VAR 0 (no tile skipping)
+		if (mode == 0) RUN((k_sweep_tiled<SW_LOAD COMMA 0>), SWQ_TILE, COMMA no_dirty); else if (mode == 1) RUN((k_sweep_tiled<SW_SHADOW COMMA 0>), SWQ_TILE, COMMA no_dirty); else RUN((k_sweep_tiled<SW_ISO COMMA 0>), SWQ_TILE, COMMA no_dirty);
+	} else if (variant == 2) {                                 // VAR 1 (SW_SHADOW has one variant only)
+		if (mode == 0) RUN((k_sweep_tiled<SW_LOAD COMMA 1>), SWQ_TILE, COMMA no_dirty); else if (mode == 1) RUN((k_sweep_tiled<SW_SHADOW COMMA 0>), SWQ_TILE, COMMA no_dirty); else RUN((k_sweep_tiled<SW_ISO COMMA 1>), SWQ_TILE, COMMA no_dirty);
+	} else if (variant == 3) {                                 // VAR 2: as 1, isoform sweep on the cluster shortcut
+		if (mode == 0) RUN((k_sweep_tiled<SW_LOAD COMMA 1>), SWQ_TILE, COMMA no_dirty); else if (mode == 1) RUN((k_sweep_tiled<SW_SHADOW COMMA 0>), SWQ_TILE, COMMA no_dirty); else RUN((k_sweep_tiled<SW_ISO COMMA 2>), SWQ_TILE, COMMA no_dirty);
+	}
 	else return -1;
 	return 0;
 }

@@ -29,6 +29,7 @@
 
 struct int2 { int32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+struct int4 { int32_t x, y, z, w; };
 static inline int2 make_int2(int32_t x, int32_t y) { int2 r; r.x = x; r.y = y; return r; }
 struct emu_dim3 { int x = 0, y = 0, z = 0; };
 static thread_local emu_dim3 threadIdx, blockIdx;

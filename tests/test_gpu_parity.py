@@ -353,3 +353,43 @@ def test_packed_reader_route(tmp_path):
         assert sorted(got.splitlines()) == sorted(want.splitlines()), common.first_diff(want, got)
         engine.release_tokens(d2, tok); engine.destroy(g2); hostio.lib().pgio_packed_destroy(C.byref(pk)); hostio.destroy(d2)
         pgoracle.destroy(g1); hostio.destroy(d1)
+
+
+_VARIANT_SCRIPT = r"""
+import hashlib, sys
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(tests)r)
+import common
+from pangene_b200 import engine, hostio
+engine.set_verbose(1)
+opt = hostio.default_opt()
+out = []
+for cfg, kw in ((3, dict(n_genome=5, n_gene=1500, iso_per_gene=4, hits_per_genome=30000, n_genome_total=5)), (2, dict(n_genome=6, n_gene=1200, iso_per_gene=1, hits_per_genome=9000, n_genome_total=6))):
+    d = hostio.synth(opt, hostio.synth_params(cfg, **kw))
+    g = engine.hot_path(opt, d)
+    out.append(hashlib.md5(b"\n".join(sorted(common.gfa_bytes(g).splitlines()))).hexdigest())
+    out.append(hashlib.md5(b"\n".join(sorted(common.bed_bytes(d).splitlines()))).hexdigest())
+print("VARIANT_RESULT", " ".join(out))
+"""
+
+
+def test_sweep_kernel_variants_agree_with_the_oracle():
+    """k_sweep_tiled<MODE, VAR> for VAR 0, 1, 2 (PGX_SWEEP_VARIANT; one process each: the choice is read once) and the plain thread-per-hit
+    kernel (PGX_SWEEP=global) give the oracle's GFA lines and per-hit flag lines on an isoform-rich and a single-isoform set."""
+    import hashlib
+    import subprocess
+    import sys
+    opt = hostio.default_opt()
+    want = []
+    for cfg, kw in ((3, dict(n_genome=5, n_gene=1500, iso_per_gene=4, hits_per_genome=30000, n_genome_total=5)), (2, dict(n_genome=6, n_gene=1200, iso_per_gene=1, hits_per_genome=9000, n_genome_total=6))):
+        d = hostio.synth(opt, hostio.synth_params(cfg, **kw))
+        g = pgoracle.hot_path(opt, d)
+        want.append(hashlib.md5(b"\n".join(sorted(common.gfa_bytes(g).splitlines()))).hexdigest())
+        want.append(hashlib.md5(b"\n".join(sorted(common.bed_bytes(d).splitlines()))).hexdigest())
+        pgoracle.destroy(g); hostio.destroy(d)
+    script = _VARIANT_SCRIPT % dict(root=common.ROOT, tests=os.path.join(common.ROOT, "tests"))
+    for env_extra in ({"PGX_SWEEP_VARIANT": "0"}, {"PGX_SWEEP_VARIANT": "1"}, {"PGX_SWEEP_VARIANT": "2"}, {"PGX_SWEEP": "global"}):
+        env = dict(os.environ); env.pop("PGX_SWEEP", None); env.pop("PGX_SWEEP_VARIANT", None); env.update(env_extra)
+        r = subprocess.run([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert r.returncode == 0, (env_extra, r.stderr[-2000:])
+        got = [l for l in r.stdout.splitlines() if l.startswith("VARIANT_RESULT")][-1].split()[1:]
+        assert got == want, (env_extra, got, want)
