@@ -400,9 +400,10 @@ struct Session {
 		if (c.n <= 0) return;
 		if (plain) { PGX_LAUNCH(k_sweep<MODE>, grid_for(c.n, 128), 128, 0, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP); return; }
 		// PGX_SWEEP_VARIANT: the A/B switch of k_sweep_tiled (pgx_kernels.cuh): 0 = the kernel as first measured in round 2, 1 (default) = 32-bit cluster
-		// maxima + staged result columns, isoform sweep on the window scan, 2 = as 1 with the isoform sweep on the cluster shortcut
-		static const int variant = []() { const char *e = getenv("PGX_SWEEP_VARIANT"); const int v = e? atoi(e) : SWEEP_VARIANT_DEFAULT; return v < 0 || v > 2? SWEEP_VARIANT_DEFAULT : v; }();
-		constexpr int V2 = MODE == SW_ISO? 2 : 1;   // (variant 2 differs from 1 in the isoform sweep only)
+		// maxima + staged result columns, isoform sweep on the window scan, 2 = as 1 with the isoform sweep on the cluster shortcut, 3 = as 1 without
+		// the cluster pass in the first sweep
+		static const int variant = []() { const char *e = getenv("PGX_SWEEP_VARIANT"); const int v = e? atoi(e) : SWEEP_VARIANT_DEFAULT; return v < 0 || v > 3? SWEEP_VARIANT_DEFAULT : v; }();
+		constexpr int V2 = MODE == SW_ISO? 2 : 1, V3 = MODE == SW_LOAD? 3 : 1;   // (variant 2 differs from 1 in the isoform sweep only, variant 3 in the first sweep only)
 		static int attr_dev = -1;              // (function attributes are per device: set again if the process moved to another one)
 		int cur_dev = 0; PGX_CHECK(cudaGetDevice(&cur_dev));
 		if (attr_dev != cur_dev) {
@@ -412,13 +413,14 @@ struct Session {
 				PGX_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 			};
 			prep((const void*)k_sweep_tiled<MODE, 0>);
-			if (MODE != SW_SHADOW) { prep((const void*)k_sweep_tiled<MODE, 1>); prep((const void*)k_sweep_tiled<MODE, V2>); }
+			if (MODE != SW_SHADOW) { prep((const void*)k_sweep_tiled<MODE, 1>); prep((const void*)k_sweep_tiled<MODE, V2>); prep((const void*)k_sweep_tiled<MODE, V3>); }
 			attr_dev = cur_dev;
 		}
 		const int v = MODE == SW_SHADOW? 0 : variant;
 		if (v == 0) PGX_LAUNCH((k_sweep_tiled<MODE, 0>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
 		else if (v == 1) PGX_LAUNCH((k_sweep_tiled<MODE, 1>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
-		else PGX_LAUNCH((k_sweep_tiled<MODE, V2>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
+		else if (v == 2) PGX_LAUNCH((k_sweep_tiled<MODE, V2>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
+		else PGX_LAUNCH((k_sweep_tiled<MODE, V3>), grid_for(c.n, SWQ_TILE), SWQ_TILE, SWQ_SMEM, st, c, so, bits_out, pdom_out, sdom_out, counters.p + C_TIE_DUP, dirty);
 	}
 
 	// stable radix sort of n (key, iota) pairs taken from the scratch arena; returns the permutation (device pointer valid until the arena is reset)

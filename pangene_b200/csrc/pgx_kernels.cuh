@@ -498,7 +498,8 @@ template<bool EARLY> __device__ __forceinline__ int32_t pair_overlap(const int2 
 // word with native 32-bit shared-memory atomics (a tie of that word at the top of a cluster sends its hits to the exact window scan), holder
 // count and slot in ONE atomic, the pid / score_ori columns staged beside the others (no global load on the result path), warp prefixes from
 // one 128-bit load, no flag-word store in SW_LOAD (the isoform sweep that follows writes every flag word), the isoform sweep on the window scan;
-// 2 = as 1 with the isoform sweep on the cluster shortcut.  SW_SHADOW is the same code for every VAR.
+// 2 = as 1 with the isoform sweep on the cluster shortcut; 3 = as 1 without the cluster pass in SW_LOAD either (every hit scans its window).
+// SW_SHADOW is the same code for every VAR.
 template<int MODE, int VAR> __global__ void __launch_bounds__(SWQ_TILE, 5) k_sweep_tiled(SweepCols c, SweepOpt o, uint32_t *bits_out, int32_t *pdom_out, int32_t *sdom_out, uint32_t *tie_cnt, const uint32_t *dirty)
 {
 	constexpr bool NEWP0 = VAR != 0 && MODE != SW_SHADOW;                                // the new cluster pass + staged result columns
@@ -565,7 +566,7 @@ template<int MODE, int VAR> __global__ void __launch_bounds__(SWQ_TILE, 5) k_swe
 	// Only usable where the loser of a pair is decided by the keys alone, i.e. where no unfiltered hit of the tile carries a weak_br mark
 	// (overlap.c:139-147): flag 1.
 	const int32_t S = hi - lo;
-	const bool rmq_mode = (MODE == SW_LOAD || (MODE == SW_ISO && VAR != 1)) && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
+	const bool rmq_mode = ((MODE == SW_LOAD && VAR != 3) || (MODE == SW_ISO && (VAR == 0 || VAR == 2))) && !o.check_strand;   // (the later sweeps run on the small active set and mostly see weak_br marks)
 	// filtered hits (25 % in the first sweep) do no work: the live ones are compacted so that they fill whole warps.
 	const int32_t i0 = t0 + tid;
 	const bool r0 = i0 < c.n;

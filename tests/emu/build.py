@@ -28,6 +28,8 @@ extern "C" int sweep_emu(int variant, int mode, const EmuCols *e, double min_ov_
 		if (mode == 0) RUN((k_sweep_tiled<SW_LOAD COMMA 1>), SWQ_TILE, COMMA no_dirty); else if (mode == 1) RUN((k_sweep_tiled<SW_SHADOW COMMA 0>), SWQ_TILE, COMMA no_dirty); else RUN((k_sweep_tiled<SW_ISO COMMA 1>), SWQ_TILE, COMMA no_dirty);
 	} else if (variant == 3) {                                 // VAR 2: as 1, isoform sweep on the cluster shortcut
 		if (mode == 0) RUN((k_sweep_tiled<SW_LOAD COMMA 1>), SWQ_TILE, COMMA no_dirty); else if (mode == 1) RUN((k_sweep_tiled<SW_SHADOW COMMA 0>), SWQ_TILE, COMMA no_dirty); else RUN((k_sweep_tiled<SW_ISO COMMA 2>), SWQ_TILE, COMMA no_dirty);
+	} else if (variant == 4) {                                 // VAR 3: as 1, no cluster pass in the first sweep
+		if (mode == 0) RUN((k_sweep_tiled<SW_LOAD COMMA 3>), SWQ_TILE, COMMA no_dirty); else if (mode == 1) RUN((k_sweep_tiled<SW_SHADOW COMMA 0>), SWQ_TILE, COMMA no_dirty); else RUN((k_sweep_tiled<SW_ISO COMMA 1>), SWQ_TILE, COMMA no_dirty);
 	}
 	else return -1;
 	return 0;

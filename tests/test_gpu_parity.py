@@ -373,7 +373,7 @@ print("VARIANT_RESULT", " ".join(out))
 
 
 def test_sweep_kernel_variants_agree_with_the_oracle():
-    """k_sweep_tiled<MODE, VAR> for VAR 0, 1, 2 (PGX_SWEEP_VARIANT; one process each: the choice is read once) and the plain thread-per-hit
+    """k_sweep_tiled<MODE, VAR> for VAR 0 ... 3 (PGX_SWEEP_VARIANT; one process each: the choice is read once) and the plain thread-per-hit
     kernel (PGX_SWEEP=global) give the oracle's GFA lines and per-hit flag lines on an isoform-rich and a single-isoform set."""
     import hashlib
     import subprocess
@@ -387,7 +387,7 @@ def test_sweep_kernel_variants_agree_with_the_oracle():
         want.append(hashlib.md5(b"\n".join(sorted(common.bed_bytes(d).splitlines()))).hexdigest())
         pgoracle.destroy(g); hostio.destroy(d)
     script = _VARIANT_SCRIPT % dict(root=common.ROOT, tests=os.path.join(common.ROOT, "tests"))
-    for env_extra in ({"PGX_SWEEP_VARIANT": "0"}, {"PGX_SWEEP_VARIANT": "1"}, {"PGX_SWEEP_VARIANT": "2"}, {"PGX_SWEEP": "global"}):
+    for env_extra in ({"PGX_SWEEP_VARIANT": "0"}, {"PGX_SWEEP_VARIANT": "1"}, {"PGX_SWEEP_VARIANT": "2"}, {"PGX_SWEEP_VARIANT": "3"}, {"PGX_SWEEP": "global"}):
         env = dict(os.environ); env.pop("PGX_SWEEP", None); env.pop("PGX_SWEEP_VARIANT", None); env.update(env_extra)
         r = subprocess.run([sys.executable, "-c", script], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
         assert r.returncode == 0, (env_extra, r.stderr[-2000:])
