@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Reads the A/B log of tools/gpu_r2q.sh (one tools/profile_run.py run per PGX_SWEEP_VARIANT) and prints the variant with the smallest median
+"""Reads the A/B log of tools/sessions/gpu_r2q.sh (one tools/profile_run.py run per PGX_SWEEP_VARIANT) and prints the variant with the smallest median
 device time per pass (first pass of every run dropped: cold caches and first-touch allocations)."""
 import re
 import statistics
