@@ -346,9 +346,10 @@ def main():
                                      "api": "pgx_set_lazy(2): pg_post_process + pg_graph_init + pg_graph_gen + pgx_walk_tokens -- host pg_data_t in, graph + walk tokens out (everything a GFA needs; no pg_hit_t record is rebuilt)"}},
         "parity": parity,
         "e2e": {"value": n_total / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                "ms_samples": [round(x * 1e3, 1) for x in e2e_t],       # the five timed calls behind the median (this leg is host-memory bound and varies from box to box: DESIGN.md 6)
                 "api": "pg_post_process + pg_graph_init + pg_graph_gen on malloc'd pg_data_t (lazy materialisation, as the CLI does); bytes are rank 0's, counted by the library: 48 B/hit + exons up, 24 B/hit + graph down"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_sweep_tiled<SW_LOAD> (first overlap sweep, pg_shadow cal_dom_sc=1; at N > 1: this rank's shard)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_sweep_tiled<SW_LOAD, 1> (first overlap sweep, pg_shadow cal_dom_sc=1; at N > 1: this rank's shard)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_t},
         "clocks": clk.summary(),
     }
