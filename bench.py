@@ -274,8 +274,9 @@ def main():
 
     # ---- the GFA-only route of the same C ABI (what the CLI runs for `pangene *.paf > out.gfa`): lazy mode 2 returns the graph, the hits stay
     # on the device and only the walk tokens of the W lines (12 B per printed hit) come back; checked against the same golden
+    # (single-GPU lines only: the sharded run's contract is value / e2e / parity above)
     gfa_t, gfa_d2h, digest_tok = [], 0, None
-    n_gfa = 1 + 3
+    n_gfa = (1 + 3) if world == 1 else 0
     for it in range(n_gfa):
         d = hostio.lib().pgio_data_clone(d0)
         barrier()
@@ -292,7 +293,7 @@ def main():
         engine.release_tokens(d, tok)
         L.pg_graph_destroy(g)
         hostio.lib().pgio_data_clone_destroy(d)
-    gfa_s = statistics.median(gfa_t)
+    gfa_s = statistics.median(gfa_t) if gfa_t else None
 
     # ---- parity gate: every rank's replicated S/L lines + the W lines of all ranks in genome order, against the reference's golden
     parity = {"status": "unchecked (--no-parity)"}
@@ -336,14 +337,16 @@ def main():
     if os.path.exists(tp) and world == 1 and a.genomes == 100:   # (a constant from the committed ncu capture of this kernel, not measured in this run: the label says which build)
         tj = json.load(open(tp))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), "%s; %s" % (tj.get("source"), tj.get("build"))
+    gfa_route = None
+    if gfa_s is not None:
+        gfa_route = {"value": n_total / gfa_s, "unit": "hits/s", "ms_per_step": gfa_s * 1e3, "d2h_bytes_per_step": int(gfa_d2h), "parity": parity_tok["status"],
+                     "api": "pgx_set_lazy(2): pg_post_process + pg_graph_init + pg_graph_gen + pgx_walk_tokens -- host pg_data_t in, graph + walk tokens out (everything a GFA needs; no pg_hit_t record is rebuilt)"}
     out = {
         "metric": METRIC, "value": n_total / (ms_step * 1e-3), "unit": "hits/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
         "config": workload_config(n_total, G_total, world),
         "detail": {"active_hits_after_load_filters_rank0": int(n_active), "wall_ms_per_step_incl_host": wall_step, "stage_ms": [stage1_ms, stage2_ms],
-                   "ms_per_step_rank0": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms)}, "fast_rounds_per_step": int(fast_rounds), "careful_redos": int(redos),
-                   "e2e_gfa_route": {"value": n_total / gfa_s, "unit": "hits/s", "ms_per_step": gfa_s * 1e3, "d2h_bytes_per_step": int(gfa_d2h), "parity": parity_tok["status"],
-                                     "api": "pgx_set_lazy(2): pg_post_process + pg_graph_init + pg_graph_gen + pgx_walk_tokens -- host pg_data_t in, graph + walk tokens out (everything a GFA needs; no pg_hit_t record is rebuilt)"}},
+                   "ms_per_step_rank0": {"min": min(dev_ms), "median": statistics.median(dev_ms), "max": max(dev_ms)}, "fast_rounds_per_step": int(fast_rounds), "careful_redos": int(redos)},
         "parity": parity,
         "e2e": {"value": n_total / e2e_s, "unit": "hits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                 "ms_samples": [round(x * 1e3, 1) for x in e2e_t],       # the five timed calls behind the median (this leg is host-memory bound and varies from box to box: DESIGN.md 6)
@@ -353,6 +356,8 @@ def main():
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_t},
         "clocks": clk.summary(),
     }
+    if gfa_route is not None:
+        out["detail"]["e2e_gfa_route"] = gfa_route
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(hostio, CPU_SAMPLE_GENOMES)[0]
     print(json.dumps(out), flush=True)        # ONE line, flushed before the teardown below can go wrong
