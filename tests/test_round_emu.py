@@ -180,6 +180,23 @@ def test_arc_build_raises_fallback_when_the_table_is_too_small(emu):
     assert out[2] == 1
 
 
+def test_arc_build_raises_fallback_when_the_overflow_table_is_too_small(emu):
+    """many (key, genome) groups of several records (tandem repeats) against an overflow table of 16 entries: k_arc_fold's group insert must
+    raise the fallback (the run is then redone on the careful path), and the table must still be handed back empty for the next round"""
+    rng = np.random.default_rng(13)
+    cols, sv, n_gene = make_case(rng, 4, 40, 200, 0.6)
+    arc_cap = 4 * len(sv) + 16
+    arc = np.zeros(arc_cap, dtype=ARC); idx = np.zeros(82, np.uint64); seg_ng = np.zeros(40, np.int32); seg_tot = np.zeros(40, np.int32); nl_off = np.zeros(88, np.uint32); out = np.zeros(4, np.uint32)
+    e = EmuArcIn(n_hit=len(cols["ctg"]), n_sv=len(sv), n_seg0=40, n_gene=n_gene, G=4, use_ori=0, grid=2, H=4096, H2=16, arc_cap=arc_cap, ranks=1)
+    for k in ("ctg", "cm", "gidp", "sori", "sdom", "pdom0", "g2s", "prot_gid", "ctg2g", "bits"):
+        setattr(e, k, cols[k].ctypes.data)
+    e.sv = sv.ctypes.data; e.arc = arc.ctypes.data; e.idx = idx.ctypes.data; e.seg_ng = seg_ng.ctypes.data; e.seg_tot = seg_tot.ctypes.data
+    e.nl_off = nl_off.ctypes.data; e.out_counts = out.ctypes.data
+    rc = emu.round_emu_arc_build(C.byref(e))
+    assert rc == 0, "the overflow table was not handed back clean (rc %d)" % rc
+    assert out[3] > 32 and out[2] == 1
+
+
 @pytest.mark.parametrize("n,with_perm", [(0, False), (1, False), (2047, True), (2048, False), (2049, True), (9000, True)])
 def test_survivor_compaction(emu, n, with_perm):
     rng = np.random.default_rng(n)
