@@ -298,6 +298,50 @@ def build_round():
     return so
 
 
+
+def build_full():
+    """tests/emu/_build/libpgx_emu.so: ALL of libpgx -- the C ABI of include/pgx.h, the engine (pgx_engine.cuh) and every kernel -- compiled for
+    the host: the product sources are copied with three kinds of textual change (the <<< >>> launch inside PGX_LAUNCH becomes a shim launch, the
+    two `extern __shared__` declarations point at the shim's dynamic shared memory, the fixed grids of the grid-stride launches shrink from
+    multiples of 148 to 2-3 CTAs) and see tests/emu/cuda_shim/cuda_runtime.h instead of the CUDA runtime.  Small inputs run through pg_post_process() / pg_graph_gen() of this library exactly as they would on the device."""
+    csrc = os.path.join(ROOT, "pangene_b200", "csrc")
+    out = os.path.join(OUT, "full")
+    os.makedirs(out, exist_ok=True)
+    texts = {}
+    for fn in sorted(os.listdir(csrc)):
+        if not (fn.endswith(".cuh") or fn.endswith(".hpp") or fn == "pgx_api.cu"):
+            continue
+        t = open(os.path.join(csrc, fn)).read()
+        if fn == "pgx_util.cuh":
+            old = "kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); \\"
+            assert t.count(old) == 1
+            t = t.replace(old, "emu::launch_any((long)(grid), (int)(block), [&] { kernel(__VA_ARGS__); }); \\")
+        for decl, name in (("extern __shared__ __align__(16) unsigned char smem_raw[];", "smem_raw"), ("extern __shared__ __align__(16) unsigned char rs_smem[];", "rs_smem")):
+            if decl in t:
+                assert t.count(decl) == 1
+                t = t.replace(decl, "unsigned char *%s = emu_dyn_smem;" % name)
+        if fn == "pgx_engine.cuh":   # grid-stride launches sized for 148 SMs: a few CTAs give the same result and spare the shim a thousand CTA turns per launch
+            for old, cnt, rep_ in (("static constexpr int GS_GRID = 148 * 8;", 1, "static constexpr int GS_GRID = 3;"), ("PGX_LAUNCH(k_round_clear, 148 * 4, 256,", 2, "PGX_LAUNCH(k_round_clear, 2, 256,"),
+                                   ("PGX_LAUNCH(k_arc_ovf_fold, 148, TB,", 1, "PGX_LAUNCH(k_arc_ovf_fold, 2, TB,"), ("PGX_LAUNCH(k_seg_compact_fast, 148, TB,", 1, "PGX_LAUNCH(k_seg_compact_fast, 2, TB,")):
+                assert t.count(old) == cnt, old
+                t = t.replace(old, rep_)
+        texts["pgx_api.cpp" if fn == "pgx_api.cu" else fn] = t
+    assert "<<<" not in "".join(texts.values()).replace("<<<>>>", "")
+    stamp = os.path.join(out, ".stamp")
+    so = os.path.join(OUT, "libpgx_emu.so")
+    deps = [os.path.join(HERE, "simt_emu.hpp"), os.path.join(HERE, "cuda_shim", "cuda_runtime.h")]
+    import hashlib
+    h = hashlib.md5(("".join(k + v for k, v in sorted(texts.items())) + "".join(open(d).read() for d in deps)).encode()).hexdigest()
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == h:
+        return so
+    for k, v in texts.items():
+        open(os.path.join(out, k), "w").write(v)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DPGX_SIMT_EMU=1", "-I", os.path.join(HERE, "cuda_shim"), "-I", HERE,
+                           "-I", out, "-I", os.path.join(ROOT, "include"), os.path.join(out, "pgx_api.cpp"), "-o", so, "-ldl", "-lrt"])
+    open(stamp, "w").write(h)
+    return so
+
+
 if __name__ == "__main__":
     print(build())
     print(build_prim())

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <thread>
+#include <mutex>
 #include <vector>
 
 #define PGX_SIMT_EMU 1
