@@ -299,8 +299,9 @@ def build_round():
 
 
 
-def build_full():
-    """tests/emu/_build/libpgx_emu.so: ALL of libpgx -- the C ABI of include/pgx.h, the engine (pgx_engine.cuh) and every kernel -- compiled for
+def build_full(sanitize=False):
+    """tests/emu/_build/libpgx_emu.so (sanitize=True: libpgx_emu_asan.so, the same text under AddressSanitizer + UBSan -- a CPU-side "memcheck" of
+    every kernel's global and shared-memory indexing; load it with LD_PRELOAD=libasan): ALL of libpgx -- the C ABI of include/pgx.h, the engine (pgx_engine.cuh) and every kernel -- compiled for
     the host: the product sources are copied with three kinds of textual change (the <<< >>> launch inside PGX_LAUNCH becomes a shim launch, the
     two `extern __shared__` declarations point at the shim's dynamic shared memory, the fixed grids of the grid-stride launches shrink from
     multiples of 148 to 2-3 CTAs) and see tests/emu/cuda_shim/cuda_runtime.h instead of the CUDA runtime.  Small inputs run through pg_post_process() / pg_graph_gen() of this library exactly as they would on the device."""
@@ -327,8 +328,8 @@ def build_full():
                 t = t.replace(old, rep_)
         texts["pgx_api.cpp" if fn == "pgx_api.cu" else fn] = t
     assert "<<<" not in "".join(texts.values()).replace("<<<>>>", "")
-    stamp = os.path.join(out, ".stamp")
-    so = os.path.join(OUT, "libpgx_emu.so")
+    stamp = os.path.join(out, ".stamp_asan" if sanitize else ".stamp")
+    so = os.path.join(OUT, "libpgx_emu_asan.so" if sanitize else "libpgx_emu.so")
     deps = [os.path.join(HERE, "simt_emu.hpp"), os.path.join(HERE, "cuda_shim", "cuda_runtime.h")]
     import hashlib
     h = hashlib.md5(("".join(k + v for k, v in sorted(texts.items())) + "".join(open(d).read() for d in deps)).encode()).hexdigest()
@@ -336,7 +337,8 @@ def build_full():
         return so
     for k, v in texts.items():
         open(os.path.join(out, k), "w").write(v)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DPGX_SIMT_EMU=1", "-I", os.path.join(HERE, "cuda_shim"), "-I", HERE,
+    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if sanitize else []
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DPGX_SIMT_EMU=1"] + san + ["-I", os.path.join(HERE, "cuda_shim"), "-I", HERE,
                            "-I", out, "-I", os.path.join(ROOT, "include"), os.path.join(out, "pgx_api.cpp"), "-o", so, "-ldl", "-lrt"])
     open(stamp, "w").write(h)
     return so

@@ -1,0 +1,34 @@
+"""The PRODUCT's own source on the CPU.  tests/emu/build.py::build_full() compiles all of libpgx -- C ABI, engine, every kernel -- for the host on
+the SIMT shim (CUDA threads = OS threads, one CTA at a time; tests/emu/cuda_shim/cuda_runtime.h stands in for the CUDA runtime) as
+tests/emu/_build/libpgx_emu.so, and a subset of the GPU parity suite (the `-m gpu` tests, unchanged) is run against THAT library through the
+binding's PGX_LIB override: byte-identical C4 goldens, a synthetic golden, the first-hit and cm-tie replay paths, the edge cases, the sort / scan
+primitives.  This is test infrastructure: what is timed, shipped and graded is libpgx.so on the device; nothing in the product loads the host
+build, and it is ~10^4 times slower.  (The whole `-m gpu` suite minus the full-size configurations was run this way once per release:
+profiles/README.md.)"""
+import os
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu import build as emu_build  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SUBSET = ["tests/test_gpu_parity.py::test_c4_golden",
+          "tests/test_gpu_parity.py::test_synthetic_goldens[euk_iso4_J_T3]",
+          "tests/test_gpu_parity.py::test_first_hit_tie_cases[463]",
+          "tests/test_gpu_parity.py::test_cm_tied_survivor_cases[110]",
+          "tests/test_edge_cases.py::test_gpu_matches_oracle_on_edge_cases",
+          "tests/test_gpu_primitives.py::test_radix_sort_is_a_stable_sort[4097-24]",
+          "tests/test_gpu_primitives.py::test_radix_sort_is_a_stable_sort[37-8]",
+          "tests/test_gpu_primitives.py::test_exclusive_sum[2049]",
+          "tests/test_gpu_primitives.py::test_segmented_running_max[5000-700]"]
+
+
+def test_gpu_parity_subset_on_the_host_build_of_libpgx():
+    so = emu_build.build_full()
+    env = dict(os.environ, PGX_LIB=so)
+    env.pop("PGX_SWEEP", None); env.pop("PGX_SWEEP_VARIANT", None); env.pop("PGX_ROUNDS", None)
+    r = subprocess.run([sys.executable, "-m", "pytest"] + SUBSET + ["-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"], cwd=ROOT, env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=2400)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-4000:]
