@@ -32,3 +32,19 @@ def test_gpu_parity_subset_on_the_host_build_of_libpgx():
     r = subprocess.run([sys.executable, "-m", "pytest"] + SUBSET + ["-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"], cwd=ROOT, env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=2400)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-4000:]
+
+
+def test_two_ranks_over_the_loopback_transport_on_the_host_build():
+    """the SHARDED path of the same host build: two processes under torchrun (gloo for the rendezvous), genomes partitioned, libpgx's collectives over
+    its shared-memory loopback transport -- tools/dist_check.py with PGX_HOST_BUILD=1: replicated graph identical on both ranks and equal to the
+    single-process oracle's, per-rank W and BED lines equal; one case leaves the second rank with an empty shard"""
+    import socket
+    so = emu_build.build_full()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PGX_LIB=so, PGX_HOST_BUILD="1")
+    env.pop("PGX_SWEEP", None); env.pop("PGX_SWEEP_VARIANT", None); env.pop("PGX_ROUNDS", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(ROOT, "tools", "dist_check.py")], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=2400)
+    assert r.returncode == 0 and "DIST_CHECK PASS" in r.stdout, r.stdout[-4000:]

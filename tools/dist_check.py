@@ -24,14 +24,23 @@ CASES = [dict(config=2, n_genome=7, n_gene=1800, iso_per_gene=4, hits_per_genome
          dict(config=2, n_genome=9, n_gene=2500, iso_per_gene=1, hits_per_genome=6000, args=["-S"]),
          dict(config=5, n_genome=64, n_gene=1200, iso_per_gene=1, hits_per_genome=1000, args=["-p0", "-a2"]),
          dict(config=2, n_genome=3, n_gene=900, iso_per_gene=4, hits_per_genome=8000, args=[])]   # fewer genomes than ranks at 4/8 GPUs: empty shards
+# PGX_HOST_BUILD=1 (tests/test_emulated_path.py): the library behind PGX_LIB is the host build of libpgx on the SIMT shim -- no device to select,
+# loopback transport, and inputs small enough for a build that is ~10^4 times slower
+CASES_HOST_BUILD = [dict(config=2, n_genome=4, n_gene=150, iso_per_gene=4, hits_per_genome=1100, args=[]),
+                    dict(config=5, n_genome=7, n_gene=160, iso_per_gene=1, hits_per_genome=150, args=["-p0", "-a2"]),
+                    dict(config=2, n_genome=1, n_gene=120, iso_per_gene=1, hits_per_genome=300, args=["-S"])]   # one genome: the second rank's shard is empty
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     loopback = os.environ.get("PGX_LOOPBACK") == "1"       # ranks share the GPUs there are; collectives through shared memory (pgx_comm.cuh)
-    if loopback:
-        local = local % torch.cuda.device_count()
-    torch.cuda.set_device(local)
+    host_build = os.environ.get("PGX_HOST_BUILD") == "1"
+    if host_build:
+        loopback, local = True, 0
+    else:
+        if loopback:
+            local = local % torch.cuda.device_count()
+        torch.cuda.set_device(local)
     if loopback:
         dist.init_process_group("gloo")
     else:
@@ -40,7 +49,7 @@ def main():
     L.pgx_set_device(local)
     engine.set_verbose(1)
     ok = True
-    for ci, case in enumerate(CASES):
+    for ci, case in enumerate(CASES_HOST_BUILD if host_build else CASES):
         G = case["n_genome"]
         b, e = pgdist.partition(G, world)[rank]
         if loopback:
