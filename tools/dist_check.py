@@ -65,6 +65,19 @@ def main():
             hostio.write_gfa(g, t.name, False, True)
             wl = open(t.name, "rb").read()
         bed = common.bed_bytes(d)
+        if host_build:   # the GFA route of the sharded run (lazy mode 2: graph + walk tokens, no pg_hit_t back) must print the same S/L and W lines
+            d2 = hostio.synth(opt, p)
+            g2, tok, off, n_tok = engine.graph_and_tokens(opt, d2)
+            with tempfile.NamedTemporaryFile() as t:
+                hostio.write_gfa_tokens(g2, tok, off, t.name, True, False)
+                sl2 = open(t.name, "rb").read()
+                hostio.write_gfa_tokens(g2, tok, off, t.name, False, True)
+                wl2 = open(t.name, "rb").read()
+            engine.release_tokens(d2, tok)
+            if sl2 != sl or wl2 != wl:
+                print("case %d rank %d: the token route differs from the pg_hit_t route (%d tokens)" % (ci, rank, n_tok), flush=True)
+                ok = False
+            engine.destroy(g2); hostio.destroy(d2)
         parts = pgdist.gather_in_rank_order((hashlib.md5(sl).hexdigest(), wl, bed), world)
         if rank == 0:
             po = hostio.synth_params(case["config"], n_genome=G, n_gene=case["n_gene"], iso_per_gene=case["iso_per_gene"], hits_per_genome=case["hits_per_genome"], n_genome_total=G)
@@ -83,6 +96,9 @@ def main():
         engine.destroy(g); hostio.destroy(d)
         L.pgx_comm_destroy()
         dist.barrier()
+    if host_build:   # (every rank checked its own token route)
+        oks = pgdist.gather_in_rank_order(ok, world)
+        ok = all(oks)
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
