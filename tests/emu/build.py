@@ -338,7 +338,7 @@ def build_full(sanitize=False):
     for k, v in texts.items():
         open(os.path.join(out, k), "w").write(v)
     san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if sanitize else []
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DPGX_SIMT_EMU=1"] + san + ["-I", os.path.join(HERE, "cuda_shim"), "-I", HERE,
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DPGX_SIMT_EMU=1"] + (["-g"] + san if sanitize else []) + ["-I", os.path.join(HERE, "cuda_shim"), "-I", HERE,
                            "-I", out, "-I", os.path.join(ROOT, "include"), os.path.join(out, "pgx_api.cpp"), "-o", so, "-ldl", "-lrt"])
     open(stamp, "w").write(h)
     return so
