@@ -49,7 +49,10 @@ def main():
     L.pgx_set_device(local)
     engine.set_verbose(1)
     ok = True
+    only = os.environ.get("PGX_HOST_BUILD_CASES")                  # (host build: a comma-separated subset of its cases)
     for ci, case in enumerate(CASES_HOST_BUILD if host_build else CASES):
+        if host_build and only and str(ci) not in only.split(","):
+            continue
         G = case["n_genome"]
         b, e = pgdist.partition(G, world)[rank]
         if loopback:
