@@ -13,6 +13,8 @@ per GPU, NCCL collectives inside libpgx.
                pg_graph_init() + pg_graph_gen() on a malloc'd pg_data_t, H2D of the raw hits and D2H of the
                finished hits + graph inside the timed region (wall clock around the calls, which return
                synchronously).
+               Median of five timed calls after two untimed ones (`ms_samples` lists the five); `detail.e2e_gfa_route`
+               (single-GPU lines) is the same C ABI on its GFA route: graph + walk tokens out, no pg_hit_t rebuilt.
   roofline     the first (load-time) overlap sweep -- the one launch that streams ~all hits: algorithmic bytes
                (52 + 8 n_exon per unfiltered hit, 4 per filtered hit) / CUDA-event time, against
                the measured HBM copy bandwidth in MEASURED_PEAKS.json.
