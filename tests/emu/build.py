@@ -328,8 +328,9 @@ def build_full(sanitize=False):
                 t = t.replace(old, rep_)
         texts["pgx_api.cpp" if fn == "pgx_api.cu" else fn] = t
     assert "<<<" not in "".join(texts.values()).replace("<<<>>>", "")
-    stamp = os.path.join(out, ".stamp_asan" if sanitize else ".stamp")
-    so = os.path.join(OUT, "libpgx_emu_asan.so" if sanitize else "libpgx_emu.so")
+    tag = {False: "", True: "_asan", "thread": "_tsan"}[sanitize]         # sanitize="thread": ThreadSanitizer instead (racecheck of every kernel)
+    stamp = os.path.join(out, ".stamp" + tag)
+    so = os.path.join(OUT, "libpgx_emu%s.so" % tag)
     deps = [os.path.join(HERE, "simt_emu.hpp"), os.path.join(HERE, "cuda_shim", "cuda_runtime.h")]
     import hashlib
     h = hashlib.md5(("".join(k + v for k, v in sorted(texts.items())) + "".join(open(d).read() for d in deps)).encode()).hexdigest()
@@ -337,7 +338,7 @@ def build_full(sanitize=False):
         return so
     for k, v in texts.items():
         open(os.path.join(out, k), "w").write(v)
-    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if sanitize else []
+    san = ["-fsanitize=thread", "-fno-omit-frame-pointer"] if sanitize == "thread" else ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"] if sanitize else []
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DPGX_SIMT_EMU=1"] + (["-g"] + san if sanitize else []) + ["-I", os.path.join(HERE, "cuda_shim"), "-I", HERE,
                            "-I", out, "-I", os.path.join(ROOT, "include"), os.path.join(out, "pgx_api.cpp"), "-o", so, "-ldl", "-lrt"])
     open(stamp, "w").write(h)
