@@ -360,6 +360,7 @@ def main():
     }
     if gfa_route is not None:
         out["detail"]["e2e_gfa_route"] = gfa_route
+    out["detail"]["library"] = os.path.relpath(getattr(engine, "LIB_PATH", "?"), ROOT)   # pangene_b200/csrc/libpgx.so unless PGX_LIB pointed the binding at another build
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(hostio, CPU_SAMPLE_GENOMES)[0]
     print(json.dumps(out), flush=True)        # ONE line, flushed before the teardown below can go wrong

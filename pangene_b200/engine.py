@@ -9,7 +9,7 @@ from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # PGX_LIB: another build of the SAME library source -- an experimental libpgx.so for A/B timing, or the test suite's host build on the SIMT shim
-# (tests/emu, tests/test_emulated_path.py).  Nothing in the product sets it; bench.py and the CLI always run csrc/libpgx.so on the device.
+# (tests/emu, tests/test_emulated_path.py).  Nothing in the product sets it; bench.py prints the path it ran (detail.library), the CLI links csrc/libpgx.so.
 LIB_PATH = os.environ.get("PGX_LIB") or os.path.join(_HERE, "csrc", "libpgx.so")
 _LIB = None
 

@@ -84,6 +84,7 @@ def test_gpu_arm_line_with_stub_engine():
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(b["e2e"]) and len(b["e2e"]["ms_samples"]) == 5
     assert b["e2e"]["h2d_bytes_per_step"] == 1904701000 and b["e2e"]["d2h_bytes_per_step"] == 483129304
     assert b["parity"]["status"] == "ok" and b["detail"]["e2e_gfa_route"]["parity"] == "ok"
+    assert "library" in b["detail"]
     assert "workload" in b["config"] and "model" not in b["config"] and "l2" in b["config"]
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(b["clocks"])
 
